@@ -1,0 +1,14 @@
+"""CPU oracle for the TinyChatEngine quantized-linear / KV-attention hot path.
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, ``__graft_entry__.smoke()`` and bench.py's
+``cpu_baseline`` / ``--impl reference`` legs.  The product package (``tinychatengine_b200``) never imports it.
+
+* :mod:`oracle.capi`   -- ctypes bindings to ``libtce_oracle.so`` (plain-C restatement, tce_oracle.c) and to the
+  reference's own kernels compiled in place (``oracle/_ref/*.so``, ref_shim.cc).
+* :mod:`oracle.quant`  -- numpy port of the reference's offline quantizer formats
+  (llm/tools/quantize_methods.py) used to make byte-identical packed inputs.
+
+Parity pinning status: the reference's golden tensors (llm/assets, a download) are absent, so the oracle is
+pinned against the reference sources compiled here (tests/test_oracle_vs_ref.py, runs whenever oracle/_ref
+exists) and against committed fixtures generated from that build (tests/golden/).
+"""

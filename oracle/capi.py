@@ -1,0 +1,253 @@
+"""ctypes bindings for the CPU oracle (libtce_oracle.so) and the in-place reference builds (oracle/_ref).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REF_DIR = HERE / "_ref"
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
+_u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def build(ref: bool = True) -> None:
+    """(Re)build the oracle .so (and oracle/_ref when /root/reference is present)."""
+    targets = ["oracle"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-s", "-C", str(HERE)] + targets, check=True)
+
+
+_ORACLE = None
+
+
+def lib() -> C.CDLL:
+    global _ORACLE
+    if _ORACLE is None:
+        so = HERE / "libtce_oracle.so"
+        if not so.exists():
+            build(ref=False)
+        _ORACLE = C.CDLL(str(so))
+        L = _ORACLE
+        L.orc_calculate_zeros_width.restype = C.c_int
+        L.orc_w4a16_gemv.restype = C.c_int
+        L.orc_w4a16_gemv.argtypes = [_u16p, _u32p, _u32p, _u16p, _f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_naive_mat_mul_int4.argtypes = [_f32p, _u8p, _f32p, C.c_float, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_naive_mat_mul_int4_with_offset.argtypes = [_f32p, _u8p, _f32p, _f32p, C.c_float, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_int4_fast_ref.argtypes = [_f32p, _u8p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.orc_naive_mat_mul_fp16_int4.argtypes = [_u16p, _i32p, _u16p, _u16p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_mat_mul_transposed.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        L.orc_int8_matmul.argtypes = [_i8p, _i8p, _i8p, _i8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.orc_int8_matmul_nobias.argtypes = [_i8p, _i8p, _i8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+        L.orc_int8_matmul_nobias_batch.argtypes = L.orc_int8_matmul_nobias.argtypes
+        L.orc_int8_matmul_bfp32_ofp32.argtypes = [_i8p, _i8p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.orc_int8_matmul_nobias_ofp32.argtypes = [_i8p, _i8p, _f32p, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.orc_int8_matmul_nobias_ofp32_batch.argtypes = L.orc_int8_matmul_nobias_ofp32.argtypes
+        L.orc_naive_mat_mul_int8.argtypes = [_i8p, _i8p, _i8p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.orc_rmsnorm.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float]
+        L.orc_layernorm_q.argtypes = [_f32p, _f32p, _f32p, _i8p, C.c_int, C.c_int]
+        L.orc_rope.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int]
+        L.orc_llama_attention_core.restype = C.c_int
+        L.orc_llama_attention_core.argtypes = [_f32p, _f32p, _f32p, C.c_void_p, C.c_void_p, _f32p, _f32p, _f32p, C.c_float,
+                                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p]
+        L.orc_opt_int8_attention_core.restype = C.c_int
+        L.orc_opt_int8_attention_core.argtypes = [_i8p, _i8p, _i8p, C.c_void_p, C.c_void_p, _f32p, C.c_float, C.c_float,
+                                                  C.c_int, C.c_int, C.c_int, C.c_int, _i8p, _i8p, _i8p]
+    return _ORACLE
+
+
+# ----------------------------------------------------------------------------------------------
+# numpy-level wrappers (the oracle's public face for tests)
+# ----------------------------------------------------------------------------------------------
+
+def zeros_width(ic: int, group: int = 128) -> int:
+    return int(lib().orc_calculate_zeros_width(ic, group))
+
+
+def w4a16_gemv(x_half: np.ndarray, w: np.ndarray, zeros: np.ndarray, scales_half: np.ndarray, group: int = 128):
+    """x fp16 [M,IC]; w uint32 [OC,IC/8]; zeros uint32 [OC,zw]; scales fp16 [OC,zw*8] -> fp32 [M,OC]."""
+    x_half = np.ascontiguousarray(x_half, dtype=np.float16)
+    M, IC = x_half.shape
+    OC = w.shape[0]
+    y = np.zeros((M, OC), np.float32)
+    rc = lib().orc_w4a16_gemv(x_half.view(np.uint16), np.ascontiguousarray(w, np.uint32), np.ascontiguousarray(zeros, np.uint32),
+                              np.ascontiguousarray(scales_half, np.float16).view(np.uint16), y, None, M, IC, OC, group)
+    assert rc == 0
+    return y
+
+
+def naive_mat_mul_int4(A, B, scales, zero_point=8.0, block_size=128):
+    A = np.ascontiguousarray(A, np.float32)
+    M, IC = A.shape
+    OC = B.shape[0]
+    out = np.zeros((M, OC), np.float32)
+    lib().orc_naive_mat_mul_int4(A, np.ascontiguousarray(B, np.uint8), np.ascontiguousarray(scales, np.float32).ravel(), zero_point, out, M, IC, OC, block_size)
+    return out
+
+
+def int8_matmul(variant: int, A, B, bias8=None, biasf=None, alpha=1.0, beta=1.0, q_min=-128, q_max=127):
+    """variant numbering = oracle/ref_shim.cc ref_int8_matmul.  B is [N,K] (or [M,N,K] for batch variants)."""
+    A = np.ascontiguousarray(A, np.int8)
+    B = np.ascontiguousarray(B, np.int8)
+    M, K = A.shape
+    N = B.shape[-2]
+    L = lib()
+    if variant in (0, 1):
+        out = np.zeros((M, N), np.int8)
+        L.orc_int8_matmul(A, B, np.ascontiguousarray(bias8, np.int8), out, M, N, K, alpha, beta, q_min, q_max)
+    elif variant == 2:
+        out = np.zeros((M, N), np.int8)
+        L.orc_int8_matmul_nobias(A, B, out, M, N, K, alpha, q_min, q_max)
+    elif variant == 3:
+        out = np.zeros((M, N), np.int8)
+        L.orc_int8_matmul_nobias_batch(A, B, out, M, N, K, alpha, q_min, q_max)
+    elif variant in (4, 5):
+        out = np.zeros((M, N), np.float32)
+        L.orc_int8_matmul_bfp32_ofp32(A, B, np.ascontiguousarray(biasf, np.float32), out, M, N, K, alpha)
+    elif variant == 6:
+        out = np.zeros((M, N), np.float32)
+        L.orc_int8_matmul_nobias_ofp32(A, B, out, M, N, K, alpha)
+    elif variant == 7:
+        out = np.zeros((M, N), np.float32)
+        L.orc_int8_matmul_nobias_ofp32_batch(A, B, out, M, N, K, alpha)
+    else:
+        raise ValueError(variant)
+    return out
+
+
+def rmsnorm(x, weight, eps):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros_like(x)
+    lib().orc_rmsnorm(x, np.ascontiguousarray(weight, np.float32), out, x.shape[0], x.shape[1], eps)
+    return out
+
+
+def rope_tables(max_len: int, head_dim: int, theta: float = 10000.0):
+    """cos/sin tables [max_len, head_dim] in the HF rotate-half convention the reference loads from
+    ``rotary_emb/{cos,sin}_cached.bin`` (llm/src/ops/RotaryPosEmb.cc indexes cos(0, pos, j), j<head_dim)."""
+    inv = 1.0 / (theta ** (np.arange(0, head_dim, 2, dtype=np.float64) / head_dim))
+    t = np.arange(max_len, dtype=np.float64)
+    fr = np.outer(t, inv)
+    emb = np.concatenate([fr, fr], axis=1)
+    return np.cos(emb).astype(np.float32), np.sin(emb).astype(np.float32)
+
+
+def llama_attention_core(q, k, v, past_k, past_v, mask, cosb, sinb, alpha, H, KVH, hd):
+    """fp32 GQA attention between the projections (see tce_oracle.c).  q [s,H*hd], k/v [s,KVH*hd],
+    past_* [KVH,past,hd] or None.  Returns (attn_out [s,H*hd], final_k [KVH,tgz,hd], final_v)."""
+    q = np.ascontiguousarray(q, np.float32)
+    k = np.ascontiguousarray(k, np.float32)
+    v = np.ascontiguousarray(v, np.float32)
+    s = q.shape[0]
+    past = 0 if past_k is None else past_k.shape[1]
+    tgz = s + past
+    out = np.zeros((s, H * hd), np.float32)
+    fk = np.zeros((KVH, tgz, hd), np.float32)
+    fv = np.zeros((KVH, tgz, hd), np.float32)
+    pk = None if past_k is None else np.ascontiguousarray(past_k, np.float32)
+    pv = None if past_v is None else np.ascontiguousarray(past_v, np.float32)
+    rc = lib().orc_llama_attention_core(q, k, v, None if pk is None else pk.ctypes.data, None if pv is None else pv.ctypes.data,
+                                        np.ascontiguousarray(mask, np.float32), np.ascontiguousarray(cosb, np.float32),
+                                        np.ascontiguousarray(sinb, np.float32), alpha, s, past, H, KVH, hd, out, fk, fv)
+    assert rc == 0
+    return out, fk, fv
+
+
+def opt_int8_attention_core(q8, k8, v8, past_k, past_v, mask, qk_alpha, pv_alpha, H, hd):
+    q8 = np.ascontiguousarray(q8, np.int8)
+    s = q8.shape[0]
+    past = 0 if past_k is None else past_k.shape[1]
+    tgz = s + past
+    out = np.zeros((s, H * hd), np.int8)
+    fk = np.zeros((H, tgz, hd), np.int8)
+    fv = np.zeros((H, tgz, hd), np.int8)
+    pk = None if past_k is None else np.ascontiguousarray(past_k, np.int8)
+    pv = None if past_v is None else np.ascontiguousarray(past_v, np.int8)
+    rc = lib().orc_opt_int8_attention_core(q8, np.ascontiguousarray(k8, np.int8), np.ascontiguousarray(v8, np.int8),
+                                           None if pk is None else pk.ctypes.data, None if pv is None else pv.ctypes.data,
+                                           np.ascontiguousarray(mask, np.float32), qk_alpha, pv_alpha, s, past, H, hd, out, fk, fv)
+    assert rc == 0
+    return out, fk, fv
+
+
+def causal_mask(sqlen: int, past: int, neg: float = -3.402823466e38):
+    """prepare_decoder_attention_mask semantics (llm/src/nn_modules/non_cuda/Int4llamaDecoder.cc): 0 on/below
+    the diagonal (shifted by `past`), lowest-float above."""
+    tgz = sqlen + past
+    m = np.zeros((sqlen, tgz), np.float32)
+    for i in range(sqlen):
+        m[i, past + i + 1:] = neg
+    return m
+
+
+# ----------------------------------------------------------------------------------------------
+# reference builds (oracle/_ref): only present when built in a container that has /root/reference
+# ----------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def ref_available(kind: str = "generic") -> bool:
+    return (REF_DIR / f"libtce_ref_{kind}.so").exists()
+
+
+def ref(kind: str = "generic") -> C.CDLL:
+    if kind not in _REF:
+        so = REF_DIR / f"libtce_ref_{kind}.so"
+        if not so.exists():
+            raise FileNotFoundError(f"{so} not built (needs /root/reference; run `make -C oracle ref`)")
+        L = C.CDLL(str(so))
+        L.ref_naive_mat_mul_int4.argtypes = [_f32p, _u8p, _f32p, _f32p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ref_int8_matmul.argtypes = [C.c_int, _i8p, _i8p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_naive_mat_mul_int8.argtypes = [_i8p, _i8p, _i8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.ref_mat_mul_transposed.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
+        if kind == "generic":
+            L.ref_naive_mat_mul_fp16_int4.argtypes = [_u16p, _i32p, _u16p, _u16p, C.c_int, C.c_int, C.c_int, C.c_int]
+        if kind == "avx":
+            L.ref_w4a8_avx.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4
+        _REF[kind] = L
+    return _REF[kind]
+
+
+def ref_naive_mat_mul_int4(A, B, scales, zero_point=8.0, block_size=128, kind="generic"):
+    A = np.ascontiguousarray(A, np.float32)
+    M, IC = A.shape
+    OC = B.shape[0]
+    out = np.zeros((M, OC), np.float32)
+    zp = np.array([zero_point], np.float32)
+    ref(kind).ref_naive_mat_mul_int4(A, np.ascontiguousarray(B, np.uint8), np.ascontiguousarray(scales, np.float32).ravel(), zp, None, out,
+                                     M, IC, OC, block_size, 0)
+    return out
+
+
+def ref_int8_matmul(variant: int, A, B, bias8=None, biasf=None, alpha=1.0, beta=1.0, q_min=-128, q_max=127, kind="generic", num_thread=1):
+    A = np.ascontiguousarray(A, np.int8)
+    B = np.ascontiguousarray(B, np.int8)
+    M, K = A.shape
+    N = B.shape[-2]
+    c8 = np.zeros((M, N), np.int8)
+    cf = np.zeros((M, N), np.float32)
+    b8 = None if bias8 is None else np.ascontiguousarray(bias8, np.int8)
+    bf = None if biasf is None else np.ascontiguousarray(biasf, np.float32)
+    ref(kind).ref_int8_matmul(variant, A, B, None if b8 is None else b8.ctypes.data, None if bf is None else bf.ctypes.data,
+                              c8.ctypes.data, cf.ctypes.data, M, N, K, alpha, beta, q_min, q_max, num_thread)
+    return c8 if variant in (0, 1, 2, 3) else cf
+
+
+def aligned_empty(shape, dtype, align: int = 64) -> np.ndarray:
+    """32-byte alignment is mandatory for the reference AVX kernels (SURVEY.md 8b Ownership)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    raw = np.empty(n + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dtype).reshape(shape)

@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF, run in this container.
+
+Two sources (both need /root/reference, which exists only in the build container, never on the GPU box):
+
+1. the reference's Python quantizer ``llm/tools/quantize_methods.py`` imported as-is -> packed INT4 formats
+   (``quant_*.npz``): pins oracle/quant.py and tinychatengine_b200/formats.py byte-for-byte;
+2. the reference's C++ kernels compiled in place (``make -C oracle ref`` -> oracle/_ref/*.so, entered through
+   oracle/ref_shim.cc) -> outputs of naive_mat_mul_int4 / int8_ref_matmul* / naive_mat_mul_int8 /
+   naive_mat_mul_fp16_int4 / the AVX W4A8 fast path (``kernels_*.npz``): pins oracle/tce_oracle.c.
+
+Inputs are stored next to outputs, so the fixtures are self-contained.   Usage:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+OUT = Path(__file__).resolve().parent
+REF_TOOLS = "/root/reference/llm/tools"
+
+
+def ref_python_quantizer(w: np.ndarray, method: str):
+    sys.path.insert(0, REF_TOOLS)
+    import quantize_methods as qm  # the reference module, unmodified
+
+    oc, ic = w.shape
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        f.write(np.ascontiguousarray(w, np.float32).tobytes())
+        path = f.name
+    try:
+        qs, d, m, zp = getattr(qm, method)(path, oc * ic, "fp32", ic, oc)
+    finally:
+        os.unlink(path)
+    return np.asarray(qs), np.asarray(d), np.asarray(zp)
+
+
+def main():
+    from oracle import capi
+
+    capi.build(ref=True)
+    rng = np.random.default_rng(20260922)
+
+    # ---------------- 1. quantizer formats ----------------
+    for name, (oc, ic) in {"a": (16, 256), "b": (8, 1408), "c": (8, 2048)}.items():
+        w = (rng.standard_normal((oc, ic)) * 0.02).astype(np.float32)
+        w[0, :128] = 0.0  # an all-zero block exercises the d == 0 branch
+        out = {"w": w}
+        qs, d, zp = ref_python_quantizer(w, "quantize_row_q4_6")
+        # files are written int32 / fp16 / int32 for CUDA (model_quantizer.py:38-46)
+        out["q4_6_qs"] = qs.astype(np.int32).view(np.uint32)
+        out["q4_6_d"] = d.astype(np.float16)
+        out["q4_6_zp"] = zp.astype(np.int32).view(np.uint32)
+        if ic % 64 == 0:
+            qs, d, zp = ref_python_quantizer(w, "quantize_row_q4_3")
+            out["q4_3_qs"] = qs.astype(np.uint8).reshape(oc, ic // 2)
+            out["q4_3_d"] = d.astype(np.float32).reshape(oc, ic // 32)
+        qs, d, zp = ref_python_quantizer(w, "quantize_row_q4_5")
+        out["q4_5_qs"] = qs.astype(np.int32)
+        out["q4_5_d"] = d.astype(np.float16)
+        np.savez_compressed(OUT / f"quant_{name}.npz", **out)
+
+    # ---------------- 2. compiled reference kernels ----------------
+    from oracle import quant
+
+    G = capi.ref("generic")
+    out = {}
+    # naive_mat_mul_int4, generic branch, block 128 and 32 (kernels/matmul_int4.cc:106-127)
+    for tag, (M, IC, OC, blk) in {"g128": (2, 512, 24, 128), "g32": (3, 256, 16, 32)}.items():
+        w = (rng.standard_normal((OC, IC)) * 0.02).astype(np.float32)
+        B, s = quant.quantize_q4_0_sequential(w, blk)
+        A = rng.standard_normal((M, IC)).astype(np.float32)
+        out[f"int4_{tag}_A"], out[f"int4_{tag}_B"], out[f"int4_{tag}_s"] = A, B, s
+        out[f"int4_{tag}_C"] = capi.ref_naive_mat_mul_int4(A, B, s, 8.0, blk)
+    # int8 family (kernels/ref/matmul_ref_int8.cc), alpha/beta from the reference's own op tests
+    # (llm/tests/non_cuda/test_ops.cc:179: alpha=0.00050354, beta=0.0213013)
+    M, N, K = 5, 24, 96
+    A = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    B = rng.integers(-127, 128, (N, K), dtype=np.int8)
+    Bb = rng.integers(-127, 128, (M, N, K), dtype=np.int8)
+    b8 = rng.integers(-127, 128, (N,), dtype=np.int8)
+    bf = rng.standard_normal(N).astype(np.float32)
+    alpha, beta = np.float32(0.00050354), np.float32(0.0213013)
+    out.update(i8_A=A, i8_B=B, i8_Bb=Bb, i8_b8=b8, i8_bf=bf, i8_alpha=alpha, i8_beta=beta)
+    for v in range(8):
+        Bv = Bb if v in (3, 7) else B
+        qmin = 0 if v == 1 else -128  # variant 1 doubles as the ReLU flavour (W8A8B8O8LinearReLU: q_min = 0)
+        out[f"i8_C{v}"] = capi.ref_int8_matmul(v, A, Bv, b8, bf, float(alpha), float(beta), qmin, 127)
+    # a large-alpha case that saturates / hits the clamp
+    out["i8_Csat"] = capi.ref_int8_matmul(0, A, B, b8, bf, 0.05, 1.0, -128, 127)
+    # naive_mat_mul_int8 (kernels/matmul_int8.cc:8-30), B is [K][N]
+    Bkn = np.ascontiguousarray(B.T)
+    Cn = np.zeros((M, N), np.int8)
+    G.ref_naive_mat_mul_int8(A, Bkn, Cn, M, N, K, 3, -2, 0.02, 0.01, 0.35, -128, 127)
+    out["i8_naive_C"] = Cn
+    # host fp16 reference, AWQ-GEMM layout (kernels/cuda/matmul_int4.cu:8-48)
+    M, IC, OC = 2, 256, 16
+    w = (rng.standard_normal((OC, IC)) * 0.02).astype(np.float32)
+    qs5, d5 = quant.quantize_q4_5(w, 128)
+    A16 = rng.standard_normal((M, IC)).astype(np.float16)
+    C16 = np.zeros((M, OC), np.uint16)
+    G.ref_naive_mat_mul_fp16_int4(A16.view(np.uint16), qs5, d5.view(np.uint16), C16, M, IC, OC, 128)
+    out.update(f16_A=A16, f16_qs=qs5, f16_d=d5, f16_C=C16)
+    # mat_mul_transposed
+    A = rng.standard_normal((3, 40)).astype(np.float32)
+    Bt = rng.standard_normal((7, 40)).astype(np.float32)
+    Ct = np.zeros((3, 7), np.float32)
+    G.ref_mat_mul_transposed(A, Bt, Ct, 3, 7, 40)
+    out.update(t_A=A, t_B=Bt, t_C=Ct)
+    np.savez_compressed(OUT / "kernels_generic.npz", **out)
+
+    # the reference's AVX fast path (W4A8, g32): the timed CPU baseline; stored so the oracle/bench plumbing
+    # can be sanity-checked on a box without /root/reference
+    X = capi.ref("avx")
+    M, IC, OC = 1, 512, 64
+    w = (rng.standard_normal((OC, IC)) * 0.02).astype(np.float32)
+    qs3, d3 = quant.quantize_q4_3(w)
+    A = capi.aligned_empty((M, IC), np.float32)
+    A[:] = rng.standard_normal((M, IC)).astype(np.float32)
+    Bq = capi.aligned_empty(qs3.shape, np.uint8)
+    Bq[:] = qs3
+    S = capi.aligned_empty(d3.shape, np.float32)
+    S[:] = d3
+    Cx = capi.aligned_empty((M, OC), np.float32)
+    xi8 = capi.aligned_empty((M * IC,), np.int8)
+    xs = capi.aligned_empty((M * IC // 32,), np.float32)
+    X.ref_w4a8_avx(A.ctypes.data, Bq.ctypes.data, S.ctypes.data, Cx.ctypes.data, xi8.ctypes.data, xs.ctypes.data, M, IC, OC, 2)
+    np.savez_compressed(OUT / "kernels_avx.npz", A=np.array(A), w=w, qs=qs3, d=d3, C=np.array(Cx))
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
