@@ -1,0 +1,138 @@
+/*
+ * tce_b200.h -- C ABI of libtce_b200.so: the B200 (sm_100a) implementation of TinyChatEngine's quantized-linear
+ * hot path (W4A16 AWQ GEMV/GEMM, W8A8 SmoothQuant GEMM, per-token KV-cache attention).
+ *
+ * Boundary contract: plain pointers and sizes, no C++/torch types.  Every data pointer is a
+ * DEVICE-accessible pointer (cudaMalloc or cudaMallocManaged, which is what the reference allocates,
+ * llm/src/nn_modules/cuda/utils.cu:93-96) unless the function name ends in `_host`.  The caller owns all data
+ * buffers; the library owns only its context workspaces.  All calls are asynchronous on the context's stream
+ * (like the reference's default-stream kernels) except `_host` calls, which return after their D2H copy.
+ * Return value: 0 on success, negative tce_status otherwise; tce_last_error() gives the message.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with TCE_ERR_CUDA.
+ *
+ * Each entry point names the reference interface it replaces (file:line under the reference tree).
+ */
+#ifndef TCE_B200_H
+#define TCE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCE_API __attribute__((visibility("default")))
+
+typedef enum tce_status {
+    TCE_OK = 0,
+    TCE_ERR_INVALID = -1,     /* bad shape / null pointer / unsupported group size (reference: assert / exit(1)) */
+    TCE_ERR_UNSUPPORTED = -2,
+    TCE_ERR_CUDA = -3
+} tce_status;
+
+typedef struct tce_ctx tce_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+TCE_API int tce_version(void);
+TCE_API const char *tce_last_error(void);
+TCE_API int tce_ctx_create(int device, tce_ctx **out);
+TCE_API int tce_ctx_destroy(tce_ctx *ctx);
+/* cudaStream_t as void*; NULL = legacy default stream (what the reference launches on) */
+TCE_API int tce_ctx_set_stream(tce_ctx *ctx, void *cuda_stream);
+TCE_API int tce_ctx_synchronize(tce_ctx *ctx);
+/* knobs: "gemv_impl" (0 simple / 1 tma+mma), "gemv_ctas_per_sm", "use_pdl", "attn_chunk" */
+TCE_API int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value);
+TCE_API int tce_ctx_num_sms(tce_ctx *ctx);
+
+/* ---- W4A16, QM_CUDA layout ------------------------------------------------------------------------------
+ * Replaces MatmulOperator::gemv_forward_cuda (kernels/cuda/gemv_cuda.cu:213-260), called by
+ * Linear_half_int4::forward (llm/src/ops/cuda/linear.cu:5-40).
+ *   x half[M][IC], w uint32[OC][IC/8], zeros uint32[OC][zeros_w], scales half[OC][zeros_w*8], y half[M][OC]
+ *   zeros_w = tce_zeros_width(IC, group); group must be 128 (QK under QM_CUDA, llm/include/common.h:17-21).
+ * Any M: M <= 8 is one pass over the weights, larger M loops in blocks of 8 rows.                        */
+TCE_API int tce_zeros_width(int in_features, int group_size);
+TCE_API int tce_w4a16_gemv(tce_ctx *ctx, const void *x, const void *w, const void *zeros, const void *scales, void *y,
+                           int M, int IC, int OC, int group_size);
+/* Same contract; the slot of the reference's declared-but-undefined prefill GEMM
+ * MatmulOperator::gemm_forward_cuda (kernels/matmul.h:142-145).                                            */
+TCE_API int tce_w4a16_gemm(tce_ctx *ctx, const void *x, const void *w, const void *zeros, const void *scales, void *y,
+                           int M, int IC, int OC, int group_size);
+
+/* ---- W8A8 family -----------------------------------------------------------------------------------------
+ * Replaces MatmulOperator::mat_mul_accelerator_int8_fast_* (kernels/ref/matmul_ref_int8.cc:11-192).
+ * variant: 0 bias int8 -> int8 out (2x2_32unroll / 32unroll_over_column), 1 nobias -> int8 (…_nobias),
+ *          2 bias fp32 -> fp32 out (…_bfp32_ofp32[_over_column]), 3 nobias -> fp32 (…_nobias_ofp32)
+ * batch != 0: row i of A uses slab B[i][N][K] (…_nobias_batch / …_nobias_ofp32_batch; variants 1 and 3 only)
+ * A int8[M][K], B int8[N][K], bias int8[N] | float[N] | NULL, C int8[M][N] | float[M][N].  Bit-exact.   */
+TCE_API int tce_w8a8_matmul(tce_ctx *ctx, int variant, int batch, const void *A, const void *B, const void *bias,
+                            void *C, int M, int N, int K, float alpha, float beta, int q_min, int q_max);
+
+/* ---- per-token KV-cache attention (fp16, GQA) ------------------------------------------------------------
+ * Replaces the body of Int4llamaAttention::forward between qkv_proj and o_proj
+ * (llm/src/nn_modules/cuda/Int4llamaAttention.cu:128-217; GQA mapping non_cuda/Int4llamaAttention.cc:166-184).
+ *   qkv   half[(H + 2*KVH)*head_dim]  current token's q|k|v projections (pre-RoPE)
+ *   k_cache, v_cache half[KVH][max_ctx][head_dim]  appended in place at *pos
+ *   cos, sin float[max_ctx][head_dim]  (rotary_emb/cos_cached layout)
+ *   pos   device int: index of the current token == number of tokens already cached
+ *   out   half[H*head_dim]                                                                                 */
+TCE_API int tce_attn_decode(tce_ctx *ctx, const void *qkv, void *k_cache, void *v_cache, const float *cos,
+                            const float *sin, const int *pos, void *out, float alpha, int num_heads, int num_kv_heads,
+                            int head_dim, int max_ctx);
+
+/* ---- small ops either side of the path -------------------------------------------------------------------
+ * LlamaRMSNorm_cuda::forward (llm/src/ops/cuda/LlamaRMSNorm.cu:96-115): half in/out, fp32 gamma             */
+TCE_API int tce_rmsnorm_f16(tce_ctx *ctx, const void *x, const float *gamma, void *y, int rows, int dim, float eps);
+TCE_API int tce_argmax_f32(tce_ctx *ctx, const float *x, int n, int *out);
+
+/* ---- fused Llama decode step -----------------------------------------------------------------------------
+ * The call sites of the path: Int4llamaDecoderLayer::forward / Int4llamaDecoder::forward /
+ * Int4LlamaForCausalLM::forward (llm/src/nn_modules/cuda/Int4llama{DecoderLayer,Decoder,ForCausalLM}.cu)
+ * restated as one CUDA graph per token: embedding -> L x [RMSNorm+QKV GEMV, RoPE+KV-append+attention,
+ * o_proj GEMV (+residual), RMSNorm+gate/up GEMV (+SiLU*mul), down GEMV (+residual)] -> RMSNorm+lm_head.  */
+typedef struct tce_w4_tensor {
+    const void *w;      /* uint32[oc][ic/8]    */
+    const void *zeros;  /* uint32[oc][zeros_w] */
+    const void *scales; /* half[oc][zeros_w*8] */
+    int oc, ic;
+} tce_w4_tensor;
+
+typedef struct tce_llama_layer {
+    tce_w4_tensor q, k, v, o, gate, up, down;
+    const float *input_norm; /* fp32 gamma[embed_dim] */
+    const float *post_norm;
+} tce_llama_layer;
+
+typedef struct tce_llama_config {
+    int num_layers, num_heads, num_kv_heads, head_dim, embed_dim, hidden_dim, vocab_size, max_ctx;
+    float rms_eps, rope_theta, qk_alpha;
+    /* tensor parallel shard of this process: heads/hidden are the LOCAL sizes when tp_size > 1 */
+    int tp_rank, tp_size;
+} tce_llama_config;
+
+typedef struct tce_llama_weights {
+    const void *embed_f16;          /* half[vocab][embed_dim] */
+    const tce_llama_layer *layers;  /* [num_layers] */
+    const float *final_norm;
+    tce_w4_tensor lm_head;
+    const float *rope_cos, *rope_sin; /* float[max_ctx][head_dim] or NULL: computed from rope_theta */
+} tce_llama_weights;
+
+typedef struct tce_llama tce_llama;
+
+TCE_API int tce_llama_create(tce_ctx *ctx, const tce_llama_config *cfg, const tce_llama_weights *w, tce_llama **out);
+TCE_API int tce_llama_destroy(tce_llama *m);
+/* inputs resident: tokpos = device int[2] {token id, position}; logits stay on the device */
+TCE_API int tce_llama_decode(tce_llama *m, const int *tokpos_dev);
+/* end to end: token/pos from the host, fp32 logits[vocab] copied back to `logits_host` (may be NULL) and the
+ * greedy arg-max to *next_token (may be NULL); returns after the copies have completed */
+TCE_API int tce_llama_decode_host(tce_llama *m, int token, int pos, float *logits_host, int *next_token);
+TCE_API const float *tce_llama_logits(tce_llama *m);          /* device float[vocab] */
+TCE_API void *tce_llama_kv_cache(tce_llama *m, int layer, int which); /* which: 0 K, 1 V; half[KVH][max_ctx][hd] */
+TCE_API int tce_llama_kernels_per_step(tce_llama *m);
+/* measurement aid: enqueue only the W4A16 GEMV launches of one decode step (4 per layer + lm_head, the same fused
+ * kernels with the same arguments) so the dominant kernel can be timed with CUDA events; returns the launch count */
+TCE_API int tce_llama_enqueue_gemvs(tce_llama *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCE_B200_H */

@@ -1,0 +1,61 @@
+"""Fused decode step (tce_llama_*: one CUDA graph per token) vs the oracle-composed step."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import oracle_decode_step, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("geom", ["tiny-gqa", "tiny-mha"])
+def test_decode_steps_match_oracle(geom):
+    from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
+    from tinychatengine_b200.runtime import Context
+
+    ctx = Context(0)
+    g = GEOMETRIES[geom]
+    model = LlamaModel(ctx, g, max_ctx=256, seed=7, random_zeros=True)
+    past_k = [None] * g.num_layers
+    past_v = [None] * g.num_layers
+    tokens = [3, 77, 1000, 5, 900]
+    logits_host = torch.empty(g.vocab_size, dtype=torch.float32).pin_memory()
+    for pos, tok in enumerate(tokens):
+        nxt = model.decode_host(tok, pos, logits_host)
+        want, past_k, past_v = oracle_decode_step(model, tok, pos, past_k, past_v)
+        got = logits_host.numpy().copy()
+        assert np.all(np.isfinite(got))
+        assert rel_err(got, want) <= 1e-2, (geom, pos, rel_err(got, want))
+        assert nxt == int(np.argmax(got))
+        # device-resident entry point gives the same logits as the host entry point
+        tp = torch.tensor([tok, pos], dtype=torch.int32, device="cuda")
+        model.decode(tp)
+        torch.cuda.synchronize()
+        assert torch.equal(model.logits().cpu(), torch.from_numpy(got))
+        for l in range(g.num_layers):
+            kc = model.kv_cache(l, 0)[:, : pos + 1].float().cpu().numpy()
+            assert np.abs(kc - past_k[l]).max() <= 2e-2 * max(1.0, np.abs(past_k[l]).max())
+    model.close()
+    ctx.close()
+
+
+def test_graph_and_eager_paths_agree():
+    import os
+
+    from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
+    from tinychatengine_b200.runtime import Context
+
+    outs = []
+    for pdl in (1, 0):
+        ctx = Context(0)
+        ctx.set_option("use_pdl", pdl)
+        model = LlamaModel(ctx, GEOMETRIES["tiny-gqa"], max_ctx=128, seed=3)
+        lg = torch.empty(model.geom.vocab_size, dtype=torch.float32)
+        seq = []
+        for pos, tok in enumerate([1, 2, 3, 4]):
+            model.decode_host(tok, pos, lg)
+            seq.append(lg.clone())
+        outs.append(torch.stack(seq))
+        model.close()
+        ctx.close()
+    assert torch.equal(outs[0], outs[1])

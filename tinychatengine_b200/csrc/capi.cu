@@ -1,0 +1,292 @@
+// capi.cu -- extern "C" surface of libtce_b200.so (include/tce_b200.h): argument checking, context and
+// workspace management, dispatch to the sm_100a kernels.  No CPU fallback anywhere in this file.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tce_b200.h"
+#include "kernels.h"
+#include "kernels_attn.h"
+#include "kernels_w8a8.h"
+#include "llama_decoder.h"
+
+using namespace tce;
+
+struct tce_ctx {
+    Ctx c;
+    int attn_chunk = 128;
+};
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+int tce_fail_cuda(cudaError_t e, const char *what) {
+    return fail(TCE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CK(call, what)                                   \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return tce_fail_cuda(e__, what); \
+    } while (0)
+
+Ctx *tce_ctx_inner(tce_ctx *ctx) { return &ctx->c; }
+int tce_ctx_attn_chunk(tce_ctx *ctx) { return ctx->attn_chunk; }
+
+extern "C" {
+
+int tce_version(void) { return 100; }
+const char *tce_last_error(void) { return g_err.c_str(); }
+
+int tce_zeros_width(int in_features, int group_size) {
+    if (group_size != 128 && group_size != 64 && group_size != 32) return TCE_ERR_INVALID;
+    return zeros_width(in_features, group_size);
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+int tce_ctx_create(int device, tce_ctx **out) {
+    if (!out) return fail(TCE_ERR_INVALID, "tce_ctx_create: out is null");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(TCE_ERR_CUDA, "no CUDA device: libtce_b200 has no CPU fallback (%s)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(TCE_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major < 10) return fail(TCE_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    tce_ctx *ctx = new tce_ctx();
+    Ctx &c = ctx->c;
+    c.device = device;
+    c.stream = nullptr;
+    c.num_sms = prop.multiProcessorCount;
+    c.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c.gemv_impl = env_int("TCE_GEMV_IMPL", 1);
+    c.gemv_ctas_per_sm = env_int("TCE_GEMV_CTAS_PER_SM", 1);
+    c.use_pdl = env_int("TCE_USE_PDL", 1) != 0;
+    ctx->attn_chunk = env_int("TCE_ATTN_CHUNK", 128);
+    c.gemv_max_ctas = c.num_sms * 4;
+    c.gemv_max_tiles = 32768;
+    CK(cudaMalloc(&c.gemv_partials, (size_t)c.gemv_max_ctas * 2 * 16 * 8 * sizeof(float)), "cudaMalloc gemv partials");
+    CK(cudaMalloc(&c.gemv_counters, (size_t)c.gemv_max_tiles * sizeof(unsigned)), "cudaMalloc gemv counters");
+    CK(cudaMemset(c.gemv_counters, 0, (size_t)c.gemv_max_tiles * sizeof(unsigned)), "cudaMemset");
+    c.attn_ws_bytes = (size_t)128 * 1024 * 130 * sizeof(float);  // heads * splits * (128 + 2): 128 heads x 1024 splits
+    CK(cudaMalloc(&c.attn_ws, c.attn_ws_bytes), "cudaMalloc attn ws");
+    CK(cudaMalloc(&c.attn_counters, 1024 * sizeof(unsigned)), "cudaMalloc attn counters");
+    CK(cudaMemset(c.attn_counters, 0, 1024 * sizeof(unsigned)), "cudaMemset");
+    CK(cudaDeviceSynchronize(), "ctx init");
+    *out = ctx;
+    return TCE_OK;
+}
+
+int tce_ctx_destroy(tce_ctx *ctx) {
+    if (!ctx) return TCE_OK;
+    cudaSetDevice(ctx->c.device);
+    cudaFree(ctx->c.gemv_partials);
+    cudaFree(ctx->c.gemv_counters);
+    cudaFree(ctx->c.attn_ws);
+    cudaFree(ctx->c.attn_counters);
+    delete ctx;
+    return TCE_OK;
+}
+
+int tce_ctx_set_stream(tce_ctx *ctx, void *s) {
+    if (!ctx) return fail(TCE_ERR_INVALID, "null ctx");
+    ctx->c.stream = (cudaStream_t)s;
+    return TCE_OK;
+}
+
+int tce_ctx_synchronize(tce_ctx *ctx) {
+    if (!ctx) return fail(TCE_ERR_INVALID, "null ctx");
+    CK(cudaStreamSynchronize(ctx->c.stream), "cudaStreamSynchronize");
+    return TCE_OK;
+}
+
+int tce_ctx_num_sms(tce_ctx *ctx) { return ctx ? ctx->c.num_sms : TCE_ERR_INVALID; }
+
+int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
+    if (!ctx || !name) return fail(TCE_ERR_INVALID, "null argument");
+    if (!strcmp(name, "gemv_impl"))
+        ctx->c.gemv_impl = value;
+    else if (!strcmp(name, "gemv_ctas_per_sm"))
+        ctx->c.gemv_ctas_per_sm = value < 1 ? 1 : (value > 4 ? 4 : value);
+    else if (!strcmp(name, "use_pdl"))
+        ctx->c.use_pdl = value != 0;
+    else if (!strcmp(name, "attn_chunk"))
+        ctx->attn_chunk = value;
+    else
+        return fail(TCE_ERR_INVALID, "unknown option %s", name);
+    return TCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- W4A16
+static int w4a16_common(tce_ctx *ctx, const void *x, const void *w, const void *zeros, const void *scales, void *y, int M, int IC,
+                        int OC, int group, const char *who) {
+    if (!ctx || !x || !w || !zeros || !scales || !y) return fail(TCE_ERR_INVALID, "%s: null pointer", who);
+    // the reference exits on any group size but 64/128 (gemv_cuda.cu:253-257) and is compiled with QK=128
+    if (group != kW4Group) return fail(TCE_ERR_INVALID, "%s: unsupported group size %d (QM_CUDA uses 128)", who, group);
+    if (M < 1 || IC < kW4Group || IC % kW4Group || OC < 1) return fail(TCE_ERR_INVALID, "%s: bad shape M=%d IC=%d OC=%d", who, M, IC, OC);
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    const int zw = zeros_width(IC, group);
+    // rows beyond the last multiple of 16 (the reference needs OC % 4 == 0; OC % 16 != 0 goes to the simple kernel)
+    const int oc_main = (ctx->c.gemv_impl == 1) ? (OC / 16) * 16 : 0;
+    for (int m0 = 0; m0 < M; m0 += 8) {
+        const int mb = (M - m0 < 8) ? (M - m0) : 8;
+        W4GemvParams p;
+        p.nseg = 1;
+        p.IC = IC;
+        p.M = mb;
+        p.x = (const __half *)x + (size_t)m0 * IC;
+        p.ldx = IC;
+        p.x_mode = X_HALF;
+        p.epi = EPI_STORE_HALF;
+        p.ldy = OC;
+        if (oc_main > 0) {
+            p.seg[0] = {(const uint32_t *)w, (const uint32_t *)zeros, (const __half *)scales, oc_main};
+            p.y = (__half *)y + (size_t)m0 * OC;
+            CK(launch_w4a16_gemv(&ctx->c, p), who);
+        }
+        if (oc_main < OC) {
+            p.seg[0] = {(const uint32_t *)w + (size_t)oc_main * (IC / 8), (const uint32_t *)zeros + (size_t)oc_main * zw,
+                        (const __half *)scales + (size_t)oc_main * zw * 8, OC - oc_main};
+            p.y = (__half *)y + (size_t)m0 * OC + oc_main;
+            CK(launch_w4a16_gemv_simple(&ctx->c, p), who);
+        }
+    }
+    return TCE_OK;
+}
+
+int tce_w4a16_gemv(tce_ctx *ctx, const void *x, const void *w, const void *zeros, const void *scales, void *y, int M, int IC, int OC,
+                   int group) {
+    return w4a16_common(ctx, x, w, zeros, scales, y, M, IC, OC, group, "tce_w4a16_gemv");
+}
+
+int tce_w4a16_gemm(tce_ctx *ctx, const void *x, const void *w, const void *zeros, const void *scales, void *y, int M, int IC, int OC,
+                   int group) {
+    // TODO(round 2): tcgen05 dequant-fused GEMM for M >= 64; until then the 8-row GEMV passes compute the same result
+    return w4a16_common(ctx, x, w, zeros, scales, y, M, IC, OC, group, "tce_w4a16_gemm");
+}
+
+// ---------------------------------------------------------------------------------------------- W8A8
+int tce_w8a8_matmul(tce_ctx *ctx, int variant, int batch, const void *A, const void *B, const void *bias, void *C, int M, int N, int K,
+                    float alpha, float beta, int q_min, int q_max) {
+    if (!ctx || !A || !B || !C) return fail(TCE_ERR_INVALID, "tce_w8a8_matmul: null pointer");
+    if (variant < 0 || variant > 3) return fail(TCE_ERR_INVALID, "tce_w8a8_matmul: variant %d", variant);
+    if ((variant == W8_BIAS8_O8 || variant == W8_BIASF_OF32) && !bias) return fail(TCE_ERR_INVALID, "tce_w8a8_matmul: bias required");
+    if (batch && (variant == W8_BIAS8_O8 || variant == W8_BIASF_OF32)) return fail(TCE_ERR_INVALID, "tce_w8a8_matmul: batch has no bias flavour");
+    if (M < 1 || N < 1 || K < 1) return fail(TCE_ERR_INVALID, "tce_w8a8_matmul: bad shape");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    W8A8Args a;
+    a.A = (const int8_t *)A;
+    a.B = (const int8_t *)B;
+    a.bias8 = (const int8_t *)bias;
+    a.biasf = (const float *)bias;
+    a.C8 = (int8_t *)C;
+    a.Cf = (float *)C;
+    a.M = M;
+    a.N = N;
+    a.K = K;
+    a.alpha = alpha;
+    a.beta = beta;
+    a.q_min = q_min;
+    a.q_max = q_max;
+    a.variant = variant;
+    a.batch = batch ? 1 : 0;
+    CK(launch_w8a8_dp4a(&ctx->c, a), "tce_w8a8_matmul");
+    return TCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- attention
+int tce_attn_decode(tce_ctx *ctx, const void *qkv, void *k_cache, void *v_cache, const float *cosb, const float *sinb, const int *pos,
+                    void *out, float alpha, int num_heads, int num_kv_heads, int head_dim, int max_ctx) {
+    if (!ctx || !qkv || !k_cache || !v_cache || !cosb || !sinb || !pos || !out) return fail(TCE_ERR_INVALID, "tce_attn_decode: null pointer");
+    if (head_dim != 128) return fail(TCE_ERR_UNSUPPORTED, "tce_attn_decode: head_dim %d (only 128)", head_dim);
+    if (num_heads < 1 || num_kv_heads < 1 || num_heads % num_kv_heads || max_ctx < 1) return fail(TCE_ERR_INVALID, "tce_attn_decode: bad shape");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    AttnDecodeArgs a = {};
+    a.qkv = (const __half *)qkv;
+    a.k_cache = (__half *)k_cache;
+    a.v_cache = (__half *)v_cache;
+    a.cos = cosb;
+    a.sin = sinb;
+    a.pos = pos;
+    a.out = (__half *)out;
+    a.alpha = alpha;
+    a.num_heads = num_heads;
+    a.num_kv_heads = num_kv_heads;
+    a.head_dim = head_dim;
+    a.max_ctx = max_ctx;
+    a.chunk = ctx->attn_chunk;
+    CK(launch_attn_decode(&ctx->c, a, false), "tce_attn_decode");
+    return TCE_OK;
+}
+
+int tce_rmsnorm_f16(tce_ctx *ctx, const void *x, const float *gamma, void *y, int rows, int dim, float eps) {
+    if (!ctx || !x || !gamma || !y || rows < 1 || dim < 1) return fail(TCE_ERR_INVALID, "tce_rmsnorm_f16: bad argument");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    CK(launch_rmsnorm_f16(&ctx->c, (const __half *)x, gamma, (__half *)y, rows, dim, eps), "tce_rmsnorm_f16");
+    return TCE_OK;
+}
+
+int tce_argmax_f32(tce_ctx *ctx, const float *x, int n, int *out) {
+    if (!ctx || !x || !out || n < 1) return fail(TCE_ERR_INVALID, "tce_argmax_f32: bad argument");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    CK(launch_argmax(&ctx->c, x, n, out, false), "tce_argmax_f32");
+    return TCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- llama
+int tce_llama_create(tce_ctx *ctx, const tce_llama_config *cfg, const tce_llama_weights *w, tce_llama **out) {
+    if (!ctx || !cfg || !w || !out) return fail(TCE_ERR_INVALID, "tce_llama_create: null argument");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    std::string err;
+    LlamaDecoder *d = LlamaDecoder::create(&ctx->c, ctx->attn_chunk, *cfg, *w, &err);
+    if (!d) return fail(TCE_ERR_INVALID, "tce_llama_create: %s", err.c_str());
+    *out = reinterpret_cast<tce_llama *>(d);
+    return TCE_OK;
+}
+int tce_llama_destroy(tce_llama *m) {
+    delete reinterpret_cast<LlamaDecoder *>(m);
+    return TCE_OK;
+}
+int tce_llama_decode(tce_llama *m, const int *tokpos_dev) {
+    if (!m || !tokpos_dev) return fail(TCE_ERR_INVALID, "tce_llama_decode: null argument");
+    std::string err;
+    cudaError_t e = reinterpret_cast<LlamaDecoder *>(m)->decode_device(tokpos_dev, &err);
+    if (e != cudaSuccess) return fail(TCE_ERR_CUDA, "tce_llama_decode: %s (%s)", cudaGetErrorString(e), err.c_str());
+    return TCE_OK;
+}
+int tce_llama_decode_host(tce_llama *m, int token, int pos, float *logits_host, int *next_token) {
+    if (!m) return fail(TCE_ERR_INVALID, "tce_llama_decode_host: null argument");
+    std::string err;
+    cudaError_t e = reinterpret_cast<LlamaDecoder *>(m)->decode_host(token, pos, logits_host, next_token, &err);
+    if (e != cudaSuccess) return fail(TCE_ERR_CUDA, "tce_llama_decode_host: %s (%s)", cudaGetErrorString(e), err.c_str());
+    return TCE_OK;
+}
+const float *tce_llama_logits(tce_llama *m) { return m ? reinterpret_cast<LlamaDecoder *>(m)->logits() : nullptr; }
+void *tce_llama_kv_cache(tce_llama *m, int layer, int which) { return m ? reinterpret_cast<LlamaDecoder *>(m)->kv_cache(layer, which) : nullptr; }
+int tce_llama_enqueue_gemvs(tce_llama *m) {
+    if (!m) return fail(TCE_ERR_INVALID, "tce_llama_enqueue_gemvs: null argument");
+    int n = 0;
+    cudaError_t e = reinterpret_cast<LlamaDecoder *>(m)->enqueue_gemvs(&n);
+    if (e != cudaSuccess) return tce_fail_cuda(e, "tce_llama_enqueue_gemvs");
+    return n;
+}
+int tce_llama_kernels_per_step(tce_llama *m) { return m ? reinterpret_cast<LlamaDecoder *>(m)->kernels_per_step() : TCE_ERR_INVALID; }
+
+}  // extern "C"

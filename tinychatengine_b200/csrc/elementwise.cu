@@ -1,0 +1,146 @@
+// elementwise.cu -- the small ops either side of the hot path: embedding gather, RMSNorm,
+// argmax.  RMSNorm / residual add / SiLU*mul of the decode block are fused into the GEMV kernels
+// (w4a16_gemv.cu); the standalone versions here serve the op-level API and the tests.
+#include "common.cuh"
+#include "kernels_attn.h"
+
+namespace tce {
+namespace {
+
+__global__ void embedding_kernel(const __half *__restrict__ table, const int *__restrict__ token, float *__restrict__ resid, int E) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tok = *token;
+    const __half2 *row = reinterpret_cast<const __half2 *>(table + (size_t)tok * E);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E / 2; i += gridDim.x * blockDim.x) {
+        const float2 f = __half22float2(row[i]);
+        reinterpret_cast<float2 *>(resid)[i] = f;
+    }
+}
+
+// two-phase argmax with a last-block finish; ties resolve to the lowest index
+struct ArgmaxWs {
+    float val[256];
+    int idx[256];
+    unsigned counter;
+};
+__device__ ArgmaxWs g_argmax_ws;
+
+__global__ void argmax_kernel(const float *__restrict__ x, int n, int *__restrict__ out) {
+    __shared__ float sval[32];
+    __shared__ int sidx[32];
+    __shared__ int is_last;
+    pdl_launch_dependents();
+    pdl_wait();
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = x[i];
+        if (v > best || (v == best && i < bi)) {
+            best = v;
+            bi = i;
+        }
+    }
+    auto combine = [](float &bv, int &bidx, float ov, int oidx) {
+        if (ov > bv || (ov == bv && oidx < bidx)) {
+            bv = ov;
+            bidx = oidx;
+        }
+    };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sval[warp] = best;
+        sidx[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        best = (lane < (blockDim.x >> 5)) ? sval[lane] : -INFINITY;
+        bi = (lane < (blockDim.x >> 5)) ? sidx[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+        if (lane == 0) {
+            g_argmax_ws.val[blockIdx.x] = best;
+            g_argmax_ws.idx[blockIdx.x] = bi;
+            __threadfence();
+            const unsigned prev = atomicAdd(&g_argmax_ws.counter, 1u);
+            is_last = (prev == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp == 0) {
+        best = -INFINITY;
+        bi = 0x7fffffff;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            const float v = *reinterpret_cast<volatile float *>(&g_argmax_ws.val[b]);
+            const int ix = *reinterpret_cast<volatile int *>(&g_argmax_ws.idx[b]);
+            combine(best, bi, v, ix);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+        if (lane == 0) {
+            *out = bi;
+            g_argmax_ws.counter = 0;
+        }
+    }
+}
+
+__global__ void rmsnorm_f16_kernel(const __half *__restrict__ x, const float *__restrict__ gamma, __half *__restrict__ y, int dim, float eps) {
+    __shared__ float sred[32];
+    const __half *xr = x + (size_t)blockIdx.x * dim;
+    __half *yr = y + (size_t)blockIdx.x * dim;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        const float v = __half2float(xr[i]);
+        ss += v * v;
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += sred[w];
+    const float inv = rsqrtf(tot / (float)dim + eps);
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) yr[i] = __float2half((__half2float(xr[i]) * inv) * gamma[i]);
+}
+
+cudaError_t launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, dim3 grid, dim3 block, cudaStream_t s, bool pdl) {
+    cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+cudaError_t launch_embedding(Ctx *ctx, const __half *table, const int *token, float *resid, int E, bool pdl) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    launch_cfg(cfg, attr, dim3(4), dim3(256), ctx->stream, pdl);
+    return cudaLaunchKernelEx(&cfg, embedding_kernel, table, token, resid, E);
+}
+
+cudaError_t launch_argmax(Ctx *ctx, const float *logits, int n, int *out, bool pdl) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    int blocks = (n + 1023) / 1024;
+    if (blocks > 128) blocks = 128;
+    if (blocks < 1) blocks = 1;
+    launch_cfg(cfg, attr, dim3(blocks), dim3(256), ctx->stream, pdl);
+    return cudaLaunchKernelEx(&cfg, argmax_kernel, logits, n, out);
+}
+
+cudaError_t launch_rmsnorm_f16(Ctx *ctx, const __half *x, const float *gamma, __half *y, int rows, int dim, float eps) {
+    rmsnorm_f16_kernel<<<rows, 256, 0, ctx->stream>>>(x, gamma, y, dim, eps);
+    return cudaGetLastError();
+}
+
+}  // namespace tce

@@ -1,0 +1,77 @@
+// kernels.h -- internal C++ launch interface of libtce_b200 (the public face is include/tce_b200.h).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tce {
+
+// One context per (device, stream).  Owns the small workspaces the kernels need; never owns caller data.
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    int smem_optin = 0;
+    // stream-K fix-up workspace of the W4A16 GEMV: 2 partial records per CTA + one arrival counter per row tile
+    float *gemv_partials = nullptr;
+    unsigned *gemv_counters = nullptr;
+    int gemv_max_ctas = 0;
+    int gemv_max_tiles = 0;
+    // flash-decode workspace (partial m, l, o per (head, split))
+    float *attn_ws = nullptr;
+    size_t attn_ws_bytes = 0;
+    unsigned *attn_counters = nullptr;
+    // tunables (env overridable, see ctx.cu)
+    int gemv_impl = 1;      // 0 = simple warp-per-row, 1 = TMA + mma.sync stream-K
+    int gemv_ctas_per_sm = 1;
+    bool use_pdl = true;
+};
+
+constexpr int kW4Group = 128;  // QK for QM_CUDA (llm/include/common.h:17-21)
+
+inline int zeros_width(int ic, int group) {  // llm/src/nn_modules/cuda/utils.cu:162-178
+    int mult = group >= 128 ? 1 : (group == 64 ? 2 : 4);
+    int base = (ic / group + 7) / 8;
+    return (base + mult - 1) / mult * mult;
+}
+
+enum XMode : int { X_HALF = 0, X_RMSNORM_F32 = 1 };
+enum EpiMode : int { EPI_STORE_HALF = 0, EPI_STORE_F32 = 1, EPI_ADD_F32 = 2, EPI_SILU_MUL_HALF = 3 };
+
+struct W4Seg {
+    const uint32_t *w;       // [rows][IC/8]
+    const uint32_t *zeros;   // [rows][zeros_w]
+    const __half *scales;    // [rows][zeros_w*8]
+    int rows;                // multiple of 16 (8 in pair mode)
+};
+
+struct W4GemvParams {
+    W4Seg seg[3];
+    int nseg = 1;
+    int pair_mode = 0;  // 1: row tile = 8 rows of seg[0] (-> MMA rows 0-7) + the same 8 rows of seg[1] (rows 8-15)
+    int IC = 0;
+    int M = 1;          // activation rows (<= 8 per launch)
+    const void *x = nullptr;
+    int x_mode = X_HALF;
+    int ldx = 0;        // elements between activation rows
+    const float *gamma = nullptr;
+    float eps = 0.f;
+    void *y = nullptr;
+    int epi = EPI_STORE_HALF;
+    int ldy = 0;        // elements between output rows
+    bool pdl = false;   // launch with programmatic stream serialization
+};
+
+cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p);
+cudaError_t launch_w4a16_gemv_simple(Ctx *ctx, const W4GemvParams &p);
+
+// host-side mirror of the stream-K partition used by the kernel (unit-tested on the CPU)
+struct StreamK {
+    long long U;   // total units = tiles * groups
+    int nc;        // CTAs
+    int NG;        // groups per row tile
+    __host__ __device__ long long start(int c) const { return (U * (long long)c) / nc; }
+    __host__ __device__ int cta_of(long long u) const { return (int)(((u + 1) * nc + U - 1) / U - 1); }
+};
+
+}  // namespace tce

@@ -1,0 +1,31 @@
+// kernels_attn.h -- launch interface of the decode attention / small fused ops (internal).
+#pragma once
+#include "kernels.h"
+
+namespace tce {
+
+struct AttnDecodeArgs {
+    const __half *qkv;   // [(H + 2*KVH) * head_dim] projections of the current token (q | k | v), pre-RoPE
+    __half *k_cache;     // [KVH][max_ctx][head_dim]
+    __half *v_cache;     // [KVH][max_ctx][head_dim]
+    const float *cos;    // [max_ctx][head_dim]  (reference rotary_emb/cos_cached layout)
+    const float *sin;    // [max_ctx][head_dim]
+    const int *pos;      // device scalar: index of the token being decoded (= number of cached tokens)
+    __half *out;         // [H * head_dim]
+    float alpha;         // qk_bmm alpha (1/sqrt(head_dim))
+    int num_heads, num_kv_heads, head_dim, max_ctx;
+    int chunk;           // cached positions per CTA
+    int nsplit_max;      // filled by the launcher
+    float *ws;           // filled by the launcher
+    unsigned *counters;  // filled by the launcher
+};
+cudaError_t launch_attn_decode(Ctx *ctx, AttnDecodeArgs a, bool pdl);
+
+// resid_f32[E] = (float) table[token][:]   (reference: CPU Embedding + float2half, cuda/Int4llamaDecoder.cu:62-69)
+cudaError_t launch_embedding(Ctx *ctx, const __half *table, const int *token, float *resid, int E, bool pdl);
+// argmax over fp32 logits -> int (first index of the maximum, like arg_max.cc)
+cudaError_t launch_argmax(Ctx *ctx, const float *logits, int n, int *out, bool pdl);
+// standalone RMSNorm fp16 -> fp16 with fp32 gamma (reference LlamaRMSNorm_cuda, ops/cuda/LlamaRMSNorm.cu:68-115)
+cudaError_t launch_rmsnorm_f16(Ctx *ctx, const __half *x, const float *gamma, __half *y, int rows, int dim, float eps);
+
+}  // namespace tce

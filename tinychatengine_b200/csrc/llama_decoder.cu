@@ -1,0 +1,333 @@
+// llama_decoder.cu -- one-token decode of an AWQ-INT4 Llama as a single CUDA graph.
+//
+// Call sites restated (reference, CUDA build): Int4LlamaForCausalLM::forward (cuda/Int4llamaForCausalLM.cu:17-50)
+// -> Int4llamaDecoder::forward (cuda/Int4llamaDecoder.cu:57-112) -> 32 x Int4llamaDecoderLayer::forward
+// (cuda/Int4llamaDecoderLayer.cu:73-115) -> Int4llamaAttention::forward (cuda/Int4llamaAttention.cu:116-229).
+// The reference issues ~19 kernels + 128 memcpys per layer on stream 0; here a layer is 5 kernels
+// (RMSNorm+QKV GEMV | RoPE+append+attention | o_proj+residual | RMSNorm+gate/up+SiLU*mul | down+residual),
+// chained with programmatic dependent launch so each GEMV prefetches its weights while its predecessor drains.
+// The residual stream is kept in fp32 (the reference's CUDA build keeps it in fp16, its CPU build in fp32).
+#include "llama_decoder.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace tce {
+
+#define DCK(call)                              \
+    do {                                       \
+        cudaError_t e__ = (call);              \
+        if (e__ != cudaSuccess) return e__;    \
+    } while (0)
+
+static bool w4_ok(const tce_w4_tensor &t, int oc, int ic) { return t.w && t.zeros && t.scales && t.oc == oc && t.ic == ic; }
+
+LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_config &cfg, const tce_llama_weights &w, std::string *err) {
+    auto bad = [&](const char *m) {
+        *err = m;
+        return (LlamaDecoder *)nullptr;
+    };
+    if (cfg.head_dim != 128) return bad("head_dim must be 128");
+    if (cfg.num_layers < 1 || cfg.num_heads < 1 || cfg.num_kv_heads < 1 || cfg.num_heads % cfg.num_kv_heads) return bad("bad head configuration");
+    if (cfg.embed_dim % 128 || cfg.hidden_dim % 128) return bad("embed_dim / hidden_dim must be multiples of the 128 group");
+    if (cfg.tp_size > 1) return bad("tensor parallel decode is not wired in this build");
+    const int E = cfg.embed_dim, F = cfg.hidden_dim, H = cfg.num_heads, KVH = cfg.num_kv_heads, hd = cfg.head_dim, V = cfg.vocab_size;
+    if (!w.embed_f16 || !w.layers || !w.final_norm) return bad("missing weights");
+    if (!w4_ok(w.lm_head, V, E) || V % 16) return bad("lm_head shape");
+    for (int l = 0; l < cfg.num_layers; l++) {
+        const tce_llama_layer &L = w.layers[l];
+        if (!w4_ok(L.q, H * hd, E) || !w4_ok(L.k, KVH * hd, E) || !w4_ok(L.v, KVH * hd, E) || !w4_ok(L.o, E, H * hd) || !w4_ok(L.gate, F, E) ||
+            !w4_ok(L.up, F, E) || !w4_ok(L.down, E, F) || !L.input_norm || !L.post_norm)
+            return bad("layer weight shape");
+    }
+    LlamaDecoder *d = new LlamaDecoder();
+    d->ctx_ = ctx;
+    d->attn_chunk_ = attn_chunk;
+    d->cfg_ = cfg;
+    d->w_ = w;
+    d->layers_.assign(w.layers, w.layers + cfg.num_layers);
+    d->w_.layers = d->layers_.data();
+    d->use_graphs_ = getenv("TCE_NO_GRAPH") == nullptr;
+    const size_t kv_elems = (size_t)cfg.num_layers * 2 * KVH * cfg.max_ctx * hd;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    };
+    A((void **)&d->d_kv_, kv_elems * sizeof(__half));
+    A((void **)&d->d_resid_, (size_t)E * sizeof(float));
+    A((void **)&d->d_qkv_, (size_t)(H + 2 * KVH) * hd * sizeof(__half));
+    A((void **)&d->d_attn_, (size_t)H * hd * sizeof(__half));
+    A((void **)&d->d_act_, (size_t)F * sizeof(__half));
+    A((void **)&d->d_logits_, (size_t)V * sizeof(float));
+    A((void **)&d->d_tokpos_, 2 * sizeof(int));
+    A((void **)&d->d_next_, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(d->d_kv_, 0, kv_elems * sizeof(__half));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_tokpos_, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_logits_, (size_t)V * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_next_, sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->cap_stream_, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        if (w.rope_cos && w.rope_sin) {
+            d->d_cos_ = const_cast<float *>(w.rope_cos);
+            d->d_sin_ = const_cast<float *>(w.rope_sin);
+        } else {
+            // HF rotate-half tables: cos/sin(pos * theta^(-2i/hd)) duplicated over both halves
+            std::vector<float> hc((size_t)cfg.max_ctx * hd), hs((size_t)cfg.max_ctx * hd);
+            const double theta = cfg.rope_theta > 0 ? cfg.rope_theta : 10000.0;
+            for (int p = 0; p < cfg.max_ctx; p++)
+                for (int i = 0; i < hd / 2; i++) {
+                    const double inv = 1.0 / pow(theta, (2.0 * i) / hd);
+                    const double ang = p * inv;
+                    hc[(size_t)p * hd + i] = hc[(size_t)p * hd + i + hd / 2] = (float)cos(ang);
+                    hs[(size_t)p * hd + i] = hs[(size_t)p * hd + i + hd / 2] = (float)sin(ang);
+                }
+            A((void **)&d->d_cos_, hc.size() * sizeof(float));
+            A((void **)&d->d_sin_, hs.size() * sizeof(float));
+            d->own_rope_ = true;
+            if (e == cudaSuccess) e = cudaMemcpy(d->d_cos_, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(d->d_sin_, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice);
+        }
+    }
+    if (e != cudaSuccess) {
+        *err = std::string("allocation failed: ") + cudaGetErrorString(e);
+        delete d;
+        return nullptr;
+    }
+    d->kernels_per_step_ = 1 + 5 * cfg.num_layers + 2;
+    return d;
+}
+
+LlamaDecoder::~LlamaDecoder() {
+    if (g_host_) cudaGraphExecDestroy(g_host_);
+    if (g_dev_) cudaGraphExecDestroy(g_dev_);
+    if (cap_stream_) cudaStreamDestroy(cap_stream_);
+    cudaFree(d_kv_);
+    cudaFree(d_resid_);
+    cudaFree(d_qkv_);
+    cudaFree(d_attn_);
+    cudaFree(d_act_);
+    cudaFree(d_logits_);
+    cudaFree(d_tokpos_);
+    cudaFree(d_next_);
+    if (own_rope_) {
+        cudaFree(d_cos_);
+        cudaFree(d_sin_);
+    }
+    if (h_tokpos_) cudaFreeHost(h_tokpos_);
+    if (h_logits_) cudaFreeHost(h_logits_);
+    if (h_next_) cudaFreeHost(h_next_);
+}
+
+void *LlamaDecoder::kv_cache(int layer, int which) const {
+    if (layer < 0 || layer >= cfg_.num_layers || which < 0 || which > 1) return nullptr;
+    const size_t per = (size_t)cfg_.num_kv_heads * cfg_.max_ctx * cfg_.head_dim;
+    return d_kv_ + ((size_t)layer * 2 + which) * per;
+}
+
+static W4Seg seg_of(const tce_w4_tensor &t) { return W4Seg{(const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, t.oc}; }
+
+cudaError_t LlamaDecoder::enqueue_gemvs(int *count) {
+    *count = 4 * cfg_.num_layers + 1;
+    return enqueue_step(d_tokpos_, ctx_->stream, false, true);
+}
+
+cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only) {
+    Ctx local = *ctx_;  // same workspaces, but launch on `s`
+    local.stream = s;
+    Ctx *c = &local;
+    const int E = cfg_.embed_dim, F = cfg_.hidden_dim, H = cfg_.num_heads, KVH = cfg_.num_kv_heads, hd = cfg_.head_dim;
+    if (!gemv_only) DCK(launch_embedding(c, (const __half *)w_.embed_f16, tokpos, d_resid_, E, false));
+    for (int l = 0; l < cfg_.num_layers; l++) {
+        const tce_llama_layer &L = layers_[l];
+        {  // RMSNorm(input_layernorm) + fused q|k|v projection
+            W4GemvParams p;
+            p.nseg = 3;
+            p.seg[0] = seg_of(L.q);
+            p.seg[1] = seg_of(L.k);
+            p.seg[2] = seg_of(L.v);
+            p.IC = E;
+            p.M = 1;
+            p.x = d_resid_;
+            p.x_mode = X_RMSNORM_F32;
+            p.ldx = E;
+            p.gamma = L.input_norm;
+            p.eps = cfg_.rms_eps;
+            p.y = d_qkv_;
+            p.epi = EPI_STORE_HALF;
+            p.pdl = pdl;
+            DCK(launch_w4a16_gemv(c, p));
+        }
+        if (!gemv_only) {  // RoPE + in-place KV append + attention over the cache
+            AttnDecodeArgs a = {};
+            a.qkv = d_qkv_;
+            a.k_cache = (__half *)kv_cache(l, 0);
+            a.v_cache = (__half *)kv_cache(l, 1);
+            a.cos = d_cos_;
+            a.sin = d_sin_;
+            a.pos = tokpos + 1;
+            a.out = d_attn_;
+            a.alpha = cfg_.qk_alpha > 0 ? cfg_.qk_alpha : 1.0f / sqrtf((float)hd);
+            a.num_heads = H;
+            a.num_kv_heads = KVH;
+            a.head_dim = hd;
+            a.max_ctx = cfg_.max_ctx;
+            a.chunk = attn_chunk_;
+            DCK(launch_attn_decode(c, a, pdl));
+        }
+        {  // o_proj, accumulated straight into the residual stream
+            W4GemvParams p;
+            p.nseg = 1;
+            p.seg[0] = seg_of(L.o);
+            p.IC = H * hd;
+            p.M = 1;
+            p.x = d_attn_;
+            p.x_mode = X_HALF;
+            p.y = d_resid_;
+            p.epi = EPI_ADD_F32;
+            p.pdl = pdl;
+            DCK(launch_w4a16_gemv(c, p));
+        }
+        {  // RMSNorm(post_attention_layernorm) + gate/up with SiLU(gate)*up epilogue
+            W4GemvParams p;
+            p.nseg = 2;
+            p.pair_mode = 1;
+            p.seg[0] = seg_of(L.gate);
+            p.seg[1] = seg_of(L.up);
+            p.IC = E;
+            p.M = 1;
+            p.x = d_resid_;
+            p.x_mode = X_RMSNORM_F32;
+            p.gamma = L.post_norm;
+            p.eps = cfg_.rms_eps;
+            p.y = d_act_;
+            p.epi = EPI_SILU_MUL_HALF;
+            p.ldy = F;
+            p.pdl = pdl;
+            DCK(launch_w4a16_gemv(c, p));
+        }
+        {  // down_proj + residual
+            W4GemvParams p;
+            p.nseg = 1;
+            p.seg[0] = seg_of(L.down);
+            p.IC = F;
+            p.M = 1;
+            p.x = d_act_;
+            p.x_mode = X_HALF;
+            p.y = d_resid_;
+            p.epi = EPI_ADD_F32;
+            p.pdl = pdl;
+            DCK(launch_w4a16_gemv(c, p));
+        }
+    }
+    {  // final RMSNorm + lm_head -> fp32 logits (reference: lm_head GEMV + half2float, cuda/Int4llamaForCausalLM.cu:33-38)
+        W4GemvParams p;
+        p.nseg = 1;
+        p.seg[0] = seg_of(w_.lm_head);
+        p.IC = E;
+        p.M = 1;
+        p.x = d_resid_;
+        p.x_mode = X_RMSNORM_F32;
+        p.gamma = w_.final_norm;
+        p.eps = cfg_.rms_eps;
+        p.y = d_logits_;
+        p.epi = EPI_STORE_F32;
+        p.pdl = pdl;
+        DCK(launch_w4a16_gemv(c, p));
+    }
+    if (!gemv_only) DCK(launch_argmax(c, d_logits_, cfg_.vocab_size, d_next_, pdl));
+    return cudaSuccess;
+}
+
+cudaError_t LlamaDecoder::build_graphs(std::string *err) {
+    // one eager step first: loads the modules and sets the kernels' shared-memory attributes outside of capture
+    // (re-running a step at the same position is idempotent: the same K/V row is rewritten)
+    DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 2 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_));
+    DCK(enqueue_step(d_tokpos_, cap_stream_, false));
+    DCK(cudaStreamSynchronize(cap_stream_));
+    // try PDL edges first; if capture/instantiate refuses them, fall back to plain edges
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const bool pdl = ctx_->use_pdl && attempt == 0;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(d_tokpos_, h_tokpos_, 2 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_);
+        if (e == cudaSuccess) e = enqueue_step(d_tokpos_, cap_stream_, pdl);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_logits_, d_logits_, (size_t)cfg_.vocab_size * sizeof(float), cudaMemcpyDeviceToHost, cap_stream_);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_next_, d_next_, sizeof(int), cudaMemcpyDeviceToHost, cap_stream_);
+        cudaError_t e2 = cudaStreamEndCapture(cap_stream_, &g);
+        if (e == cudaSuccess) e = e2;
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&g_host_, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e == cudaSuccess) {
+            graphs_ok_ = true;
+            if (!pdl) ctx_->use_pdl = false;
+            return cudaSuccess;
+        }
+        cudaGetLastError();
+        if (err) *err = std::string("graph capture failed (pdl=") + (pdl ? "1" : "0") + "): " + cudaGetErrorString(e);
+        g_host_ = nullptr;
+        if (!ctx_->use_pdl) return e;
+    }
+    return cudaErrorUnknown;
+}
+
+cudaError_t LlamaDecoder::decode_host(int token, int pos, float *logits_host, int *next_token, std::string *err) {
+    if (pos < 0 || pos >= cfg_.max_ctx || token < 0 || token >= cfg_.vocab_size) return cudaErrorInvalidValue;
+    h_tokpos_[0] = token;
+    h_tokpos_[1] = pos;
+    cudaStream_t s = ctx_->stream;
+    if (use_graphs_ && !graphs_ok_) {
+        cudaError_t e = build_graphs(err);
+        if (e != cudaSuccess) use_graphs_ = false;
+    }
+    if (use_graphs_ && graphs_ok_) {
+        DCK(cudaGraphLaunch(g_host_, s));
+    } else {
+        DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+        DCK(enqueue_step(d_tokpos_, s, ctx_->use_pdl));
+        DCK(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)cfg_.vocab_size * sizeof(float), cudaMemcpyDeviceToHost, s));
+        DCK(cudaMemcpyAsync(h_next_, d_next_, sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    DCK(cudaStreamSynchronize(s));
+    if (logits_host) memcpy(logits_host, h_logits_, (size_t)cfg_.vocab_size * sizeof(float));
+    if (next_token) *next_token = *h_next_;
+    return cudaSuccess;
+}
+
+cudaError_t LlamaDecoder::decode_device(const int *tokpos_dev, std::string *err) {
+    cudaStream_t s = ctx_->stream;
+    if (use_graphs_ && (g_dev_ == nullptr || g_dev_src_ != tokpos_dev)) {
+        if (g_dev_) {
+            cudaGraphExecDestroy(g_dev_);
+            g_dev_ = nullptr;
+        }
+        DCK(cudaStreamSynchronize(s));
+        DCK(enqueue_step(tokpos_dev, cap_stream_, false));  // eager warm-up outside of capture (idempotent)
+        DCK(cudaStreamSynchronize(cap_stream_));
+        for (int attempt = 0; attempt < 2 && !g_dev_; attempt++) {
+            const bool pdl = ctx_->use_pdl && attempt == 0;
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) e = enqueue_step(tokpos_dev, cap_stream_, pdl);
+            cudaError_t e2 = cudaStreamEndCapture(cap_stream_, &g);
+            if (e == cudaSuccess) e = e2;
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&g_dev_, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                g_dev_ = nullptr;
+                if (err) *err = std::string("graph capture failed: ") + cudaGetErrorString(e);
+                if (!pdl) use_graphs_ = false;
+            } else if (!pdl) {
+                ctx_->use_pdl = false;
+            }
+        }
+        g_dev_src_ = tokpos_dev;
+    }
+    if (use_graphs_ && g_dev_) return cudaGraphLaunch(g_dev_, s);
+    return enqueue_step(tokpos_dev, s, ctx_->use_pdl);
+}
+
+}  // namespace tce

@@ -1,0 +1,58 @@
+// llama_decoder.h -- host-side runner of the fused Llama decode step (one CUDA graph per token).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/tce_b200.h"
+#include "kernels.h"
+#include "kernels_attn.h"
+
+namespace tce {
+
+class LlamaDecoder {
+   public:
+    static LlamaDecoder *create(Ctx *ctx, int attn_chunk, const tce_llama_config &cfg, const tce_llama_weights &w, std::string *err);
+    ~LlamaDecoder();
+    cudaError_t decode_device(const int *tokpos_dev, std::string *err);
+    cudaError_t decode_host(int token, int pos, float *logits_host, int *next_token, std::string *err);
+    const float *logits() const { return d_logits_; }
+    void *kv_cache(int layer, int which) const;
+    int kernels_per_step() const { return kernels_per_step_; }
+    cudaError_t enqueue_gemvs(int *count);
+
+   private:
+    LlamaDecoder() = default;
+    cudaError_t enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only = false);  // raw kernel sequence
+    cudaError_t build_graphs(std::string *err);
+
+    Ctx *ctx_ = nullptr;
+    int attn_chunk_ = 128;
+    tce_llama_config cfg_{};
+    std::vector<tce_llama_layer> layers_;
+    tce_llama_weights w_{};
+    // device state
+    __half *d_kv_ = nullptr;        // [L][2][KVH][max_ctx][hd]
+    float *d_resid_ = nullptr;      // fp32 residual stream [E]
+    __half *d_qkv_ = nullptr;       // [(H+2KVH)*hd]
+    __half *d_attn_ = nullptr;      // [H*hd]
+    __half *d_act_ = nullptr;       // [F] SiLU(gate)*up
+    float *d_logits_ = nullptr;     // [V]
+    int *d_tokpos_ = nullptr;       // {token, pos} staged for the host entry point
+    int *d_next_ = nullptr;         // greedy arg-max
+    float *d_cos_ = nullptr, *d_sin_ = nullptr;
+    bool own_rope_ = false;
+    // pinned host staging for the end-to-end entry point
+    int *h_tokpos_ = nullptr;
+    float *h_logits_ = nullptr;
+    int *h_next_ = nullptr;
+    // graphs
+    cudaStream_t cap_stream_ = nullptr;
+    cudaGraphExec_t g_host_ = nullptr;    // H2D(tokpos) + step + argmax + D2H(logits,next)
+    cudaGraphExec_t g_dev_ = nullptr;     // copy tokpos (D2D) + step
+    const int *g_dev_src_ = nullptr;
+    bool graphs_ok_ = false;
+    bool use_graphs_ = true;
+    int kernels_per_step_ = 0;
+};
+
+}  // namespace tce

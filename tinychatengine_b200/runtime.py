@@ -1,0 +1,110 @@
+"""Device-side plumbing on top of the C ABI: contexts, torch tensors as raw device pointers, synthetic weights.
+
+torch supplies memory + streams; every computation goes through libtce_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .formats import GROUP, zeros_width
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One tce_ctx per (device, stream)."""
+
+    def __init__(self, device: int | None = None, stream: torch.cuda.Stream | None = None):
+        if not torch.cuda.is_available():
+            raise _lib.TceError("no CUDA device: tinychatengine_b200 has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else device
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(self.L.tce_ctx_create(self.device, C.byref(h)), "tce_ctx_create")
+        self.h = h
+        self.stream = None
+        self.set_stream(stream if stream is not None else torch.cuda.current_stream(self.device))
+
+    def set_stream(self, stream: torch.cuda.Stream):
+        self.stream = stream
+        _lib.check(self.L.tce_ctx_set_stream(self.h, C.c_void_p(stream.cuda_stream)), "tce_ctx_set_stream")
+
+    def set_option(self, name: str, value: int):
+        _lib.check(self.L.tce_ctx_set_option(self.h, name.encode(), int(value)), "tce_ctx_set_option")
+
+    def synchronize(self):
+        _lib.check(self.L.tce_ctx_synchronize(self.h), "tce_ctx_synchronize")
+
+    @property
+    def num_sms(self) -> int:
+        return self.L.tce_ctx_num_sms(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.tce_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- ops (thin: argument marshalling only) ----
+    def w4a16_gemv(self, x, w, zeros, scales, out=None, group: int = GROUP, gemm: bool = False):
+        M, IC = x.shape
+        OC = w.shape[0]
+        if out is None:
+            out = torch.empty((M, OC), dtype=torch.float16, device=x.device)
+        fn = self.L.tce_w4a16_gemm if gemm else self.L.tce_w4a16_gemv
+        _lib.check(fn(self.h, _ptr(x), _ptr(w), _ptr(zeros), _ptr(scales), _ptr(out), M, IC, OC, group), "tce_w4a16_gemv")
+        return out
+
+    def w8a8_matmul(self, variant: int, A, B, bias=None, alpha=1.0, beta=1.0, q_min=-128, q_max=127, batch=False, out=None):
+        M, K = A.shape
+        N = B.shape[-2]
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.int8 if variant in (0, 1) else torch.float32, device=A.device)
+        _lib.check(self.L.tce_w8a8_matmul(self.h, variant, int(batch), _ptr(A), _ptr(B), _ptr(bias), _ptr(out), M, N, K, alpha, beta, q_min, q_max),
+                   "tce_w8a8_matmul")
+        return out
+
+    def attn_decode(self, qkv, k_cache, v_cache, cos, sin, pos_dev, out, alpha, H, KVH, hd, max_ctx):
+        _lib.check(self.L.tce_attn_decode(self.h, _ptr(qkv), _ptr(k_cache), _ptr(v_cache), _ptr(cos), _ptr(sin), _ptr(pos_dev), _ptr(out), alpha, H, KVH,
+                                          hd, max_ctx), "tce_attn_decode")
+        return out
+
+    def rmsnorm_f16(self, x, gamma, eps, out=None):
+        if out is None:
+            out = torch.empty_like(x)
+        _lib.check(self.L.tce_rmsnorm_f16(self.h, _ptr(x), _ptr(gamma), _ptr(out), x.shape[0], x.shape[1], eps), "tce_rmsnorm_f16")
+        return out
+
+    def argmax_f32(self, x, out=None):
+        if out is None:
+            out = torch.empty((1,), dtype=torch.int32, device=x.device)
+        _lib.check(self.L.tce_argmax_f32(self.h, _ptr(x), x.numel(), _ptr(out)), "tce_argmax_f32")
+        return out
+
+
+def random_w4(oc: int, ic: int, device, seed: int, scale: float = 0.02, random_zeros: bool = False, group: int = GROUP):
+    """Synthetic QM_CUDA tensors generated on the device: uniform nibbles, per-group fp16 scales such that the
+    dequantised weights have std ~ `scale`, zero points 8 (or random)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    zw = zeros_width(ic, group)
+    w = torch.randint(-(2**31), 2**31 - 1, (oc, ic // 8), dtype=torch.int32, device=device, generator=g)
+    ng = ic // group
+    s = torch.zeros((oc, zw * 8), dtype=torch.float16, device=device)
+    # uniform nibbles minus 8 have std ~4.6
+    s[:, :ng] = ((0.5 + torch.rand((oc, ng), device=device, generator=g)) * (scale / 4.6)).to(torch.float16)
+    if random_zeros:
+        z = torch.randint(-(2**31), 2**31 - 1, (oc, zw), dtype=torch.int32, device=device, generator=g)
+    else:
+        z = torch.full((oc, zw), -0x77777778, dtype=torch.int32, device=device)  # 0x88888888
+    return w, z, s
