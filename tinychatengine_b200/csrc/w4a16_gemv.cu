@@ -194,9 +194,13 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
                 for (int w = 0; w < kConsumerWarps; w++) tot += rms[col * kConsumerWarps + w];
                 inv = rsqrtf(tot / (float)a.IC + a.eps);
             }
-            for (int ui = ctid; ui < units; ui += kConsumerThreads) {
+            // `units` is a multiple of 16, not of 32: the trip count is made warp-uniform so that the half-warp
+            // shuffles below always run with all 32 lanes (an idle half-warp contributes zeros to nobody)
+            for (int ui0 = 0; ui0 < units; ui0 += kConsumerThreads) {
+                const int ui = ui0 + ctid;
+                const bool valid = ui < units;
                 float v[8];
-                if (col < a.M) {
+                if (valid && col < a.M) {
                     if (a.x_mode == X_RMSNORM_F32) {
                         const float *xr = reinterpret_cast<const float *>(a.x) + (size_t)col * a.ldx + ui * 8;
                         float4 v0 = *reinterpret_cast<const float4 *>(xr);
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
                 o.w = pack_half2(v[3], v[7]);
                 const int G = ui >> 4, tj = ui & 15;  // ui = G*16 + 4*t + j
                 const int pos = G * 16 + (tj & 3) * 4 + (tj >> 2);
-                *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = o;
+                if (valid) *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = o;
                 // group sum of the fp16-rounded values the tensor core will actually see
                 const __half2 *oh = reinterpret_cast<const __half2 *>(&o);
                 float s = 0.f;
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
                 s += __shfl_xor_sync(0xffffffffu, s, 4);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
-                if ((lane & 15) == 0) gx[col * a.NG + G] = s;
+                if (valid && (lane & 15) == 0) gx[col * a.NG + G] = s;
             }
         }
         named_bar_sync(1, kConsumerThreads);
