@@ -24,6 +24,7 @@ struct Ctx {
     // tunables (env overridable, see ctx.cu)
     int gemv_impl = 1;      // 0 = simple warp-per-row, 1 = TMA + mma.sync stream-K
     int gemv_ctas_per_sm = 1;
+    int gemv_consumer_warps = 16;  // 8 or 16 consumer warps per CTA
     bool use_pdl = true;
 };
 
@@ -64,6 +65,7 @@ struct W4GemvParams {
 
 cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p);
 cudaError_t launch_w4a16_gemv_simple(Ctx *ctx, const W4GemvParams &p);
+size_t w4a16_gemv_smem_bytes(int ncols, int consumer_warps, int IC);
 
 // host-side mirror of the stream-K partition used by the kernel (unit-tested on the CPU)
 struct StreamK {

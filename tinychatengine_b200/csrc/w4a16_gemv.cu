@@ -10,16 +10,19 @@
 //    into equal contiguous ranges, one per CTA (stream-K), so every CTA streams the same number of bytes no
 //    matter the shape; a row tile split between CTAs is finished by whichever CTA arrives last (fixed
 //    summation order -> deterministic), no atomics on data, no pre-zeroed outputs.
-//  * a producer warp streams [16 rows x <=16 groups] weight slabs with 1-D TMA bulk copies (UBLKCP) into a
+//  * warp roles: warp 0 = TMA producer, warp 1 = epilogue, warps 2.. = CW consumers.
+//    The producer streams [16 rows x <=16 groups] weight slabs with 1-D TMA bulk copies (UBLKCP) into a
 //    4-stage shared-memory ring guarded by full/empty mbarriers; weights are tagged L2 evict-first.
 //    The ring starts filling BEFORE griddepcontrol.wait, so under programmatic dependent launch the next
 //    GEMV's weights are already in flight while the previous kernel drains.
-//  * 8 consumer warps: 128-bit conflict-free LDS of packed nibbles (row pitch = 64 mod 128 B), int4 -> fp16
-//    by lop3 + magic-number subtract (exact, centred at 8), products on the legacy tensor path
-//    (mma.sync m16n8k16, fp32 accumulate; the 8 MMA columns are the <=8 activation rows), per-group epilogue
-//    tot += s * (acc - (z-8) * sum_x) in fp32.
-//  * optional fused prologue (RMSNorm of an fp32 residual stream) and epilogues (fp16/fp32 store,
-//    residual += , SiLU(gate)*up with gate/up rows paired inside one MMA tile).
+//  * consumers: 128-bit conflict-free LDS of packed nibbles (row pitch = 64 mod 128 B), int4 -> fp16 by
+//    lop3 + magic-number subtract (exact, centred at 8), products on the legacy tensor path (mma.sync
+//    m16n8k16, fp32 accumulate, 4 independent accumulators per group; the 8 MMA columns are the <=8
+//    activation rows), per-group fp32 epilogue tot += s * (acc - (z-8) * sum_x).
+//  * consumers never wait for each other at a tile boundary: each drops its 16-row partial into a
+//    triple-buffered smem slot and arrives on an mbarrier; the epilogue warp reduces the CW partials and runs
+//    the fused epilogue (fp16/fp32 store, residual +=, SiLU(gate)*up) or the stream-K fix-up.
+//  * optional fused prologue: RMSNorm of an fp32 residual stream (LlamaRMSNorm semantics).
 #include <stdio.h>
 
 #include "common.cuh"
@@ -29,13 +32,11 @@ namespace tce {
 
 namespace {
 
-constexpr int kConsumerWarps = 8;
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = 32 + kConsumerThreads;  // warp 0 = TMA producer
-constexpr int kStageGroups = 16;                 // 128-k groups per pipeline stage (per row: 1024 B)
+constexpr int kStageGroups = 16;                   // 128-k groups per pipeline stage (per row: 1024 B)
 constexpr int kRowPitch = kStageGroups * 64 + 64;  // 1088 B: == 64 (mod 128) -> conflict-free LDS.128
 constexpr int kStageBytes = 16 * kRowPitch;        // 17408 B
 constexpr int kStages = 4;
+constexpr int kRedBufs = 3;
 
 struct KArgs {
     W4Seg seg[3];
@@ -83,24 +84,36 @@ TCE_DEVINL RowRef tile_row(const KArgs &a, int rt, int l) {
     return ref;
 }
 
-template <int NCOLS>
+template <int NCOLS, int CW>
 struct Smem {
     static constexpr int kXPad = (NCOLS > 1) ? 64 : 0;  // column pitch = 64 (mod 128) B for the per-column B loads
+    static constexpr int kVals = 16 * NCOLS;
     static __host__ __device__ int x_pitch(int IC) { return IC * 2 + kXPad; }
     static __host__ __device__ size_t off_xs() { return (size_t)kStages * kStageBytes; }
     static __host__ __device__ size_t off_gx(int IC) { return off_xs() + (size_t)NCOLS * x_pitch(IC); }
     static __host__ __device__ size_t off_red(int IC) { return off_gx(IC) + (size_t)NCOLS * (IC / 128) * sizeof(float); }
-    static __host__ __device__ size_t off_rms(int IC) { return off_red(IC) + (size_t)2 * kConsumerWarps * 16 * NCOLS * sizeof(float); }
-    static __host__ __device__ size_t off_bar(int IC) {
-        return (off_rms(IC) + (size_t)NCOLS * kConsumerWarps * sizeof(float) + 15) & ~(size_t)15;
-    }
-    static __host__ __device__ size_t bytes(int IC) { return off_bar(IC) + 2 * kStages * sizeof(uint64_t) + 16; }
+    static __host__ __device__ size_t off_rms(int IC) { return off_red(IC) + (size_t)kRedBufs * CW * kVals * sizeof(float); }
+    static __host__ __device__ size_t off_bar(int IC) { return (off_rms(IC) + (size_t)NCOLS * CW * sizeof(float) + 15) & ~(size_t)15; }
+    static __host__ __device__ size_t bytes(int IC) { return off_bar(IC) + (2 * kStages + 2 * kRedBufs) * sizeof(uint64_t) + 16; }
 };
 
-template <int NCOLS>
-__global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_constant__ KArgs a) {
+// nibble -> fp16: low nibbles ride on 1024 (0x6400), high nibbles on 64 (0x5400); subtracting 1032 / 72
+// yields q - 8 exactly.  One packed word -> four half2 (n0,n4)(n1,n5)(n2,n6)(n3,n7).
+TCE_DEVINL void dequant8(uint32_t w, uint32_t &p0, uint32_t &p1, uint32_t &p2, uint32_t &p3) {
+    const uint32_t w8 = w >> 8;
+    p0 = hsub2_u32(lop3_and_or(w, 0x000f000fu, 0x64006400u), 0x64086408u);
+    p1 = hsub2_u32(lop3_and_or(w, 0x00f000f0u, 0x54005400u), 0x54805480u);
+    p2 = hsub2_u32(lop3_and_or(w8, 0x000f000fu, 0x64006400u), 0x64086408u);
+    p3 = hsub2_u32(lop3_and_or(w8, 0x00f000f0u, 0x54005400u), 0x54805480u);
+}
+
+template <int NCOLS, int CW>
+__global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    using SM = Smem<NCOLS>;
+    using SM = Smem<NCOLS, CW>;
+    constexpr int kConsumerThreads = CW * 32;
+    constexpr int kVals = SM::kVals;
+    constexpr int GPW = kStageGroups / CW;  // groups per consumer warp per stage
     uint8_t *stages = smem;
     uint8_t *xs = smem + SM::off_xs();
     float *gx = reinterpret_cast<float *>(smem + SM::off_gx(a.IC));
@@ -108,7 +121,8 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
     float *rms = reinterpret_cast<float *>(smem + SM::off_rms(a.IC));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + SM::off_bar(a.IC));
     uint64_t *empty_bar = full_bar + kStages;
-    int *flag = reinterpret_cast<int *>(empty_bar + kStages);
+    uint64_t *red_full = empty_bar + kStages;
+    uint64_t *red_empty = red_full + kRedBufs;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -118,7 +132,12 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
 #pragma unroll
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kConsumerWarps);
+            mbar_init(&empty_bar[s], CW);
+        }
+#pragma unroll
+        for (int s = 0; s < kRedBufs; s++) {
+            mbar_init(&red_full[s], CW);
+            mbar_init(&red_empty[s], 1);
         }
         mbar_fence_init();
     }
@@ -163,12 +182,127 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
         return;
     }
 
+    if (warp == 1) {
+        // =========================== epilogue warp ===========================
+        // reduces the CW consumer partials of every tile this CTA touches, then either finishes the tile or
+        // takes part in the stream-K fix-up.  Lane l owns values idx = l + 32*i  (idx = row*NCOLS + col).
+        constexpr int VPL = (kVals + 31) / 32;  // values per lane
+        pdl_wait();                             // outputs (and the residual we add into) belong to earlier kernels
+        int rb = 0;
+        uint32_t rphase = 0;
+        long long u = u0;
+        while (u < u1) {
+            const int rt = (int)(u / a.NG);
+            const int gb = (int)(u % a.NG);
+            const int ge = (int)min((long long)a.NG, gb + (u1 - u));
+            const bool full_tile = (gb == 0 && ge == a.NG);
+            mbar_wait(&red_full[rb], rphase);
+            const float *rbuf = red + (size_t)rb * CW * kVals;
+            float v[VPL];
+#pragma unroll
+            for (int i = 0; i < VPL; i++) {
+                const int idx = lane + 32 * i;
+                float acc = 0.f;
+                if (idx < kVals) {
+#pragma unroll
+                    for (int w = 0; w < CW; w++) acc += rbuf[w * kVals + idx];
+                }
+                v[i] = acc;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&red_empty[rb]);
+            if (++rb == kRedBufs) {
+                rb = 0;
+                rphase ^= 1;
+            }
+            bool do_final = full_tile;
+            if (!full_tile) {
+                // stream-K fix-up: park the partial; the last contributor to arrive sums all of them in CTA order
+                const long long tb = (long long)rt * a.NG;
+                const int c_first = sk.cta_of(tb);
+                const int c_last = sk.cta_of(tb + a.NG - 1);
+                const int rec = (u0 >= tb) ? 0 : 1;  // 0: this tile holds my first unit, 1: it is my tail tile
+                float *mine = a.partials + ((size_t)blockIdx.x * 2 + rec) * kVals;
+#pragma unroll
+                for (int i = 0; i < VPL; i++)
+                    if (lane + 32 * i < kVals) mine[lane + 32 * i] = v[i];
+                __threadfence();
+                __syncwarp();
+                int last = 0;
+                if (lane == 0) {
+                    const unsigned prev = atomicAdd(&a.counters[rt], 1u);
+                    last = (prev == (unsigned)(c_last - c_first)) ? 1 : 0;
+                    if (last) a.counters[rt] = 0;  // every contributor has arrived: re-arm for the next launch
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                do_final = last != 0;
+                if (do_final) {
+                    __threadfence();
+#pragma unroll
+                    for (int i = 0; i < VPL; i++) {
+                        const int idx = lane + 32 * i;
+                        float acc = 0.f;
+                        if (idx < kVals) {
+                            for (int c = c_first; c <= c_last; c++) {
+                                const int r = (sk.start(c) >= tb) ? 0 : 1;
+                                acc += ldg_cg_f32(a.partials + ((size_t)c * 2 + r) * kVals + idx);
+                            }
+                        }
+                        v[i] = acc;
+                    }
+                }
+            }
+            if (do_final) {
+                if (a.pair_mode) {
+                    // rows 0-7 = gate, rows 8-15 = up of the same output channel: y = SiLU(gate) * up
+                    // (reference SiLuMul_half, llm/src/nn_modules/cuda/Int4llamaDecoderLayer.cu:21-30; fp32 here)
+                    if (NCOLS == 1) {
+                        const float up = __shfl_down_sync(0xffffffffu, v[0], 8);
+                        if (lane < 8) {
+                            const float gte = v[0];
+                            const float act = gte / (1.f + __expf(-gte));
+                            reinterpret_cast<__half *>(a.y)[(size_t)rt * 8 + lane] = __float2half(act * up);
+                        }
+                    } else {
+                        // idx = row*8 + col: lane holds rows 4i + lane/8; the partner row+8 is slot i+2 of the same lane
+#pragma unroll
+                        for (int i = 0; i < VPL / 2; i++) {
+                            const int row = 4 * i + (lane >> 3), col = lane & 7;
+                            if (col < a.M) {
+                                const float gte = v[i], up = v[i + VPL / 2];
+                                const float act = gte / (1.f + __expf(-gte));
+                                reinterpret_cast<__half *>(a.y)[(size_t)col * a.ldy + (size_t)rt * 8 + row] = __float2half(act * up);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VPL; i++) {
+                        const int idx = lane + 32 * i;
+                        const int row = idx / NCOLS, col = idx % NCOLS;
+                        if (idx < kVals && col < a.M) {
+                            const size_t o = (size_t)col * a.ldy + (size_t)rt * 16 + row;
+                            if (a.epi == EPI_STORE_HALF)
+                                reinterpret_cast<__half *>(a.y)[o] = __float2half(v[i]);
+                            else if (a.epi == EPI_STORE_F32)
+                                reinterpret_cast<float *>(a.y)[o] = v[i];
+                            else
+                                reinterpret_cast<float *>(a.y)[o] += v[i];
+                        }
+                    }
+                }
+            }
+            u += ge - gb;
+        }
+        return;
+    }
+
     // =========================== consumers ===========================
-    const int ctid = tid - 32;  // 0..255
-    const int cw = warp - 1;    // 0..7
+    const int ctid = tid - 64;  // 0 .. CW*32-1
+    const int cw = warp - 2;    // 0 .. CW-1
     const int g = lane >> 2, t = lane & 3;
 
-    pdl_wait();  // activations (and any buffer we write) belong to the previous kernel until here
+    pdl_wait();  // activations belong to the previous kernel until here
 
     // ---- activation prologue: x -> fp16, permuted into MMA-B order in smem, plus per-group sums ----
     {
@@ -187,15 +321,15 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
                     ss += v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
                 }
                 ss = warp_sum(ss);
-                if (lane == 0) rms[col * kConsumerWarps + cw] = ss;
+                if (lane == 0) rms[col * CW + cw] = ss;
                 named_bar_sync(1, kConsumerThreads);
                 float tot = 0.f;
 #pragma unroll
-                for (int w = 0; w < kConsumerWarps; w++) tot += rms[col * kConsumerWarps + w];
+                for (int w = 0; w < CW; w++) tot += rms[col * CW + w];
                 inv = rsqrtf(tot / (float)a.IC + a.eps);
             }
             // `units` is a multiple of 16, not of 32: the trip count is made warp-uniform so that the half-warp
-            // shuffles below always run with all 32 lanes (an idle half-warp contributes zeros to nobody)
+            // shuffles below always run with all 32 lanes
             for (int ui0 = 0; ui0 < units; ui0 += kConsumerThreads) {
                 const int ui = ui0 + ctid;
                 const bool valid = ui < units;
@@ -254,24 +388,26 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
 
     int stage = 0;
     uint32_t phase = 0;
-    int flush_idx = 0;
+    int rb = 0;
+    uint32_t rphase = 0;
     long long u = u0;
     while (u < u1) {
         const int rt = (int)(u / a.NG);
         const int gb = (int)(u % a.NG);
         const int ge = (int)min((long long)a.NG, gb + (u1 - u));
         const RowRef rA = tile_row(a, rt, g), rB = tile_row(a, rt, g + 8);
-        float tot[(NCOLS == 1) ? 2 : 4];
+        constexpr int NT = (NCOLS == 1) ? 2 : 4;
+        float tot[NT];
 #pragma unroll
-        for (int i = 0; i < ((NCOLS == 1) ? 2 : 4); i++) tot[i] = 0.f;
+        for (int i = 0; i < NT; i++) tot[i] = 0.f;
 
         for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
             const int n = min(kStageGroups, ge - g0);
-            // scales / zeros for this warp's (up to two) groups: issued before the barrier wait
-            float sA[2], sB[2], zA[2], zB[2];
+            // scales / zeros of this warp's group(s): issued before the barrier wait
+            float sA[GPW], sB[GPW], zA[GPW], zB[GPW];
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int gi = cw + q * kConsumerWarps;
+            for (int q = 0; q < GPW; q++) {
+                const int gi = cw + q * CW;
                 if (gi < n) {
                     const int G = g0 + gi;
                     sA[q] = __half2float(__ldg(rA.s + G));
@@ -283,8 +419,8 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
             mbar_wait(&full_bar[stage], phase);
             const uint8_t *sbase = stages + (size_t)stage * kStageBytes;
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int gi = cw + q * kConsumerWarps;
+            for (int q = 0; q < GPW; q++) {
+                const int gi = cw + q * CW;
                 if (gi < n) {
                     const int G = g0 + gi;
                     const uint8_t *sp = sbase + gi * 64 + t * 16;
@@ -293,35 +429,31 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
                     const uint32_t wav[4] = {wa.x, wa.y, wa.z, wa.w};
                     const uint32_t wbv[4] = {wb.x, wb.y, wb.z, wb.w};
                     const uint8_t *xp = xs + ((NCOLS == 1) ? 0 : (size_t)g * SM::x_pitch(a.IC)) + ((size_t)G * 16 + t) * 16;
-                    float c[4] = {0.f, 0.f, 0.f, 0.f};
+                    float c[4][4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
+                        c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
                         const uint4 xv = *reinterpret_cast<const uint4 *>(xp + j * 64);
-                        const uint32_t a_w = wav[j], b_w = wbv[j];
-                        const uint32_t a_w8 = a_w >> 8, b_w8 = b_w >> 8;
-                        // nibble -> fp16: low nibbles ride on 1024 (0x6400), high nibbles on 64 (0x5400);
-                        // subtracting 1032 / 72 yields q - 8 exactly.
-                        const uint32_t p0a = hsub2_u32(lop3_and_or(a_w, 0x000f000fu, 0x64006400u), 0x64086408u);
-                        const uint32_t p1a = hsub2_u32(lop3_and_or(a_w, 0x00f000f0u, 0x54005400u), 0x54805480u);
-                        const uint32_t p2a = hsub2_u32(lop3_and_or(a_w8, 0x000f000fu, 0x64006400u), 0x64086408u);
-                        const uint32_t p3a = hsub2_u32(lop3_and_or(a_w8, 0x00f000f0u, 0x54005400u), 0x54805480u);
-                        const uint32_t p0b = hsub2_u32(lop3_and_or(b_w, 0x000f000fu, 0x64006400u), 0x64086408u);
-                        const uint32_t p1b = hsub2_u32(lop3_and_or(b_w, 0x00f000f0u, 0x54005400u), 0x54805480u);
-                        const uint32_t p2b = hsub2_u32(lop3_and_or(b_w8, 0x000f000fu, 0x64006400u), 0x64086408u);
-                        const uint32_t p3b = hsub2_u32(lop3_and_or(b_w8, 0x00f000f0u, 0x54005400u), 0x54805480u);
-                        mma_m16n8k16(c, p0a, p0b, p1a, p1b, xv.x, xv.y);
-                        mma_m16n8k16(c, p2a, p2b, p3a, p3b, xv.z, xv.w);
+                        uint32_t p0a, p1a, p2a, p3a, p0b, p1b, p2b, p3b;
+                        dequant8(wav[j], p0a, p1a, p2a, p3a);
+                        dequant8(wbv[j], p0b, p1b, p2b, p3b);
+                        mma_m16n8k16(c[j], p0a, p0b, p1a, p1b, xv.x, xv.y);
+                        mma_m16n8k16(c[j], p2a, p2b, p3a, p3b, xv.z, xv.w);
                     }
+                    const float c0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+                    const float c2 = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]);
                     if (NCOLS == 1) {
                         const float gxv = gx[G];
-                        tot[0] += sA[q] * (c[0] - zA[q] * gxv);
-                        tot[1] += sB[q] * (c[2] - zB[q] * gxv);
+                        tot[0] += sA[q] * (c0 - zA[q] * gxv);
+                        tot[1] += sB[q] * (c2 - zB[q] * gxv);
                     } else {
+                        const float c1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+                        const float c3 = (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]);
                         const float gx0 = gx[(2 * t) * a.NG + G], gx1 = gx[(2 * t + 1) * a.NG + G];
-                        tot[0] += sA[q] * (c[0] - zA[q] * gx0);
-                        tot[1] += sA[q] * (c[1] - zA[q] * gx1);
-                        tot[2] += sB[q] * (c[2] - zB[q] * gx0);
-                        tot[3] += sB[q] * (c[3] - zB[q] * gx1);
+                        tot[0] += sA[q] * (c0 - zA[q] * gx0);
+                        tot[1] += sA[q] * (c1 - zA[q] * gx1);
+                        tot[2] += sB[q] * (c2 - zB[q] * gx0);
+                        tot[3] += sB[q] * (c3 - zB[q] * gx1);
                     }
                 }
             }
@@ -333,9 +465,9 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
             }
         }
 
-        // ---------------- flush the tile: cross-warp reduce, then epilogue or stream-K fix-up ----------------
-        float *rbuf = red + (size_t)(flush_idx & 1) * kConsumerWarps * 16 * NCOLS + (size_t)cw * 16 * NCOLS;
-        flush_idx++;
+        // ---- hand the tile partial to the epilogue warp (no consumer-to-consumer wait) ----
+        mbar_wait(&red_empty[rb], rphase ^ 1);
+        float *rbuf = red + ((size_t)rb * CW + cw) * kVals;
         if (NCOLS == 1) {
             if (t == 0) {
                 rbuf[g] = tot[0];
@@ -347,81 +479,11 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
             rbuf[(g + 8) * NCOLS + 2 * t] = tot[2];
             rbuf[(g + 8) * NCOLS + 2 * t + 1] = tot[3];
         }
-        named_bar_sync(1, kConsumerThreads);
-
-        constexpr int kVals = 16 * NCOLS;                 // values per tile
-        constexpr int kWriterWarps = (kVals + 31) / 32;   // consumer warps 0..kWriterWarps-1 own the flush
-        const bool full_tile = (gb == 0 && ge == a.NG);
-        if (cw < kWriterWarps) {
-            auto writer_sync = [&]() {
-                if (kWriterWarps > 1)
-                    named_bar_sync(2, kWriterWarps * 32);
-                else
-                    __syncwarp();
-            };
-            float *rb0 = red + (size_t)((flush_idx - 1) & 1) * kConsumerWarps * 16 * NCOLS;
-            float v = 0.f;
-            if (ctid < kVals) {
-#pragma unroll
-                for (int w = 0; w < kConsumerWarps; w++) v += rb0[w * kVals + ctid];
-            }
-            bool do_final = full_tile;
-            if (!full_tile) {
-                // stream-K fix-up: park the partial, the last contributor to arrive sums all of them in CTA order
-                const long long tb = (long long)rt * a.NG;
-                const int c_first = sk.cta_of(tb);
-                const int c_last = sk.cta_of(tb + a.NG - 1);
-                const int rec = (u0 >= tb) ? 0 : 1;  // 0: this tile holds my first unit, 1: it is my tail tile
-                float *mine = a.partials + ((size_t)blockIdx.x * 2 + rec) * kVals;
-                if (ctid < kVals) mine[ctid] = v;
-                __threadfence();
-                writer_sync();
-                if (ctid == 0) {
-                    const unsigned prev = atomicAdd(&a.counters[rt], 1u);
-                    const int last = (prev == (unsigned)(c_last - c_first)) ? 1 : 0;
-                    if (last) a.counters[rt] = 0;  // every contributor has arrived: re-arm for the next launch
-                    *flag = last;
-                }
-                writer_sync();
-                do_final = (*reinterpret_cast<volatile int *>(flag) != 0);
-                if (do_final) {
-                    __threadfence();
-                    if (ctid < kVals) {
-                        v = 0.f;
-                        for (int c = c_first; c <= c_last; c++) {
-                            const int r = (sk.start(c) >= tb) ? 0 : 1;
-                            v += ldg_cg_f32(a.partials + ((size_t)c * 2 + r) * kVals + ctid);
-                        }
-                    }
-                }
-            }
-            if (a.pair_mode) {
-                // rows 0-7 = gate, rows 8-15 = up of the same output channel: exchange through the (now idle)
-                // reduction buffer of this flush, then y = SiLU(gate) * up   (reference: SiLuMul_half,
-                // llm/src/nn_modules/cuda/Int4llamaDecoderLayer.cu:21-30, evaluated here in fp32)
-                writer_sync();
-                if (do_final && ctid < kVals) rb0[ctid] = v;
-                writer_sync();
-                if (do_final && ctid < 8 * NCOLS) {
-                    const int row = ctid / NCOLS, col = ctid % NCOLS;
-                    if (col < a.M) {
-                        const float gte = rb0[row * NCOLS + col], up = rb0[(row + 8) * NCOLS + col];
-                        const float act = gte / (1.f + __expf(-gte));
-                        reinterpret_cast<__half *>(a.y)[(size_t)col * a.ldy + (size_t)rt * 8 + row] = __float2half(act * up);
-                    }
-                }
-            } else if (do_final && ctid < kVals) {
-                const int row = ctid / NCOLS, col = ctid % NCOLS;
-                if (col < a.M) {
-                    const size_t o = (size_t)col * a.ldy + (size_t)rt * 16 + row;
-                    if (a.epi == EPI_STORE_HALF)
-                        reinterpret_cast<__half *>(a.y)[o] = __float2half(v);
-                    else if (a.epi == EPI_STORE_F32)
-                        reinterpret_cast<float *>(a.y)[o] = v;
-                    else
-                        reinterpret_cast<float *>(a.y)[o] += v;
-                }
-            }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&red_full[rb]);
+        if (++rb == kRedBufs) {
+            rb = 0;
+            rphase ^= 1;
         }
         u += ge - gb;
     }
@@ -429,7 +491,8 @@ __global__ void __launch_bounds__(kThreads, 1) w4a16_gemv_kernel(const __grid_co
 
 // ------------------------------------------------------------------------------------------------------
 // Simple cross-check kernel: one warp per output row, 128-bit loads, scalar fp32 math.  Not the product
-// path for performance; kept as an independently-written second implementation (TCE_GEMV_IMPL=0).
+// path for performance; kept as an independently-written second implementation ("gemv_impl" = 0) and for
+// the < 16 trailing rows of an OC that is not a multiple of 16.
 // ------------------------------------------------------------------------------------------------------
 __global__ void w4a16_gemv_simple_kernel(const KArgs a, int total_rows) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -506,17 +569,15 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     return a;
 }
 
-template <int NCOLS>
+template <int NCOLS, int CW>
 cudaError_t launch_mma(Ctx *ctx, const KArgs &a, bool pdl) {
-    const size_t smem = Smem<NCOLS>::bytes(a.IC);
+    const size_t smem = Smem<NCOLS, CW>::bytes(a.IC);
     if ((int)smem > ctx->smem_optin) return cudaErrorInvalidConfiguration;
     static bool attr_set = false;  // per template instantiation
-    static size_t attr_smem = 0;
-    if (!attr_set || smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(w4a16_gemv_kernel<NCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(w4a16_gemv_kernel<NCOLS, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e != cudaSuccess) return e;
         attr_set = true;
-        attr_smem = ctx->smem_optin;
     }
     const long long U = (long long)a.num_tiles * a.NG;
     int nc = ctx->num_sms * ctx->gemv_ctas_per_sm;
@@ -524,7 +585,7 @@ cudaError_t launch_mma(Ctx *ctx, const KArgs &a, bool pdl) {
     if ((long long)nc > U) nc = (int)U;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nc);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(32 * (2 + CW));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -532,10 +593,15 @@ cudaError_t launch_mma(Ctx *ctx, const KArgs &a, bool pdl) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, w4a16_gemv_kernel<NCOLS>, a);
+    return cudaLaunchKernelEx(&cfg, w4a16_gemv_kernel<NCOLS, CW>, a);
 }
 
 }  // namespace
+
+size_t w4a16_gemv_smem_bytes(int ncols, int cw, int IC) {
+    if (ncols == 1) return cw == 16 ? Smem<1, 16>::bytes(IC) : Smem<1, 8>::bytes(IC);
+    return cw == 16 ? Smem<8, 16>::bytes(IC) : Smem<8, 8>::bytes(IC);
+}
 
 cudaError_t launch_w4a16_gemv_simple(Ctx *ctx, const W4GemvParams &p) {
     if (p.pair_mode || p.x_mode != X_HALF) return cudaErrorNotSupported;
@@ -554,8 +620,24 @@ cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p) {
         if (p.seg[i].rows % (p.pair_mode ? 8 : 16)) return cudaErrorInvalidValue;
     if (p.pair_mode && (p.nseg != 2 || p.seg[0].rows != p.seg[1].rows)) return cudaErrorInvalidValue;
     if (a.num_tiles > ctx->gemv_max_tiles) return cudaErrorInvalidValue;
-    if (p.M == 1) return launch_mma<1>(ctx, a, p.pdl);
-    return launch_mma<8>(ctx, a, p.pdl);
+    const int cw = ctx->gemv_consumer_warps == 8 ? 8 : 16;
+    if (p.M > 1 && (int)w4a16_gemv_smem_bytes(8, cw, p.IC) > ctx->smem_optin) {
+        // the 8-column activation tile does not fit next to the weight ring: one pass per activation row
+        if (p.pair_mode && p.ldy == 0) return cudaErrorInvalidValue;
+        for (int m = 0; m < p.M; m++) {
+            KArgs am = a;
+            am.M = 1;
+            const size_t xel = (p.x_mode == X_RMSNORM_F32) ? sizeof(float) : sizeof(__half);
+            am.x = reinterpret_cast<const uint8_t *>(a.x) + (size_t)m * a.ldx * xel;
+            const size_t yel = (p.pair_mode || p.epi == EPI_STORE_HALF) ? sizeof(__half) : sizeof(float);
+            am.y = reinterpret_cast<uint8_t *>(a.y) + (size_t)m * a.ldy * yel;
+            cudaError_t e = (cw == 16) ? launch_mma<1, 16>(ctx, am, p.pdl) : launch_mma<1, 8>(ctx, am, p.pdl);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    if (p.M == 1) return (cw == 16) ? launch_mma<1, 16>(ctx, a, p.pdl) : launch_mma<1, 8>(ctx, a, p.pdl);
+    return (cw == 16) ? launch_mma<8, 16>(ctx, a, p.pdl) : launch_mma<8, 8>(ctx, a, p.pdl);
 }
 
 }  // namespace tce
