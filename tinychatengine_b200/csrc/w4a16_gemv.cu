@@ -37,6 +37,7 @@ constexpr int kRowPitch = kStageGroups * 64 + 64;  // 1088 B: == 64 (mod 128) ->
 constexpr int kStageBytes = 16 * kRowPitch;        // 17408 B
 constexpr int kStages = 4;
 constexpr int kRedBufs = 3;
+constexpr int kMetaSlots = kStages + 1;  // per-tile scales/zeros slabs in flight (a tile spans >= 1 stage)
 
 struct KArgs {
     W4Seg seg[3];
@@ -89,8 +90,11 @@ struct Smem {
     static constexpr int kXPad = (NCOLS > 1) ? 64 : 0;  // column pitch = 64 (mod 128) B for the per-column B loads
     static constexpr int kVals = 16 * NCOLS;
     static __host__ __device__ int x_pitch(int IC) { return IC * 2 + kXPad; }
-    static __host__ __device__ size_t off_xs() { return (size_t)kStages * kStageBytes; }
-    static __host__ __device__ size_t off_gx(int IC) { return off_xs() + (size_t)NCOLS * x_pitch(IC); }
+    // one meta slot = scales half[16][zeros_w*8] followed by zeros uint32[16][zeros_w] = 320 * zeros_w bytes
+    static __host__ __device__ int meta_slot_bytes(int IC) { return 320 * (((IC / 128) + 7) / 8); }
+    static __host__ __device__ size_t off_meta() { return (size_t)kStages * kStageBytes; }
+    static __host__ __device__ size_t off_xs(int IC) { return off_meta() + (size_t)kMetaSlots * meta_slot_bytes(IC); }
+    static __host__ __device__ size_t off_gx(int IC) { return off_xs(IC) + (size_t)NCOLS * x_pitch(IC); }
     static __host__ __device__ size_t off_red(int IC) { return off_gx(IC) + (size_t)NCOLS * (IC / 128) * sizeof(float); }
     static __host__ __device__ size_t off_rms(int IC) { return off_red(IC) + (size_t)kRedBufs * CW * kVals * sizeof(float); }
     static __host__ __device__ size_t off_bar(int IC) { return (off_rms(IC) + (size_t)NCOLS * CW * sizeof(float) + 15) & ~(size_t)15; }
@@ -115,7 +119,9 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
     constexpr int kVals = SM::kVals;
     constexpr int GPW = kStageGroups / CW;  // groups per consumer warp per stage
     uint8_t *stages = smem;
-    uint8_t *xs = smem + SM::off_xs();
+    uint8_t *meta = smem + SM::off_meta();
+    const int meta_bytes = SM::meta_slot_bytes(a.IC);
+    uint8_t *xs = smem + SM::off_xs(a.IC);
     float *gx = reinterpret_cast<float *>(smem + SM::off_gx(a.IC));
     float *red = reinterpret_cast<float *>(smem + SM::off_red(a.IC));
     float *rms = reinterpret_cast<float *>(smem + SM::off_rms(a.IC));
@@ -157,27 +163,59 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
         const uint64_t policy = l2_policy_evict_first();
         int stage = 0;
         uint32_t phase = 0;
-        long long u = u0;
-        while (u < u1) {
-            const int rt = (int)(u / a.NG);
-            const int gb = (int)(u % a.NG);
-            const int ge = (int)min((long long)a.NG, gb + (u1 - u));
+        int u = (int)u0;
+        const int uend = (int)u1;
+        int rt = u / a.NG;
+        int gb = u - rt * a.NG;
+        int mslot = 0;
+        while (u < uend) {
+            const int ge = min(a.NG, gb + (uend - u));
             const uint8_t *src = nullptr;
-            if (lane < 16) src = tile_row(a, rt, lane).w;
+            uint32_t nbytes = 0;
+            uint8_t *mdst = meta + (size_t)mslot * meta_bytes;
+            if (lane < 16) {
+                src = tile_row(a, rt, lane).w;
+            } else {
+                // lanes 16.. fetch this tile's scales / zeros slabs (contiguous rows of one segment; in pair mode 8
+                // rows of gate then 8 rows of up): they ride on the full barrier of the tile's first stage
+                const int k = lane - 16;
+                const int halves = a.pair_mode ? 2 : 1;
+                if (k < 2 * halves) {
+                    const int is_zero = k / halves, part = k % halves;
+                    const RowRef rr = tile_row(a, rt, part * 8);
+                    const int rows = 16 / halves;
+                    if (is_zero) {
+                        src = reinterpret_cast<const uint8_t *>(rr.z);
+                        nbytes = (uint32_t)rows * a.zeros_w * 4;
+                        mdst += 16 * a.sf_w * 2 + part * nbytes;
+                    } else {
+                        src = reinterpret_cast<const uint8_t *>(rr.s);
+                        nbytes = (uint32_t)rows * a.sf_w * 2;
+                        mdst += part * nbytes;
+                    }
+                }
+            }
+            bool first = true;
             for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
                 const int n = min(kStageGroups, ge - g0);
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], 16u * n * 64u);
+                if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], 16u * n * 64u + (first ? (uint32_t)meta_bytes : 0u));
                 __syncwarp();
                 if (lane < 16)
                     bulk_g2s(stages + (size_t)stage * kStageBytes + lane * kRowPitch, src + (size_t)g0 * 64, n * 64, &full_bar[stage],
                              policy);
+                else if (first && nbytes)
+                    bulk_g2s(mdst, src, nbytes, &full_bar[stage], policy);
+                first = false;
                 if (++stage == kStages) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
+            if (++mslot == kMetaSlots) mslot = 0;
             u += ge - gb;
+            rt++;
+            gb = 0;
         }
         return;
     }
@@ -190,11 +228,12 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
         pdl_wait();                             // outputs (and the residual we add into) belong to earlier kernels
         int rb = 0;
         uint32_t rphase = 0;
-        long long u = u0;
-        while (u < u1) {
-            const int rt = (int)(u / a.NG);
-            const int gb = (int)(u % a.NG);
-            const int ge = (int)min((long long)a.NG, gb + (u1 - u));
+        int u = (int)u0;
+        const int uend = (int)u1;
+        int rt = u / a.NG;
+        int gb = u - rt * a.NG;
+        while (u < uend) {
+            const int ge = min(a.NG, gb + (uend - u));
             const bool full_tile = (gb == 0 && ge == a.NG);
             mbar_wait(&red_full[rb], rphase);
             const float *rbuf = red + (size_t)rb * CW * kVals;
@@ -293,6 +332,8 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
                 }
             }
             u += ge - gb;
+            rt++;
+            gb = 0;
         }
         return;
     }
@@ -390,12 +431,18 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
     uint32_t phase = 0;
     int rb = 0;
     uint32_t rphase = 0;
-    long long u = u0;
-    while (u < u1) {
-        const int rt = (int)(u / a.NG);
-        const int gb = (int)(u % a.NG);
-        const int ge = (int)min((long long)a.NG, gb + (u1 - u));
-        const RowRef rA = tile_row(a, rt, g), rB = tile_row(a, rt, g + 8);
+    int u = (int)u0;
+    const int uend = (int)u1;
+    int rt = u / a.NG;
+    int gb = u - rt * a.NG;
+    int mslot = 0;
+    while (u < uend) {
+        const int ge = min(a.NG, gb + (uend - u));
+        // this tile's scales / zeros slab (it lands together with the tile's first weight stage)
+        const __half *msA = reinterpret_cast<const __half *>(meta + (size_t)mslot * meta_bytes) + g * a.sf_w;
+        const __half *msB = msA + 8 * a.sf_w;
+        const uint32_t *mzA = reinterpret_cast<const uint32_t *>(meta + (size_t)mslot * meta_bytes + 16 * a.sf_w * 2) + g * a.zeros_w;
+        const uint32_t *mzB = mzA + 8 * a.zeros_w;
         constexpr int NT = (NCOLS == 1) ? 2 : 4;
         float tot[NT];
 #pragma unroll
@@ -403,19 +450,6 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
 
         for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
             const int n = min(kStageGroups, ge - g0);
-            // scales / zeros of this warp's group(s): issued before the barrier wait
-            float sA[GPW], sB[GPW], zA[GPW], zB[GPW];
-#pragma unroll
-            for (int q = 0; q < GPW; q++) {
-                const int gi = cw + q * CW;
-                if (gi < n) {
-                    const int G = g0 + gi;
-                    sA[q] = __half2float(__ldg(rA.s + G));
-                    sB[q] = __half2float(__ldg(rB.s + G));
-                    zA[q] = (float)((__ldg(rA.z + (G >> 3)) >> ((G & 7) * 4)) & 0xF) - 8.f;
-                    zB[q] = (float)((__ldg(rB.z + (G >> 3)) >> ((G & 7) * 4)) & 0xF) - 8.f;
-                }
-            }
             mbar_wait(&full_bar[stage], phase);
             const uint8_t *sbase = stages + (size_t)stage * kStageBytes;
 #pragma unroll
@@ -423,6 +457,11 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
                 const int gi = cw + q * CW;
                 if (gi < n) {
                     const int G = g0 + gi;
+                    // per-group scale and (zero - 8) of rows g and g+8; zero nibble -> float through the 2^23 magic
+                    const float sAq = __half2float(msA[G]), sBq = __half2float(msB[G]);
+                    const int zsh = (G & 7) * 4;
+                    const float zAq = __uint_as_float(lop3_and_or(mzA[G >> 3] >> zsh, 0xFu, 0x4B000000u)) - 8388616.f;
+                    const float zBq = __uint_as_float(lop3_and_or(mzB[G >> 3] >> zsh, 0xFu, 0x4B000000u)) - 8388616.f;
                     const uint8_t *sp = sbase + gi * 64 + t * 16;
                     const uint4 wa = *reinterpret_cast<const uint4 *>(sp + g * kRowPitch);
                     const uint4 wb = *reinterpret_cast<const uint4 *>(sp + (g + 8) * kRowPitch);
@@ -444,16 +483,16 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
                     const float c2 = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]);
                     if (NCOLS == 1) {
                         const float gxv = gx[G];
-                        tot[0] += sA[q] * (c0 - zA[q] * gxv);
-                        tot[1] += sB[q] * (c2 - zB[q] * gxv);
+                        tot[0] += sAq * (c0 - zAq * gxv);
+                        tot[1] += sBq * (c2 - zBq * gxv);
                     } else {
                         const float c1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
                         const float c3 = (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]);
                         const float gx0 = gx[(2 * t) * a.NG + G], gx1 = gx[(2 * t + 1) * a.NG + G];
-                        tot[0] += sA[q] * (c0 - zA[q] * gx0);
-                        tot[1] += sA[q] * (c1 - zA[q] * gx1);
-                        tot[2] += sB[q] * (c2 - zB[q] * gx0);
-                        tot[3] += sB[q] * (c3 - zB[q] * gx1);
+                        tot[0] += sAq * (c0 - zAq * gx0);
+                        tot[1] += sAq * (c1 - zAq * gx1);
+                        tot[2] += sBq * (c2 - zBq * gx0);
+                        tot[3] += sBq * (c3 - zBq * gx1);
                     }
                 }
             }
@@ -485,7 +524,10 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
             rb = 0;
             rphase ^= 1;
         }
+        if (++mslot == kMetaSlots) mslot = 0;
         u += ge - gb;
+        rt++;
+        gb = 0;
     }
 }
 

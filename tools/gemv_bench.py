@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--reps", type=int, default=40)
     ap.add_argument("--configs", default="16x1,8x1,8x2,simple")
     ap.add_argument("--m", type=int, default=1)
+    ap.add_argument("--shapes", default="", help="comma separated substrings to select shapes")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     ctx = Context(0)
@@ -37,6 +38,8 @@ def main():
         peak = json.loads(p.read_text())["hbm_gbs"]
     rows = []
     for name, (oc, ic) in SHAPES.items():
+        if args.shapes and not any(k in name for k in args.shapes.split(",")):
+            continue
         nbuf = max(2, int(300e6 // alg_bytes(oc, ic)) + 1)
         bufs = [random_w4(oc, ic, dev, 100 + i) for i in range(nbuf)]
         x = torch.randn((args.m, ic), device=dev).to(torch.float16)
@@ -49,13 +52,22 @@ def main():
                 ctx.set_option("gemv_impl", 1)
                 ctx.set_option("gemv_consumer_warps", int(cw))
                 ctx.set_option("gemv_ctas_per_sm", int(cps))
-            for i in range(3):
-                ctx.w4a16_gemv(x, *bufs[i % nbuf], out=y)
+            side = torch.cuda.Stream()
+            ctx.set_stream(side)
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    ctx.w4a16_gemv(x, *bufs[i % nbuf], out=y)
+            side.synchronize()
+            # the launches are replayed from a CUDA graph so that Python / launch overhead does not hide the kernel
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(args.reps):
+                    ctx.w4a16_gemv(x, *bufs[i % nbuf], out=y)
+            graph.replay()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for i in range(args.reps):
-                ctx.w4a16_gemv(x, *bufs[i % nbuf], out=y)
+            graph.replay()
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / args.reps
