@@ -58,6 +58,24 @@ TCE_DEVINL void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, u
         : "memory");
 }
 
+// Predicated forms for warp-convergent producers: every lane evaluates the (warp-uniform) operands, one lane issues.
+// Keeping the call site convergent lets ptxas hold the addresses in uniform registers instead of emitting a
+// per-lane waterfall loop around UBLKCP.
+TCE_DEVINL void bulk_g2s_pred(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t policy, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n\t}" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy), "r"(pred)
+        : "memory");
+}
+TCE_DEVINL void mbar_arrive_expect_tx_pred(uint64_t *bar, uint32_t bytes, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(
+                     smem_u32(bar)),
+                 "r"(bytes), "r"(pred)
+                 : "memory");
+}
+
 TCE_DEVINL void bulk_g2s_nohint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))

@@ -10,7 +10,7 @@
 //    into equal contiguous ranges, one per CTA (stream-K), so every CTA streams the same number of bytes no
 //    matter the shape; a row tile split between CTAs is finished by whichever CTA arrives last (fixed
 //    summation order -> deterministic), no atomics on data, no pre-zeroed outputs.
-//  * warp roles: warp 0 = TMA producer, warp 1 = epilogue, warps 2.. = CW consumers.
+//  * warp roles: warps 0-3 = TMA producers (4 rows each), warp 4 = epilogue, warps 5.. = CW consumers.
 //    The producer streams [16 rows x <=16 groups] weight slabs with 1-D TMA bulk copies (UBLKCP) into a
 //    4-stage shared-memory ring guarded by full/empty mbarriers; weights are tagged L2 evict-first.
 //    The ring starts filling BEFORE griddepcontrol.wait, so under programmatic dependent launch the next
@@ -37,6 +37,7 @@ constexpr int kRowPitch = kStageGroups * 64 + 64;  // 1088 B: == 64 (mod 128) ->
 constexpr int kStageBytes = 16 * kRowPitch;        // 17408 B
 constexpr int kStages = 4;
 constexpr int kRedBufs = 3;
+constexpr int kProducerWarps = 4;         // UBLKCP issue is ~100+ cycles per copy through one warp: four warps share the 16 rows
 constexpr int kMetaSlots = kStages + 1;  // per-tile scales/zeros slabs in flight (a tile spans >= 1 stage)
 
 struct KArgs {
@@ -112,7 +113,7 @@ TCE_DEVINL void dequant8(uint32_t w, uint32_t &p0, uint32_t &p1, uint32_t &p2, u
 }
 
 template <int NCOLS, int CW>
-__global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), 1) w4a16_gemv_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     using SM = Smem<NCOLS, CW>;
     constexpr int kConsumerThreads = CW * 32;
@@ -158,9 +159,10 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
     sk.NG = a.NG;
     const long long u0 = sk.start(blockIdx.x), u1 = sk.start(blockIdx.x + 1);
 
-    if (warp == 0) {
-        // =========================== TMA producer ===========================
+    if (warp < kProducerWarps) {
+        // =========================== TMA producers (4 warps x 4 rows) ===========================
         const uint64_t policy = l2_policy_evict_first();
+        const uint32_t leader = (lane == 0) ? 1u : 0u;
         int stage = 0;
         uint32_t phase = 0;
         int u = (int)u0;
@@ -170,42 +172,37 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
         int mslot = 0;
         while (u < uend) {
             const int ge = min(a.NG, gb + (uend - u));
-            const uint8_t *src = nullptr;
-            uint32_t nbytes = 0;
+            // All addresses below are warp-uniform (kernel arguments and loop counters only), so the compiler keeps
+            // them in uniform registers and lane 0 issues each UBLKCP directly -- no per-lane waterfall loop.
+            const RowRef r0 = tile_row(a, rt, 0), r8 = tile_row(a, rt, 8);  // rows 0-7 / 8-15 are contiguous each
+            const size_t wpitch = (size_t)(a.IC / 2);
             uint8_t *mdst = meta + (size_t)mslot * meta_bytes;
-            if (lane < 16) {
-                src = tile_row(a, rt, lane).w;
-            } else {
-                // lanes 16.. fetch this tile's scales / zeros slabs (contiguous rows of one segment; in pair mode 8
-                // rows of gate then 8 rows of up): they ride on the full barrier of the tile's first stage
-                const int k = lane - 16;
-                const int halves = a.pair_mode ? 2 : 1;
-                if (k < 2 * halves) {
-                    const int is_zero = k / halves, part = k % halves;
-                    const RowRef rr = tile_row(a, rt, part * 8);
-                    const int rows = 16 / halves;
-                    if (is_zero) {
-                        src = reinterpret_cast<const uint8_t *>(rr.z);
-                        nbytes = (uint32_t)rows * a.zeros_w * 4;
-                        mdst += 16 * a.sf_w * 2 + part * nbytes;
-                    } else {
-                        src = reinterpret_cast<const uint8_t *>(rr.s);
-                        nbytes = (uint32_t)rows * a.sf_w * 2;
-                        mdst += part * nbytes;
-                    }
-                }
-            }
             bool first = true;
             for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
                 const int n = min(kStageGroups, ge - g0);
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], 16u * n * 64u + (first ? (uint32_t)meta_bytes : 0u));
+                {
+                    uint64_t *bar = &full_bar[stage];
+                    // producer 0 posts the byte count; the other producers' complete_tx may land first (the phase
+                    // cannot complete before this single arrival, and a transiently negative tx-count is legal)
+                    if (warp == 0) mbar_arrive_expect_tx_pred(bar, 16u * n * 64u + (first ? (uint32_t)meta_bytes : 0u), leader);
+                    uint8_t *dst = stages + (size_t)stage * kStageBytes;
+                    const uint32_t nb = (uint32_t)n * 64u;
+                    const RowRef &rr = (warp < 2) ? r0 : r8;  // rows 4*warp .. 4*warp+3
+                    const int lr = (warp & 1) * 4;
+#pragma unroll
+                    for (int l = 0; l < 4; l++)
+                        bulk_g2s_pred(dst + (warp * 4 + l) * kRowPitch, rr.w + (lr + l) * wpitch + (size_t)g0 * 64, nb, bar, policy, leader);
+                    if (first && warp == 1) {
+                        // this tile's scales / zeros slabs ride on the full barrier of its first stage
+                        const uint32_t sb = 8u * a.sf_w * 2u, zb = 8u * a.zeros_w * 4u;
+                        bulk_g2s_pred(mdst, r0.s, sb, bar, policy, leader);
+                        bulk_g2s_pred(mdst + sb, r8.s, sb, bar, policy, leader);
+                        bulk_g2s_pred(mdst + 2 * sb, r0.z, zb, bar, policy, leader);
+                        bulk_g2s_pred(mdst + 2 * sb + zb, r8.z, zb, bar, policy, leader);
+                    }
+                }
                 __syncwarp();
-                if (lane < 16)
-                    bulk_g2s(stages + (size_t)stage * kStageBytes + lane * kRowPitch, src + (size_t)g0 * 64, n * 64, &full_bar[stage],
-                             policy);
-                else if (first && nbytes)
-                    bulk_g2s(mdst, src, nbytes, &full_bar[stage], policy);
                 first = false;
                 if (++stage == kStages) {
                     stage = 0;
@@ -220,7 +217,7 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
         return;
     }
 
-    if (warp == 1) {
+    if (warp == kProducerWarps) {
         // =========================== epilogue warp ===========================
         // reduces the CW consumer partials of every tile this CTA touches, then either finishes the tile or
         // takes part in the stream-K fix-up.  Lane l owns values idx = l + 32*i  (idx = row*NCOLS + col).
@@ -339,8 +336,8 @@ __global__ void __launch_bounds__(32 * (2 + CW), 1) w4a16_gemv_kernel(const __gr
     }
 
     // =========================== consumers ===========================
-    const int ctid = tid - 64;  // 0 .. CW*32-1
-    const int cw = warp - 2;    // 0 .. CW-1
+    const int ctid = tid - 32 * (kProducerWarps + 1);  // 0 .. CW*32-1
+    const int cw = warp - (kProducerWarps + 1);        // 0 .. CW-1
     const int g = lane >> 2, t = lane & 3;
 
     pdl_wait();  // activations belong to the previous kernel until here
@@ -627,7 +624,7 @@ cudaError_t launch_mma(Ctx *ctx, const KArgs &a, bool pdl) {
     if ((long long)nc > U) nc = (int)U;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nc);
-    cfg.blockDim = dim3(32 * (2 + CW));
+    cfg.blockDim = dim3(32 * (kProducerWarps + 1 + CW));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
