@@ -78,7 +78,7 @@ int tce_ctx_create(int device, tce_ctx **out) {
     c.smem_optin = (int)prop.sharedMemPerBlockOptin;
     c.gemv_impl = env_int("TCE_GEMV_IMPL", 1);
     c.gemv_ctas_per_sm = env_int("TCE_GEMV_CTAS_PER_SM", 1);
-    c.gemv_consumer_warps = env_int("TCE_GEMV_CONSUMER_WARPS", 16) == 8 ? 8 : 16;
+    c.gemv_consumer_warps = env_int("TCE_GEMV_CONSUMER_WARPS", 8) == 16 ? 16 : 8;
     c.use_pdl = env_int("TCE_USE_PDL", 1) != 0;
     ctx->attn_chunk = env_int("TCE_ATTN_CHUNK", 128);
     c.gemv_max_ctas = c.num_sms * 4;
@@ -127,7 +127,7 @@ int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "gemv_ctas_per_sm"))
         ctx->c.gemv_ctas_per_sm = value < 1 ? 1 : (value > 4 ? 4 : value);
     else if (!strcmp(name, "gemv_consumer_warps"))
-        ctx->c.gemv_consumer_warps = (value == 8) ? 8 : 16;
+        ctx->c.gemv_consumer_warps = (value == 16) ? 16 : 8;
     else if (!strcmp(name, "use_pdl"))
         ctx->c.use_pdl = value != 0;
     else if (!strcmp(name, "attn_chunk"))

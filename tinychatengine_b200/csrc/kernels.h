@@ -24,7 +24,7 @@ struct Ctx {
     // tunables (env overridable, see ctx.cu)
     int gemv_impl = 1;      // 0 = simple warp-per-row, 1 = TMA + mma.sync stream-K
     int gemv_ctas_per_sm = 1;
-    int gemv_consumer_warps = 16;  // 8 or 16 consumer warps per CTA
+    int gemv_consumer_warps = 8;   // 8 or 16 consumer warps per CTA
     bool use_pdl = true;
 };
 

@@ -113,7 +113,7 @@ TCE_DEVINL void dequant8(uint32_t w, uint32_t &p0, uint32_t &p1, uint32_t &p2, u
 }
 
 template <int NCOLS, int CW>
-__global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), 1) w4a16_gemv_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 && CW == 8) ? 2 : 1) w4a16_gemv_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     using SM = Smem<NCOLS, CW>;
     constexpr int kConsumerThreads = CW * 32;
@@ -659,7 +659,7 @@ cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p) {
         if (p.seg[i].rows % (p.pair_mode ? 8 : 16)) return cudaErrorInvalidValue;
     if (p.pair_mode && (p.nseg != 2 || p.seg[0].rows != p.seg[1].rows)) return cudaErrorInvalidValue;
     if (a.num_tiles > ctx->gemv_max_tiles) return cudaErrorInvalidValue;
-    const int cw = ctx->gemv_consumer_warps == 8 ? 8 : 16;
+    const int cw = ctx->gemv_consumer_warps == 16 ? 16 : 8;
     if (p.M > 1 && (int)w4a16_gemv_smem_bytes(8, cw, p.IC) > ctx->smem_optin) {
         // the 8-column activation tile does not fit next to the weight ring: one pass per activation row
         if (p.pair_mode && p.ldy == 0) return cudaErrorInvalidValue;
