@@ -42,6 +42,10 @@ TCE_API int tce_ctx_synchronize(tce_ctx *ctx);
 /* knobs: "gemv_impl" (0 simple / 1 tma+mma), "gemv_ctas_per_sm", "use_pdl", "attn_chunk" */
 TCE_API int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value);
 TCE_API int tce_ctx_num_sms(tce_ctx *ctx);
+/* measurement aid (option "gemv_debug" = 1): per-CTA phase timestamps of the last W4A16 GEMV launch, 8 x u64
+ * globaltimer ns per CTA: entry, first TMA issued, activations staged, first stage landed, consumers done,
+ * epilogue done, first tile flushed.  Returns the number of CTAs copied.                                       */
+TCE_API int tce_ctx_read_gemv_timing(tce_ctx *ctx, unsigned long long *host_out, int max_ctas);
 
 /* ---- W4A16, QM_CUDA layout ------------------------------------------------------------------------------
  * Replaces MatmulOperator::gemv_forward_cuda (kernels/cuda/gemv_cuda.cu:213-260), called by

@@ -41,6 +41,7 @@ SIGNATURES = {
     "tce_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "tce_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "tce_ctx_num_sms": (C.c_int, [C.c_void_p]),
+    "tce_ctx_read_gemv_timing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "tce_zeros_width": (C.c_int, [C.c_int, C.c_int]),
     "tce_w4a16_gemv": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4),
     "tce_w4a16_gemm": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4),

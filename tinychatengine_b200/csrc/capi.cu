@@ -120,6 +120,14 @@ int tce_ctx_synchronize(tce_ctx *ctx) {
 
 int tce_ctx_num_sms(tce_ctx *ctx) { return ctx ? ctx->c.num_sms : TCE_ERR_INVALID; }
 
+int tce_ctx_read_gemv_timing(tce_ctx *ctx, unsigned long long *host_out, int max_ctas) {
+    if (!ctx || !host_out || !ctx->c.gemv_dbg) return fail(TCE_ERR_INVALID, "gemv_debug option is off");
+    const int n = max_ctas < ctx->c.gemv_max_ctas ? max_ctas : ctx->c.gemv_max_ctas;
+    CK(cudaStreamSynchronize(ctx->c.stream), "sync");
+    CK(cudaMemcpy(host_out, ctx->c.gemv_dbg, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "memcpy");
+    return n;
+}
+
 int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return fail(TCE_ERR_INVALID, "null argument");
     if (!strcmp(name, "gemv_impl"))
@@ -128,7 +136,15 @@ int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
         ctx->c.gemv_ctas_per_sm = value < 1 ? 1 : (value > 4 ? 4 : value);
     else if (!strcmp(name, "gemv_consumer_warps"))
         ctx->c.gemv_consumer_warps = (value == 16) ? 16 : 8;
-    else if (!strcmp(name, "use_pdl"))
+    else if (!strcmp(name, "gemv_debug")) {
+        if (value && !ctx->c.gemv_dbg) {
+            CK(cudaMalloc(&ctx->c.gemv_dbg, (size_t)ctx->c.gemv_max_ctas * 8 * sizeof(unsigned long long)), "cudaMalloc dbg");
+            CK(cudaMemset(ctx->c.gemv_dbg, 0, (size_t)ctx->c.gemv_max_ctas * 8 * sizeof(unsigned long long)), "cudaMemset");
+        } else if (!value && ctx->c.gemv_dbg) {
+            cudaFree(ctx->c.gemv_dbg);
+            ctx->c.gemv_dbg = nullptr;
+        }
+    } else if (!strcmp(name, "use_pdl"))
         ctx->c.use_pdl = value != 0;
     else if (!strcmp(name, "attn_chunk"))
         ctx->attn_chunk = value;

@@ -17,6 +17,7 @@ struct Ctx {
     unsigned *gemv_counters = nullptr;
     int gemv_max_ctas = 0;
     int gemv_max_tiles = 0;
+    unsigned long long *gemv_dbg = nullptr;  // optional phase timestamps (option "gemv_debug")
     // flash-decode workspace (partial m, l, o per (head, split))
     float *attn_ws = nullptr;
     size_t attn_ws_bytes = 0;

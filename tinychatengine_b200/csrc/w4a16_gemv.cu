@@ -53,6 +53,7 @@ struct KArgs {
     int epi, ldy;
     float *partials;
     unsigned *counters;
+    unsigned long long *dbg;  // optional per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
 };
 
 struct RowRef {
@@ -84,6 +85,14 @@ TCE_DEVINL RowRef tile_row(const KArgs &a, int rt, int l) {
     ref.z = s.zeros + (size_t)r * a.zeros_w;
     ref.s = s.scales + (size_t)r * a.sf_w;
     return ref;
+}
+
+TCE_DEVINL void dbg_stamp(const KArgs &a, int k) {
+    if (a.dbg) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.dbg[(size_t)blockIdx.x * 8 + k] = t;
+    }
 }
 
 template <int NCOLS, int CW>
@@ -136,6 +145,7 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
     const int lane = tid & 31;
 
     if (tid == 0) {
+        dbg_stamp(a, 0);
 #pragma unroll
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full_bar[s], 1);
@@ -203,6 +213,7 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
                     }
                 }
                 __syncwarp();
+                if (first && u == (int)u0 && tid == 0) dbg_stamp(a, 1);
                 first = false;
                 if (++stage == kStages) {
                     stage = 0;
@@ -328,10 +339,12 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
                     }
                 }
             }
+            if (lane == 0 && u == (int)u0) dbg_stamp(a, 6);
             u += ge - gb;
             rt++;
             gb = 0;
         }
+        if (lane == 0) dbg_stamp(a, 5);
         return;
     }
 
@@ -423,6 +436,7 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
         }
         named_bar_sync(1, kConsumerThreads);
     }
+    if (ctid == 0) dbg_stamp(a, 2);
 
     int stage = 0;
     uint32_t phase = 0;
@@ -448,6 +462,7 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
         for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
             const int n = min(kStageGroups, ge - g0);
             mbar_wait(&full_bar[stage], phase);
+            if (ctid == 0 && u == (int)u0 && g0 == gb) dbg_stamp(a, 3);
             const uint8_t *sbase = stages + (size_t)stage * kStageBytes;
 #pragma unroll
             for (int q = 0; q < GPW; q++) {
@@ -526,6 +541,7 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
         rt++;
         gb = 0;
     }
+    if (ctid == 0) dbg_stamp(a, 4);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -605,6 +621,7 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     a.ldy = p.ldy ? p.ldy : (p.pair_mode ? rows / 2 : rows);
     a.partials = ctx->gemv_partials;
     a.counters = ctx->gemv_counters;
+    a.dbg = ctx->gemv_dbg;
     return a;
 }
 
