@@ -285,7 +285,7 @@ def run_ours(args):
             "config": {"workload": f"{geom.name} AWQ-INT4 g128 batch-1 decode, timed steps spread over ctx 1->{args.max_ctx}" if args.ctx < 0
                        else f"{geom.name} AWQ-INT4 g128 batch-1 decode at ctx {args.ctx}", "model": geom.name, "global_batch": world, "max_ctx": args.max_ctx,
                        "mean_ctx": mean_ctx, "parallelism": "1 sequence per GPU (replicas)" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: 3.9 GB of weights stream per step vs 126 MB L2", "pdl": bool(int(os.environ.get("TCE_USE_PDL", "1")))},
+                       "l2": "inputs larger than L2: 3.9 GB of weights stream per step vs 126 MB L2", "pdl": bool(int(os.environ.get("TCE_USE_PDL", "0")))},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": geom.vocab_size * 4 + 4},
             "gpu_launches": K * model.kernels_per_step,

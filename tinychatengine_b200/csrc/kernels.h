@@ -26,7 +26,7 @@ struct Ctx {
     int gemv_impl = 1;      // 0 = simple warp-per-row, 1 = TMA + mma.sync stream-K
     int gemv_ctas_per_sm = 1;
     int gemv_consumer_warps = 8;   // 8 or 16 consumer warps per CTA
-    bool use_pdl = true;
+    bool use_pdl = false;
 };
 
 constexpr int kW4Group = 128;  // QK for QM_CUDA (llm/include/common.h:17-21)

@@ -213,7 +213,9 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
                     }
                 }
                 __syncwarp();
+#ifdef TCE_GEMV_TIMING_HOT
                 if (first && u == (int)u0 && tid == 0) dbg_stamp(a, 1);
+#endif
                 first = false;
                 if (++stage == kStages) {
                     stage = 0;
@@ -339,7 +341,9 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
                     }
                 }
             }
+#ifdef TCE_GEMV_TIMING_HOT
             if (lane == 0 && u == (int)u0) dbg_stamp(a, 6);
+#endif
             u += ge - gb;
             rt++;
             gb = 0;
@@ -462,7 +466,9 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
         for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
             const int n = min(kStageGroups, ge - g0);
             mbar_wait(&full_bar[stage], phase);
+#ifdef TCE_GEMV_TIMING_HOT
             if (ctid == 0 && u == (int)u0 && g0 == gb) dbg_stamp(a, 3);
+#endif
             const uint8_t *sbase = stages + (size_t)stage * kStageBytes;
 #pragma unroll
             for (int q = 0; q < GPW; q++) {
