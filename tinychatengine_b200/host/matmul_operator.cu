@@ -1,0 +1,88 @@
+// matmul_operator.cu -- MatmulOperator methods of the CUDA backend, forwarding to the C ABI (include/tce_b200.h).
+// Field conventions per op are those of the reference call sites (SURVEY.md 8(b) "Field conventions per op").
+#include <assert.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/tce_b200.h"
+#include "matmul.h"
+
+static tce_ctx *g_ctx = nullptr;
+
+extern "C" tce_ctx *tce_host_ctx(void) {
+    if (!g_ctx) {
+        if (tce_ctx_create(0, &g_ctx) != TCE_OK) {
+            fprintf(stderr, "libtce_b200: %s\n", tce_last_error());
+            abort();  // the reference's CHECK_CUDA throws; there is no CPU fallback to continue on
+        }
+    }
+    return g_ctx;
+}
+extern "C" void tce_host_set_stream(void *s) { tce_ctx_set_stream(tce_host_ctx(), s); }
+
+static void must(int rc, const char *what) {
+    if (rc != TCE_OK) {
+        fprintf(stderr, "libtce_b200: %s failed: %s\n", what, tce_last_error());
+        exit(1);  // reference behaviour on an unsupported configuration (gemv_cuda.cu:253-257)
+    }
+}
+
+namespace matmul {
+
+// reference: kernels/cuda/gemv_cuda.cu:213-260.  A.row=M, A.column=IC, B.row=IC/8, B.column=OC, C.row=M, C.column=OC
+void MatmulOperator::gemv_forward_cuda(const struct matmul_params *p) {
+    const int M = p->A.row, IC = p->A.column, OC = p->C.column;
+    assert(p->C.row == M);
+    // the reference ignores params->block_size and uses the compile-time QK (=128 under QM_CUDA), gemv_cuda.cu:221
+    must(tce_w4a16_gemv(tce_host_ctx(), p->A.half_data_ptr, p->B.int32_data_ptr, p->int32_zero_point, p->half_scales, p->C.half_data_ptr, M, IC, OC, 128),
+         "gemv_forward_cuda");
+}
+
+// the prefill slot the reference declares but never defines (kernels/matmul.h:142-145); same operand convention
+void MatmulOperator::gemm_forward_cuda(const struct matmul_params *p, int /*split_k_iters*/) {
+    must(tce_w4a16_gemm(tce_host_ctx(), p->A.half_data_ptr, p->B.int32_data_ptr, p->int32_zero_point, p->half_scales, p->C.half_data_ptr, p->A.row,
+                        p->A.column, p->C.column, 128),
+         "gemm_forward_cuda");
+}
+void MatmulOperator::gemm_forward_cuda_8splits(const struct matmul_params *p, float16_t *) { gemm_forward_cuda(p, 8); }
+void MatmulOperator::gemm_forward_cuda_half(const struct matmul_params *p, int s) { gemm_forward_cuda(p, s); }
+void MatmulOperator::gemm_forward_cuda_half_test(const struct matmul_params *p, int s) { gemm_forward_cuda(p, s); }
+
+// stubs, exactly like the reference CUDA build (gemv_cuda.cu:262-268)
+void MatmulOperator::mat_mul_accelerator_int4_fast(const struct matmul_params *) {}
+void MatmulOperator::mat_mul_accelerator_int4_fast_no_offset(const struct matmul_params *) {}
+
+// INT8 family (reference kernels/cuda/matmul_ref_int8.cc == kernels/ref/matmul_ref_int8.cc): B.row=K, B.column=N
+static void w8(const struct matmul_params *p, int variant, int batch, const void *bias, void *C, const char *who) {
+    const int M = p->A.row, K = p->A.column, N = p->B.column;
+    assert(p->A.column == p->B.row && p->C.row == M && p->C.column == N);
+    must(tce_w8a8_matmul(tce_host_ctx(), variant, batch, p->A.int8_data_ptr, p->B.int8_data_ptr, bias, C, M, N, K, p->alpha, p->beta,
+                         p->C.qparams.q_min, p->C.qparams.q_max),
+         who);
+}
+void MatmulOperator::mat_mul_accelerator_int8_fast_2x2_32unroll(const struct matmul_params *p) {
+    w8(p, 0, 0, p->bias.int8_data_ptr, p->C.int8_data_ptr, "int8_fast_2x2_32unroll");
+}
+void MatmulOperator::mat_mul_accelerator_int8_fast_32unroll_over_column(const struct matmul_params *p) {
+    w8(p, 0, 0, p->bias.int8_data_ptr, p->C.int8_data_ptr, "int8_fast_32unroll_over_column");
+}
+void MatmulOperator::mat_mul_accelerator_int8_fast_2x2_32unroll_nobias(const struct matmul_params *p) {
+    w8(p, 1, 0, nullptr, p->C.int8_data_ptr, "int8_fast_2x2_32unroll_nobias");
+}
+void MatmulOperator::mat_mul_accelerator_int8_fast_2x2_32unroll_nobias_batch(const struct matmul_params *p) {
+    w8(p, 1, 1, nullptr, p->C.int8_data_ptr, "int8_fast_2x2_32unroll_nobias_batch");
+}
+void MatmulOperator::mat_mul_accelerator_int8_fast_2x2_32unroll_bfp32_ofp32(const struct matmul_params *p) {
+    w8(p, 2, 0, p->bias.data_ptr, p->C.data_ptr, "int8_fast_2x2_32unroll_bfp32_ofp32");
+}
+void MatmulOperator::mat_mul_accelerator_int8_fast_2x2_32unroll_bfp32_ofp32_over_column(const struct matmul_params *p) {
+    w8(p, 2, 0, p->bias.data_ptr, p->C.data_ptr, "int8_fast_2x2_32unroll_bfp32_ofp32_over_column");
+}
+void MatmulOperator::mat_mul_accelerator_int8_fast_2x2_32unroll_nobias_ofp32(const struct matmul_params *p) {
+    w8(p, 3, 0, nullptr, p->C.data_ptr, "int8_fast_2x2_32unroll_nobias_ofp32");
+}
+void MatmulOperator::mat_mul_accelerator_int8_fast_2x2_32unroll_nobias_ofp32_batch(const struct matmul_params *p) {
+    w8(p, 3, 1, nullptr, p->C.data_ptr, "int8_fast_2x2_32unroll_nobias_ofp32_batch");
+}
+
+}  // namespace matmul

@@ -1,0 +1,170 @@
+// test_host.cu -- reference-style op tests (llm/tests/cuda/test_ops.cu, llm/tests/non_cuda/test_ops.cc) driven through
+// the reference's own class / MatmulOperator surface, with synthetic inputs in cudaMallocManaged buffers (what the
+// reference allocates) and the CPU oracle as the expected output.  Unlike the reference mains it returns non-zero on
+// failure.  TEST CODE: links oracle/libtce_oracle.so as the checker.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "ops.h"
+
+extern "C" {
+int orc_w4a16_gemv(const uint16_t *x, const uint32_t *w, const uint32_t *zeros, const uint16_t *scales, float *y, uint16_t *y_half, int M, int IC,
+                   int OC, int group);
+int orc_calculate_zeros_width(int in_features, int group_size);
+void orc_int8_matmul(const int8_t *A, const int8_t *B, const int8_t *bias, int8_t *C, int M, int N, int K, float alpha, float beta, int q_min, int q_max);
+void orc_int8_matmul_nobias(const int8_t *A, const int8_t *B, int8_t *C, int M, int N, int K, float alpha, int q_min, int q_max);
+void orc_int8_matmul_nobias_batch(const int8_t *A, const int8_t *B, int8_t *C, int M, int N, int K, float alpha, int q_min, int q_max);
+void orc_int8_matmul_bfp32_ofp32(const int8_t *A, const int8_t *B, const float *bias, float *C, int M, int N, int K, float alpha);
+void orc_int8_matmul_nobias_ofp32(const int8_t *A, const int8_t *B, float *C, int M, int N, int K, float alpha);
+void orc_int8_matmul_nobias_ofp32_batch(const int8_t *A, const int8_t *B, float *C, int M, int N, int K, float alpha);
+uint16_t orc_float_to_half(float f);
+float orc_half_to_float(uint16_t h);
+}
+
+static uint64_t rng_state = 88172645463325252ull;
+static uint32_t rnd() {
+    rng_state ^= rng_state << 13;
+    rng_state ^= rng_state >> 7;
+    rng_state ^= rng_state << 17;
+    return (uint32_t)(rng_state >> 11);
+}
+static float rndf() { return (float)(rnd() & 0xffffff) / (float)0x1000000; }
+static float rndn() { return sqrtf(-2.f * logf(rndf() + 1e-7f)) * cosf(6.2831853f * rndf()); }
+
+template <typename T>
+static T *managed(size_t n) {
+    T *p = nullptr;
+    if (cudaMallocManaged(&p, n * sizeof(T)) != cudaSuccess) {
+        fprintf(stderr, "cudaMallocManaged failed\n");
+        exit(2);
+    }
+    return p;
+}
+
+static int failures = 0;
+static void report(const char *name, bool ok) {
+    printf("-------- Test of %s: %s --------\n", name, ok ? "Passed!" : "Fail!");
+    if (!ok) failures++;
+}
+
+static void test_Linear_half_int4(int m, int n, int k) {
+    const int zw = orc_calculate_zeros_width(k, QK);
+    int *w = managed<int>((size_t)n * k / 8);
+    int *z = managed<int>((size_t)n * zw);
+    float16_t *s = managed<float16_t>((size_t)n * zw * 8);
+    float16_t *x = managed<float16_t>((size_t)m * k);
+    float16_t *y = managed<float16_t>((size_t)m * n);
+    for (size_t i = 0; i < (size_t)n * k / 8; i++) w[i] = (int)rnd();
+    for (size_t i = 0; i < (size_t)n * zw; i++) z[i] = (int)rnd();
+    uint16_t *s16 = reinterpret_cast<uint16_t *>(s), *x16 = reinterpret_cast<uint16_t *>(x);
+    for (size_t i = 0; i < (size_t)n * zw * 8; i++) s16[i] = orc_float_to_half((0.5f + rndf()) * 0.004f);
+    for (size_t i = 0; i < (size_t)m * k; i++) x16[i] = orc_float_to_half(rndn());
+    Linear_half_int4 op(Matrix3D<int>(w, 1, n, k / 8), Matrix3D<float16_t>(s, 1, n, zw * 8), Matrix3D<int>(z, 1, n, zw));
+    Matrix3D<float16_t> X(x, 1, m, k), Y(y, 1, m, n);
+    op.forward(X, Y);
+    cudaDeviceSynchronize();
+    std::vector<float> ref((size_t)m * n);
+    orc_w4a16_gemv(x16, (const uint32_t *)w, (const uint32_t *)z, s16, ref.data(), nullptr, m, k, n, QK);
+    double maxref = 0, maxerr = 0;
+    for (size_t i = 0; i < ref.size(); i++) {
+        const double got = orc_half_to_float(reinterpret_cast<uint16_t *>(y)[i]);
+        maxref = fmax(maxref, fabs(ref[i]));
+        maxerr = fmax(maxerr, fabs(got - ref[i]));
+    }
+    char name[128];
+    snprintf(name, sizeof(name), "Linear_half_int4 %dx%d->%d (rel err %.2e, bar 1e-2)", m, k, n, maxerr / maxref);
+    report(name, maxerr / maxref <= 1e-2);
+    cudaFree(w); cudaFree(z); cudaFree(s); cudaFree(x); cudaFree(y);
+}
+
+static int8_t *rand_s8(size_t n) {
+    int8_t *p = managed<int8_t>(n);
+    for (size_t i = 0; i < n; i++) p[i] = (int8_t)((int)(rnd() % 255) - 127);
+    return p;
+}
+
+static void test_W8A8B8O8Linear(int b, int m, int k, int n, bool relu, float alpha, float beta) {
+    int8_t *x = rand_s8((size_t)b * m * k), *w = rand_s8((size_t)n * k), *bias = rand_s8(n), *y = managed<int8_t>((size_t)b * m * n);
+    W8A8B8O8Linear_params p = {Matrix3D<int8_t>(w, 1, n, k), Matrix3D<int8_t>(bias, 1, 1, n), alpha, beta};
+    Matrix3D<int8_t> X(x, b, m, k), Y(y, b, m, n);
+    if (relu) {
+        W8A8B8O8LinearReLU op(p);
+        op.forward(X, Y);
+    } else {
+        W8A8B8O8Linear op(p);
+        op.forward(X, Y);
+    }
+    cudaDeviceSynchronize();
+    std::vector<int8_t> ref((size_t)b * m * n);
+    for (int bz = 0; bz < b; bz++) orc_int8_matmul(x + (size_t)bz * m * k, w, bias, ref.data() + (size_t)bz * m * n, m, n, k, alpha, beta, relu ? 0 : -128, 127);
+    bool ok = true;
+    for (size_t i = 0; i < ref.size(); i++) ok &= (ref[i] == y[i]);
+    report(relu ? "W8A8B8O8LinearReLU (bit exact)" : "W8A8B8O8Linear (bit exact)", ok);
+    cudaFree(x); cudaFree(w); cudaFree(bias); cudaFree(y);
+}
+
+static void test_W8A8BFP32OFP32Linear(int m, int k, int n, float alpha) {
+    int8_t *x = rand_s8((size_t)m * k), *w = rand_s8((size_t)n * k);
+    float *bias = managed<float>(n), *y = managed<float>((size_t)m * n);
+    for (int i = 0; i < n; i++) bias[i] = rndn();
+    W8A8BFP32OFP32Linear_params p = {Matrix3D<int8_t>(w, 1, n, k), Matrix3D<float>(bias, 1, 1, n), alpha};
+    W8A8BFP32OFP32Linear op(p);
+    Matrix3D<int8_t> X(x, 1, m, k);
+    Matrix3D<float> Y(y, 1, m, n);
+    op.forward(X, Y);
+    cudaDeviceSynchronize();
+    std::vector<float> ref((size_t)m * n);
+    orc_int8_matmul_bfp32_ofp32(x, w, bias, ref.data(), m, n, k, alpha);
+    bool ok = true;
+    for (size_t i = 0; i < ref.size(); i++) ok &= (ref[i] == y[i]);
+    report("W8A8BFP32OFP32Linear (bit exact fp32)", ok);
+    cudaFree(x); cudaFree(w); cudaFree(bias); cudaFree(y);
+}
+
+static void test_BMMs(int heads, int m, int t, int d, float alpha) {
+    // QK^T: x [heads, m, d], weight [heads, t, d] -> [heads, m, t] fp32 ; PV: p [heads, m, t], V^T [heads, d, t] -> int8
+    int8_t *q = rand_s8((size_t)heads * m * d), *kk = rand_s8((size_t)heads * t * d);
+    float *s = managed<float>((size_t)heads * m * t);
+    BMM_S8T_S8N_F32T qk(alpha);
+    Matrix3D<int8_t> Q(q, heads, m, d), K(kk, heads, t, d);
+    Matrix3D<float> S(s, heads, m, t);
+    qk.forward(Q, K, S);
+    int8_t *p = rand_s8((size_t)heads * m * t), *vt = rand_s8((size_t)heads * d * t), *o = managed<int8_t>((size_t)heads * m * d);
+    BMM_S8T_S8N_S8T pv(0.0031f);
+    Matrix3D<int8_t> P(p, heads, m, t), VT(vt, heads, d, t), O(o, heads, m, d);
+    pv.forward(P, VT, O);
+    cudaDeviceSynchronize();
+    bool ok1 = true, ok2 = true;
+    std::vector<float> sref((size_t)m * t);
+    std::vector<int8_t> oref((size_t)m * d);
+    for (int h = 0; h < heads; h++) {
+        orc_int8_matmul_nobias_ofp32(q + (size_t)h * m * d, kk + (size_t)h * t * d, sref.data(), m, t, d, alpha);
+        for (size_t i = 0; i < sref.size(); i++) ok1 &= (sref[i] == s[(size_t)h * m * t + i]);
+        orc_int8_matmul_nobias(p + (size_t)h * m * t, vt + (size_t)h * d * t, oref.data(), m, d, t, 0.0031f, -128, 127);
+        for (size_t i = 0; i < oref.size(); i++) ok2 &= (oref[i] == o[(size_t)h * m * d + i]);
+    }
+    char name[96];
+    snprintf(name, sizeof(name), "BMM_S8T_S8N_F32T heads=%d m=%d (bit exact)", heads, m);
+    report(name, ok1);
+    snprintf(name, sizeof(name), "BMM_S8T_S8N_S8T heads=%d m=%d (bit exact)", heads, m);
+    report(name, ok2);
+    cudaFree(q); cudaFree(kk); cudaFree(s); cudaFree(p); cudaFree(vt); cudaFree(o);
+}
+
+int main() {
+    // shapes of the reference's op tests (llm/tests/cuda/test_ops.cu:671-724, non_cuda/test_ops.cc:177-478)
+    test_Linear_half_int4(1, 11008, 4096);
+    test_Linear_half_int4(1, 4096, 11008);
+    test_Linear_half_int4(9, 512, 1024);
+    test_W8A8B8O8Linear(1, 108, 768, 768, false, 0.00050354f, 0.0213013f);
+    test_W8A8B8O8Linear(1, 108, 768, 3072, true, 0.00050354f, 0.0213013f);
+    test_W8A8B8O8Linear(2, 1, 2048, 2048, false, 0.00050354f, 0.0213013f);
+    test_W8A8BFP32OFP32Linear(512, 768, 768, 0.0012f);
+    test_BMMs(12, 64, 64, 64, 0.0021f);
+    test_BMMs(12, 1, 300, 64, 0.0021f);
+    printf("%d failure(s)\n", failures);
+    return failures ? 1 : 0;
+}
