@@ -46,7 +46,7 @@ def test_sass_is_blackwell_native(built_lib):
     sass = subprocess.run(["cuobjdump", "-sass", str(built_lib)], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
     assert "UBLKCP" in sass, "TMA bulk copies missing from the W4A16 GEMV / attention kernels"
-    assert "HMMA" in sass, "mma.sync path missing from the W4A16 GEMV"
+    assert "IMMA" in sass or "HMMA" in sass, "mma.sync path missing from the W4A16 GEMV"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="this checks the no-GPU behaviour")

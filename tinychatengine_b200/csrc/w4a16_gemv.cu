@@ -105,21 +105,12 @@ struct Smem {
     static __host__ __device__ size_t off_meta() { return (size_t)kStages * kStageBytes; }
     static __host__ __device__ size_t off_xs(int IC) { return off_meta() + (size_t)kMetaSlots * meta_slot_bytes(IC); }
     static __host__ __device__ size_t off_gx(int IC) { return off_xs(IC) + (size_t)NCOLS * x_pitch(IC); }
-    static __host__ __device__ size_t off_red(int IC) { return off_gx(IC) + (size_t)NCOLS * (IC / 128) * sizeof(float); }
+    // gx: float step[NCOLS][NG] followed by int gsum[NCOLS][NG]
+    static __host__ __device__ size_t off_red(int IC) { return off_gx(IC) + (size_t)2 * NCOLS * (IC / 128) * sizeof(float); }
     static __host__ __device__ size_t off_rms(int IC) { return off_red(IC) + (size_t)kRedBufs * CW * kVals * sizeof(float); }
     static __host__ __device__ size_t off_bar(int IC) { return (off_rms(IC) + (size_t)NCOLS * CW * sizeof(float) + 15) & ~(size_t)15; }
     static __host__ __device__ size_t bytes(int IC) { return off_bar(IC) + (2 * kStages + 2 * kRedBufs) * sizeof(uint64_t) + 16; }
 };
-
-// nibble -> fp16: low nibbles ride on 1024 (0x6400), high nibbles on 64 (0x5400); subtracting 1032 / 72
-// yields q - 8 exactly.  One packed word -> four half2 (n0,n4)(n1,n5)(n2,n6)(n3,n7).
-TCE_DEVINL void dequant8(uint32_t w, uint32_t &p0, uint32_t &p1, uint32_t &p2, uint32_t &p3) {
-    const uint32_t w8 = w >> 8;
-    p0 = hsub2_u32(lop3_and_or(w, 0x000f000fu, 0x64006400u), 0x64086408u);
-    p1 = hsub2_u32(lop3_and_or(w, 0x00f000f0u, 0x54005400u), 0x54805480u);
-    p2 = hsub2_u32(lop3_and_or(w8, 0x000f000fu, 0x64006400u), 0x64086408u);
-    p3 = hsub2_u32(lop3_and_or(w8, 0x00f000f0u, 0x54005400u), 0x54805480u);
-}
 
 template <int NCOLS, int CW>
 __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 && CW == 8) ? 2 : 1) w4a16_gemv_kernel(const __grid_constant__ KArgs a) {
@@ -132,7 +123,8 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
     uint8_t *meta = smem + SM::off_meta();
     const int meta_bytes = SM::meta_slot_bytes(a.IC);
     uint8_t *xs = smem + SM::off_xs(a.IC);
-    float *gx = reinterpret_cast<float *>(smem + SM::off_gx(a.IC));
+    float *gx = reinterpret_cast<float *>(smem + SM::off_gx(a.IC));  // quantisation step of each activation group
+    int *gsum = reinterpret_cast<int *>(gx + (size_t)NCOLS * a.NG);    // integer sum of each quantised group
     float *red = reinterpret_cast<float *>(smem + SM::off_red(a.IC));
     float *rms = reinterpret_cast<float *>(smem + SM::off_rms(a.IC));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + SM::off_bar(a.IC));
@@ -413,29 +405,48 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[i] = 0.f;
                 }
-                // MMA-B order inside a 16-byte unit: (x0,x4)(x1,x5)(x2,x6)(x3,x7); units of a group are stored
-                // j-major so that the four t-lanes of one LDS.128 hit consecutive 16-B slots.
+                // Activations enter the integer tensor path as 15-bit block fixed point: per 128-group,
+                // X = rint(x * 16256 / max|x|) = 128*hi + lo with hi in [-127,127], lo in [-64,63] (two int8 planes).
+                // |x - step*X| <= max|x_group| / 32512, i.e. below fp16's own rounding for all but the smallest
+                // elements of a group; the integer dot products that follow are exact.
+                float amax = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                const float inv = (amax > 0.f) ? (16256.f / amax) : 0.f;
+                int hi[8], lo[8], sx = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int X = __float2int_rn(v[i] * inv);
+                    hi[i] = (X + 64) >> 7;
+                    lo[i] = X - (hi[i] << 7);
+                    sx += X;
+                }
+                // B-fragment order of mma.m16n8k32: k-slots 4t..4t+3 <- elements (0,2,4,6) of the word (the bytes of
+                // w & 0x0f0f0f0f), k-slots 16+4t.. <- elements (1,3,5,7) (the bytes of (w>>4) & 0x0f0f0f0f).
+                auto pack4 = [](int b0, int b1, int b2, int b3) {
+                    return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
+                };
                 uint4 o;
-                o.x = pack_half2(v[0], v[4]);
-                o.y = pack_half2(v[1], v[5]);
-                o.z = pack_half2(v[2], v[6]);
-                o.w = pack_half2(v[3], v[7]);
+                o.x = pack4(hi[0], hi[2], hi[4], hi[6]);
+                o.y = pack4(hi[1], hi[3], hi[5], hi[7]);
+                o.z = pack4(lo[0], lo[2], lo[4], lo[6]);
+                o.w = pack4(lo[1], lo[3], lo[5], lo[7]);
+                // units of a group are stored j-major so that the four t-lanes of one LDS.128 hit consecutive slots
                 const int G = ui >> 4, tj = ui & 15;  // ui = G*16 + 4*t + j
                 const int pos = G * 16 + (tj & 3) * 4 + (tj >> 2);
                 if (valid) *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = o;
-                // group sum of the fp16-rounded values the tensor core will actually see
-                const __half2 *oh = reinterpret_cast<const __half2 *>(&o);
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    float2 f = __half22float2(oh[i]);
-                    s += f.x + f.y;
+                sx += __shfl_xor_sync(0xffffffffu, sx, 8);
+                sx += __shfl_xor_sync(0xffffffffu, sx, 4);
+                sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+                sx += __shfl_xor_sync(0xffffffffu, sx, 1);
+                if (valid && (lane & 15) == 0) {
+                    gx[col * a.NG + G] = (amax > 0.f) ? (amax / 16256.f) : 0.f;  // step of the group
+                    gsum[col * a.NG + G] = sx;                                     // sum of X over the group
                 }
-                s += __shfl_xor_sync(0xffffffffu, s, 8);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                if (valid && (lane & 15) == 0) gx[col * a.NG + G] = s;
             }
         }
         named_bar_sync(1, kConsumerThreads);
@@ -475,42 +486,51 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
                 const int gi = cw + q * CW;
                 if (gi < n) {
                     const int G = g0 + gi;
-                    // per-group scale and (zero - 8) of rows g and g+8; zero nibble -> float through the 2^23 magic
+                    // per-group scale and zero point of rows g and g+8
                     const float sAq = __half2float(msA[G]), sBq = __half2float(msB[G]);
                     const int zsh = (G & 7) * 4;
-                    const float zAq = __uint_as_float(lop3_and_or(mzA[G >> 3] >> zsh, 0xFu, 0x4B000000u)) - 8388616.f;
-                    const float zBq = __uint_as_float(lop3_and_or(mzB[G >> 3] >> zsh, 0xFu, 0x4B000000u)) - 8388616.f;
+                    const int zAq = (int)((mzA[G >> 3] >> zsh) & 0xFu);
+                    const int zBq = (int)((mzB[G >> 3] >> zsh) & 0xFu);
                     const uint8_t *sp = sbase + gi * 64 + t * 16;
                     const uint4 wa = *reinterpret_cast<const uint4 *>(sp + g * kRowPitch);
                     const uint4 wb = *reinterpret_cast<const uint4 *>(sp + (g + 8) * kRowPitch);
                     const uint32_t wav[4] = {wa.x, wa.y, wa.z, wa.w};
                     const uint32_t wbv[4] = {wb.x, wb.y, wb.z, wb.w};
                     const uint8_t *xp = xs + ((NCOLS == 1) ? 0 : (size_t)g * SM::x_pitch(a.IC)) + ((size_t)G * 16 + t) * 16;
-                    float c[4][4];
+                    // nibbles -> bytes: w & 0x0f0f0f0f = (n0,n2,n4,n6), (w>>4) & 0x0f0f0f0f = (n1,n3,n5,n7): 3 ALU ops per
+                    // 8 weights.  Two independent accumulator chains per activation plane.
+                    int ch[2][4], cl[2][4];
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) ch[e][i] = cl[e][i] = 0;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
                         const uint4 xv = *reinterpret_cast<const uint4 *>(xp + j * 64);
-                        uint32_t p0a, p1a, p2a, p3a, p0b, p1b, p2b, p3b;
-                        dequant8(wav[j], p0a, p1a, p2a, p3a);
-                        dequant8(wbv[j], p0b, p1b, p2b, p3b);
-                        mma_m16n8k16(c[j], p0a, p0b, p1a, p1b, xv.x, xv.y);
-                        mma_m16n8k16(c[j], p2a, p2b, p3a, p3b, xv.z, xv.w);
+                        const uint32_t a0 = wav[j] & 0x0f0f0f0fu, a2 = (wav[j] >> 4) & 0x0f0f0f0fu;
+                        const uint32_t a1 = wbv[j] & 0x0f0f0f0fu, a3 = (wbv[j] >> 4) & 0x0f0f0f0fu;
+                        mma_m16n8k32_u8s8(ch[j & 1], a0, a1, a2, a3, xv.x, xv.y);
+                        mma_m16n8k32_u8s8(cl[j & 1], a0, a1, a2, a3, xv.z, xv.w);
                     }
-                    const float c0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
-                    const float c2 = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]);
+                    // exact integer group result: sum_k q*X - z*sum_k X, X = 128*hi + lo
                     if (NCOLS == 1) {
-                        const float gxv = gx[G];
-                        tot[0] += sAq * (c0 - zAq * gxv);
-                        tot[1] += sBq * (c2 - zBq * gxv);
+                        const int sxv = gsum[G];
+                        const float st = gx[G];
+                        const int vA = ((ch[0][0] + ch[1][0]) << 7) + (cl[0][0] + cl[1][0]) - zAq * sxv;
+                        const int vB = ((ch[0][2] + ch[1][2]) << 7) + (cl[0][2] + cl[1][2]) - zBq * sxv;
+                        tot[0] += (sAq * st) * (float)vA;
+                        tot[1] += (sBq * st) * (float)vB;
                     } else {
-                        const float c1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
-                        const float c3 = (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]);
-                        const float gx0 = gx[(2 * t) * a.NG + G], gx1 = gx[(2 * t + 1) * a.NG + G];
-                        tot[0] += sAq * (c0 - zAq * gx0);
-                        tot[1] += sAq * (c1 - zAq * gx1);
-                        tot[2] += sBq * (c2 - zBq * gx0);
-                        tot[3] += sBq * (c3 - zBq * gx1);
+                        const int sx0 = gsum[(2 * t) * a.NG + G], sx1 = gsum[(2 * t + 1) * a.NG + G];
+                        const float st0 = gx[(2 * t) * a.NG + G], st1 = gx[(2 * t + 1) * a.NG + G];
+                        const int vA0 = ((ch[0][0] + ch[1][0]) << 7) + (cl[0][0] + cl[1][0]) - zAq * sx0;
+                        const int vA1 = ((ch[0][1] + ch[1][1]) << 7) + (cl[0][1] + cl[1][1]) - zAq * sx1;
+                        const int vB0 = ((ch[0][2] + ch[1][2]) << 7) + (cl[0][2] + cl[1][2]) - zBq * sx0;
+                        const int vB1 = ((ch[0][3] + ch[1][3]) << 7) + (cl[0][3] + cl[1][3]) - zBq * sx1;
+                        tot[0] += (sAq * st0) * (float)vA0;
+                        tot[1] += (sAq * st1) * (float)vA1;
+                        tot[2] += (sBq * st0) * (float)vB0;
+                        tot[3] += (sBq * st1) * (float)vB1;
                     }
                 }
             }
