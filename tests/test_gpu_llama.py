@@ -31,7 +31,8 @@ def test_decode_steps_match_oracle(geom):
         tp = torch.tensor([tok, pos], dtype=torch.int32, device="cuda")
         model.decode(tp)
         torch.cuda.synchronize()
-        assert torch.equal(model.logits().cpu(), torch.from_numpy(got))
+        # (o_proj / down_proj split tiles accumulate with RED.ADD by default: last-bit differences are expected)
+        assert torch.allclose(model.logits().cpu(), torch.from_numpy(got), rtol=1e-4, atol=1e-4)
         for l in range(g.num_layers):
             kc = model.kv_cache(l, 0)[:, : pos + 1].float().cpu().numpy()
             assert np.abs(kc - past_k[l]).max() <= 2e-2 * max(1.0, np.abs(past_k[l]).max())
@@ -39,8 +40,10 @@ def test_decode_steps_match_oracle(geom):
     ctx.close()
 
 
-def test_graph_and_eager_paths_agree():
+def test_graph_and_eager_paths_agree(monkeypatch):
     import os
+
+    monkeypatch.setenv("TCE_DETERMINISTIC", "1")  # ordered stream-K fix-up instead of RED.ADD: bit-reproducible
 
     from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
     from tinychatengine_b200.runtime import Context

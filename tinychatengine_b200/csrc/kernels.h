@@ -62,6 +62,7 @@ struct W4GemvParams {
     int epi = EPI_STORE_HALF;
     int ldy = 0;        // elements between output rows
     bool pdl = false;   // launch with programmatic stream serialization
+    bool atomic_residual = false;  // EPI_ADD_F32 only: allow RED.ADD for split tiles (non-deterministic last bit)
 };
 
 cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p);
@@ -73,7 +74,11 @@ struct StreamK {
     long long U;   // total units = tiles * groups
     int nc;        // CTAs
     int NG;        // groups per row tile
-    __host__ __device__ long long start(int c) const { return (U * (long long)c) / nc; }
+    int aligned = 0;  // cut at row-tile boundaries instead of unit boundaries
+    int T = 0;        // row tiles (aligned mode)
+    __host__ __device__ long long start(int c) const {
+        return aligned ? (((long long)T * c) / nc) * NG : (U * (long long)c) / nc;
+    }
     __host__ __device__ int cta_of(long long u) const { return (int)(((u + 1) * nc + U - 1) / U - 1); }
 };
 

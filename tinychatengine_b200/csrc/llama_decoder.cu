@@ -50,6 +50,7 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
     d->layers_.assign(w.layers, w.layers + cfg.num_layers);
     d->w_.layers = d->layers_.data();
     d->use_graphs_ = getenv("TCE_NO_GRAPH") == nullptr;
+    d->atomic_residual_ = getenv("TCE_DETERMINISTIC") == nullptr;
     const size_t kv_elems = (size_t)cfg.num_layers * 2 * KVH * cfg.max_ctx * hd;
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) {
@@ -186,6 +187,7 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
             p.x_mode = X_HALF;
             p.y = d_resid_;
             p.epi = EPI_ADD_F32;
+            p.atomic_residual = atomic_residual_;
             p.pdl = pdl;
             DCK(launch_w4a16_gemv(c, p));
         }
@@ -217,6 +219,7 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
             p.x_mode = X_HALF;
             p.y = d_resid_;
             p.epi = EPI_ADD_F32;
+            p.atomic_residual = atomic_residual_;
             p.pdl = pdl;
             DCK(launch_w4a16_gemv(c, p));
         }

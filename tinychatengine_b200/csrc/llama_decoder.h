@@ -52,6 +52,7 @@ class LlamaDecoder {
     const int *g_dev_src_ = nullptr;
     bool graphs_ok_ = false;
     bool use_graphs_ = true;
+    bool atomic_residual_ = true;  // o_proj/down_proj partial tiles use RED.ADD (TCE_DETERMINISTIC=1 turns it off)
     int kernels_per_step_ = 0;
 };
 

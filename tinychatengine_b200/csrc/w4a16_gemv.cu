@@ -53,6 +53,8 @@ struct KArgs {
     int epi, ldy;
     float *partials;
     unsigned *counters;
+    int aligned;     // 1: CTA ranges are cut at row-tile boundaries (no split tiles, no fix-up)
+    int atomic_add;  // 1: EPI_ADD_F32 partial tiles use RED.ADD.F32 instead of the ordered fix-up
     unsigned long long *dbg;  // optional per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
 };
 
@@ -150,7 +152,14 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
         }
         mbar_fence_init();
     }
-    __syncthreads();
+    // warp 0 (which initialised the barriers) only signals; everyone else waits.  The first TMA copies therefore do
+    // not wait for 400+ threads to reach a CTA-wide barrier.
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("bar.arrive 3, %0;" ::"r"(32 * (kProducerWarps + 1 + CW)) : "memory");
+    } else {
+        asm volatile("bar.sync 3, %0;" ::"r"(32 * (kProducerWarps + 1 + CW)) : "memory");
+    }
     // let the next kernel in the stream become resident right away: it may only prefetch its (static) weights
     // until its own griddepcontrol.wait releases, which happens when this whole grid has finished.
     pdl_launch_dependents();
@@ -159,6 +168,8 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
     sk.U = (long long)a.num_tiles * a.NG;
     sk.nc = gridDim.x;
     sk.NG = a.NG;
+    sk.aligned = a.aligned;
+    sk.T = a.num_tiles;
     const long long u0 = sk.start(blockIdx.x), u1 = sk.start(blockIdx.x + 1);
 
     if (warp < kProducerWarps) {
@@ -257,7 +268,17 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
                 rphase ^= 1;
             }
             bool do_final = full_tile;
-            if (!full_tile) {
+            if (!full_tile && a.atomic_add) {
+                // residual accumulate: every contributor of a split tile adds its partial straight into the fp32
+                // residual with RED.ADD (fire and forget: no fence, no counter, nothing on the critical path).  The
+                // order of the <= 3 partial adds is not fixed, so the last bit of the residual may vary run to run.
+#pragma unroll
+                for (int i = 0; i < VPL; i++) {
+                    const int idx = lane + 32 * i;
+                    const int row = idx / NCOLS, col = idx % NCOLS;
+                    if (idx < kVals && col < a.M) atomicAdd(reinterpret_cast<float *>(a.y) + (size_t)col * a.ldy + (size_t)rt * 16 + row, v[i]);
+                }
+            } else if (!full_tile) {
                 // stream-K fix-up: park the partial; the last contributor to arrive sums all of them in CTA order
                 const long long tb = (long long)rt * a.NG;
                 const int c_first = sk.cta_of(tb);
@@ -375,36 +396,8 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
                 for (int w = 0; w < CW; w++) tot += rms[col * CW + w];
                 inv = rsqrtf(tot / (float)a.IC + a.eps);
             }
-            // `units` is a multiple of 16, not of 32: the trip count is made warp-uniform so that the half-warp
-            // shuffles below always run with all 32 lanes
-            for (int ui0 = 0; ui0 < units; ui0 += kConsumerThreads) {
-                const int ui = ui0 + ctid;
-                const bool valid = ui < units;
-                float v[8];
-                if (valid && col < a.M) {
-                    if (a.x_mode == X_RMSNORM_F32) {
-                        const float *xr = reinterpret_cast<const float *>(a.x) + (size_t)col * a.ldx + ui * 8;
-                        float4 v0 = *reinterpret_cast<const float4 *>(xr);
-                        float4 v1 = *reinterpret_cast<const float4 *>(xr + 4);
-                        float4 g0 = *reinterpret_cast<const float4 *>(a.gamma + ui * 8);
-                        float4 g1 = *reinterpret_cast<const float4 *>(a.gamma + ui * 8 + 4);
-                        v[0] = (v0.x * inv) * g0.x; v[1] = (v0.y * inv) * g0.y; v[2] = (v0.z * inv) * g0.z; v[3] = (v0.w * inv) * g0.w;
-                        v[4] = (v1.x * inv) * g1.x; v[5] = (v1.y * inv) * g1.y; v[6] = (v1.z * inv) * g1.z; v[7] = (v1.w * inv) * g1.w;
-                    } else {
-                        const __half *xr = reinterpret_cast<const __half *>(a.x) + (size_t)col * a.ldx + ui * 8;
-                        uint4 raw = *reinterpret_cast<const uint4 *>(xr);
-                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            float2 f = __half22float2(h2[i]);
-                            v[2 * i] = f.x;
-                            v[2 * i + 1] = f.y;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) v[i] = 0.f;
-                }
+            // quantise + stage one 8-element unit (v) of activation column `col`
+            auto emit = [&](int ui, bool valid, const float (&v)[8]) {
                 // Activations enter the integer tensor path as 15-bit block fixed point: per 128-group,
                 // X = rint(x * 16256 / max|x|) = 128*hi + lo with hi in [-127,127], lo in [-64,63] (two int8 planes).
                 // |x - step*X| <= max|x_group| / 32512, i.e. below fp16's own rounding for all but the smallest
@@ -416,11 +409,11 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
                 amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
                 amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
                 amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-                const float inv = (amax > 0.f) ? (16256.f / amax) : 0.f;
+                const float qinv = (amax > 0.f) ? (16256.f / amax) : 0.f;
                 int hi[8], lo[8], sx = 0;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const int X = __float2int_rn(v[i] * inv);
+                    const int X = __float2int_rn(v[i] * qinv);
                     hi[i] = (X + 64) >> 7;
                     lo[i] = X - (hi[i] << 7);
                     sx += X;
@@ -446,6 +439,62 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
                 if (valid && (lane & 15) == 0) {
                     gx[col * a.NG + G] = (amax > 0.f) ? (amax / 16256.f) : 0.f;  // step of the group
                     gsum[col * a.NG + G] = sx;                                     // sum of X over the group
+                }
+            };
+            // `units` is a multiple of 16, not of 32: trip counts are warp-uniform so that the half-warp shuffles in
+            // emit() always run with all 32 lanes.  Loads of several iterations are issued before any is consumed
+            // (IC = 14336 is 7 iterations per thread: one exposed L2 latency instead of seven).
+            if (a.x_mode == X_RMSNORM_F32) {
+                constexpr int PRE = 2;
+                for (int ui0 = 0; ui0 < units; ui0 += PRE * kConsumerThreads) {
+                    float4 r0[PRE], r1[PRE], g0[PRE], g1[PRE];
+#pragma unroll
+                    for (int k = 0; k < PRE; k++) {
+                        const int ui = ui0 + k * kConsumerThreads + ctid;
+                        if (ui < units && col < a.M) {
+                            const float *xr = reinterpret_cast<const float *>(a.x) + (size_t)col * a.ldx + ui * 8;
+                            r0[k] = *reinterpret_cast<const float4 *>(xr);
+                            r1[k] = *reinterpret_cast<const float4 *>(xr + 4);
+                            g0[k] = *reinterpret_cast<const float4 *>(a.gamma + ui * 8);
+                            g1[k] = *reinterpret_cast<const float4 *>(a.gamma + ui * 8 + 4);
+                        } else {
+                            r0[k] = r1[k] = g0[k] = g1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < PRE; k++) {
+                        if (ui0 + k * kConsumerThreads >= units) break;  // warp-uniform
+                        const int ui = ui0 + k * kConsumerThreads + ctid;
+                        float v[8];
+                        v[0] = (r0[k].x * inv) * g0[k].x; v[1] = (r0[k].y * inv) * g0[k].y; v[2] = (r0[k].z * inv) * g0[k].z; v[3] = (r0[k].w * inv) * g0[k].w;
+                        v[4] = (r1[k].x * inv) * g1[k].x; v[5] = (r1[k].y * inv) * g1[k].y; v[6] = (r1[k].z * inv) * g1[k].z; v[7] = (r1[k].w * inv) * g1[k].w;
+                        emit(ui, ui < units, v);
+                    }
+                }
+            } else {
+                constexpr int PRE = 4;
+                for (int ui0 = 0; ui0 < units; ui0 += PRE * kConsumerThreads) {
+                    uint4 raw[PRE];
+#pragma unroll
+                    for (int k = 0; k < PRE; k++) {
+                        const int ui = ui0 + k * kConsumerThreads + ctid;
+                        raw[k] = make_uint4(0u, 0u, 0u, 0u);
+                        if (ui < units && col < a.M) raw[k] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(a.x) + (size_t)col * a.ldx + ui * 8);
+                    }
+#pragma unroll
+                    for (int k = 0; k < PRE; k++) {
+                        if (ui0 + k * kConsumerThreads >= units) break;  // warp-uniform
+                        const int ui = ui0 + k * kConsumerThreads + ctid;
+                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw[k]);
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const float2 f = __half22float2(h2[i]);
+                            v[2 * i] = f.x;
+                            v[2 * i + 1] = f.y;
+                        }
+                        emit(ui, ui < units, v);
+                    }
                 }
             }
         }
@@ -648,11 +697,14 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     a.partials = ctx->gemv_partials;
     a.counters = ctx->gemv_counters;
     a.dbg = ctx->gemv_dbg;
+    a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
+    a.aligned = 0;
     return a;
 }
 
 template <int NCOLS, int CW>
-cudaError_t launch_mma(Ctx *ctx, const KArgs &a, bool pdl) {
+cudaError_t launch_mma(Ctx *ctx, const KArgs &a_in, bool pdl) {
+    KArgs a = a_in;
     const size_t smem = Smem<NCOLS, CW>::bytes(a.IC);
     if ((int)smem > ctx->smem_optin) return cudaErrorInvalidConfiguration;
     static bool attr_set = false;  // per template instantiation
@@ -665,6 +717,10 @@ cudaError_t launch_mma(Ctx *ctx, const KArgs &a, bool pdl) {
     int nc = ctx->num_sms * ctx->gemv_ctas_per_sm;
     if (nc > ctx->gemv_max_ctas) nc = ctx->gemv_max_ctas;
     if ((long long)nc > U) nc = (int)U;
+    // Epilogues that need a single ordered writer per output (stores, SiLU*mul, deterministic residual) avoid split
+    // tiles altogether when there is at least one whole tile per CTA: the fix-up protocol costs ~2.5 us of tail per
+    // launch (profiles/r01_gemv_phase_timeline.txt), more than the <= 1/tiles_per_cta imbalance it removes.
+    a.aligned = (!a.atomic_add && a.num_tiles >= nc) ? 1 : 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nc);
     cfg.blockDim = dim3(32 * (kProducerWarps + 1 + CW));
