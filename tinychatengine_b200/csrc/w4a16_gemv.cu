@@ -160,9 +160,6 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
     } else {
         asm volatile("bar.sync 3, %0;" ::"r"(32 * (kProducerWarps + 1 + CW)) : "memory");
     }
-    // let the next kernel in the stream become resident right away: it may only prefetch its (static) weights
-    // until its own griddepcontrol.wait releases, which happens when this whole grid has finished.
-    pdl_launch_dependents();
 
     StreamK sk;
     sk.U = (long long)a.num_tiles * a.NG;
@@ -230,6 +227,10 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
             rt++;
             gb = 0;
         }
+        // Programmatic dependent launch trigger: this CTA has requested its last byte of weights, so from here on
+        // HBM is free for the next kernel in the stream -- it may become resident now and prefetch its own (static)
+        // weights; its consumers still block in griddepcontrol.wait until this whole grid has finished.
+        pdl_launch_dependents();
         return;
     }
 
