@@ -33,8 +33,12 @@ TCE_DEVINL bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Bounded wait: a protocol bug must surface as a launch failure within seconds, never as a hung GPU.
 TCE_DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) __trap();  // ~3 s
     }
 }
 

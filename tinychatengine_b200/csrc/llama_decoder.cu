@@ -9,6 +9,8 @@
 // The residual stream is kept in fp32 (the reference's CUDA build keeps it in fp16, its CPU build in fp32).
 #include "llama_decoder.h"
 
+#include "megakernel.h"
+
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -96,7 +98,18 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
         delete d;
         return nullptr;
     }
-    d->kernels_per_step_ = 1 + 5 * cfg.num_layers + 2;
+    d->mega_ = getenv("TCE_MEGAKERNEL") ? atoi(getenv("TCE_MEGAKERNEL")) != 0 : true;
+    d->mega_attn_chunk_ = getenv("TCE_MEGA_ATTN_CHUNK") ? atoi(getenv("TCE_MEGA_ATTN_CHUNK")) : 64;
+    d->build_ops();
+    if (d->mega_) {
+        cudaError_t me = d->build_megakernel();
+        if (me != cudaSuccess) {
+            *err = std::string("persistent kernel setup failed: ") + cudaGetErrorString(me);
+            delete d;
+            return nullptr;
+        }
+    }
+    d->kernels_per_step_ = d->mega_ ? 1 : 1 + 5 * cfg.num_layers + 2;
     return d;
 }
 
@@ -112,6 +125,8 @@ LlamaDecoder::~LlamaDecoder() {
     cudaFree(d_logits_);
     cudaFree(d_tokpos_);
     cudaFree(d_next_);
+    cudaFree(d_phases_);
+    cudaFree(d_sync_);
     if (own_rope_) {
         cudaFree(d_cos_);
         cudaFree(d_sin_);
@@ -134,16 +149,20 @@ cudaError_t LlamaDecoder::enqueue_gemvs(int *count) {
     return enqueue_step(d_tokpos_, ctx_->stream, false, true);
 }
 
-cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only) {
-    Ctx local = *ctx_;  // same workspaces, but launch on `s`
-    local.stream = s;
-    Ctx *c = &local;
+// The op list of one decode step (built once): the graph path launches one kernel per op, the persistent kernel
+// turns the same list into its phase table.
+void LlamaDecoder::build_ops() {
     const int E = cfg_.embed_dim, F = cfg_.hidden_dim, H = cfg_.num_heads, KVH = cfg_.num_kv_heads, hd = cfg_.head_dim;
-    if (!gemv_only) DCK(launch_embedding(c, (const __half *)w_.embed_f16, tokpos, d_resid_, E, false));
+    ops_.clear();
+    StepOp emb;
+    emb.type = OP_EMBED;
+    ops_.push_back(emb);
     for (int l = 0; l < cfg_.num_layers; l++) {
         const tce_llama_layer &L = layers_[l];
         {  // RMSNorm(input_layernorm) + fused q|k|v projection
-            W4GemvParams p;
+            StepOp op;
+            op.type = OP_GEMV;
+            W4GemvParams &p = op.g;
             p.nseg = 3;
             p.seg[0] = seg_of(L.q);
             p.seg[1] = seg_of(L.k);
@@ -157,17 +176,18 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
             p.eps = cfg_.rms_eps;
             p.y = d_qkv_;
             p.epi = EPI_STORE_HALF;
-            p.pdl = pdl;
-            DCK(launch_w4a16_gemv(c, p));
+            ops_.push_back(op);
         }
-        if (!gemv_only) {  // RoPE + in-place KV append + attention over the cache
-            AttnDecodeArgs a = {};
+        {  // RoPE + in-place KV append + attention over the cache
+            StepOp op;
+            op.type = OP_ATTN;
+            AttnDecodeArgs &a = op.at;
+            a = AttnDecodeArgs{};
             a.qkv = d_qkv_;
             a.k_cache = (__half *)kv_cache(l, 0);
             a.v_cache = (__half *)kv_cache(l, 1);
             a.cos = d_cos_;
             a.sin = d_sin_;
-            a.pos = tokpos + 1;
             a.out = d_attn_;
             a.alpha = cfg_.qk_alpha > 0 ? cfg_.qk_alpha : 1.0f / sqrtf((float)hd);
             a.num_heads = H;
@@ -175,10 +195,12 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
             a.head_dim = hd;
             a.max_ctx = cfg_.max_ctx;
             a.chunk = attn_chunk_;
-            DCK(launch_attn_decode(c, a, pdl));
+            ops_.push_back(op);
         }
         {  // o_proj, accumulated straight into the residual stream
-            W4GemvParams p;
+            StepOp op;
+            op.type = OP_GEMV;
+            W4GemvParams &p = op.g;
             p.nseg = 1;
             p.seg[0] = seg_of(L.o);
             p.IC = H * hd;
@@ -188,11 +210,12 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
             p.y = d_resid_;
             p.epi = EPI_ADD_F32;
             p.atomic_residual = atomic_residual_;
-            p.pdl = pdl;
-            DCK(launch_w4a16_gemv(c, p));
+            ops_.push_back(op);
         }
         {  // RMSNorm(post_attention_layernorm) + gate/up with SiLU(gate)*up epilogue
-            W4GemvParams p;
+            StepOp op;
+            op.type = OP_GEMV;
+            W4GemvParams &p = op.g;
             p.nseg = 2;
             p.pair_mode = 1;
             p.seg[0] = seg_of(L.gate);
@@ -206,11 +229,12 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
             p.y = d_act_;
             p.epi = EPI_SILU_MUL_HALF;
             p.ldy = F;
-            p.pdl = pdl;
-            DCK(launch_w4a16_gemv(c, p));
+            ops_.push_back(op);
         }
         {  // down_proj + residual
-            W4GemvParams p;
+            StepOp op;
+            op.type = OP_GEMV;
+            W4GemvParams &p = op.g;
             p.nseg = 1;
             p.seg[0] = seg_of(L.down);
             p.IC = F;
@@ -220,12 +244,13 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
             p.y = d_resid_;
             p.epi = EPI_ADD_F32;
             p.atomic_residual = atomic_residual_;
-            p.pdl = pdl;
-            DCK(launch_w4a16_gemv(c, p));
+            ops_.push_back(op);
         }
     }
     {  // final RMSNorm + lm_head -> fp32 logits (reference: lm_head GEMV + half2float, cuda/Int4llamaForCausalLM.cu:33-38)
-        W4GemvParams p;
+        StepOp op;
+        op.type = OP_GEMV;
+        W4GemvParams &p = op.g;
         p.nseg = 1;
         p.seg[0] = seg_of(w_.lm_head);
         p.IC = E;
@@ -236,10 +261,98 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
         p.eps = cfg_.rms_eps;
         p.y = d_logits_;
         p.epi = EPI_STORE_F32;
-        p.pdl = pdl;
-        DCK(launch_w4a16_gemv(c, p));
+        ops_.push_back(op);
     }
-    if (!gemv_only) DCK(launch_argmax(c, d_logits_, cfg_.vocab_size, d_next_, pdl));
+    StepOp am;
+    am.type = OP_ARGMAX;
+    ops_.push_back(am);
+}
+
+cudaError_t LlamaDecoder::build_megakernel() {
+    const int ncta = ctx_->num_sms;
+    std::vector<MegaPhase> ph(ops_.size());
+    int max_ic = 0;
+    for (size_t i = 0; i < ops_.size(); i++) {
+        memset(&ph[i], 0, sizeof(MegaPhase));
+        switch (ops_[i].type) {
+            case OP_EMBED: ph[i].type = PH_EMBED; break;
+            case OP_ARGMAX: ph[i].type = PH_ARGMAX; break;
+            case OP_ATTN: {
+                ph[i].type = PH_ATTN;
+                AttnDecodeArgs a = ops_[i].at;
+                a.chunk = mega_attn_chunk_;
+                a.nsplit_max = (a.max_ctx + a.chunk - 1) / a.chunk;
+                a.ws = ctx_->attn_ws;
+                a.counters = ctx_->attn_counters;
+                if ((size_t)a.num_heads * a.nsplit_max * 130 * sizeof(float) > ctx_->attn_ws_bytes) return cudaErrorInvalidValue;
+                ph[i].at = a;
+                break;
+            }
+            case OP_GEMV:
+                megakernel_fill_gemv(ctx_, ops_[i].g, &ph[i], ncta);
+                if (ops_[i].g.IC > max_ic) max_ic = ops_[i].g.IC;
+                if (ph[i].g.num_tiles > ctx_->gemv_max_tiles) return cudaErrorInvalidValue;
+                break;
+        }
+    }
+    DCK(cudaMalloc((void **)&d_phases_, ph.size() * sizeof(MegaPhase)));
+    DCK(cudaMemcpy(d_phases_, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+    DCK(cudaMalloc((void **)&d_sync_, 2 * sizeof(unsigned long long)));
+    DCK(cudaMemset(d_sync_, 0, 2 * sizeof(unsigned long long)));
+    margs_ = MegaArgs{};
+    margs_.phases = d_phases_;
+    margs_.nphases = (int)ph.size();
+    margs_.sync = reinterpret_cast<unsigned *>(d_sync_);
+    margs_.argmax_cell = d_sync_ + 1;
+    margs_.embed = (const __half *)w_.embed_f16;
+    margs_.resid = d_resid_;
+    margs_.E = cfg_.embed_dim;
+    margs_.logits = d_logits_;
+    margs_.V = cfg_.vocab_size;
+    margs_.next_token = d_next_;
+    margs_.max_ic = max_ic;
+    margs_.attn_nrep = cfg_.num_heads / cfg_.num_kv_heads;
+    margs_.attn_chunk = mega_attn_chunk_;
+    if ((int)megakernel_smem_bytes(max_ic, margs_.attn_nrep, mega_attn_chunk_) > ctx_->smem_optin) return cudaErrorInvalidConfiguration;
+    return cudaSuccess;
+}
+
+cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only) {
+    if (mega_ && !gemv_only) {
+        DCK(cudaMemsetAsync(d_sync_, 0, sizeof(unsigned), s));
+        MegaArgs m = margs_;
+        m.tokpos = tokpos;
+        return launch_megakernel(ctx_, m, s);
+    }
+    Ctx local = *ctx_;  // same workspaces, but launch on `s`
+    local.stream = s;
+    Ctx *c = &local;
+    bool first = true;
+    for (const StepOp &op : ops_) {
+        const bool use_pdl = pdl && !first;
+        switch (op.type) {
+            case OP_EMBED:
+                if (!gemv_only) DCK(launch_embedding(c, (const __half *)w_.embed_f16, tokpos, d_resid_, cfg_.embed_dim, false));
+                break;
+            case OP_GEMV: {
+                W4GemvParams p = op.g;
+                p.pdl = use_pdl;
+                DCK(launch_w4a16_gemv(c, p));
+                break;
+            }
+            case OP_ATTN:
+                if (!gemv_only) {
+                    AttnDecodeArgs a = op.at;
+                    a.pos = tokpos + 1;
+                    DCK(launch_attn_decode(c, a, use_pdl));
+                }
+                break;
+            case OP_ARGMAX:
+                if (!gemv_only) DCK(launch_argmax(c, d_logits_, cfg_.vocab_size, d_next_, use_pdl));
+                break;
+        }
+        first = false;
+    }
     return cudaSuccess;
 }
 

@@ -6,6 +6,7 @@
 #include "../../include/tce_b200.h"
 #include "kernels.h"
 #include "kernels_attn.h"
+#include "megakernel.h"
 
 namespace tce {
 
@@ -24,6 +25,21 @@ class LlamaDecoder {
     LlamaDecoder() = default;
     cudaError_t enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only = false);  // raw kernel sequence
     cudaError_t build_graphs(std::string *err);
+    void build_ops();
+    cudaError_t build_megakernel();
+
+    enum OpType { OP_EMBED, OP_GEMV, OP_ATTN, OP_ARGMAX };
+    struct StepOp {
+        OpType type;
+        W4GemvParams g;
+        AttnDecodeArgs at;
+    };
+    std::vector<StepOp> ops_;
+    bool mega_ = true;              // one persistent kernel per token (TCE_MEGAKERNEL=0: one kernel per op in a CUDA graph)
+    int mega_attn_chunk_ = 64;
+    MegaPhase *d_phases_ = nullptr;
+    unsigned long long *d_sync_ = nullptr;  // [0] grid barrier counter, [1] arg-max cell
+    MegaArgs margs_{};
 
     Ctx *ctx_ = nullptr;
     int attn_chunk_ = 128;

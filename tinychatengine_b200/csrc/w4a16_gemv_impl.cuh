@@ -1,0 +1,612 @@
+// w4a16_gemv_impl.cuh -- device-side roles of the W4A16 group-128 GEMV (producer / consumer / epilogue), shared by
+// the stand-alone kernel (w4a16_gemv.cu) and the persistent decode kernel (decode_megakernel.cu).
+//
+// Data contract = the reference's QM_CUDA layout (kernels/cuda/gemv_cuda.cu:140-260, quantize_methods.py:370-442):
+//     w uint32[OC][IC/8] sequential nibbles, zeros uint32[OC][zeros_w] (nibble g = zero of group g),
+//     scales half[OC][zeros_w*8];   y[m][oc] = sum_ic s[oc,g] * (q[oc,ic] - z[oc,g]) * x[m][ic]
+//
+//  * work unit = (16-row tile, one 128-k group) = 1 KiB of packed weights; the units of a launch are cut into equal
+//    contiguous per-CTA ranges (stream-K) or, for epilogues that need one ordered writer, at row-tile boundaries.
+//  * producers (4 warps x 4 rows): 1-D TMA bulk copies (UBLKCP) of [16 rows x <=16 groups] weight slabs into a
+//    4-stage ring guarded by full/empty mbarriers, L2 evict-first; the tile's scales/zeros slabs ride on the first
+//    stage's barrier.  Producers depend on nothing but the weights, so they may run ahead of everything else.
+//  * consumers (CW warps): conflict-free 128-bit LDS (row pitch = 64 mod 128 B); nibbles -> bytes with
+//    w & 0x0f0f0f0f / (w>>4) & 0x0f0f0f0f (3 ALU ops per 8 weights); mma.sync.m16n8k32 u8 x s8 -> s32 against the
+//    activations held as two int8 planes (15-bit block fixed point per 128-group, exact integer accumulation);
+//    per-group epilogue tot += (s * step) * (acc - z * sum_X).  The 8 MMA columns carry up to 8 activation rows.
+//  * tile partials go to the epilogue warp through a triple-buffered smem slot + mbarrier (consumers never wait for
+//    each other); the epilogue warp runs the fused epilogue (fp16/fp32 store, residual +=, SiLU(gate)*up), the
+//    RED.ADD residual path or the ordered stream-K fix-up.
+//  * fused prologue: RMSNorm of an fp32 residual stream (LlamaRMSNorm semantics) + activation quantisation.
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tce {
+namespace gemv {
+
+constexpr int kStageGroups = 16;                   // 128-k groups per pipeline stage (per row: 1024 B)
+constexpr int kRowPitch = kStageGroups * 64 + 64;  // 1088 B: == 64 (mod 128) -> conflict-free LDS.128
+constexpr int kStageBytes = 16 * kRowPitch;        // 17408 B
+constexpr int kStages = 4;
+constexpr int kRedBufs = 3;
+constexpr int kProducerWarps = 4;        // UBLKCP issue costs ~100 cycles per copy through one warp: four warps share the rows
+constexpr int kMetaSlots = kStages + 1;  // per-tile scales/zeros slabs in flight (a tile spans >= 1 stage)
+
+struct KArgs {
+    W4Seg seg[3];
+    int nseg, pair_mode;
+    int IC, NG, zeros_w, sf_w;
+    int num_tiles;
+    int M, ldx, x_mode;
+    const void *x;
+    const float *gamma;
+    float eps;
+    void *y;
+    int epi, ldy;
+    float *partials;
+    unsigned *counters;
+    int aligned;     // 1: CTA ranges are cut at row-tile boundaries (no split tiles, no fix-up)
+    int atomic_add;  // 1: EPI_ADD_F32 partial tiles use RED.ADD.F32 instead of the ordered fix-up
+    unsigned long long *dbg;  // optional per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
+};
+
+struct RowRef {
+    const uint8_t *w;
+    const uint32_t *z;
+    const __half *s;
+};
+
+// source row `l` (0..15) of row tile `rt`
+TCE_DEVINL RowRef tile_row(const KArgs &a, int rt, int l) {
+    int si = 0, r;
+    if (a.pair_mode) {
+        si = l >> 3;
+        r = rt * 8 + (l & 7);
+    } else {
+        r = rt * 16 + l;
+        if (a.nseg > 1 && r >= a.seg[0].rows) {
+            r -= a.seg[0].rows;
+            si = 1;
+            if (a.nseg > 2 && r >= a.seg[1].rows) {
+                r -= a.seg[1].rows;
+                si = 2;
+            }
+        }
+    }
+    const W4Seg &s = a.seg[si];
+    RowRef ref;
+    ref.w = reinterpret_cast<const uint8_t *>(s.w) + (size_t)r * (a.IC / 2);
+    ref.z = s.zeros + (size_t)r * a.zeros_w;
+    ref.s = s.scales + (size_t)r * a.sf_w;
+    return ref;
+}
+
+TCE_DEVINL void dbg_stamp(const KArgs &a, int cta, int k) {
+    if (a.dbg) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.dbg[(size_t)cta * 8 + k] = t;
+    }
+}
+
+// shared-memory layout (offsets from a 128-B aligned base)
+template <int NCOLS, int CW>
+struct Layout {
+    static constexpr int kXPad = (NCOLS > 1) ? 64 : 0;  // column pitch = 64 (mod 128) B for the per-column B loads
+    static constexpr int kVals = 16 * NCOLS;
+    static __host__ __device__ int x_pitch(int IC) { return IC * 2 + kXPad; }
+    // one meta slot = scales half[16][zeros_w*8] followed by zeros uint32[16][zeros_w] = 320 * zeros_w bytes
+    static __host__ __device__ int meta_slot_bytes(int IC) { return 320 * (((IC / 128) + 7) / 8); }
+    static __host__ __device__ size_t off_meta() { return (size_t)kStages * kStageBytes; }
+    static __host__ __device__ size_t off_xs(int IC) { return off_meta() + (size_t)kMetaSlots * meta_slot_bytes(IC); }
+    static __host__ __device__ size_t off_gx(int IC) { return off_xs(IC) + (size_t)NCOLS * x_pitch(IC); }
+    // gx: float step[NCOLS][NG] followed by int gsum[NCOLS][NG]
+    static __host__ __device__ size_t off_red(int IC) { return off_gx(IC) + (size_t)2 * NCOLS * (IC / 128) * sizeof(float); }
+    static __host__ __device__ size_t off_rms(int IC) { return off_red(IC) + (size_t)kRedBufs * CW * kVals * sizeof(float); }
+    static __host__ __device__ size_t off_bar(int IC) { return (off_rms(IC) + (size_t)NCOLS * CW * sizeof(float) + 15) & ~(size_t)15; }
+    static __host__ __device__ size_t bytes(int IC) { return off_bar(IC) + (2 * kStages + 2 * kRedBufs) * sizeof(uint64_t) + 16; }
+};
+
+struct Smem {
+    uint8_t *stages, *meta, *xs;
+    float *gx;
+    int *gsum;
+    float *red, *rms;
+    uint64_t *full_bar, *empty_bar, *red_full, *red_empty;
+    int meta_bytes;
+};
+
+// `IC` here is the LARGEST IC the kernel will see (the persistent kernel carves once for all phases)
+template <int NCOLS, int CW>
+TCE_DEVINL Smem carve(uint8_t *base, int IC) {
+    using L = Layout<NCOLS, CW>;
+    Smem s;
+    s.stages = base;
+    s.meta = base + L::off_meta();
+    s.xs = base + L::off_xs(IC);
+    s.gx = reinterpret_cast<float *>(base + L::off_gx(IC));
+    s.gsum = reinterpret_cast<int *>(s.gx + (size_t)NCOLS * (IC / 128));
+    s.red = reinterpret_cast<float *>(base + L::off_red(IC));
+    s.rms = reinterpret_cast<float *>(base + L::off_rms(IC));
+    s.full_bar = reinterpret_cast<uint64_t *>(base + L::off_bar(IC));
+    s.empty_bar = s.full_bar + kStages;
+    s.red_full = s.empty_bar + kStages;
+    s.red_empty = s.red_full + kRedBufs;
+    s.meta_bytes = L::meta_slot_bytes(IC);
+    return s;
+}
+
+template <int CW>
+TCE_DEVINL void init_barriers(const Smem &sm) {  // one thread
+#pragma unroll
+    for (int s = 0; s < kStages; s++) {
+        mbar_init(&sm.full_bar[s], 1);
+        mbar_init(&sm.empty_bar[s], CW);
+    }
+#pragma unroll
+    for (int s = 0; s < kRedBufs; s++) {
+        mbar_init(&sm.red_full[s], CW);
+        mbar_init(&sm.red_empty[s], 1);
+    }
+    mbar_fence_init();
+}
+
+// pipeline positions; every role keeps its own copy and all copies advance identically because every role walks the
+// same (tile, stage) sequence
+struct RingState {
+    int stage = 0;
+    uint32_t phase = 0;
+    int mslot = 0;
+};
+struct RedState {
+    int rb = 0;
+    uint32_t rphase = 0;
+};
+
+TCE_DEVINL StreamK make_sk(const KArgs &a, int ncta) {
+    StreamK sk;
+    sk.U = (long long)a.num_tiles * a.NG;
+    sk.nc = ncta;
+    sk.NG = a.NG;
+    sk.aligned = a.aligned;
+    sk.T = a.num_tiles;
+    return sk;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// producer warps (pw = 0..3): stream this CTA's unit range into the ring.  Warp-convergent, lane 0 issues.
+// ------------------------------------------------------------------------------------------------------------------
+TCE_DEVINL void produce(const KArgs &a, const Smem &sm, RingState &rs, int cta, int ncta, int pw, int lane, uint64_t policy) {
+    const StreamK sk = make_sk(a, ncta);
+    const uint32_t leader = (lane == 0) ? 1u : 0u;
+    const int meta_bytes_cur = 320 * a.zeros_w;  // bytes actually copied for this IC (<= sm.meta_bytes)
+    int u = (int)sk.start(cta);
+    const int uend = (int)sk.start(cta + 1);
+    int rt = u / a.NG;
+    int gb = u - rt * a.NG;
+    while (u < uend) {
+        const int ge = min(a.NG, gb + (uend - u));
+        // All addresses below are warp-uniform (kernel arguments and loop counters only)
+        const RowRef r0 = tile_row(a, rt, 0), r8 = tile_row(a, rt, 8);  // rows 0-7 / 8-15 are contiguous each
+        const size_t wpitch = (size_t)(a.IC / 2);
+        uint8_t *mdst = sm.meta + (size_t)rs.mslot * sm.meta_bytes;
+        bool first = true;
+        for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
+            const int n = min(kStageGroups, ge - g0);
+            mbar_wait(&sm.empty_bar[rs.stage], rs.phase ^ 1);
+            {
+                uint64_t *bar = &sm.full_bar[rs.stage];
+                // producer 0 posts the byte count; the other producers' complete_tx may land first (the phase cannot
+                // complete before this single arrival, and a transiently negative tx-count is legal)
+                if (pw == 0) mbar_arrive_expect_tx_pred(bar, 16u * n * 64u + (first ? (uint32_t)meta_bytes_cur : 0u), leader);
+                uint8_t *dst = sm.stages + (size_t)rs.stage * kStageBytes;
+                const uint32_t nb = (uint32_t)n * 64u;
+                const RowRef &rr = (pw < 2) ? r0 : r8;  // rows 4*pw .. 4*pw+3
+                const int lr = (pw & 1) * 4;
+#pragma unroll
+                for (int l = 0; l < 4; l++)
+                    bulk_g2s_pred(dst + (pw * 4 + l) * kRowPitch, rr.w + (lr + l) * wpitch + (size_t)g0 * 64, nb, bar, policy, leader);
+                if (first && pw == 1) {
+                    // this tile's scales / zeros slabs ride on the full barrier of its first stage
+                    const uint32_t sb = 8u * a.sf_w * 2u, zb = 8u * a.zeros_w * 4u;
+                    bulk_g2s_pred(mdst, r0.s, sb, bar, policy, leader);
+                    bulk_g2s_pred(mdst + sb, r8.s, sb, bar, policy, leader);
+                    bulk_g2s_pred(mdst + 2 * sb, r0.z, zb, bar, policy, leader);
+                    bulk_g2s_pred(mdst + 2 * sb + zb, r8.z, zb, bar, policy, leader);
+                }
+            }
+            __syncwarp();
+            first = false;
+            if (++rs.stage == kStages) {
+                rs.stage = 0;
+                rs.phase ^= 1;
+            }
+        }
+        if (++rs.mslot == kMetaSlots) rs.mslot = 0;
+        u += ge - gb;
+        rt++;
+        gb = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// epilogue warp: reduces the CW consumer partials of every tile this CTA touches, then either finishes the tile or
+// takes part in the stream-K fix-up.  Lane l owns values idx = l + 32*i  (idx = row*NCOLS + col).
+// ------------------------------------------------------------------------------------------------------------------
+template <int NCOLS, int CW>
+TCE_DEVINL void epilogue(const KArgs &a, const Smem &sm, RedState &es, int cta, int ncta, int lane) {
+    constexpr int kVals = 16 * NCOLS;
+    constexpr int VPL = (kVals + 31) / 32;  // values per lane
+    const StreamK sk = make_sk(a, ncta);
+    const long long u0 = sk.start(cta);
+    int u = (int)u0;
+    const int uend = (int)sk.start(cta + 1);
+    int rt = u / a.NG;
+    int gb = u - rt * a.NG;
+    while (u < uend) {
+        const int ge = min(a.NG, gb + (uend - u));
+        const bool full_tile = (gb == 0 && ge == a.NG);
+        mbar_wait(&sm.red_full[es.rb], es.rphase);
+        const float *rbuf = sm.red + (size_t)es.rb * CW * kVals;
+        float v[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; i++) {
+            const int idx = lane + 32 * i;
+            float acc = 0.f;
+            if (idx < kVals) {
+#pragma unroll
+                for (int w = 0; w < CW; w++) acc += rbuf[w * kVals + idx];
+            }
+            v[i] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.red_empty[es.rb]);
+        if (++es.rb == kRedBufs) {
+            es.rb = 0;
+            es.rphase ^= 1;
+        }
+        bool do_final = full_tile;
+        if (!full_tile && a.atomic_add) {
+            // residual accumulate: every contributor of a split tile adds its partial straight into the fp32 residual
+            // with RED.ADD (fire and forget: no fence, no counter, nothing on the critical path).  The order of the
+            // <= 3 partial adds is not fixed, so the last bit of the residual may vary run to run.
+#pragma unroll
+            for (int i = 0; i < VPL; i++) {
+                const int idx = lane + 32 * i;
+                const int row = idx / NCOLS, col = idx % NCOLS;
+                if (idx < kVals && col < a.M) atomicAdd(reinterpret_cast<float *>(a.y) + (size_t)col * a.ldy + (size_t)rt * 16 + row, v[i]);
+            }
+        } else if (!full_tile) {
+            // stream-K fix-up: park the partial; the last contributor to arrive sums all of them in CTA order
+            const long long tb = (long long)rt * a.NG;
+            const int c_first = sk.cta_of(tb);
+            const int c_last = sk.cta_of(tb + a.NG - 1);
+            const int rec = (u0 >= tb) ? 0 : 1;  // 0: this tile holds my first unit, 1: it is my tail tile
+            float *mine = a.partials + ((size_t)cta * 2 + rec) * kVals;
+#pragma unroll
+            for (int i = 0; i < VPL; i++)
+                if (lane + 32 * i < kVals) mine[lane + 32 * i] = v[i];
+            __threadfence();
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) {
+                const unsigned prev = atomicAdd(&a.counters[rt], 1u);
+                last = (prev == (unsigned)(c_last - c_first)) ? 1 : 0;
+                if (last) a.counters[rt] = 0;  // every contributor has arrived: re-arm for the next launch
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            do_final = last != 0;
+            if (do_final) {
+                __threadfence();
+#pragma unroll
+                for (int i = 0; i < VPL; i++) {
+                    const int idx = lane + 32 * i;
+                    float acc = 0.f;
+                    if (idx < kVals) {
+                        for (int c = c_first; c <= c_last; c++) {
+                            const int r = (sk.start(c) >= tb) ? 0 : 1;
+                            acc += ldg_cg_f32(a.partials + ((size_t)c * 2 + r) * kVals + idx);
+                        }
+                    }
+                    v[i] = acc;
+                }
+            }
+        }
+        if (do_final) {
+            if (a.pair_mode) {
+                // rows 0-7 = gate, rows 8-15 = up of the same output channel: y = SiLU(gate) * up
+                // (reference SiLuMul_half, llm/src/nn_modules/cuda/Int4llamaDecoderLayer.cu:21-30; fp32 here)
+                if (NCOLS == 1) {
+                    const float up = __shfl_down_sync(0xffffffffu, v[0], 8);
+                    if (lane < 8) {
+                        const float gte = v[0];
+                        const float act = gte / (1.f + __expf(-gte));
+                        reinterpret_cast<__half *>(a.y)[(size_t)rt * 8 + lane] = __float2half(act * up);
+                    }
+                } else {
+                    // idx = row*8 + col: lane holds rows 4i + lane/8; the partner row+8 is slot i+2 of the same lane
+#pragma unroll
+                    for (int i = 0; i < VPL / 2; i++) {
+                        const int row = 4 * i + (lane >> 3), col = lane & 7;
+                        if (col < a.M) {
+                            const float gte = v[i], up = v[i + VPL / 2];
+                            const float act = gte / (1.f + __expf(-gte));
+                            reinterpret_cast<__half *>(a.y)[(size_t)col * a.ldy + (size_t)rt * 8 + row] = __float2half(act * up);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < VPL; i++) {
+                    const int idx = lane + 32 * i;
+                    const int row = idx / NCOLS, col = idx % NCOLS;
+                    if (idx < kVals && col < a.M) {
+                        const size_t o = (size_t)col * a.ldy + (size_t)rt * 16 + row;
+                        if (a.epi == EPI_STORE_HALF)
+                            reinterpret_cast<__half *>(a.y)[o] = __float2half(v[i]);
+                        else if (a.epi == EPI_STORE_F32)
+                            reinterpret_cast<float *>(a.y)[o] = v[i];
+                        else
+                            reinterpret_cast<float *>(a.y)[o] += v[i];
+                    }
+                }
+            }
+        }
+        u += ge - gb;
+        rt++;
+        gb = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// consumer prologue: activations -> (optional RMSNorm) -> two int8 planes per 128-group in MMA-B order, plus the
+// per-group step and integer sum.  Ends with a consumer-wide named barrier (id 1).
+// ------------------------------------------------------------------------------------------------------------------
+template <int NCOLS, int CW>
+TCE_DEVINL void stage_activations(const KArgs &a, const Smem &sm, int x_pitch, int ctid, int cw, int lane) {
+    constexpr int kConsumerThreads = CW * 32;
+    const int units = a.IC / 8;
+#pragma unroll 1
+    for (int col = 0; col < NCOLS; col++) {
+        uint8_t *xcol = sm.xs + (size_t)col * x_pitch;
+        float inv = 1.f;
+        if (a.x_mode == X_RMSNORM_F32 && col < a.M) {
+            const float *xr = reinterpret_cast<const float *>(a.x) + (size_t)col * a.ldx;
+            float ss = 0.f;
+            for (int ui = ctid; ui < units; ui += kConsumerThreads) {
+                float4 v0 = *reinterpret_cast<const float4 *>(xr + ui * 8);
+                float4 v1 = *reinterpret_cast<const float4 *>(xr + ui * 8 + 4);
+                ss += v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w;
+                ss += v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) sm.rms[col * CW + cw] = ss;
+            named_bar_sync(1, kConsumerThreads);
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < CW; w++) tot += sm.rms[col * CW + w];
+            inv = rsqrtf(tot / (float)a.IC + a.eps);
+        }
+        // quantise + stage one 8-element unit (v) of activation column `col`
+        auto emit = [&](int ui, bool valid, const float(&v)[8]) {
+            // Activations enter the integer tensor path as 15-bit block fixed point: per 128-group,
+            // X = rint(x * 16256 / max|x|) = 128*hi + lo with hi in [-127,127], lo in [-64,63] (two int8 planes).
+            // |x - step*X| <= max|x_group| / 32512, i.e. below fp16's own rounding for all but the smallest elements
+            // of a group; the integer dot products that follow are exact.
+            float amax = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            const float qinv = (amax > 0.f) ? (16256.f / amax) : 0.f;
+            int hi[8], lo[8], sx = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int X = __float2int_rn(v[i] * qinv);
+                hi[i] = (X + 64) >> 7;
+                lo[i] = X - (hi[i] << 7);
+                sx += X;
+            }
+            // B-fragment order of mma.m16n8k32: k-slots 4t..4t+3 <- elements (0,2,4,6) of the word (the bytes of
+            // w & 0x0f0f0f0f), k-slots 16+4t.. <- elements (1,3,5,7) (the bytes of (w>>4) & 0x0f0f0f0f).
+            auto pack4 = [](int b0, int b1, int b2, int b3) {
+                return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
+            };
+            uint4 o;
+            o.x = pack4(hi[0], hi[2], hi[4], hi[6]);
+            o.y = pack4(hi[1], hi[3], hi[5], hi[7]);
+            o.z = pack4(lo[0], lo[2], lo[4], lo[6]);
+            o.w = pack4(lo[1], lo[3], lo[5], lo[7]);
+            // units of a group are stored j-major so that the four t-lanes of one LDS.128 hit consecutive slots
+            const int G = ui >> 4, tj = ui & 15;  // ui = G*16 + 4*t + j
+            const int pos = G * 16 + (tj & 3) * 4 + (tj >> 2);
+            if (valid) *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = o;
+            sx += __shfl_xor_sync(0xffffffffu, sx, 8);
+            sx += __shfl_xor_sync(0xffffffffu, sx, 4);
+            sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+            sx += __shfl_xor_sync(0xffffffffu, sx, 1);
+            if (valid && (lane & 15) == 0) {
+                sm.gx[col * a.NG + G] = (amax > 0.f) ? (amax / 16256.f) : 0.f;  // step of the group
+                sm.gsum[col * a.NG + G] = sx;                                     // sum of X over the group
+            }
+        };
+        // `units` is a multiple of 16, not of 32: trip counts are warp-uniform so that the half-warp shuffles in emit()
+        // always run with all 32 lanes.  Loads of several iterations are issued before any is consumed.
+        if (a.x_mode == X_RMSNORM_F32) {
+            constexpr int PRE = 2;
+            for (int ui0 = 0; ui0 < units; ui0 += PRE * kConsumerThreads) {
+                float4 r0[PRE], r1[PRE], g0[PRE], g1[PRE];
+#pragma unroll
+                for (int k = 0; k < PRE; k++) {
+                    const int ui = ui0 + k * kConsumerThreads + ctid;
+                    if (ui < units && col < a.M) {
+                        const float *xr = reinterpret_cast<const float *>(a.x) + (size_t)col * a.ldx + ui * 8;
+                        r0[k] = *reinterpret_cast<const float4 *>(xr);
+                        r1[k] = *reinterpret_cast<const float4 *>(xr + 4);
+                        g0[k] = *reinterpret_cast<const float4 *>(a.gamma + ui * 8);
+                        g1[k] = *reinterpret_cast<const float4 *>(a.gamma + ui * 8 + 4);
+                    } else {
+                        r0[k] = r1[k] = g0[k] = g1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < PRE; k++) {
+                    if (ui0 + k * kConsumerThreads >= units) break;  // warp-uniform
+                    const int ui = ui0 + k * kConsumerThreads + ctid;
+                    float v[8];
+                    v[0] = (r0[k].x * inv) * g0[k].x; v[1] = (r0[k].y * inv) * g0[k].y; v[2] = (r0[k].z * inv) * g0[k].z; v[3] = (r0[k].w * inv) * g0[k].w;
+                    v[4] = (r1[k].x * inv) * g1[k].x; v[5] = (r1[k].y * inv) * g1[k].y; v[6] = (r1[k].z * inv) * g1[k].z; v[7] = (r1[k].w * inv) * g1[k].w;
+                    emit(ui, ui < units, v);
+                }
+            }
+        } else {
+            constexpr int PRE = 4;
+            for (int ui0 = 0; ui0 < units; ui0 += PRE * kConsumerThreads) {
+                uint4 raw[PRE];
+#pragma unroll
+                for (int k = 0; k < PRE; k++) {
+                    const int ui = ui0 + k * kConsumerThreads + ctid;
+                    raw[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (ui < units && col < a.M) raw[k] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(a.x) + (size_t)col * a.ldx + ui * 8);
+                }
+#pragma unroll
+                for (int k = 0; k < PRE; k++) {
+                    if (ui0 + k * kConsumerThreads >= units) break;  // warp-uniform
+                    const int ui = ui0 + k * kConsumerThreads + ctid;
+                    const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw[k]);
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float2 f = __half22float2(h2[i]);
+                        v[2 * i] = f.x;
+                        v[2 * i + 1] = f.y;
+                    }
+                    emit(ui, ui < units, v);
+                }
+            }
+        }
+    }
+    named_bar_sync(1, kConsumerThreads);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// consumer main loop
+// ------------------------------------------------------------------------------------------------------------------
+template <int NCOLS, int CW>
+TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState &cs, int x_pitch, int cta, int ncta, int cw, int lane) {
+    constexpr int kVals = 16 * NCOLS;
+    constexpr int GPW = kStageGroups / CW;  // groups per consumer warp per stage
+    const int g = lane >> 2, t = lane & 3;
+    const StreamK sk = make_sk(a, ncta);
+    int u = (int)sk.start(cta);
+    const int uend = (int)sk.start(cta + 1);
+    int gb = u - (u / a.NG) * a.NG;
+    while (u < uend) {
+        const int ge = min(a.NG, gb + (uend - u));
+        // this tile's scales / zeros slab (it lands together with the tile's first weight stage)
+        const uint8_t *mbase = sm.meta + (size_t)rs.mslot * sm.meta_bytes;
+        const __half *msA = reinterpret_cast<const __half *>(mbase) + g * a.sf_w;
+        const __half *msB = msA + 8 * a.sf_w;
+        const uint32_t *mzA = reinterpret_cast<const uint32_t *>(mbase + 16 * a.sf_w * 2) + g * a.zeros_w;
+        const uint32_t *mzB = mzA + 8 * a.zeros_w;
+        constexpr int NT = (NCOLS == 1) ? 2 : 4;
+        float tot[NT];
+#pragma unroll
+        for (int i = 0; i < NT; i++) tot[i] = 0.f;
+
+        for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
+            const int n = min(kStageGroups, ge - g0);
+            mbar_wait(&sm.full_bar[rs.stage], rs.phase);
+            const uint8_t *sbase = sm.stages + (size_t)rs.stage * kStageBytes;
+#pragma unroll
+            for (int q = 0; q < GPW; q++) {
+                const int gi = cw + q * CW;
+                if (gi < n) {
+                    const int G = g0 + gi;
+                    // per-group scale and zero point of rows g and g+8
+                    const float sAq = __half2float(msA[G]), sBq = __half2float(msB[G]);
+                    const int zsh = (G & 7) * 4;
+                    const int zAq = (int)((mzA[G >> 3] >> zsh) & 0xFu);
+                    const int zBq = (int)((mzB[G >> 3] >> zsh) & 0xFu);
+                    const uint8_t *sp = sbase + gi * 64 + t * 16;
+                    const uint4 wa = *reinterpret_cast<const uint4 *>(sp + g * kRowPitch);
+                    const uint4 wb = *reinterpret_cast<const uint4 *>(sp + (g + 8) * kRowPitch);
+                    const uint32_t wav[4] = {wa.x, wa.y, wa.z, wa.w};
+                    const uint32_t wbv[4] = {wb.x, wb.y, wb.z, wb.w};
+                    const uint8_t *xp = sm.xs + ((NCOLS == 1) ? 0 : (size_t)g * x_pitch) + ((size_t)G * 16 + t) * 16;
+                    // nibbles -> bytes: w & 0x0f0f0f0f = (n0,n2,n4,n6), (w>>4) & 0x0f0f0f0f = (n1,n3,n5,n7): 3 ALU ops per
+                    // 8 weights.  Two independent accumulator chains per activation plane.
+                    int ch[2][4], cl[2][4];
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) ch[e][i] = cl[e][i] = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint4 xv = *reinterpret_cast<const uint4 *>(xp + j * 64);
+                        const uint32_t a0 = wav[j] & 0x0f0f0f0fu, a2 = (wav[j] >> 4) & 0x0f0f0f0fu;
+                        const uint32_t a1 = wbv[j] & 0x0f0f0f0fu, a3 = (wbv[j] >> 4) & 0x0f0f0f0fu;
+                        mma_m16n8k32_u8s8(ch[j & 1], a0, a1, a2, a3, xv.x, xv.y);
+                        mma_m16n8k32_u8s8(cl[j & 1], a0, a1, a2, a3, xv.z, xv.w);
+                    }
+                    // exact integer group result: sum_k q*X - z*sum_k X, X = 128*hi + lo
+                    if (NCOLS == 1) {
+                        const int sxv = sm.gsum[G];
+                        const float st = sm.gx[G];
+                        const int vA = ((ch[0][0] + ch[1][0]) << 7) + (cl[0][0] + cl[1][0]) - zAq * sxv;
+                        const int vB = ((ch[0][2] + ch[1][2]) << 7) + (cl[0][2] + cl[1][2]) - zBq * sxv;
+                        tot[0] += (sAq * st) * (float)vA;
+                        tot[1] += (sBq * st) * (float)vB;
+                    } else {
+                        const int sx0 = sm.gsum[(2 * t) * a.NG + G], sx1 = sm.gsum[(2 * t + 1) * a.NG + G];
+                        const float st0 = sm.gx[(2 * t) * a.NG + G], st1 = sm.gx[(2 * t + 1) * a.NG + G];
+                        const int vA0 = ((ch[0][0] + ch[1][0]) << 7) + (cl[0][0] + cl[1][0]) - zAq * sx0;
+                        const int vA1 = ((ch[0][1] + ch[1][1]) << 7) + (cl[0][1] + cl[1][1]) - zAq * sx1;
+                        const int vB0 = ((ch[0][2] + ch[1][2]) << 7) + (cl[0][2] + cl[1][2]) - zBq * sx0;
+                        const int vB1 = ((ch[0][3] + ch[1][3]) << 7) + (cl[0][3] + cl[1][3]) - zBq * sx1;
+                        tot[0] += (sAq * st0) * (float)vA0;
+                        tot[1] += (sAq * st1) * (float)vA1;
+                        tot[2] += (sBq * st0) * (float)vB0;
+                        tot[3] += (sBq * st1) * (float)vB1;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty_bar[rs.stage]);
+            if (++rs.stage == kStages) {
+                rs.stage = 0;
+                rs.phase ^= 1;
+            }
+        }
+
+        // ---- hand the tile partial to the epilogue warp (no consumer-to-consumer wait) ----
+        mbar_wait(&sm.red_empty[cs.rb], cs.rphase ^ 1);
+        float *rbuf = sm.red + ((size_t)cs.rb * CW + cw) * kVals;
+        if (NCOLS == 1) {
+            if (t == 0) {
+                rbuf[g] = tot[0];
+                rbuf[g + 8] = tot[1];
+            }
+        } else {
+            rbuf[g * NCOLS + 2 * t] = tot[0];
+            rbuf[g * NCOLS + 2 * t + 1] = tot[1];
+            rbuf[(g + 8) * NCOLS + 2 * t] = tot[2];
+            rbuf[(g + 8) * NCOLS + 2 * t + 1] = tot[3];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.red_full[cs.rb]);
+        if (++cs.rb == kRedBufs) {
+            cs.rb = 0;
+            cs.rphase ^= 1;
+        }
+        if (++rs.mslot == kMetaSlots) rs.mslot = 0;
+        u += ge - gb;
+        gb = 0;
+    }
+}
+
+}  // namespace gemv
+}  // namespace tce
