@@ -132,6 +132,9 @@ TCE_API int tce_llama_decode_host(tce_llama *m, int token, int pos, float *logit
 TCE_API const float *tce_llama_logits(tce_llama *m);          /* device float[vocab] */
 TCE_API void *tce_llama_kv_cache(tce_llama *m, int layer, int which); /* which: 0 K, 1 V; half[KVH][max_ctx][hd] */
 TCE_API int tce_llama_kernels_per_step(tce_llama *m);
+/* debugging aid: device pointers of the step's intermediate buffers: 0 residual float[E], 1 qkv half[(H+2KVH)*hd],
+ * 2 attention output half[H*hd], 3 SiLU(gate)*up half[F] (values of the LAST layer after a step) */
+TCE_API void *tce_llama_debug_buffer(tce_llama *m, int which);
 /* measurement aid: enqueue only the W4A16 GEMV launches of one decode step (4 per layer + lm_head, the same fused
  * kernels with the same arguments) so the dominant kernel can be timed with CUDA events; returns the launch count */
 TCE_API int tce_llama_enqueue_gemvs(tce_llama *m);

@@ -306,6 +306,7 @@ int tce_llama_enqueue_gemvs(tce_llama *m) {
     if (e != cudaSuccess) return tce_fail_cuda(e, "tce_llama_enqueue_gemvs");
     return n;
 }
+void *tce_llama_debug_buffer(tce_llama *m, int which) { return m ? reinterpret_cast<LlamaDecoder *>(m)->debug_buffer(which) : nullptr; }
 int tce_llama_kernels_per_step(tce_llama *m) { return m ? reinterpret_cast<LlamaDecoder *>(m)->kernels_per_step() : TCE_ERR_INVALID; }
 
 }  // extern "C"

@@ -19,6 +19,15 @@ class LlamaDecoder {
     const float *logits() const { return d_logits_; }
     void *kv_cache(int layer, int which) const;
     int kernels_per_step() const { return kernels_per_step_; }
+    void *debug_buffer(int which) const {
+        switch (which) {
+            case 0: return d_resid_;
+            case 1: return d_qkv_;
+            case 2: return d_attn_;
+            case 3: return d_act_;
+            default: return nullptr;
+        }
+    }
     cudaError_t enqueue_gemvs(int *count);
 
    private:

@@ -135,6 +135,12 @@ class LlamaModel:
         ptr = self.ctx.L.tce_llama_kv_cache(self.h, layer, which)
         return _tensor_from_ptr(ptr, (self.geom.num_kv_heads, self.max_ctx, self.geom.head_dim), torch.float16, self.ctx.device)
 
+    def debug_buffer(self, which: int) -> torch.Tensor:
+        g = self.geom
+        shape, dt = {0: ((g.embed_dim,), torch.float32), 1: (((g.num_heads + 2 * g.num_kv_heads) * g.head_dim,), torch.float16),
+                     2: ((g.num_heads * g.head_dim,), torch.float16), 3: ((g.hidden_dim,), torch.float16)}[which]
+        return _tensor_from_ptr(self.ctx.L.tce_llama_debug_buffer(self.h, which), shape, dt, self.ctx.device)
+
     def close(self):
         if self.h:
             self.ctx.L.tce_llama_destroy(self.h)
