@@ -35,9 +35,13 @@ TCE_DEVINL void grid_wait(const unsigned *sync, unsigned target) {  // one threa
     while (true) {
         unsigned v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
-        if (v >= target) return;
+        if (v >= target) break;
         if (clock64() - t0 > 6000000000LL) __trap();
     }
+    // L1 is not coherent: buffers produced by other CTAs earlier in THIS kernel (residual, qkv, attention output...)
+    // may still sit in this SM's L1 from a previous phase.  A gpu-scope fence makes ptxas emit CCTL.IVALL, which drops
+    // every L1 line of the SM before the consumers (released by the named barrier that follows) read them.
+    __threadfence();
 }
 TCE_DEVINL void grid_arrive(unsigned *sync) {  // one thread, after the role's writes were fenced
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync) : "memory");
