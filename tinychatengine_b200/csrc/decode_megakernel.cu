@@ -11,8 +11,9 @@
 //     activations (fused RMSNorm), run the integer-MMA GEMV, or execute attention / embedding / arg-max work items.
 //   * 1 epilogue warp: fused epilogues (fp16 store, residual RED.ADD, SiLU*mul, fp32 logits), then signals the grid
 //     barrier for the phase.
-// Grid barrier = one monotonically increasing counter (red.release / ld.acquire at gpu scope); every CTA arrives once
-// per phase.  All waits are bounded (trap after ~3 s) so a protocol bug is a launch failure, not a hung GPU.
+// Grid barrier = one arrival counter PER PHASE (red.release / ld.acquire at gpu scope); every CTA arrives exactly once
+// per phase and phase p starts when counter[p-1] == #CTAs.  (A single running counter would be wrong: the epilogue
+// warp of a CTA that owns no tile of a phase arrives for it immediately, possibly phases ahead of everybody else.)  All waits are bounded (trap after ~3 s) so a protocol bug is a launch failure, not a hung GPU.
 #include <stdio.h>
 
 #include "attention_impl.cuh"
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const __grid_co
             epilogue<1, kCW>(a, sm, es, cta, ncta, lane);
             __threadfence();
             __syncwarp();
-            if (lane == 0) grid_arrive(m.sync);
+            if (lane == 0) grid_arrive(m.sync + p);
         }
         return;
     }
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const __grid_co
     uint32_t aparity = 0;
     for (int p = 0; p < m.nphases; p++) {
         if (p > 0) {
-            if (ctid == 0) grid_wait(m.sync, (unsigned)ncta * (unsigned)p);
+            if (ctid == 0) grid_wait(m.sync + (p - 1), (unsigned)ncta);
             named_bar_sync(1, kConsumerThreads);
         }
         const int type = m.phases[p].type;
@@ -162,11 +163,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const __grid_co
         // phases executed by the consumers: everyone's writes fenced, then one arrival per CTA
         __threadfence();
         named_bar_sync(1, kConsumerThreads);
-        if (ctid == 0) grid_arrive(m.sync);
+        if (ctid == 0) grid_arrive(m.sync + p);
     }
     // greedy token: decoded once every CTA has contributed its local maximum
     if (cta == 0 && ctid == 0 && m.next_token) {
-        grid_wait(m.sync, (unsigned)ncta * (unsigned)m.nphases);
+        grid_wait(m.sync + (m.nphases - 1), (unsigned)ncta);
         const unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(m.argmax_cell);
         *m.next_token = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
     }

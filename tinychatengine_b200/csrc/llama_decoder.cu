@@ -297,13 +297,14 @@ cudaError_t LlamaDecoder::build_megakernel() {
     }
     DCK(cudaMalloc((void **)&d_phases_, ph.size() * sizeof(MegaPhase)));
     DCK(cudaMemcpy(d_phases_, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
-    DCK(cudaMalloc((void **)&d_sync_, 2 * sizeof(unsigned long long)));
-    DCK(cudaMemset(d_sync_, 0, 2 * sizeof(unsigned long long)));
+    sync_bytes_ = ph.size() * sizeof(unsigned);
+    DCK(cudaMalloc((void **)&d_sync_, sizeof(unsigned long long) + sync_bytes_));
+    DCK(cudaMemset(d_sync_, 0, sizeof(unsigned long long) + sync_bytes_));
     margs_ = MegaArgs{};
     margs_.phases = d_phases_;
     margs_.nphases = (int)ph.size();
-    margs_.sync = reinterpret_cast<unsigned *>(d_sync_);
-    margs_.argmax_cell = d_sync_ + 1;
+    margs_.argmax_cell = d_sync_;
+    margs_.sync = reinterpret_cast<unsigned *>(d_sync_ + 1);
     margs_.embed = (const __half *)w_.embed_f16;
     margs_.resid = d_resid_;
     margs_.E = cfg_.embed_dim;
@@ -319,7 +320,7 @@ cudaError_t LlamaDecoder::build_megakernel() {
 
 cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only) {
     if (mega_ && !gemv_only) {
-        DCK(cudaMemsetAsync(d_sync_, 0, sizeof(unsigned), s));
+        DCK(cudaMemsetAsync(d_sync_ + 1, 0, sync_bytes_, s));
         MegaArgs m = margs_;
         m.tokpos = tokpos;
         return launch_megakernel(ctx_, m, s);

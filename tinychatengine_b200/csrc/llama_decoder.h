@@ -47,7 +47,8 @@ class LlamaDecoder {
     bool mega_ = true;              // one persistent kernel per token (TCE_MEGAKERNEL=0: one kernel per op in a CUDA graph)
     int mega_attn_chunk_ = 64;
     MegaPhase *d_phases_ = nullptr;
-    unsigned long long *d_sync_ = nullptr;  // [0] grid barrier counter, [1] arg-max cell
+    unsigned long long *d_sync_ = nullptr;  // [0] arg-max cell, then one 32-bit grid-barrier counter per phase
+    size_t sync_bytes_ = 0;
     MegaArgs margs_{};
 
     Ctx *ctx_ = nullptr;

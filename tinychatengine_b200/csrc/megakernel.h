@@ -18,7 +18,7 @@ struct MegaPhase {
 struct MegaArgs {
     const MegaPhase *phases;  // device array
     int nphases;
-    unsigned *sync;           // grid barrier counter, zeroed before every launch
+    unsigned *sync;           // grid barrier counters [nphases], zeroed before every launch
     const int *tokpos;        // {token, position}
     const __half *embed;      // [vocab][E]
     float *resid;             // [E]
