@@ -1,6 +1,7 @@
 // common.cuh -- device-side building blocks shared by the sm_100a kernels of libtce_b200.
 // Raw PTX wrappers only (mbarrier, bulk async copy = TMA 1-D, mma.sync, PDL); no CUTLASS, no Triton.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -78,6 +79,16 @@ TCE_DEVINL void mbar_arrive_expect_tx_pred(uint64_t *bar, uint32_t bytes, uint32
                      smem_u32(bar)),
                  "r"(bytes), "r"(pred)
                  : "memory");
+}
+
+// 2-D tiled TMA load (UTMALDG): one instruction moves a [rows x bytes] box; coordinates in elements of the map.
+TCE_DEVINL void tma_load_2d_pred(void *dst_smem, const void *tmap, int x, int y, uint64_t *bar, uint64_t policy, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;\n\t}" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy), "r"(pred)
+        : "memory");
 }
 
 TCE_DEVINL void bulk_g2s_nohint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {

@@ -90,8 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const __grid_co
         const uint64_t policy = l2_policy_evict_first();
         for (int p = 0; p < m.nphases; p++) {
             if (m.phases[p].type != PH_GEMV) continue;
-            const KArgs a = m.phases[p].g;
-            produce(a, sm, rs, cta, ncta, warp, lane, policy);
+            produce(m.phases[p].g, sm, rs, cta, ncta, lane, policy);  // by reference: the TMA unit needs the map's global address
         }
         return;
     }
@@ -179,7 +178,7 @@ size_t megakernel_smem_bytes(int max_ic, int nrep, int chunk) {
     return ((Layout<1, kCW>::bytes(max_ic) + 127) & ~(size_t)127) + attn::smem_bytes(nrep, chunk) + 2 * sizeof(uint64_t) + 16;
 }
 
-void megakernel_fill_gemv(Ctx *ctx, const W4GemvParams &p, MegaPhase *ph, int ncta) {
+cudaError_t megakernel_fill_gemv(Ctx *ctx, const W4GemvParams &p, MegaPhase *ph, int ncta) {
     KArgs &a = ph->g;
     ph->type = PH_GEMV;
     for (int i = 0; i < 3; i++) a.seg[i] = p.seg[i < p.nseg ? i : 0];
@@ -206,6 +205,12 @@ void megakernel_fill_gemv(Ctx *ctx, const W4GemvParams &p, MegaPhase *ph, int nc
     a.dbg = nullptr;
     a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
     a.aligned = (!a.atomic_add && a.num_tiles >= ncta) ? 1 : 0;
+    a.sg = a.NG < kStageGroups ? a.NG : kStageGroups;
+    for (int i = 0; i < p.nseg; i++) {
+        cudaError_t e = encode_w4_tmap(&a.tmap[i], p.seg[i].w, p.seg[i].rows, p.IC, a.sg, p.pair_mode ? 8 : 16);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_megakernel(Ctx *ctx, const MegaArgs &m, cudaStream_t stream) {

@@ -1,5 +1,6 @@
 // kernels.h -- internal C++ launch interface of libtce_b200 (the public face is include/tce_b200.h).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -68,6 +69,7 @@ struct W4GemvParams {
 cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p);
 cudaError_t launch_w4a16_gemv_simple(Ctx *ctx, const W4GemvParams &p);
 size_t w4a16_gemv_smem_bytes(int ncols, int consumer_warps, int IC);
+cudaError_t encode_w4_tmap(CUtensorMap *out, const void *w, int rows, int IC, int sg, int box_rows);
 
 // host-side mirror of the stream-K partition used by the kernel (unit-tested on the CPU)
 struct StreamK {

@@ -270,7 +270,7 @@ void LlamaDecoder::build_ops() {
 
 cudaError_t LlamaDecoder::build_megakernel() {
     const int ncta = ctx_->num_sms;
-    std::vector<MegaPhase> ph(ops_.size());
+    std::vector<MegaPhase> ph(ops_.size());  // (operator new honours alignas(64) in C++17)
     int max_ic = 0;
     for (size_t i = 0; i < ops_.size(); i++) {
         memset(&ph[i], 0, sizeof(MegaPhase));
@@ -289,7 +289,7 @@ cudaError_t LlamaDecoder::build_megakernel() {
                 break;
             }
             case OP_GEMV:
-                megakernel_fill_gemv(ctx_, ops_[i].g, &ph[i], ncta);
+                DCK(megakernel_fill_gemv(ctx_, ops_[i].g, &ph[i], ncta));
                 if (ops_[i].g.IC > max_ic) max_ic = ops_[i].g.IC;
                 if (ph[i].g.num_tiles > ctx_->gemv_max_tiles) return cudaErrorInvalidValue;
                 break;

@@ -8,9 +8,9 @@ namespace tce {
 
 enum MegaPhaseType : int { PH_EMBED = 0, PH_GEMV = 1, PH_ATTN = 2, PH_ARGMAX = 3 };
 
-struct MegaPhase {
+struct alignas(64) MegaPhase {
     int type;
-    int pad[3];
+    int pad[15];
     gemv::KArgs g;      // PH_GEMV
     AttnDecodeArgs at;  // PH_ATTN
 };
@@ -32,7 +32,7 @@ struct MegaArgs {
 };
 
 size_t megakernel_smem_bytes(int max_ic, int nrep, int chunk);
-void megakernel_fill_gemv(Ctx *ctx, const W4GemvParams &p, MegaPhase *ph, int ncta);
+cudaError_t megakernel_fill_gemv(Ctx *ctx, const W4GemvParams &p, MegaPhase *ph, int ncta);
 cudaError_t launch_megakernel(Ctx *ctx, const MegaArgs &m, cudaStream_t stream);
 
 }  // namespace tce

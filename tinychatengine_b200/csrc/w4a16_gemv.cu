@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
 
     if (warp < kProducerWarps) {
         RingState rs;
-        produce(a, sm, rs, cta, ncta, warp, lane, l2_policy_evict_first());
+        produce(a, sm, rs, cta, ncta, lane, l2_policy_evict_first());
         // this CTA has requested its last byte of weights: a programmatically dependent kernel may become resident
         pdl_launch_dependents();
         return;
@@ -112,6 +112,33 @@ __global__ void w4a16_gemv_simple_kernel(const KArgs a, int total_rows) {
     }
 }
 
+}  // namespace
+
+// 2-D tensor map of one packed weight segment: uint32 [rows][IC/8], box = [box_rows][sg*16 words], no swizzle.
+// cuTensorMapEncodeTiled is a pure host-side encoder; it is reached through the runtime's driver entry point so the
+// library does not link libcuda directly.
+cudaError_t encode_w4_tmap(CUtensorMap *out, const void *w, int rows, int IC, int sg, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !sym) return e != cudaSuccess ? e : cudaErrorNotSupported;
+        fn = reinterpret_cast<EncodeFn>(sym);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)(IC / 8), (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(IC / 2)};
+    const cuuint32_t box[2] = {(cuuint32_t)(sg * 16), (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(w), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+namespace {
+
 KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     KArgs a;
     for (int i = 0; i < 3; i++) a.seg[i] = p.seg[i < p.nseg ? i : 0];
@@ -139,6 +166,7 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     a.dbg = ctx->gemv_dbg;
     a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
     a.aligned = 0;
+    a.sg = a.NG < kStageGroups ? a.NG : kStageGroups;
     return a;
 }
 
@@ -198,6 +226,10 @@ cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p) {
         if (p.seg[i].rows % (p.pair_mode ? 8 : 16)) return cudaErrorInvalidValue;
     if (p.pair_mode && (p.nseg != 2 || p.seg[0].rows != p.seg[1].rows)) return cudaErrorInvalidValue;
     if (a.num_tiles > ctx->gemv_max_tiles) return cudaErrorInvalidValue;
+    for (int i = 0; i < p.nseg; i++) {
+        cudaError_t e = encode_w4_tmap(&a.tmap[i], p.seg[i].w, p.seg[i].rows, p.IC, a.sg, p.pair_mode ? 8 : 16);
+        if (e != cudaSuccess) return e;
+    }
     const int cw = ctx->gemv_consumer_warps == 16 ? 16 : 8;
     if (p.M > 1 && (int)w4a16_gemv_smem_bytes(8, cw, p.IC) > ctx->smem_optin) {
         // the 8-column activation tile does not fit next to the weight ring: one pass per activation row

@@ -7,10 +7,10 @@
 //
 //  * work unit = (16-row tile, one 128-k group) = 1 KiB of packed weights; the units of a launch are cut into equal
 //    contiguous per-CTA ranges (stream-K) or, for epilogues that need one ordered writer, at row-tile boundaries.
-//  * producers (4 warps x 4 rows): 1-D TMA bulk copies (UBLKCP) of [16 rows x <=16 groups] weight slabs into a
-//    4-stage ring guarded by full/empty mbarriers, L2 evict-first; the tile's scales/zeros slabs ride on the first
-//    stage's barrier.  Producers depend on nothing but the weights, so they may run ahead of everything else.
-//  * consumers (CW warps): conflict-free 128-bit LDS (row pitch = 64 mod 128 B); nibbles -> bytes with
+//  * producer (1 warp, 1 elected lane): ONE 2-D TMA tensor copy (UTMALDG) per stage moves the [16 rows x <=16 groups]
+//    weight box into a 4-stage ring guarded by full/empty mbarriers, L2 evict-first; the tile's scales/zeros slabs
+//    (1-D bulk copies, UBLKCP) ride on the first stage's barrier.  Producers depend on nothing but the weights, so they may run ahead of everything else.
+//  * consumers (CW warps): 128-bit LDS of the packed nibbles; nibbles -> bytes with
 //    w & 0x0f0f0f0f / (w>>4) & 0x0f0f0f0f (3 ALU ops per 8 weights); mma.sync.m16n8k32 u8 x s8 -> s32 against the
 //    activations held as two int8 planes (15-bit block fixed point per 128-group, exact integer accumulation);
 //    per-group epilogue tot += (s * step) * (acc - z * sum_X).  The 8 MMA columns carry up to 8 activation rows.
@@ -25,12 +25,11 @@
 namespace tce {
 namespace gemv {
 
-constexpr int kStageGroups = 16;                   // 128-k groups per pipeline stage (per row: 1024 B)
-constexpr int kRowPitch = kStageGroups * 64 + 64;  // 1088 B: == 64 (mod 128) -> conflict-free LDS.128
-constexpr int kStageBytes = 16 * kRowPitch;        // 17408 B
+constexpr int kStageGroups = 16;               // 128-k groups per pipeline stage (per row: up to 1024 B)
+constexpr int kStageBytes = 16 * kStageGroups * 64;  // 16 KiB: dense [16 rows][sg*64 B] box written by ONE 2-D TMA instruction
 constexpr int kStages = 4;
 constexpr int kRedBufs = 3;
-constexpr int kProducerWarps = 4;        // UBLKCP issue costs ~100 cycles per copy through one warp: four warps share the rows
+constexpr int kProducerWarps = 1;        // a stage is one UTMALDG (two in gate/up pair mode): a single elected lane keeps up
 constexpr int kMetaSlots = kStages + 1;  // per-tile scales/zeros slabs in flight (a tile spans >= 1 stage)
 
 struct KArgs {
@@ -46,9 +45,12 @@ struct KArgs {
     int epi, ldy;
     float *partials;
     unsigned *counters;
+    int sg;          // groups per stage = min(16, NG); the stage row pitch is sg*64 bytes (dense TMA box)
     int aligned;     // 1: CTA ranges are cut at row-tile boundaries (no split tiles, no fix-up)
     int atomic_add;  // 1: EPI_ADD_F32 partial tiles use RED.ADD.F32 instead of the ordered fix-up
     unsigned long long *dbg;  // optional per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
+    // one 2-D tensor map per weight segment: uint32 [rows][IC/8], box = [16 (8 in pair mode) rows][sg*16 words]
+    alignas(64) CUtensorMap tmap[3];
 };
 
 struct RowRef {
@@ -175,46 +177,56 @@ TCE_DEVINL StreamK make_sk(const KArgs &a, int ncta) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// producer warps (pw = 0..3): stream this CTA's unit range into the ring.  Warp-convergent, lane 0 issues.
+// producer warp: streams this CTA's unit range into the ring.  Warp-convergent, lane 0 issues.  `a` must be the
+// original argument block (kernel parameter or global memory), never a local copy: the TMA unit reads the tensor map
+// through its address.
 // ------------------------------------------------------------------------------------------------------------------
-TCE_DEVINL void produce(const KArgs &a, const Smem &sm, RingState &rs, int cta, int ncta, int pw, int lane, uint64_t policy) {
+TCE_DEVINL void produce(const KArgs &a, const Smem &sm, RingState &rs, int cta, int ncta, int lane, uint64_t policy) {
     const StreamK sk = make_sk(a, ncta);
     const uint32_t leader = (lane == 0) ? 1u : 0u;
-    const int meta_bytes_cur = 320 * a.zeros_w;  // bytes actually copied for this IC (<= sm.meta_bytes)
+    const uint32_t meta_bytes_cur = 320u * a.zeros_w;  // bytes actually copied for this IC (<= sm.meta_bytes)
+    const uint32_t box_bytes = 16u * a.sg * 64u;       // a stage always receives the full box (out-of-range parts are zero-filled)
     int u = (int)sk.start(cta);
     const int uend = (int)sk.start(cta + 1);
     int rt = u / a.NG;
     int gb = u - rt * a.NG;
     while (u < uend) {
         const int ge = min(a.NG, gb + (uend - u));
-        // All addresses below are warp-uniform (kernel arguments and loop counters only)
-        const RowRef r0 = tile_row(a, rt, 0), r8 = tile_row(a, rt, 8);  // rows 0-7 / 8-15 are contiguous each
-        const size_t wpitch = (size_t)(a.IC / 2);
+        // segment / row of the tile (warp-uniform)
+        int si0 = 0, row0 = rt * 16, si1 = 0, row1 = 0;
+        if (a.pair_mode) {
+            row0 = rt * 8;
+            si1 = 1;
+            row1 = rt * 8;
+        } else if (a.nseg > 1 && row0 >= a.seg[0].rows) {
+            row0 -= a.seg[0].rows;
+            si0 = 1;
+            if (a.nseg > 2 && row0 >= a.seg[1].rows) {
+                row0 -= a.seg[1].rows;
+                si0 = 2;
+            }
+        }
+        const RowRef r0 = tile_row(a, rt, 0), r8 = tile_row(a, rt, 8);
         uint8_t *mdst = sm.meta + (size_t)rs.mslot * sm.meta_bytes;
         bool first = true;
-        for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
-            const int n = min(kStageGroups, ge - g0);
+        for (int g0 = gb; g0 < ge; g0 += a.sg) {
             mbar_wait(&sm.empty_bar[rs.stage], rs.phase ^ 1);
-            {
-                uint64_t *bar = &sm.full_bar[rs.stage];
-                // producer 0 posts the byte count; the other producers' complete_tx may land first (the phase cannot
-                // complete before this single arrival, and a transiently negative tx-count is legal)
-                if (pw == 0) mbar_arrive_expect_tx_pred(bar, 16u * n * 64u + (first ? (uint32_t)meta_bytes_cur : 0u), leader);
-                uint8_t *dst = sm.stages + (size_t)rs.stage * kStageBytes;
-                const uint32_t nb = (uint32_t)n * 64u;
-                const RowRef &rr = (pw < 2) ? r0 : r8;  // rows 4*pw .. 4*pw+3
-                const int lr = (pw & 1) * 4;
-#pragma unroll
-                for (int l = 0; l < 4; l++)
-                    bulk_g2s_pred(dst + (pw * 4 + l) * kRowPitch, rr.w + (lr + l) * wpitch + (size_t)g0 * 64, nb, bar, policy, leader);
-                if (first && pw == 1) {
-                    // this tile's scales / zeros slabs ride on the full barrier of its first stage
-                    const uint32_t sb = 8u * a.sf_w * 2u, zb = 8u * a.zeros_w * 4u;
-                    bulk_g2s_pred(mdst, r0.s, sb, bar, policy, leader);
-                    bulk_g2s_pred(mdst + sb, r8.s, sb, bar, policy, leader);
-                    bulk_g2s_pred(mdst + 2 * sb, r0.z, zb, bar, policy, leader);
-                    bulk_g2s_pred(mdst + 2 * sb + zb, r8.z, zb, bar, policy, leader);
-                }
+            uint64_t *bar = &sm.full_bar[rs.stage];
+            mbar_arrive_expect_tx_pred(bar, box_bytes + (first ? meta_bytes_cur : 0u), leader);
+            uint8_t *dst = sm.stages + (size_t)rs.stage * kStageBytes;
+            if (a.pair_mode) {
+                tma_load_2d_pred(dst, &a.tmap[si0], g0 * 16, row0, bar, policy, leader);
+                tma_load_2d_pred(dst + 8 * a.sg * 64, &a.tmap[si1], g0 * 16, row1, bar, policy, leader);
+            } else {
+                tma_load_2d_pred(dst, &a.tmap[si0], g0 * 16, row0, bar, policy, leader);
+            }
+            if (first) {
+                // this tile's scales / zeros slabs ride on the full barrier of its first stage
+                const uint32_t sb = 8u * a.sf_w * 2u, zb = 8u * a.zeros_w * 4u;
+                bulk_g2s_pred(mdst, r0.s, sb, bar, policy, leader);
+                bulk_g2s_pred(mdst + sb, r8.s, sb, bar, policy, leader);
+                bulk_g2s_pred(mdst + 2 * sb, r0.z, zb, bar, policy, leader);
+                bulk_g2s_pred(mdst + 2 * sb + zb, r8.z, zb, bar, policy, leader);
             }
             __syncwarp();
             first = false;
@@ -517,8 +529,9 @@ TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState 
 #pragma unroll
         for (int i = 0; i < NT; i++) tot[i] = 0.f;
 
-        for (int g0 = gb; g0 < ge; g0 += kStageGroups) {
-            const int n = min(kStageGroups, ge - g0);
+        const int rp = a.sg * 64;  // dense row pitch of the TMA box (2-way bank conflict on the weight LDS)
+        for (int g0 = gb; g0 < ge; g0 += a.sg) {
+            const int n = min(a.sg, ge - g0);
             mbar_wait(&sm.full_bar[rs.stage], rs.phase);
             const uint8_t *sbase = sm.stages + (size_t)rs.stage * kStageBytes;
 #pragma unroll
@@ -532,8 +545,8 @@ TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState 
                     const int zAq = (int)((mzA[G >> 3] >> zsh) & 0xFu);
                     const int zBq = (int)((mzB[G >> 3] >> zsh) & 0xFu);
                     const uint8_t *sp = sbase + gi * 64 + t * 16;
-                    const uint4 wa = *reinterpret_cast<const uint4 *>(sp + g * kRowPitch);
-                    const uint4 wb = *reinterpret_cast<const uint4 *>(sp + (g + 8) * kRowPitch);
+                    const uint4 wa = *reinterpret_cast<const uint4 *>(sp + g * rp);
+                    const uint4 wb = *reinterpret_cast<const uint4 *>(sp + (g + 8) * rp);
                     const uint32_t wav[4] = {wa.x, wa.y, wa.z, wa.w};
                     const uint32_t wbv[4] = {wb.x, wb.y, wb.z, wb.w};
                     const uint8_t *xp = sm.xs + ((NCOLS == 1) ? 0 : (size_t)g * x_pitch) + ((size_t)G * 16 + t) * 16;
