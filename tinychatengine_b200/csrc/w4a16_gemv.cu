@@ -182,7 +182,13 @@ cudaError_t launch_mma(Ctx *ctx, const KArgs &a_in, bool pdl) {
         attr_set = true;
     }
     const long long U = (long long)a.num_tiles * a.NG;
-    int nc = ctx->num_sms * ctx->gemv_ctas_per_sm;
+    // Two co-resident CTAs per SM (two independent TMA rings, 16 consumer warps) stream ~25 % faster than one on large
+    // matrices (profiles/r01_gemv_microbench.jsonl: lm_head 5.1 vs 4.0 TB/s) but double the per-launch activation
+    // staging, which dominates small launches and long rows: only used when every CTA still gets >= 128 units and the
+    // activation vector is short.  "gemv_ctas_per_sm" > 1 forces it.
+    int per_sm = ctx->gemv_ctas_per_sm;
+    if (per_sm == 1 && NCOLS == 1 && CW == 8 && a.IC <= 8192 && U >= (long long)ctx->num_sms * 2 * 128) per_sm = 2;
+    int nc = ctx->num_sms * per_sm;
     if (nc > ctx->gemv_max_ctas) nc = ctx->gemv_max_ctas;
     if ((long long)nc > U) nc = (int)U;
     // Epilogues that need a single ordered writer per output (stores, SiLU*mul, deterministic residual) avoid split
