@@ -132,6 +132,15 @@ TCE_API int tce_llama_decode_host(tce_llama *m, int token, int pos, float *logit
 TCE_API const float *tce_llama_logits(tce_llama *m);          /* device float[vocab] */
 TCE_API void *tce_llama_kv_cache(tce_llama *m, int layer, int which); /* which: 0 K, 1 V; half[KVH][max_ctx][hd] */
 TCE_API int tce_llama_kernels_per_step(tce_llama *m);
+/* ---- tensor-parallel decode across the GPUs of one box (one process per GPU) --------------------------------
+ * cfg.tp_size = P > 1: heads / kv heads / hidden_dim / vocab_size in tce_llama_config are the LOCAL (1/P) sizes and the
+ * weights are the local shards (q,k,v,gate,up,lm_head: row shards; o,down: column (input-channel) shards repacked as
+ * [E][IC/P]).  The all-reduce after o_proj and down_proj runs over NVLink peer memory inside the GEMV kernels.
+ * Setup: every rank exports a 64-byte IPC handle, the host exchanges them (e.g. torch.distributed.all_gather) and
+ * every rank connects with the P handles in rank order.  tce_llama_decode_host then returns the local logits shard
+ * (float[vocab_local]) and the GLOBAL greedy token; all ranks must call it with the same token/pos sequence.   */
+TCE_API int tce_llama_tp_handle(tce_llama *m, void *handle_out_64_bytes);
+TCE_API int tce_llama_tp_connect(tce_llama *m, const void *handles_P_times_64_bytes);
 /* debugging aid: device pointers of the step's intermediate buffers: 0 residual float[E], 1 qkv half[(H+2KVH)*hd],
  * 2 attention output half[H*hd], 3 SiLU(gate)*up half[F] (values of the LAST layer after a step) */
 TCE_API void *tce_llama_debug_buffer(tce_llama *m, int which);

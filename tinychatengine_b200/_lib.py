@@ -57,6 +57,8 @@ SIGNATURES = {
     "tce_llama_logits": (C.c_void_p, [C.c_void_p]),
     "tce_llama_kv_cache": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "tce_llama_kernels_per_step": (C.c_int, [C.c_void_p]),
+    "tce_llama_tp_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tce_llama_tp_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tce_llama_debug_buffer": (C.c_void_p, [C.c_void_p, C.c_int]),
     "tce_llama_enqueue_gemvs": (C.c_int, [C.c_void_p]),
 }

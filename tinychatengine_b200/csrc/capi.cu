@@ -307,6 +307,18 @@ int tce_llama_enqueue_gemvs(tce_llama *m) {
     return n;
 }
 void *tce_llama_debug_buffer(tce_llama *m, int which) { return m ? reinterpret_cast<LlamaDecoder *>(m)->debug_buffer(which) : nullptr; }
+int tce_llama_tp_handle(tce_llama *m, void *out) {
+    if (!m || !out) return fail(TCE_ERR_INVALID, "tce_llama_tp_handle: null argument");
+    cudaError_t e = reinterpret_cast<LlamaDecoder *>(m)->tp_handle(out);
+    if (e != cudaSuccess) return tce_fail_cuda(e, "tce_llama_tp_handle");
+    return TCE_OK;
+}
+int tce_llama_tp_connect(tce_llama *m, const void *handles) {
+    if (!m || !handles) return fail(TCE_ERR_INVALID, "tce_llama_tp_connect: null argument");
+    cudaError_t e = reinterpret_cast<LlamaDecoder *>(m)->tp_connect(handles);
+    if (e != cudaSuccess) return tce_fail_cuda(e, "tce_llama_tp_connect");
+    return TCE_OK;
+}
 int tce_llama_kernels_per_step(tce_llama *m) { return m ? reinterpret_cast<LlamaDecoder *>(m)->kernels_per_step() : TCE_ERR_INVALID; }
 
 }  // extern "C"

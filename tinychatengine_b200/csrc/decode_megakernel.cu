@@ -206,6 +206,14 @@ cudaError_t megakernel_fill_gemv(Ctx *ctx, const W4GemvParams &p, MegaPhase *ph,
     a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
     a.aligned = (!a.atomic_add && a.num_tiles >= ncta) ? 1 : 0;
     a.sg = a.NG < kStageGroups ? a.NG : kStageGroups;
+    a.tp_size = 1;
+    a.tp_in = nullptr;
+    a.tp_flags = nullptr;
+    a.tp_step = nullptr;
+    a.tp_k = 0;
+    a.tp_per_step = 1;
+    a.resid_out = nullptr;
+    for (int i = 0; i < kMaxTP; i++) a.tp_out[i] = nullptr;
     for (int i = 0; i < p.nseg; i++) {
         cudaError_t e = encode_w4_tmap(&a.tmap[i], p.seg[i].w, p.seg[i].rows, p.IC, a.sg, p.pair_mode ? 8 : 16);
         if (e != cudaSuccess) return e;

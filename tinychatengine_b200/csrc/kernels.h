@@ -39,7 +39,8 @@ inline int zeros_width(int ic, int group) {  // llm/src/nn_modules/cuda/utils.cu
 }
 
 enum XMode : int { X_HALF = 0, X_RMSNORM_F32 = 1 };
-enum EpiMode : int { EPI_STORE_HALF = 0, EPI_STORE_F32 = 1, EPI_ADD_F32 = 2, EPI_SILU_MUL_HALF = 3 };
+enum EpiMode : int { EPI_STORE_HALF = 0, EPI_STORE_F32 = 1, EPI_ADD_F32 = 2, EPI_SILU_MUL_HALF = 3, EPI_TP_SCATTER_F32 = 4 };
+constexpr int kMaxTP = 8;
 
 struct W4Seg {
     const uint32_t *w;       // [rows][IC/8]
@@ -64,6 +65,16 @@ struct W4GemvParams {
     int ldy = 0;        // elements between output rows
     bool pdl = false;   // launch with programmatic stream serialization
     bool atomic_residual = false;  // EPI_ADD_F32 only: allow RED.ADD for split tiles (non-deterministic last bit)
+    // ---- tensor parallel (tp_size > 1) ----
+    int tp_size = 1;
+    // prologue (X_RMSNORM_F32): x = resid + sum_p tp_in[p][:] once tp_flags[p] >= expected, written back to resid_out
+    const float *tp_in = nullptr;        // local gather buffer [tp_size][IC] fp32 (peers store into it)
+    const unsigned *tp_flags = nullptr;  // local arrival flags [tp_size]
+    const int *tp_step = nullptr;        // device int: decode step index (flags carry step * tp_per_step + tp_k + 1)
+    int tp_k = 0, tp_per_step = 1;
+    float *resid_out = nullptr;
+    // epilogue (EPI_TP_SCATTER_F32): the finished fp32 outputs are stored into slot `rank` of every peer's gather buffer
+    float *tp_out[kMaxTP] = {};
 };
 
 cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p);

@@ -9,6 +9,7 @@
 // The residual stream is kept in fp32 (the reference's CUDA build keeps it in fp16, its CPU build in fp32).
 #include "llama_decoder.h"
 
+#include "kernels_tp.h"
 #include "megakernel.h"
 
 #include <math.h>
@@ -34,7 +35,7 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
     if (cfg.head_dim != 128) return bad("head_dim must be 128");
     if (cfg.num_layers < 1 || cfg.num_heads < 1 || cfg.num_kv_heads < 1 || cfg.num_heads % cfg.num_kv_heads) return bad("bad head configuration");
     if (cfg.embed_dim % 128 || cfg.hidden_dim % 128) return bad("embed_dim / hidden_dim must be multiples of the 128 group");
-    if (cfg.tp_size > 1) return bad("tensor parallel decode is not wired in this build");
+    if (cfg.tp_size > kMaxTP || cfg.tp_size < 0 || (cfg.tp_size > 1 && (cfg.tp_rank < 0 || cfg.tp_rank >= cfg.tp_size))) return bad("bad tensor-parallel rank/size");
     const int E = cfg.embed_dim, F = cfg.hidden_dim, H = cfg.num_heads, KVH = cfg.num_kv_heads, hd = cfg.head_dim, V = cfg.vocab_size;
     if (!w.embed_f16 || !w.layers || !w.final_norm) return bad("missing weights");
     if (!w4_ok(w.lm_head, V, E) || V % 16) return bad("lm_head shape");
@@ -59,15 +60,15 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
         if (e == cudaSuccess) e = cudaMalloc(p, bytes);
     };
     A((void **)&d->d_kv_, kv_elems * sizeof(__half));
-    A((void **)&d->d_resid_, (size_t)E * sizeof(float));
+    A((void **)&d->d_resid_, (size_t)2 * E * sizeof(float));  // two buffers: the tensor-parallel path ping-pongs the residual
     A((void **)&d->d_qkv_, (size_t)(H + 2 * KVH) * hd * sizeof(__half));
     A((void **)&d->d_attn_, (size_t)H * hd * sizeof(__half));
     A((void **)&d->d_act_, (size_t)F * sizeof(__half));
     A((void **)&d->d_logits_, (size_t)V * sizeof(float));
-    A((void **)&d->d_tokpos_, 2 * sizeof(int));
+    A((void **)&d->d_tokpos_, 4 * sizeof(int));
     A((void **)&d->d_next_, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(d->d_kv_, 0, kv_elems * sizeof(__half));
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_tokpos_, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_tokpos_, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_logits_, (size_t)V * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_next_, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->cap_stream_, cudaStreamNonBlocking);
@@ -100,6 +101,21 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
     }
     d->mega_ = getenv("TCE_MEGAKERNEL") ? atoi(getenv("TCE_MEGAKERNEL")) != 0 : true;
     d->mega_attn_chunk_ = getenv("TCE_MEGA_ATTN_CHUNK") ? atoi(getenv("TCE_MEGA_ATTN_CHUNK")) : 64;
+    d->tp_ = cfg.tp_size > 1 ? cfg.tp_size : 1;
+    if (d->tp_ > 1) {
+        // tensor parallel: one peer-visible allocation [gather A|B: 2 x P x E fp32][flags: 3 x P u32 (256-B padded)][keys: P u64]
+        d->mega_ = false;
+        d->tp_gather_floats_ = (size_t)2 * d->tp_ * E;
+        d->tp_bytes_ = d->tp_gather_floats_ * sizeof(float) + 256 + (size_t)kMaxTP * sizeof(unsigned long long);
+        if (cudaMalloc((void **)&d->tp_buf_, d->tp_bytes_) != cudaSuccess || cudaMemset(d->tp_buf_, 0, d->tp_bytes_) != cudaSuccess) {
+            *err = "tensor-parallel buffer allocation failed";
+            delete d;
+            return nullptr;
+        }
+        cudaDeviceSynchronize();
+        d->kernels_per_step_ = 1 + 7 * cfg.num_layers + 4;
+        return d;  // the op list needs the peers' pointers: built in tp_connect()
+    }
     d->build_ops();
     if (d->mega_) {
         cudaError_t me = d->build_megakernel();
@@ -127,6 +143,9 @@ LlamaDecoder::~LlamaDecoder() {
     cudaFree(d_next_);
     cudaFree(d_phases_);
     cudaFree(d_sync_);
+    for (int p = 0; p < tp_; p++)
+        if (p != cfg_.tp_rank && tp_peer_[p]) cudaIpcCloseMemHandle(tp_peer_[p]);
+    cudaFree(tp_buf_);
     if (own_rope_) {
         cudaFree(d_cos_);
         cudaFree(d_sin_);
@@ -149,6 +168,27 @@ cudaError_t LlamaDecoder::enqueue_gemvs(int *count) {
     return enqueue_step(d_tokpos_, ctx_->stream, false, true);
 }
 
+cudaError_t LlamaDecoder::tp_handle(void *out64) {
+    if (tp_ <= 1 || !tp_buf_) return cudaErrorInvalidValue;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    return cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(out64), tp_buf_);
+}
+
+cudaError_t LlamaDecoder::tp_connect(const void *handles) {
+    if (tp_ <= 1) return cudaErrorInvalidValue;
+    const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(handles);
+    for (int p = 0; p < tp_; p++) {
+        if (p == cfg_.tp_rank) {
+            tp_peer_[p] = tp_buf_;
+        } else {
+            DCK(cudaIpcOpenMemHandle((void **)&tp_peer_[p], h[p], cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    tp_connected_ = true;
+    build_ops();
+    return cudaSuccess;
+}
+
 // The op list of one decode step (built once): the graph path launches one kernel per op, the persistent kernel
 // turns the same list into its phase table.
 void LlamaDecoder::build_ops() {
@@ -157,6 +197,46 @@ void LlamaDecoder::build_ops() {
     StepOp emb;
     emb.type = OP_EMBED;
     ops_.push_back(emb);
+    // ---- tensor-parallel plumbing (tp_ == 1: every helper below is a no-op) ----
+    const int P = tp_, per_step = 2 * cfg_.num_layers + 1;
+    float *resid[2] = {d_resid_, d_resid_ + E};
+    int cur = 0;  // residual buffer holding the stream
+    auto gather_of = [&](int peer, int buf) { return reinterpret_cast<float *>(tp_peer_[peer]) + ((size_t)buf * P) * E; };            // [P][E]
+    auto flags_of = [&](int peer, int buf) { return reinterpret_cast<unsigned *>(reinterpret_cast<float *>(tp_peer_[peer]) + tp_gather_floats_) + buf * kMaxTP; };
+    auto keys_of = [&](int peer) { return reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(tp_peer_[peer]) + tp_gather_floats_ * sizeof(float) + 256); };
+    const int me = cfg_.tp_rank;
+    // receive side of collective k (the buffer it used): fold the gathered partials into the residual in this prologue
+    auto tp_recv = [&](W4GemvParams &p, int buf, int k) {
+        if (P <= 1) return;
+        p.tp_size = P;
+        p.x = resid[cur];
+        p.tp_in = gather_of(me, buf);
+        p.tp_flags = flags_of(me, buf);
+        p.tp_step = d_tokpos_ + 2;
+        p.tp_k = k;
+        p.tp_per_step = per_step;
+        p.resid_out = resid[cur ^ 1];
+        cur ^= 1;
+    };
+    // send side: scatter epilogue + signal op
+    auto tp_send = [&](W4GemvParams &p, int buf) {
+        p.tp_size = P;
+        p.epi = EPI_TP_SCATTER_F32;
+        p.atomic_residual = false;
+        p.y = nullptr;
+        for (int q = 0; q < P; q++) p.tp_out[q] = gather_of(q, buf) + (size_t)me * E;
+    };
+    auto push_signal = [&](int buf, int k) {
+        StepOp op;
+        op.type = OP_TP_SIGNAL;
+        op.sig = TpSignalArgs{};
+        for (int q = 0; q < P; q++) op.sig.peer_flag[q] = flags_of(q, buf) + me;
+        op.sig.tp_size = P;
+        op.sig.step = d_tokpos_ + 2;
+        op.sig.k = k;
+        op.sig.per_step = per_step;
+        ops_.push_back(op);
+    };
     for (int l = 0; l < cfg_.num_layers; l++) {
         const tce_llama_layer &L = layers_[l];
         {  // RMSNorm(input_layernorm) + fused q|k|v projection
@@ -176,6 +256,8 @@ void LlamaDecoder::build_ops() {
             p.eps = cfg_.rms_eps;
             p.y = d_qkv_;
             p.epi = EPI_STORE_HALF;
+            p.x = resid[cur];
+            if (l > 0) tp_recv(p, 1, 2 * (l - 1) + 1);
             ops_.push_back(op);
         }
         {  // RoPE + in-place KV append + attention over the cache
@@ -207,10 +289,12 @@ void LlamaDecoder::build_ops() {
             p.M = 1;
             p.x = d_attn_;
             p.x_mode = X_HALF;
-            p.y = d_resid_;
+            p.y = resid[cur];
             p.epi = EPI_ADD_F32;
             p.atomic_residual = atomic_residual_;
+            if (P > 1) tp_send(p, 0);
             ops_.push_back(op);
+            if (P > 1) push_signal(0, 2 * l);
         }
         {  // RMSNorm(post_attention_layernorm) + gate/up with SiLU(gate)*up epilogue
             StepOp op;
@@ -222,13 +306,14 @@ void LlamaDecoder::build_ops() {
             p.seg[1] = seg_of(L.up);
             p.IC = E;
             p.M = 1;
-            p.x = d_resid_;
+            p.x = resid[cur];
             p.x_mode = X_RMSNORM_F32;
             p.gamma = L.post_norm;
             p.eps = cfg_.rms_eps;
             p.y = d_act_;
             p.epi = EPI_SILU_MUL_HALF;
             p.ldy = F;
+            tp_recv(p, 0, 2 * l);
             ops_.push_back(op);
         }
         {  // down_proj + residual
@@ -241,10 +326,12 @@ void LlamaDecoder::build_ops() {
             p.M = 1;
             p.x = d_act_;
             p.x_mode = X_HALF;
-            p.y = d_resid_;
+            p.y = resid[cur];
             p.epi = EPI_ADD_F32;
             p.atomic_residual = atomic_residual_;
+            if (P > 1) tp_send(p, 1);
             ops_.push_back(op);
+            if (P > 1) push_signal(1, 2 * l + 1);
         }
     }
     {  // final RMSNorm + lm_head -> fp32 logits (reference: lm_head GEMV + half2float, cuda/Int4llamaForCausalLM.cu:33-38)
@@ -255,17 +342,43 @@ void LlamaDecoder::build_ops() {
         p.seg[0] = seg_of(w_.lm_head);
         p.IC = E;
         p.M = 1;
-        p.x = d_resid_;
+        p.x = resid[cur];
         p.x_mode = X_RMSNORM_F32;
         p.gamma = w_.final_norm;
         p.eps = cfg_.rms_eps;
         p.y = d_logits_;
         p.epi = EPI_STORE_F32;
+        tp_recv(p, 1, 2 * (cfg_.num_layers - 1) + 1);
         ops_.push_back(op);
     }
-    StepOp am;
-    am.type = OP_ARGMAX;
-    ops_.push_back(am);
+    if (P > 1) {
+        // greedy token over the vocabulary shards: scatter the local key, signal, pick the global maximum
+        StepOp sc;
+        sc.type = OP_TP_ARGMAX_SCATTER;
+        sc.am = TpArgmaxArgs{};
+        sc.am.logits = d_logits_;
+        sc.am.n_local = cfg_.vocab_size;
+        sc.am.index_base = me * cfg_.vocab_size;
+        for (int q = 0; q < P; q++) sc.am.peer_key[q] = keys_of(q) + me;
+        sc.am.tp_size = P;
+        ops_.push_back(sc);
+        push_signal(2, 2 * cfg_.num_layers);
+        StepOp fin;
+        fin.type = OP_TP_ARGMAX_FINISH;
+        fin.amf = TpArgmaxFinishArgs{};
+        fin.amf.keys = keys_of(me);
+        fin.amf.flags = flags_of(me, 2);
+        fin.amf.step = d_tokpos_ + 2;
+        fin.amf.k = 2 * cfg_.num_layers;
+        fin.amf.per_step = per_step;
+        fin.amf.tp_size = P;
+        fin.amf.next_token = d_next_;
+        ops_.push_back(fin);
+    } else {
+        StepOp am;
+        am.type = OP_ARGMAX;
+        ops_.push_back(am);
+    }
 }
 
 cudaError_t LlamaDecoder::build_megakernel() {
@@ -288,6 +401,7 @@ cudaError_t LlamaDecoder::build_megakernel() {
                 ph[i].at = a;
                 break;
             }
+            default: return cudaErrorNotSupported;
             case OP_GEMV:
                 DCK(megakernel_fill_gemv(ctx_, ops_[i].g, &ph[i], ncta));
                 if (ops_[i].g.IC > max_ic) max_ic = ops_[i].g.IC;
@@ -333,7 +447,7 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
         const bool use_pdl = pdl && !first;
         switch (op.type) {
             case OP_EMBED:
-                if (!gemv_only) DCK(launch_embedding(c, (const __half *)w_.embed_f16, tokpos, d_resid_, cfg_.embed_dim, false));
+                if (!gemv_only) DCK(launch_embedding(c, (const __half *)w_.embed_f16, tokpos, d_resid_, cfg_.embed_dim, false));  // residual buffer 0
                 break;
             case OP_GEMV: {
                 W4GemvParams p = op.g;
@@ -351,6 +465,15 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
             case OP_ARGMAX:
                 if (!gemv_only) DCK(launch_argmax(c, d_logits_, cfg_.vocab_size, d_next_, use_pdl));
                 break;
+            case OP_TP_SIGNAL:
+                if (!gemv_only) DCK(launch_tp_signal(c, op.sig));
+                break;
+            case OP_TP_ARGMAX_SCATTER:
+                if (!gemv_only) DCK(launch_tp_argmax_scatter(c, op.am));
+                break;
+            case OP_TP_ARGMAX_FINISH:
+                if (!gemv_only) DCK(launch_tp_argmax_finish(c, op.amf));
+                break;
         }
         first = false;
     }
@@ -360,7 +483,7 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
 cudaError_t LlamaDecoder::build_graphs(std::string *err) {
     // one eager step first: loads the modules and sets the kernels' shared-memory attributes outside of capture
     // (re-running a step at the same position is idempotent: the same K/V row is rewritten)
-    DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 2 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_));
+    DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 4 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_));
     DCK(enqueue_step(d_tokpos_, cap_stream_, false));
     DCK(cudaStreamSynchronize(cap_stream_));
     // try PDL edges first; if capture/instantiate refuses them, fall back to plain edges
@@ -369,7 +492,7 @@ cudaError_t LlamaDecoder::build_graphs(std::string *err) {
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal);
         if (e != cudaSuccess) return e;
-        e = cudaMemcpyAsync(d_tokpos_, h_tokpos_, 2 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_);
+        e = cudaMemcpyAsync(d_tokpos_, h_tokpos_, 4 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_);
         if (e == cudaSuccess) e = enqueue_step(d_tokpos_, cap_stream_, pdl);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_logits_, d_logits_, (size_t)cfg_.vocab_size * sizeof(float), cudaMemcpyDeviceToHost, cap_stream_);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_next_, d_next_, sizeof(int), cudaMemcpyDeviceToHost, cap_stream_);
@@ -391,9 +514,13 @@ cudaError_t LlamaDecoder::build_graphs(std::string *err) {
 }
 
 cudaError_t LlamaDecoder::decode_host(int token, int pos, float *logits_host, int *next_token, std::string *err) {
-    if (pos < 0 || pos >= cfg_.max_ctx || token < 0 || token >= cfg_.vocab_size) return cudaErrorInvalidValue;
+    const int tp = cfg_.tp_size > 1 ? cfg_.tp_size : 1;
+    if (pos < 0 || pos >= cfg_.max_ctx || token < 0 || token >= cfg_.vocab_size * tp) return cudaErrorInvalidValue;
+    if (tp > 1 && !tp_connected_) return cudaErrorNotReady;
     h_tokpos_[0] = token;
     h_tokpos_[1] = pos;
+    h_tokpos_[2] = step_index_++;  // sequence base of the tensor-parallel flags (ignored otherwise)
+    h_tokpos_[3] = 0;
     cudaStream_t s = ctx_->stream;
     if (use_graphs_ && !graphs_ok_) {
         cudaError_t e = build_graphs(err);
@@ -402,7 +529,7 @@ cudaError_t LlamaDecoder::decode_host(int token, int pos, float *logits_host, in
     if (use_graphs_ && graphs_ok_) {
         DCK(cudaGraphLaunch(g_host_, s));
     } else {
-        DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+        DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 4 * sizeof(int), cudaMemcpyHostToDevice, s));
         DCK(enqueue_step(d_tokpos_, s, ctx_->use_pdl));
         DCK(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)cfg_.vocab_size * sizeof(float), cudaMemcpyDeviceToHost, s));
         DCK(cudaMemcpyAsync(h_next_, d_next_, sizeof(int), cudaMemcpyDeviceToHost, s));

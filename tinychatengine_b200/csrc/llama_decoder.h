@@ -6,6 +6,7 @@
 #include "../../include/tce_b200.h"
 #include "kernels.h"
 #include "kernels_attn.h"
+#include "kernels_tp.h"
 #include "megakernel.h"
 
 namespace tce {
@@ -29,6 +30,8 @@ class LlamaDecoder {
         }
     }
     cudaError_t enqueue_gemvs(int *count);
+    cudaError_t tp_handle(void *out64);
+    cudaError_t tp_connect(const void *handles);
 
    private:
     LlamaDecoder() = default;
@@ -37,12 +40,22 @@ class LlamaDecoder {
     void build_ops();
     cudaError_t build_megakernel();
 
-    enum OpType { OP_EMBED, OP_GEMV, OP_ATTN, OP_ARGMAX };
+    enum OpType { OP_EMBED, OP_GEMV, OP_ATTN, OP_ARGMAX, OP_TP_SIGNAL, OP_TP_ARGMAX_SCATTER, OP_TP_ARGMAX_FINISH };
     struct StepOp {
         OpType type;
         W4GemvParams g;
         AttnDecodeArgs at;
+        TpSignalArgs sig;
+        TpArgmaxArgs am;
+        TpArgmaxFinishArgs amf;
     };
+    // tensor parallel state
+    int tp_ = 1;
+    bool tp_connected_ = false;
+    uint8_t *tp_buf_ = nullptr;          // peer-visible allocation of this rank
+    size_t tp_bytes_ = 0, tp_gather_floats_ = 0;
+    uint8_t *tp_peer_[kMaxTP] = {};      // every rank's allocation as mapped into this process
+    int step_index_ = 0;
     std::vector<StepOp> ops_;
     bool mega_ = true;              // one persistent kernel per token (TCE_MEGAKERNEL=0: one kernel per op in a CUDA graph)
     int mega_attn_chunk_ = 64;

@@ -167,6 +167,14 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
     a.aligned = 0;
     a.sg = a.NG < kStageGroups ? a.NG : kStageGroups;
+    a.tp_size = p.tp_size;
+    a.tp_in = p.tp_in;
+    a.tp_flags = p.tp_flags;
+    a.tp_step = p.tp_step;
+    a.tp_k = p.tp_k;
+    a.tp_per_step = p.tp_per_step;
+    a.resid_out = p.resid_out;
+    for (int i = 0; i < kMaxTP; i++) a.tp_out[i] = p.tp_out[i];
     return a;
 }
 

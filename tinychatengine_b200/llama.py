@@ -58,57 +58,145 @@ def kv_bytes_per_token(g: LlamaGeometry, ctx_len: int) -> int:
     return per_pos * ctx_len + per_pos
 
 
-class LlamaModel:
-    """Synthetic-weight Llama + tce_llama handle.  Holds the torch tensors alive (the C side borrows pointers)."""
+def make_random_weights(geom: LlamaGeometry, dev, seed: int = 1234, random_zeros: bool = False):
+    """Synthetic AWQ-INT4 Llama weights (QM_CUDA layout) as a plain dict of torch tensors on `dev`."""
+    g = geom
+    hd = g.head_dim
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    W = {"layers": []}
+    for l in range(g.num_layers):
+        s = seed * 1000 + l * 16
+        L = {"q": random_w4(g.num_heads * hd, g.embed_dim, dev, s + 1, 0.02, random_zeros),
+             "k": random_w4(g.num_kv_heads * hd, g.embed_dim, dev, s + 2, 0.02, random_zeros),
+             "v": random_w4(g.num_kv_heads * hd, g.embed_dim, dev, s + 3, 0.02, random_zeros),
+             "o": random_w4(g.embed_dim, g.num_heads * hd, dev, s + 4, 0.02, random_zeros),
+             "gate": random_w4(g.hidden_dim, g.embed_dim, dev, s + 5, 0.02, random_zeros),
+             "up": random_w4(g.hidden_dim, g.embed_dim, dev, s + 6, 0.02, random_zeros),
+             "down": random_w4(g.embed_dim, g.hidden_dim, dev, s + 7, 0.02, random_zeros),
+             "input_norm": (1.0 + 0.02 * torch.randn(g.embed_dim, device=dev, generator=gen)).float(),
+             "post_norm": (1.0 + 0.02 * torch.randn(g.embed_dim, device=dev, generator=gen)).float()}
+        W["layers"].append(L)
+    W["embed"] = (torch.randn((g.vocab_size, g.embed_dim), device=dev, generator=gen) * 0.5).to(torch.float16)
+    W["final_norm"] = (1.0 + 0.02 * torch.randn(g.embed_dim, device=dev, generator=gen)).float()
+    W["lm_head"] = random_w4(g.vocab_size, g.embed_dim, dev, seed * 1000 + 999983, 0.02, random_zeros)
+    return W
 
-    def __init__(self, ctx: Context, geom: LlamaGeometry, max_ctx: int = 4096, seed: int = 1234, random_zeros: bool = False):
+
+def shard_w4_rows(t, rank: int, P: int):
+    """Output-channel (row) shard of a QM_CUDA tensor triple: contiguous rows [rank*OC/P, (rank+1)*OC/P)."""
+    w, z, s = t
+    n = w.shape[0] // P
+    return tuple(x[rank * n:(rank + 1) * n].contiguous() for x in (w, z, s))
+
+
+def shard_w4_cols(t, ic: int, rank: int, P: int, group: int = 128):
+    """Input-channel shard (row-parallel linear): columns [rank*IC/P, (rank+1)*IC/P) repacked as a QM_CUDA tensor of
+    its own: the packed words are a contiguous slice per row, scales/zeros are re-padded to the shard's zeros_width."""
+    from .formats import zeros_width
+
+    w, z, s = t
+    icl = ic // P
+    assert icl % group == 0
+    ngl = icl // group
+    zwl = zeros_width(icl, group)
+    wl = w[:, rank * icl // 8:(rank + 1) * icl // 8].contiguous()
+    sl = torch.zeros((w.shape[0], zwl * 8), dtype=s.dtype, device=s.device)
+    sl[:, :ngl] = s[:, rank * ngl:(rank + 1) * ngl]
+    zi = z.to(torch.int64) & 0xFFFFFFFF
+    nib = torch.stack([(zi >> (4 * i)) & 0xF for i in range(8)], dim=2).reshape(z.shape[0], -1)  # [OC, zw*8]
+    nl = torch.full((z.shape[0], zwl * 8), 8, dtype=torch.int64, device=z.device)
+    nl[:, :ngl] = nib[:, rank * ngl:(rank + 1) * ngl]
+    packed = torch.zeros((z.shape[0], zwl), dtype=torch.int64, device=z.device)
+    for i in range(8):
+        packed |= nl[:, i::8] << (4 * i)
+    packed = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32)
+    return wl, packed.contiguous(), sl.contiguous()
+
+
+def shard_weights(W, geom: LlamaGeometry, rank: int, P: int):
+    """Megatron-style shard: q/k/v/gate/up/lm_head by rows, o/down by input channels."""
+    hd = geom.head_dim
+    gl = LlamaGeometry(geom.name, geom.num_layers, geom.num_heads // P, geom.num_kv_heads // P, geom.embed_dim, geom.hidden_dim // P,
+                       geom.vocab_size // P, geom.rms_eps, geom.rope_theta, hd)
+    Wl = {"layers": [], "embed": W["embed"], "final_norm": W["final_norm"], "lm_head": shard_w4_rows(W["lm_head"], rank, P)}
+    for L in W["layers"]:
+        Wl["layers"].append({"q": shard_w4_rows(L["q"], rank, P), "k": shard_w4_rows(L["k"], rank, P), "v": shard_w4_rows(L["v"], rank, P),
+                             "o": shard_w4_cols(L["o"], geom.num_heads * hd, rank, P), "gate": shard_w4_rows(L["gate"], rank, P),
+                             "up": shard_w4_rows(L["up"], rank, P), "down": shard_w4_cols(L["down"], geom.hidden_dim, rank, P),
+                             "input_norm": L["input_norm"], "post_norm": L["post_norm"]})
+    return Wl, gl
+
+
+class LlamaModel:
+    """Llama weights (synthetic by default) + tce_llama handle.  Holds the torch tensors alive (the C side borrows
+    pointers).  `geom` describes the LOCAL shard when tp_size > 1 (see shard_weights)."""
+
+    def __init__(self, ctx: Context, geom: LlamaGeometry, max_ctx: int = 4096, seed: int = 1234, random_zeros: bool = False, weights=None,
+                 tp_rank: int = 0, tp_size: int = 1):
         self.ctx, self.geom, self.max_ctx = ctx, geom, max_ctx
+        self.tp_rank, self.tp_size = tp_rank, tp_size
         dev = torch.device("cuda", ctx.device)
         g = geom
         hd = g.head_dim
+        W = weights if weights is not None else make_random_weights(geom, dev, seed, random_zeros)
+        self.W = W
         self.tensors = []
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(seed)
 
-        def w4(oc, ic, s):
-            t = random_w4(oc, ic, dev, s, scale=0.02, random_zeros=random_zeros)
+        def w4(t, oc, ic):
+            assert t[0].shape == (oc, ic // 8), (t[0].shape, oc, ic)
             self.tensors.append(t)
             return _lib.W4Tensor(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), oc, ic)
 
-        def norm():
-            t = (1.0 + 0.02 * torch.randn(g.embed_dim, device=dev, generator=gen)).float()
+        def norm(t):
             self.tensors.append(t)
             return t.data_ptr()
 
         self.layers = (_lib.LlamaLayer * g.num_layers)()
         for l in range(g.num_layers):
-            L = self.layers[l]
-            s = seed * 1000 + l * 16
-            L.q = w4(g.num_heads * hd, g.embed_dim, s + 1)
-            L.k = w4(g.num_kv_heads * hd, g.embed_dim, s + 2)
-            L.v = w4(g.num_kv_heads * hd, g.embed_dim, s + 3)
-            L.o = w4(g.embed_dim, g.num_heads * hd, s + 4)
-            L.gate = w4(g.hidden_dim, g.embed_dim, s + 5)
-            L.up = w4(g.hidden_dim, g.embed_dim, s + 6)
-            L.down = w4(g.embed_dim, g.hidden_dim, s + 7)
-            L.input_norm = norm()
-            L.post_norm = norm()
-        self.embed = (torch.randn((g.vocab_size, g.embed_dim), device=dev, generator=gen) * 0.5).to(torch.float16)
-        self.final_norm = (1.0 + 0.02 * torch.randn(g.embed_dim, device=dev, generator=gen)).float()
+            L, T = self.layers[l], W["layers"][l]
+            L.q = w4(T["q"], g.num_heads * hd, g.embed_dim)
+            L.k = w4(T["k"], g.num_kv_heads * hd, g.embed_dim)
+            L.v = w4(T["v"], g.num_kv_heads * hd, g.embed_dim)
+            L.o = w4(T["o"], g.embed_dim, g.num_heads * hd)
+            L.gate = w4(T["gate"], g.hidden_dim, g.embed_dim)
+            L.up = w4(T["up"], g.hidden_dim, g.embed_dim)
+            L.down = w4(T["down"], g.embed_dim, g.hidden_dim)
+            L.input_norm = norm(T["input_norm"])
+            L.post_norm = norm(T["post_norm"])
+        self.embed = W["embed"]
+        self.final_norm = W["final_norm"]
         self.weights = _lib.LlamaWeights()
         self.weights.embed_f16 = self.embed.data_ptr()
         self.weights.layers = C.cast(self.layers, C.POINTER(_lib.LlamaLayer))
         self.weights.final_norm = self.final_norm.data_ptr()
-        self.weights.lm_head = w4(g.vocab_size, g.embed_dim, seed * 1000 + 999983)
+        self.weights.lm_head = w4(W["lm_head"], g.vocab_size, g.embed_dim)
         self.weights.rope_cos = None
         self.weights.rope_sin = None
         self.cfg = _lib.LlamaConfig(g.num_layers, g.num_heads, g.num_kv_heads, hd, g.embed_dim, g.hidden_dim, g.vocab_size, max_ctx,
-                                    g.rms_eps, g.rope_theta, 0.0, 0, 1)
+                                    g.rms_eps, g.rope_theta, 0.0, tp_rank, tp_size)
         h = C.c_void_p()
         _lib.check(ctx.L.tce_llama_create(ctx.h, C.byref(self.cfg), C.byref(self.weights), C.byref(h)), "tce_llama_create")
         self.h = h
         self.kernels_per_step = ctx.L.tce_llama_kernels_per_step(h)
         torch.cuda.synchronize(dev)
+
+    def tp_connect(self, group=None):
+        """Exchange the IPC handles of the peer-visible buffers over torch.distributed and map the peers."""
+        import torch.distributed as dist
+
+        mine = (C.c_ubyte * 64)()
+        _lib.check(self.ctx.L.tce_llama_tp_handle(self.h, C.cast(mine, C.c_void_p)), "tce_llama_tp_handle")
+        t = torch.tensor(list(mine), dtype=torch.uint8)
+        backend = dist.get_backend(group)
+        if backend == "nccl":
+            t = t.cuda(self.ctx.device)
+        out = [torch.empty_like(t) for _ in range(self.tp_size)]
+        dist.all_gather(out, t, group=group)
+        blob = b"".join(bytes(o.cpu().tolist()) for o in out)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _lib.check(self.ctx.L.tce_llama_tp_connect(self.h, C.cast(buf, C.c_void_p)), "tce_llama_tp_connect")
+        dist.barrier(group=group)
 
     def layer_tensors(self, l: int):
         """(q, k, v, o, gate, up, down) each as (w, zeros, scales) torch tensors, plus the two norm gammas."""
