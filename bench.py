@@ -207,7 +207,19 @@ def run_ours(args):
     stream = torch.cuda.Stream(dev)
     with torch.cuda.stream(stream):
         ctx = Context(local_rank, stream)
-        model = LL.LlamaModel(ctx, geom, max_ctx=args.max_ctx, seed=1234 + rank)
+        tp = world > 1 and args.parallel == "tp"
+        if tp:
+            # tensor-parallel decode of ONE sequence: every rank holds a 1/N shard of every matrix (random shards of the
+            # right shapes), all-reduce over NVLink peer memory inside the GEMV kernels
+            if geom.num_kv_heads % world or geom.num_heads % world:
+                raise SystemExit(f"{geom.name}: heads do not split over {world} ranks")
+            gl = LL.LlamaGeometry(geom.name, geom.num_layers, geom.num_heads // world, geom.num_kv_heads // world, geom.embed_dim,
+                                  geom.hidden_dim // world, geom.vocab_size // world, geom.rms_eps, geom.rope_theta, geom.head_dim)
+            model = LL.LlamaModel(ctx, gl, max_ctx=args.max_ctx, seed=1234 + rank, tp_rank=rank, tp_size=world)
+            model.tp_connect()
+        else:
+            gl = geom
+            model = LL.LlamaModel(ctx, geom, max_ctx=args.max_ctx, seed=1234 + rank)
         # random-filled KV cache so every context length is "already generated"
         for l in range(geom.num_layers):
             model.kv_cache(l, 0).normal_(0, 0.5)
@@ -222,7 +234,7 @@ def run_ours(args):
             pos_list = [args.ctx] * (W + K)
         tokpos_all = torch.tensor(list(zip(toks, pos_list)), dtype=torch.int32, device=dev)
         tokpos = torch.zeros(2, dtype=torch.int32, device=dev)
-        logits_pinned = torch.empty(geom.vocab_size, dtype=torch.float32).pin_memory()
+        logits_pinned = torch.empty(gl.vocab_size, dtype=torch.float32).pin_memory()
 
         def barrier():
             if world > 1:
@@ -255,16 +267,19 @@ def run_ours(args):
         barrier()
         ms_e2e = e2.elapsed_time(e3)
         # ---- dominant kernel: the W4A16 GEMV launches of one step, timed alone with events ----
-        n_gemv = ctx.L.tce_llama_enqueue_gemvs(model.h)
-        barrier()
-        reps = 20
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        for _ in range(reps):
-            ctx.L.tce_llama_enqueue_gemvs(model.h)
-        g1.record(stream)
-        barrier()
-        ms_gemv_step = g0.elapsed_time(g1) / reps
+        if tp:
+            n_gemv, ms_gemv_step = 4 * geom.num_layers + 1, None  # the sharded GEMVs wait for their peers: not timed alone
+        else:
+            n_gemv = ctx.L.tce_llama_enqueue_gemvs(model.h)
+            barrier()
+            reps = 20
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(reps):
+                ctx.L.tce_llama_enqueue_gemvs(model.h)
+            g1.record(stream)
+            barrier()
+            ms_gemv_step = g0.elapsed_time(g1) / reps
 
     times = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -275,23 +290,27 @@ def run_ours(args):
         wbytes = LL.weight_bytes_per_token(geom)
         mean_ctx = sum(pos_list[W:]) / K
         kvbytes = LL.kv_bytes_per_token(geom, int(mean_ctx))
-        tok_s = world * K / (ms_dev * 1e-3)
-        e2e_tok_s = world * K / (ms_e2e * 1e-3)
-        gemv_gbs = wbytes / (ms_gemv_step * 1e-3) / 1e9
+        seqs = 1 if tp else world
+        tok_s = seqs * K / (ms_dev * 1e-3)
+        e2e_tok_s = seqs * K / (ms_e2e * 1e-3)
+        gemv_gbs = None if tp else wbytes / (ms_gemv_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "w4a16 (int4 weights, fp16 activations, fp32 accumulate)",
+            "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
+            "dtype": "w4a16 (int4 weights; activations fp16 -> 15-bit block fixed point; int32 accumulate)",
             "data": "synthetic",
             "config": {"workload": f"{geom.name} AWQ-INT4 g128 batch-1 decode, timed steps spread over ctx 1->{args.max_ctx}" if args.ctx < 0
-                       else f"{geom.name} AWQ-INT4 g128 batch-1 decode at ctx {args.ctx}", "model": geom.name, "global_batch": world, "max_ctx": args.max_ctx,
-                       "mean_ctx": mean_ctx, "parallelism": "1 sequence per GPU (replicas)" if world > 1 else "single GPU",
+                       else f"{geom.name} AWQ-INT4 g128 batch-1 decode at ctx {args.ctx}", "model": geom.name, "global_batch": 1 if (world == 1 or tp) else world, "max_ctx": args.max_ctx,
+                       "mean_ctx": mean_ctx, "global_batch_note": "one sequence" if (tp or world == 1) else "one sequence per GPU",
+                       "parallelism": (f"tp{world} (column/row sharded linears, 2 all-reduces per layer over NVLink peer memory)" if tp else
+                                       ("1 sequence per GPU (replicas)" if world > 1 else "single GPU")),
                        "l2": "inputs larger than L2: 3.9 GB of weights stream per step vs 126 MB L2", "pdl": bool(int(os.environ.get("TCE_USE_PDL", "0")))},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": geom.vocab_size * 4 + 4},
+            "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 12, "d2h_bytes_per_step": gl.vocab_size * 4 + 4},
             "gpu_launches": K * model.kernels_per_step,
             "roofline": {"bound": "hbm", "kernel": "w4a16_gemv_kernel<1> (161 launches/step: 4 per layer + lm_head)",
-                         "achieved": gemv_gbs, "peak": peak, "unit": "GB/s", "frac": gemv_gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": wbytes / n_gemv, "avg_launch_us": ms_gemv_step * 1e3 / n_gemv,
+                         "achieved": gemv_gbs, "peak": peak, "unit": "GB/s", "frac": None if tp else gemv_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": wbytes / n_gemv, "avg_launch_us": None if tp else ms_gemv_step * 1e3 / n_gemv,
                          "step": {"bytes_per_token": wbytes + kvbytes, "achieved": (wbytes + kvbytes) / (ms_dev / K * 1e-3) / 1e9,
                                   "frac": (wbytes + kvbytes) / (ms_dev / K * 1e-3) / 1e9 / peak}},
         }
@@ -318,6 +337,7 @@ def main():
     ap.add_argument("--ctx", type=int, default=-1, help="fixed context length for every step (default: sweep 1 -> max_ctx)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallel", default="tp", choices=["tp", "replicas"], help="N>1: tensor-parallel decode of one sequence, or one sequence per GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -19,7 +19,7 @@ struct TpArgmaxArgs {
 struct TpArgmaxFinishArgs {
     const unsigned long long *keys;  // local [tp_size]
     const unsigned *flags;           // local [tp_size]
-    const int *step;
+    int *step;                       // device step counter, incremented here
     int k, per_step, tp_size;
     int *next_token;
 };

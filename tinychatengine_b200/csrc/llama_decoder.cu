@@ -68,6 +68,7 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
     A((void **)&d->d_tokpos_, 4 * sizeof(int));
     A((void **)&d->d_next_, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(d->d_kv_, 0, kv_elems * sizeof(__half));
+    if (e == cudaSuccess) e = cudaMemset(d->d_tokpos_, 0, 4 * sizeof(int));  // [3] = tensor-parallel step counter, advanced on the device
     if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_tokpos_, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_logits_, (size_t)V * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_next_, sizeof(int));
@@ -212,7 +213,7 @@ void LlamaDecoder::build_ops() {
         p.x = resid[cur];
         p.tp_in = gather_of(me, buf);
         p.tp_flags = flags_of(me, buf);
-        p.tp_step = d_tokpos_ + 2;
+        p.tp_step = d_tokpos_ + 3;
         p.tp_k = k;
         p.tp_per_step = per_step;
         p.resid_out = resid[cur ^ 1];
@@ -232,7 +233,7 @@ void LlamaDecoder::build_ops() {
         op.sig = TpSignalArgs{};
         for (int q = 0; q < P; q++) op.sig.peer_flag[q] = flags_of(q, buf) + me;
         op.sig.tp_size = P;
-        op.sig.step = d_tokpos_ + 2;
+        op.sig.step = d_tokpos_ + 3;
         op.sig.k = k;
         op.sig.per_step = per_step;
         ops_.push_back(op);
@@ -368,7 +369,7 @@ void LlamaDecoder::build_ops() {
         fin.amf = TpArgmaxFinishArgs{};
         fin.amf.keys = keys_of(me);
         fin.amf.flags = flags_of(me, 2);
-        fin.amf.step = d_tokpos_ + 2;
+        fin.amf.step = d_tokpos_ + 3;
         fin.amf.k = 2 * cfg_.num_layers;
         fin.amf.per_step = per_step;
         fin.amf.tp_size = P;
@@ -483,7 +484,7 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
 cudaError_t LlamaDecoder::build_graphs(std::string *err) {
     // one eager step first: loads the modules and sets the kernels' shared-memory attributes outside of capture
     // (re-running a step at the same position is idempotent: the same K/V row is rewritten)
-    DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 4 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_));
+    DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 3 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_));
     DCK(enqueue_step(d_tokpos_, cap_stream_, false));
     DCK(cudaStreamSynchronize(cap_stream_));
     // try PDL edges first; if capture/instantiate refuses them, fall back to plain edges
@@ -492,7 +493,7 @@ cudaError_t LlamaDecoder::build_graphs(std::string *err) {
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal);
         if (e != cudaSuccess) return e;
-        e = cudaMemcpyAsync(d_tokpos_, h_tokpos_, 4 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_);
+        e = cudaMemcpyAsync(d_tokpos_, h_tokpos_, 3 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_);
         if (e == cudaSuccess) e = enqueue_step(d_tokpos_, cap_stream_, pdl);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_logits_, d_logits_, (size_t)cfg_.vocab_size * sizeof(float), cudaMemcpyDeviceToHost, cap_stream_);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_next_, d_next_, sizeof(int), cudaMemcpyDeviceToHost, cap_stream_);
@@ -519,8 +520,7 @@ cudaError_t LlamaDecoder::decode_host(int token, int pos, float *logits_host, in
     if (tp > 1 && !tp_connected_) return cudaErrorNotReady;
     h_tokpos_[0] = token;
     h_tokpos_[1] = pos;
-    h_tokpos_[2] = step_index_++;  // sequence base of the tensor-parallel flags (ignored otherwise)
-    h_tokpos_[3] = 0;
+    h_tokpos_[2] = 0;
     cudaStream_t s = ctx_->stream;
     if (use_graphs_ && !graphs_ok_) {
         cudaError_t e = build_graphs(err);
@@ -529,7 +529,7 @@ cudaError_t LlamaDecoder::decode_host(int token, int pos, float *logits_host, in
     if (use_graphs_ && graphs_ok_) {
         DCK(cudaGraphLaunch(g_host_, s));
     } else {
-        DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 4 * sizeof(int), cudaMemcpyHostToDevice, s));
+        DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 3 * sizeof(int), cudaMemcpyHostToDevice, s));
         DCK(enqueue_step(d_tokpos_, s, ctx_->use_pdl));
         DCK(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)cfg_.vocab_size * sizeof(float), cudaMemcpyDeviceToHost, s));
         DCK(cudaMemcpyAsync(h_next_, d_next_, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -542,6 +542,7 @@ cudaError_t LlamaDecoder::decode_host(int token, int pos, float *logits_host, in
 
 cudaError_t LlamaDecoder::decode_device(const int *tokpos_dev, std::string *err) {
     cudaStream_t s = ctx_->stream;
+    if (tp_ > 1 && !tp_connected_) return cudaErrorNotReady;
     if (use_graphs_ && (g_dev_ == nullptr || g_dev_src_ != tokpos_dev)) {
         if (g_dev_) {
             cudaGraphExecDestroy(g_dev_);

@@ -71,6 +71,10 @@ __global__ void tp_argmax_finish_kernel(const TpArgmaxFinishArgs a) {
             best = k > best ? k : best;
         }
         *a.next_token = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
+        // last tensor-parallel op of the step: advance the step counter ON THE DEVICE, so that any re-execution (warm-up
+        // run, graph replay) uses fresh flag values.  A replayed index would leave every arrival flag already satisfied,
+        // ranks could drift apart and overwrite gather buffers a slower peer is still reading.
+        *a.step = *a.step + 1;
     }
 }
 

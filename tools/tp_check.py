@@ -43,8 +43,11 @@ def main():
         full = torch.cat(shards).cpu()
         nxt_all = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
         dist.all_gather(nxt_all, torch.tensor([nxt], dtype=torch.int32, device=dev))
-        assert all(int(t) == nxt for t in nxt_all), "ranks disagree on the greedy token"
+        agree = all(int(t) == nxt for t in nxt_all)
         if rank == 0:
+            if not agree:
+                ok = False
+                print(f"pos {pos}: ranks disagree on the greedy token: {[int(t) for t in nxt_all]}", flush=True)
             nref = ref.decode_host(tok, pos, lg_ref)
             err = (full - lg_ref).abs().max().item() / lg_ref.abs().max().item()
             worst = max(worst, err)
