@@ -57,7 +57,7 @@ class LlamaDecoder {
     uint8_t *tp_peer_[kMaxTP] = {};      // every rank's allocation as mapped into this process
     int step_index_ = 0;
     std::vector<StepOp> ops_;
-    bool mega_ = true;              // one persistent kernel per token (TCE_MEGAKERNEL=0: one kernel per op in a CUDA graph)
+    bool mega_ = false;             // TCE_MEGAKERNEL=1: one persistent cooperative kernel per token instead of one kernel per op
     int mega_attn_chunk_ = 64;
     MegaPhase *d_phases_ = nullptr;
     unsigned long long *d_sync_ = nullptr;  // [0] arg-max cell, then one 32-bit grid-barrier counter per phase

@@ -22,8 +22,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     name = sys.argv[1] if len(sys.argv) > 1 else "tiny-gqa"
     g = GEOMETRIES[name]
-    if g.num_kv_heads % world:
-        raise SystemExit(f"{name}: {g.num_kv_heads} kv heads do not split over {world} ranks")
+    if g.num_kv_heads % world or (g.hidden_dim // world) % 128:
+        raise SystemExit(f"{name}: does not split over {world} ranks on 128-channel group boundaries")
     ctx = Context(local)
     W = make_random_weights(g, dev, seed=21, random_zeros=True)
     Wl, gl = shard_weights(W, g, rank, world)
