@@ -61,6 +61,16 @@ TCE_API int tce_w4a16_gemv(tce_ctx *ctx, const void *x, const void *w, const voi
 TCE_API int tce_w4a16_gemm(tce_ctx *ctx, const void *x, const void *w, const void *zeros, const void *scales, void *y,
                            int M, int IC, int OC, int group_size);
 
+/* fp16-accumulate reference of the AWQ-GEMM layout, replaces MatmulOperator::naive_mat_mul_fp16_int4
+ * (kernels/cuda/matmul_int4.cu:8-48, call site Linear_FP16_int4_ref::forward_ref llm/src/ops/cuda/linear.cu:43-76):
+ * A half[M][IC], B int32[IC][OC/8] nibble order 0 2 4 6 1 3 5 7, scales half[IC/block][OC], zero 8, C half[M][OC].
+ * Bit-identical to the host reference (float op + round to half, serial k).                                   */
+TCE_API int tce_naive_fp16_int4(tce_ctx *ctx, const void *A, const void *B, const void *scales, void *C, int M, int IC, int OC,
+                                int block_size);
+/* fp32 C[M][N] = A[M][K] * B[N][K]^T, serial k, no FMA: MatmulOperator::mat_mul_accelerator_transposed_fastover_column
+ * of the CUDA build (kernels/cuda/matmul_ref_fp32.cc:11-34).                                                   */
+TCE_API int tce_f32_matmul_transposed(tce_ctx *ctx, const float *A, const float *B, float *C, int M, int N, int K);
+
 /* ---- W8A8 family -----------------------------------------------------------------------------------------
  * Replaces MatmulOperator::mat_mul_accelerator_int8_fast_* (kernels/ref/matmul_ref_int8.cc:11-192).
  * variant: 0 bias int8 -> int8 out (2x2_32unroll / 32unroll_over_column), 1 nobias -> int8 (…_nobias),
@@ -69,6 +79,20 @@ TCE_API int tce_w4a16_gemm(tce_ctx *ctx, const void *x, const void *w, const voi
  * A int8[M][K], B int8[N][K], bias int8[N] | float[N] | NULL, C int8[M][N] | float[M][N].  Bit-exact.   */
 TCE_API int tce_w8a8_matmul(tce_ctx *ctx, int variant, int batch, const void *A, const void *B, const void *bias,
                             void *C, int M, int N, int K, float alpha, float beta, int q_min, int q_max);
+
+/* int8 attention core of Int8OPTAttention::forward (llm/src/nn_modules/Int8OPTAttention.cc:183-284): everything between the
+ * q/k/v projections and out_proj -- shape(), cat_past_keys_values, BMM_S8T_S8N_F32T(qk_alpha), batch_Add(mask), softmax,
+ * round(p*127), transpose_1_2idx, BMM_S8T_S8N_S8T(pv_alpha), unshape().  Bit-identical to the CPU reference.
+ *   q8,k8,v8 int8 [sqlen][H*hd] (the three projections' outputs);  attn_out int8 [sqlen][H*hd]
+ *   past_k/past_v int8 [H][past][hd] with `past_head_stride` bytes between heads (ignored when past == 0)
+ *   final_k/final_v int8 [H][past+sqlen][hd] with `final_head_stride` between heads (Int8OPTAttention_output::past_key_value).
+ *     Passing final == past with equal strides (>= (past+sqlen)*hd) updates a preallocated cache in place: only the new rows
+ *     are written.
+ *   mask fp32 [sqlen][past+sqlen] (Int8OPTAttention_input::attention_mask) or NULL for the causal mask.
+ * hd % 4 == 0, hd <= 512.                                                                                                     */
+TCE_API int tce_opt_int8_attention(tce_ctx *ctx, const void *q8, const void *k8, const void *v8, const void *past_k, const void *past_v,
+                                   long long past_head_stride, void *final_k, void *final_v, long long final_head_stride, const float *mask,
+                                   float qk_alpha, float pv_alpha, int sqlen, int past, int num_heads, int head_dim, void *attn_out);
 
 /* ---- per-token KV-cache attention (fp16, GQA) ------------------------------------------------------------
  * Replaces the body of Int4llamaAttention::forward between qkv_proj and o_proj

@@ -45,8 +45,11 @@ SIGNATURES = {
     "tce_zeros_width": (C.c_int, [C.c_int, C.c_int]),
     "tce_w4a16_gemv": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4),
     "tce_w4a16_gemm": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4),
+    "tce_naive_fp16_int4": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4),
+    "tce_f32_matmul_transposed": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3),
     "tce_w8a8_matmul": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_float, C.c_int, C.c_int]),
+    "tce_opt_int8_attention": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong] + [C.c_void_p] * 2 + [C.c_longlong, C.c_void_p, C.c_float, C.c_float] + [C.c_int] * 4 + [C.c_void_p]),
     "tce_attn_decode": (C.c_int, [C.c_void_p] * 8 + [C.c_float] + [C.c_int] * 4),
     "tce_rmsnorm_f16": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float]),
     "tce_argmax_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

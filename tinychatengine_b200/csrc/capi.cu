@@ -102,6 +102,7 @@ int tce_ctx_destroy(tce_ctx *ctx) {
     cudaFree(ctx->c.gemv_counters);
     cudaFree(ctx->c.attn_ws);
     cudaFree(ctx->c.attn_counters);
+    cudaFree(ctx->c.w16_scratch);
     delete ctx;
     return TCE_OK;
 }
@@ -146,6 +147,8 @@ int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
         }
     } else if (!strcmp(name, "use_pdl"))
         ctx->c.use_pdl = value != 0;
+    else if (!strcmp(name, "gemm_min_m"))  // smallest M served by the tcgen05 GEMMs (W4A16 prefill slot, W8A8); below it the weight-streaming kernels run
+        ctx->c.gemm_min_m = value < 1 ? 1 : value;
     else if (!strcmp(name, "attn_chunk"))
         ctx->attn_chunk = value;
     else
@@ -197,8 +200,37 @@ int tce_w4a16_gemv(tce_ctx *ctx, const void *x, const void *w, const void *zeros
 
 int tce_w4a16_gemm(tce_ctx *ctx, const void *x, const void *w, const void *zeros, const void *scales, void *y, int M, int IC, int OC,
                    int group) {
-    // TODO(round 2): tcgen05 dequant-fused GEMM for M >= 64; until then the 8-row GEMV passes compute the same result
-    return w4a16_common(ctx, x, w, zeros, scales, y, M, IC, OC, group, "tce_w4a16_gemm");
+    if (!ctx || M < ctx->c.gemm_min_m) return w4a16_common(ctx, x, w, zeros, scales, y, M, IC, OC, group, "tce_w4a16_gemm");  // weight-streaming GEMV passes
+    if (!x || !w || !zeros || !scales || !y) return fail(TCE_ERR_INVALID, "tce_w4a16_gemm: null pointer");
+    if (group != kW4Group) return fail(TCE_ERR_INVALID, "tce_w4a16_gemm: unsupported group size %d (QM_CUDA uses 128)", group);
+    if (IC < kW4Group || IC % kW4Group || OC < 1) return fail(TCE_ERR_INVALID, "tce_w4a16_gemm: bad shape M=%d IC=%d OC=%d", M, IC, OC);
+    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return fail(TCE_ERR_INVALID, "tce_w4a16_gemm: x, w, y must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    const size_t need = (size_t)OC * IC;
+    if (ctx->c.w16_scratch_elems < need) {  // rare: grows to the largest weight matrix seen (cudaFree synchronises)
+        if (ctx->c.w16_scratch) CK(cudaFree(ctx->c.w16_scratch), "cudaFree w16 scratch");
+        ctx->c.w16_scratch = nullptr;
+        ctx->c.w16_scratch_elems = 0;
+        CK(cudaMalloc(&ctx->c.w16_scratch, need * sizeof(__half)), "cudaMalloc w16 scratch");
+        ctx->c.w16_scratch_elems = need;
+    }
+    CK(launch_w4_expand(&ctx->c, (const uint32_t *)w, (const uint32_t *)zeros, (const __half *)scales, ctx->c.w16_scratch, OC, IC), "w4_expand");
+    CK(launch_gemm_f16_tc(&ctx->c, (const __half *)x, IC, ctx->c.w16_scratch, IC, (__half *)y, OC, M, OC, IC), "tce_w4a16_gemm");
+    return TCE_OK;
+}
+
+int tce_naive_fp16_int4(tce_ctx *ctx, const void *A, const void *B, const void *scales, void *C, int M, int IC, int OC, int block) {
+    if (!ctx || !A || !B || !scales || !C || M < 1 || IC < 1 || OC < 8 || OC % 8 || block < 1) return fail(TCE_ERR_INVALID, "tce_naive_fp16_int4: bad argument");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    CK(launch_naive_fp16_int4(&ctx->c, (const __half *)A, (const int32_t *)B, (const __half *)scales, (__half *)C, M, IC, OC, block), "tce_naive_fp16_int4");
+    return TCE_OK;
+}
+
+int tce_f32_matmul_transposed(tce_ctx *ctx, const float *A, const float *B, float *C, int M, int N, int K) {
+    if (!ctx || !A || !B || !C || M < 1 || N < 1 || K < 1) return fail(TCE_ERR_INVALID, "tce_f32_matmul_transposed: bad argument");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    CK(launch_f32_matmul_transposed(&ctx->c, A, B, C, M, N, K), "tce_f32_matmul_transposed");
+    return TCE_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- W8A8
@@ -226,7 +258,44 @@ int tce_w8a8_matmul(tce_ctx *ctx, int variant, int batch, const void *A, const v
     a.q_max = q_max;
     a.variant = variant;
     a.batch = batch ? 1 : 0;
+    if (!a.batch && M >= ctx->c.gemm_min_m && K % 128 == 0 && !(((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15)) {
+        CK(launch_w8a8_tc(&ctx->c, a), "tce_w8a8_matmul (tcgen05)");
+        return TCE_OK;
+    }
     CK(launch_w8a8_dp4a(&ctx->c, a), "tce_w8a8_matmul");
+    return TCE_OK;
+}
+
+int tce_opt_int8_attention(tce_ctx *ctx, const void *q8, const void *k8, const void *v8, const void *past_k, const void *past_v, long long past_hs,
+                           void *final_k, void *final_v, long long final_hs, const float *mask, float qk_alpha, float pv_alpha, int sqlen, int past,
+                           int H, int hd, void *attn_out) {
+    if (!ctx || !q8 || !k8 || !v8 || !final_k || !final_v || !attn_out) return fail(TCE_ERR_INVALID, "tce_opt_int8_attention: null pointer");
+    if (sqlen < 1 || past < 0 || H < 1 || hd < 4 || hd % 4 || hd > 512) return fail(TCE_ERR_INVALID, "tce_opt_int8_attention: bad shape");
+    if (past > 0 && (!past_k || !past_v || past_hs < (long long)past * hd)) return fail(TCE_ERR_INVALID, "tce_opt_int8_attention: bad past cache");
+    if (final_hs < (long long)(past + sqlen) * hd || final_hs % 4) return fail(TCE_ERR_INVALID, "tce_opt_int8_attention: final_head_stride too small");
+    if (((uintptr_t)q8 | (uintptr_t)final_k | (uintptr_t)final_v) & 3) return fail(TCE_ERR_INVALID, "tce_opt_int8_attention: pointers must be 4-byte aligned");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    OptAttnParams p = {};
+    p.q8 = (const int8_t *)q8;
+    p.k8 = (const int8_t *)k8;
+    p.v8 = (const int8_t *)v8;
+    p.past_k = (const int8_t *)past_k;
+    p.past_v = (const int8_t *)past_v;
+    p.past_hs = past_hs;
+    p.final_k = (int8_t *)final_k;
+    p.final_v = (int8_t *)final_v;
+    p.final_hs = final_hs;
+    p.mask = mask;
+    p.qk_alpha = qk_alpha;
+    p.pv_alpha = pv_alpha;
+    p.sqlen = sqlen;
+    p.past = past;
+    p.H = H;
+    p.hd = hd;
+    p.out = (int8_t *)attn_out;
+    cudaError_t e = launch_opt_int8_attention(&ctx->c, p);
+    if (e == cudaErrorInvalidValue) return fail(TCE_ERR_UNSUPPORTED, "tce_opt_int8_attention: context %d too long for one CTA's shared memory", past + sqlen);
+    CK(e, "tce_opt_int8_attention");
     return TCE_OK;
 }
 

@@ -28,6 +28,10 @@ struct Ctx {
     int gemv_ctas_per_sm = 1;
     int gemv_consumer_warps = 8;   // 8 or 16 consumer warps per CTA
     bool use_pdl = false;
+    // large-M (prefill) path: fp16 expansion of one int4 weight matrix, grown on demand; M >= gemm_min_m goes to the tcgen05 GEMM
+    __half *w16_scratch = nullptr;
+    size_t w16_scratch_elems = 0;
+    int gemm_min_m = 16;
 };
 
 constexpr int kW4Group = 128;  // QK for QM_CUDA (llm/include/common.h:17-21)
@@ -81,6 +85,12 @@ cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p);
 cudaError_t launch_w4a16_gemv_simple(Ctx *ctx, const W4GemvParams &p);
 size_t w4a16_gemv_smem_bytes(int ncols, int consumer_warps, int IC);
 cudaError_t encode_w4_tmap(CUtensorMap *out, const void *w, int rows, int IC, int sg, int box_rows);
+
+cudaError_t launch_naive_fp16_int4(Ctx *ctx, const __half *A, const int32_t *B, const __half *scales, __half *C, int M, int IC, int OC, int block);
+cudaError_t launch_f32_matmul_transposed(Ctx *ctx, const float *A, const float *B, float *C, int M, int N, int K);
+
+cudaError_t launch_w4_expand(Ctx *ctx, const uint32_t *w, const uint32_t *zeros, const __half *scales, __half *out, int OC, int IC);
+cudaError_t launch_gemm_f16_tc(Ctx *ctx, const __half *A, long long lda, const __half *B, long long ldb, __half *C, long long ldc, int M, int N, int K);
 
 // host-side mirror of the stream-K partition used by the kernel (unit-tested on the CPU)
 struct StreamK {

@@ -26,5 +26,20 @@ struct W8A8Args {
 };
 
 cudaError_t launch_w8a8_dp4a(Ctx *ctx, const W8A8Args &a);
+cudaError_t launch_w8a8_tc(Ctx *ctx, const W8A8Args &a);  // tcgen05 kind::i8, non-batched, K % 128 == 0
+
+// int8 attention core of Int8OPTAttention::forward (llm/src/nn_modules/Int8OPTAttention.cc:183-284)
+struct OptAttnParams {
+    const int8_t *q8, *k8, *v8;        // [sqlen][H*hd]
+    const int8_t *past_k, *past_v;     // [H][past][hd], head stride past_hs (null when past == 0)
+    long long past_hs;
+    int8_t *final_k, *final_v;         // [H][tgz][hd], head stride final_hs; == past_* with equal stride -> in-place cache
+    long long final_hs;
+    const float *mask;                 // [sqlen][tgz] or null (causal)
+    float qk_alpha, pv_alpha;
+    int sqlen, past, H, hd;
+    int8_t *out;                       // [sqlen][H*hd]
+};
+cudaError_t launch_opt_int8_attention(Ctx *ctx, const OptAttnParams &p);
 
 }  // namespace tce

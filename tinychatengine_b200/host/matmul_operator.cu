@@ -48,6 +48,19 @@ void MatmulOperator::gemm_forward_cuda_8splits(const struct matmul_params *p, fl
 void MatmulOperator::gemm_forward_cuda_half(const struct matmul_params *p, int s) { gemm_forward_cuda(p, s); }
 void MatmulOperator::gemm_forward_cuda_half_test(const struct matmul_params *p, int s) { gemm_forward_cuda(p, s); }
 
+// reference: kernels/cuda/matmul_int4.cu:8-48 (host fp16 reference; here on the device, bit-identical).  B.row=IC, B.column=OC/8
+void MatmulOperator::naive_mat_mul_fp16_int4(const struct matmul_params *p) {
+    must(tce_naive_fp16_int4(tce_host_ctx(), p->A.fp16_data_ptr, p->B.int32_data_ptr, p->fp16_scales, p->C.fp16_data_ptr, p->C.row, p->B.row,
+                             p->C.column, p->block_size),
+         "naive_mat_mul_fp16_int4");
+}
+
+// reference: kernels/cuda/matmul_ref_fp32.cc:11-34.  A.row=M, A.column=K, B stored [N][K] with B.row=K? (Linear_FP: B.row=k, B.column=n)
+void MatmulOperator::mat_mul_accelerator_transposed_fastover_column(const struct matmul_params *p) {
+    must(tce_f32_matmul_transposed(tce_host_ctx(), p->A.data_ptr, p->B.data_ptr, p->C.data_ptr, p->A.row, p->B.column, p->A.column),
+         "mat_mul_accelerator_transposed_fastover_column");
+}
+
 // stubs, exactly like the reference CUDA build (gemv_cuda.cu:262-268)
 void MatmulOperator::mat_mul_accelerator_int4_fast(const struct matmul_params *) {}
 void MatmulOperator::mat_mul_accelerator_int4_fast_no_offset(const struct matmul_params *) {}

@@ -8,6 +8,7 @@
 
 #include <vector>
 
+#include "Int8OPTAttention.h"
 #include "ops.h"
 
 extern "C" {
@@ -20,6 +21,8 @@ void orc_int8_matmul_nobias_batch(const int8_t *A, const int8_t *B, int8_t *C, i
 void orc_int8_matmul_bfp32_ofp32(const int8_t *A, const int8_t *B, const float *bias, float *C, int M, int N, int K, float alpha);
 void orc_int8_matmul_nobias_ofp32(const int8_t *A, const int8_t *B, float *C, int M, int N, int K, float alpha);
 void orc_int8_matmul_nobias_ofp32_batch(const int8_t *A, const int8_t *B, float *C, int M, int N, int K, float alpha);
+int orc_opt_int8_attention_core(const int8_t *q8, const int8_t *k8, const int8_t *v8, const int8_t *past_k, const int8_t *past_v, const float *mask,
+                                float qk_alpha, float pv_alpha, int sqlen, int past, int H, int hd, int8_t *attn_out, int8_t *final_k, int8_t *final_v);
 uint16_t orc_float_to_half(float f);
 float orc_half_to_float(uint16_t h);
 }
@@ -154,6 +157,68 @@ static void test_BMMs(int heads, int m, int t, int d, float alpha) {
     cudaFree(q); cudaFree(kk); cudaFree(s); cudaFree(p); cudaFree(vt); cudaFree(o);
 }
 
+// Int8OPTAttention::forward, prefill then two decode steps fed with the returned past_key_value (the reference's
+// test_Int8OPTAttention / _len512 flow, llm/tests/non_cuda/test_Int8OPTAttention.cc), expected values from the oracle.
+static void test_Int8OPTAttention(int E, int H, int prefill) {
+    const int hd = E / H;
+    struct model_config cfg;
+    cfg.num_heads = H; cfg.embed_dim = E; cfg.num_layers = 1; cfg.max_sqlen = 256;
+    Int8OPTAttention::initialized_memory(cfg);
+    const float a_qkv = 0.0009f, b_qkv = 0.9f, qk_alpha = 0.0007f, pv_alpha = 0.011f, a_out = 0.0008f;
+    int8_t *wq = rand_s8((size_t)E * E), *wk = rand_s8((size_t)E * E), *wv = rand_s8((size_t)E * E), *wo = rand_s8((size_t)E * E);
+    int8_t *bq = rand_s8(E), *bk = rand_s8(E), *bv = rand_s8(E);
+    float *bo = managed<float>(E);
+    for (int i = 0; i < E; i++) bo[i] = rndn();
+    W8A8B8O8Linear_params pq = {Matrix3D<int8_t>(wq, 1, E, E), Matrix3D<int8_t>(bq, 1, 1, E), a_qkv, b_qkv};
+    W8A8B8O8Linear_params pk = {Matrix3D<int8_t>(wk, 1, E, E), Matrix3D<int8_t>(bk, 1, 1, E), a_qkv, b_qkv};
+    W8A8B8O8Linear_params pv = {Matrix3D<int8_t>(wv, 1, E, E), Matrix3D<int8_t>(bv, 1, 1, E), a_qkv, b_qkv};
+    W8A8BFP32OFP32Linear_params po = {Matrix3D<int8_t>(wo, 1, E, E), Matrix3D<float>(bo, 1, 1, E), a_out};
+    W8A8B8O8Linear q_proj(pq), k_proj(pk), v_proj(pv);
+    W8A8BFP32OFP32Linear out_proj(po);
+    BMM_S8T_S8N_F32T qk_bmm(qk_alpha);
+    BMM_S8T_S8N_S8T pv_bmm(pv_alpha);
+    Int8OPTAttention attn(cfg, qk_bmm, pv_bmm, k_proj, v_proj, q_proj, out_proj);
+
+    bool ok = true;
+    std::vector<int8_t> past_k, past_v;  // oracle-side cache [H][past][hd]
+    Matrix3D<int8_t> dev_pk, dev_pv;
+    int past = 0;
+    for (int step = 0; step < 3; step++) {
+        const int sqlen = step == 0 ? prefill : 1, tgz = past + sqlen;
+        int8_t *x = rand_s8((size_t)sqlen * E);
+        float *mask = managed<float>((size_t)sqlen * tgz);
+        for (int i = 0; i < sqlen; i++)
+            for (int j = 0; j < tgz; j++) mask[(size_t)i * tgz + j] = j > past + i ? -3.402823466e38f : 0.f;
+        Matrix3D<int8_t> X(x, 1, sqlen, E);
+        Matrix3D<float> M(mask, 1, sqlen, tgz);
+        Int8OPTAttention_output out = step == 0 ? attn.forward(Int8OPTAttention_input(X, M, 0)) : attn.forward(Int8OPTAttention_input(X, M, dev_pk, dev_pv, true, 0));
+        cudaDeviceSynchronize();
+        // oracle
+        std::vector<int8_t> q((size_t)sqlen * E), k((size_t)sqlen * E), v((size_t)sqlen * E), core((size_t)sqlen * E), fk((size_t)H * tgz * hd), fv(fk.size());
+        orc_int8_matmul(x, wq, bq, q.data(), sqlen, E, E, a_qkv, b_qkv, -128, 127);
+        orc_int8_matmul(x, wk, bk, k.data(), sqlen, E, E, a_qkv, b_qkv, -128, 127);
+        orc_int8_matmul(x, wv, bv, v.data(), sqlen, E, E, a_qkv, b_qkv, -128, 127);
+        orc_opt_int8_attention_core(q.data(), k.data(), v.data(), past ? past_k.data() : nullptr, past ? past_v.data() : nullptr, mask, qk_alpha, pv_alpha, sqlen,
+                                    past, H, hd, core.data(), fk.data(), fv.data());
+        std::vector<float> ref((size_t)sqlen * E);
+        orc_int8_matmul_bfp32_ofp32(core.data(), wo, bo, ref.data(), sqlen, E, E, a_out);
+        std::vector<float> got(ref.size());
+        std::vector<int8_t> gk(fk.size()), gv(fv.size());
+        cudaMemcpy(got.data(), out.attn_output.m_data, got.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(gk.data(), out.past_key_value.first.m_data, gk.size(), cudaMemcpyDeviceToHost);
+        cudaMemcpy(gv.data(), out.past_key_value.second.m_data, gv.size(), cudaMemcpyDeviceToHost);
+        ok &= out.past_key_value.first.m_dim_y == tgz;
+        for (size_t i = 0; i < ref.size(); i++) ok &= (ref[i] == got[i]);
+        for (size_t i = 0; i < fk.size(); i++) ok &= (fk[i] == gk[i]) && (fv[i] == gv[i]);
+        past_k = fk; past_v = fv; past = tgz;
+        dev_pk = out.past_key_value.first; dev_pv = out.past_key_value.second;
+        cudaFree(x); cudaFree(mask);
+    }
+    char name[96];
+    snprintf(name, sizeof(name), "Int8OPTAttention E=%d H=%d prefill %d + 2 decode steps (bit exact)", E, H, prefill);
+    report(name, ok);
+}
+
 int main() {
     // shapes of the reference's op tests (llm/tests/cuda/test_ops.cu:671-724, non_cuda/test_ops.cc:177-478)
     test_Linear_half_int4(1, 11008, 4096);
@@ -165,6 +230,7 @@ int main() {
     test_W8A8BFP32OFP32Linear(512, 768, 768, 0.0012f);
     test_BMMs(12, 64, 64, 64, 0.0021f);
     test_BMMs(12, 1, 300, 64, 0.0021f);
+    test_Int8OPTAttention(768, 12, 9);
     printf("%d failure(s)\n", failures);
     return failures ? 1 : 0;
 }

@@ -74,6 +74,30 @@ class Context:
                    "tce_w8a8_matmul")
         return out
 
+    def naive_fp16_int4(self, A, B, scales, block: int = GROUP):
+        M, IC = A.shape
+        OC = scales.shape[1]
+        out = torch.empty((M, OC), dtype=torch.float16, device=A.device)
+        _lib.check(self.L.tce_naive_fp16_int4(self.h, _ptr(A), _ptr(B), _ptr(scales), _ptr(out), M, IC, OC, block), "tce_naive_fp16_int4")
+        return out
+
+    def f32_matmul_transposed(self, A, B):
+        M, K = A.shape
+        N = B.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        _lib.check(self.L.tce_f32_matmul_transposed(self.h, _ptr(A), _ptr(B), _ptr(out), M, N, K), "tce_f32_matmul_transposed")
+        return out
+
+    def opt_int8_attention(self, q8, k8, v8, past_k, past_v, final_k, final_v, mask, qk_alpha, pv_alpha, past: int, H: int, hd: int):
+        """final_k/final_v: int8 [H][>=past+sqlen][hd] tensors (may be the same storage as past_k/past_v -> in place)."""
+        sqlen = q8.shape[0]
+        out = torch.empty((sqlen, H * hd), dtype=torch.int8, device=q8.device)
+        phs = past_k.stride(0) if past_k is not None else 0
+        _lib.check(self.L.tce_opt_int8_attention(self.h, _ptr(q8), _ptr(k8), _ptr(v8), _ptr(past_k), _ptr(past_v), phs, _ptr(final_k), _ptr(final_v),
+                                                 final_k.stride(0), _ptr(mask), qk_alpha, pv_alpha, sqlen, past, H, hd, _ptr(out)),
+                   "tce_opt_int8_attention")
+        return out
+
     def attn_decode(self, qkv, k_cache, v_cache, cos, sin, pos_dev, out, alpha, H, KVH, hd, max_ctx):
         _lib.check(self.L.tce_attn_decode(self.h, _ptr(qkv), _ptr(k_cache), _ptr(v_cache), _ptr(cos), _ptr(sin), _ptr(pos_dev), _ptr(out), alpha, H, KVH,
                                           hd, max_ctx), "tce_attn_decode")
