@@ -153,6 +153,11 @@ TCE_API int tce_llama_decode(tce_llama *m, const int *tokpos_dev);
 /* end to end: token/pos from the host, fp32 logits[vocab] copied back to `logits_host` (may be NULL) and the
  * greedy arg-max to *next_token (may be NULL); returns after the copies have completed */
 TCE_API int tce_llama_decode_host(tce_llama *m, int token, int pos, float *logits_host, int *next_token);
+/* Prompt processing (the reference's Int4LlamaForCausalLM::forward with sqlen = n > 1, cuda/Int4llamaForCausalLM.cu:20-47): n host
+ * token ids at positions pos0..pos0+n-1 in one pass -- KV cache rows written, logits of the LAST position (the only row the
+ * sampler reads, LLaMAGenerate.cu:160-166) copied to logits_host (may be NULL), greedy token to next_token (may be NULL).
+ * Linears run as tcgen05 GEMMs, attention as a causal flash kernel.  Synchronous.  Single GPU (tp_size == 1).                */
+TCE_API int tce_llama_prefill(tce_llama *m, const int *tokens_host, int n, int pos0, float *logits_host, int *next_token);
 TCE_API const float *tce_llama_logits(tce_llama *m);          /* device float[vocab] */
 TCE_API void *tce_llama_kv_cache(tce_llama *m, int layer, int which); /* which: 0 K, 1 V; half[KVH][max_ctx][hd] */
 TCE_API int tce_llama_kernels_per_step(tce_llama *m);

@@ -57,6 +57,7 @@ SIGNATURES = {
     "tce_llama_destroy": (C.c_int, [C.c_void_p]),
     "tce_llama_decode": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tce_llama_decode_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "tce_llama_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tce_llama_logits": (C.c_void_p, [C.c_void_p]),
     "tce_llama_kv_cache": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "tce_llama_kernels_per_step": (C.c_int, [C.c_void_p]),

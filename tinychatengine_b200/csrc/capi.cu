@@ -206,14 +206,7 @@ int tce_w4a16_gemm(tce_ctx *ctx, const void *x, const void *w, const void *zeros
     if (IC < kW4Group || IC % kW4Group || OC < 1) return fail(TCE_ERR_INVALID, "tce_w4a16_gemm: bad shape M=%d IC=%d OC=%d", M, IC, OC);
     if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return fail(TCE_ERR_INVALID, "tce_w4a16_gemm: x, w, y must be 16-byte aligned");
     CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
-    const size_t need = (size_t)OC * IC;
-    if (ctx->c.w16_scratch_elems < need) {  // rare: grows to the largest weight matrix seen (cudaFree synchronises)
-        if (ctx->c.w16_scratch) CK(cudaFree(ctx->c.w16_scratch), "cudaFree w16 scratch");
-        ctx->c.w16_scratch = nullptr;
-        ctx->c.w16_scratch_elems = 0;
-        CK(cudaMalloc(&ctx->c.w16_scratch, need * sizeof(__half)), "cudaMalloc w16 scratch");
-        ctx->c.w16_scratch_elems = need;
-    }
+    CK(w4_scratch_reserve(&ctx->c, (size_t)OC * IC), "w16 scratch");
     CK(launch_w4_expand(&ctx->c, (const uint32_t *)w, (const uint32_t *)zeros, (const __half *)scales, ctx->c.w16_scratch, OC, IC), "w4_expand");
     CK(launch_gemm_f16_tc(&ctx->c, (const __half *)x, IC, ctx->c.w16_scratch, IC, (__half *)y, OC, M, OC, IC), "tce_w4a16_gemm");
     return TCE_OK;
@@ -364,6 +357,15 @@ int tce_llama_decode_host(tce_llama *m, int token, int pos, float *logits_host, 
     std::string err;
     cudaError_t e = reinterpret_cast<LlamaDecoder *>(m)->decode_host(token, pos, logits_host, next_token, &err);
     if (e != cudaSuccess) return fail(TCE_ERR_CUDA, "tce_llama_decode_host: %s (%s)", cudaGetErrorString(e), err.c_str());
+    return TCE_OK;
+}
+int tce_llama_prefill(tce_llama *m, const int *tokens_host, int n, int pos0, float *logits_host, int *next_token) {
+    if (!m || !tokens_host) return fail(TCE_ERR_INVALID, "tce_llama_prefill: null argument");
+    std::string err;
+    cudaError_t e = reinterpret_cast<LlamaDecoder *>(m)->prefill(tokens_host, n, pos0, logits_host, next_token, &err);
+    if (e == cudaErrorNotSupported) return fail(TCE_ERR_UNSUPPORTED, "tce_llama_prefill: %s", err.c_str());
+    if (e == cudaErrorInvalidValue) return fail(TCE_ERR_INVALID, "tce_llama_prefill: bad tokens / n=%d pos0=%d", n, pos0);
+    if (e != cudaSuccess) return fail(TCE_ERR_CUDA, "tce_llama_prefill: %s (%s)", cudaGetErrorString(e), err.c_str());
     return TCE_OK;
 }
 const float *tce_llama_logits(tce_llama *m) { return m ? reinterpret_cast<LlamaDecoder *>(m)->logits() : nullptr; }

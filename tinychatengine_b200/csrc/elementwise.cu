@@ -106,6 +106,38 @@ __global__ void rmsnorm_f16_kernel(const __half *__restrict__ x, const float *__
     for (int i = threadIdx.x; i < dim; i += blockDim.x) yr[i] = __float2half((__half2float(xr[i]) * inv) * gamma[i]);
 }
 
+// ---- row-wise versions for prompt processing (n tokens at once)
+__global__ void embedding_rows_kernel(const __half *__restrict__ table, const int *__restrict__ tokens, float *__restrict__ resid, int E) {
+    const __half2 *row = reinterpret_cast<const __half2 *>(table + (size_t)tokens[blockIdx.x] * E);
+    float2 *dst = reinterpret_cast<float2 *>(resid + (size_t)blockIdx.x * E);
+    for (int i = threadIdx.x; i < E / 2; i += blockDim.x) dst[i] = __half22float2(row[i]);
+}
+
+__global__ void rmsnorm_rows_f32_kernel(const float *__restrict__ x, const float *__restrict__ gamma, __half *__restrict__ y, int dim, float eps) {
+    __shared__ float sred[32];
+    const float *xr = x + (size_t)blockIdx.x * dim;
+    __half *yr = y + (size_t)blockIdx.x * dim;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) ss += xr[i] * xr[i];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += sred[w];
+    const float inv = rsqrtf(tot / (float)dim + eps);
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) yr[i] = __float2half((xr[i] * inv) * gamma[i]);
+}
+
+// act[r][c] = SiLU(gu[r][c]) * gu[r][F + c]   (SiLuMul_half, cuda/Int4llamaDecoderLayer.cu:12-30; fp32 math)
+__global__ void silu_mul_rows_kernel(const __half *__restrict__ gu, __half *__restrict__ act, int F, long long total) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / F;
+        const int c = (int)(e % F);
+        const float g = __half2float(gu[r * 2 * F + c]), u = __half2float(gu[r * 2 * F + F + c]);
+        act[e] = __float2half((g / (1.f + __expf(-g))) * u);
+    }
+}
+
 cudaError_t launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, dim3 grid, dim3 block, cudaStream_t s, bool pdl) {
     cfg = {};
     cfg.gridDim = grid;
@@ -136,6 +168,21 @@ cudaError_t launch_argmax(Ctx *ctx, const float *logits, int n, int *out, bool p
     if (blocks < 1) blocks = 1;
     launch_cfg(cfg, attr, dim3(blocks), dim3(256), ctx->stream, pdl);
     return cudaLaunchKernelEx(&cfg, argmax_kernel, logits, n, out);
+}
+
+cudaError_t launch_embedding_rows(Ctx *ctx, const __half *table, const int *tokens, float *resid, int n, int E) {
+    embedding_rows_kernel<<<n, 256, 0, ctx->stream>>>(table, tokens, resid, E);
+    return cudaGetLastError();
+}
+cudaError_t launch_rmsnorm_rows_f32(Ctx *ctx, const float *x, const float *gamma, __half *y, int rows, int dim, float eps) {
+    rmsnorm_rows_f32_kernel<<<rows, 256, 0, ctx->stream>>>(x, gamma, y, dim, eps);
+    return cudaGetLastError();
+}
+cudaError_t launch_silu_mul_rows(Ctx *ctx, const __half *gu, __half *act, int rows, int F) {
+    const long long total = (long long)rows * F;
+    const long long nb = (total + 255) / 256;
+    silu_mul_rows_kernel<<<(unsigned)(nb < 4096 ? nb : 4096), 256, 0, ctx->stream>>>(gu, act, F, total);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_rmsnorm_f16(Ctx *ctx, const __half *x, const float *gamma, __half *y, int rows, int dim, float eps) {

@@ -36,6 +36,27 @@ struct EpiHalf {  // fp32 accumulator -> fp16 C
     }
 };
 
+struct EpiAddF32 {  // fp32 accumulator added into an fp32 C (residual stream)
+    TCE_DEVINL static void apply(const GemmArgs &a, int row, int col0, int n, const uint32_t (&v)[32]) {
+        float *dst = reinterpret_cast<float *>(a.C) + (size_t)row * a.ldc + col0;
+        if (n == 32 && (a.ldc & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float4 c = reinterpret_cast<float4 *>(dst)[i];
+                c.x += __uint_as_float(v[4 * i + 0]);
+                c.y += __uint_as_float(v[4 * i + 1]);
+                c.z += __uint_as_float(v[4 * i + 2]);
+                c.w += __uint_as_float(v[4 * i + 3]);
+                reinterpret_cast<float4 *>(dst)[i] = c;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+                if (i < n) dst[i] += __uint_as_float(v[i]);
+        }
+    }
+};
+
 template <int VARIANT>
 struct EpiW8 {  // int32 accumulator -> the four W8A8 epilogues (same float op order as w8a8.cu / kernels/ref)
     TCE_DEVINL static void apply(const GemmArgs &a, int row, int col0, int n, const uint32_t (&v)[32]) {
@@ -161,6 +182,19 @@ cudaError_t dispatch(Ctx *ctx, GemmArgs &a, const void *A, long long lda, const 
 
 }  // namespace
 
+cudaError_t w4_scratch_reserve(Ctx *ctx, size_t elems) {
+    if (ctx->w16_scratch_elems >= elems) return cudaSuccess;
+    if (ctx->w16_scratch) {  // rare: grows to the largest weight matrix seen (cudaFree synchronises)
+        cudaError_t e = cudaFree(ctx->w16_scratch);
+        ctx->w16_scratch = nullptr;
+        ctx->w16_scratch_elems = 0;
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaMalloc(&ctx->w16_scratch, elems * sizeof(__half));
+    if (e == cudaSuccess) ctx->w16_scratch_elems = elems;
+    return e;
+}
+
 cudaError_t launch_w4_expand(Ctx *ctx, const uint32_t *w, const uint32_t *zeros, const __half *scales, __half *out, int OC, int IC) {
     const int wpr = IC / 8, zw = zeros_width(IC, kW4Group);
     const long long n = (long long)OC * wpr;
@@ -168,14 +202,16 @@ cudaError_t launch_w4_expand(Ctx *ctx, const uint32_t *w, const uint32_t *zeros,
     return cudaGetLastError();
 }
 
-// C[M][N] fp16 = A[M][K] fp16 * B[N][K]^T fp16, fp32 accumulation.  K % 64 == 0, pointers 16-byte aligned, lda/ldb % 8 == 0.
-cudaError_t launch_gemm_f16_tc(Ctx *ctx, const __half *A, long long lda, const __half *B, long long ldb, __half *C, long long ldc, int M, int N, int K) {
+// C[M][N] = A[M][K] fp16 * B[N][K]^T fp16, fp32 accumulation; C is fp16 (stored) or, with add_f32, fp32 (accumulated into).  K % 64 == 0, pointers 16-byte aligned, lda/ldb % 8 == 0.
+cudaError_t launch_gemm_f16_tc(Ctx *ctx, const __half *A, long long lda, const __half *B, long long ldb, void *C, long long ldc, int M, int N, int K,
+                               int add_f32) {
     if (M < 1 || N < 1 || K < 64 || (K % 64) || (lda % 8) || (ldb % 8)) return cudaErrorInvalidValue;
     GemmArgs a = {};
     a.M = M;
     a.N = N;
     a.C = C;
     a.ldc = ldc;
+    if (add_f32) return dispatch<EpiAddF32, false>(ctx, a, A, lda, B, ldb, K);
     return dispatch<EpiHalf, false>(ctx, a, A, lda, B, ldb, K);
 }
 

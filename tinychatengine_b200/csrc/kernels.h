@@ -90,7 +90,9 @@ cudaError_t launch_naive_fp16_int4(Ctx *ctx, const __half *A, const int32_t *B, 
 cudaError_t launch_f32_matmul_transposed(Ctx *ctx, const float *A, const float *B, float *C, int M, int N, int K);
 
 cudaError_t launch_w4_expand(Ctx *ctx, const uint32_t *w, const uint32_t *zeros, const __half *scales, __half *out, int OC, int IC);
-cudaError_t launch_gemm_f16_tc(Ctx *ctx, const __half *A, long long lda, const __half *B, long long ldb, __half *C, long long ldc, int M, int N, int K);
+cudaError_t launch_gemm_f16_tc(Ctx *ctx, const __half *A, long long lda, const __half *B, long long ldb, void *C, long long ldc, int M, int N, int K,
+                               int add_f32 = 0);
+cudaError_t w4_scratch_reserve(Ctx *ctx, size_t elems);  // grows ctx->w16_scratch (may synchronise the device)
 
 // host-side mirror of the stream-K partition used by the kernel (unit-tested on the CPU)
 struct StreamK {

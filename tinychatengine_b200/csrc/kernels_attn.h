@@ -21,6 +21,21 @@ struct AttnDecodeArgs {
 };
 cudaError_t launch_attn_decode(Ctx *ctx, AttnDecodeArgs a, bool pdl);
 
+// prompt processing (sqlen = n > 1): RoPE + KV append for rows pos0..pos0+n-1, causal attention over the cache
+struct AttnPrefillArgs {
+    __half *qkv;         // [n][(H + 2*KVH) * head_dim]; q is rotated in place
+    __half *k_cache;     // [KVH][max_ctx][head_dim]
+    __half *v_cache;
+    const float *cos, *sin;
+    __half *out;         // [n][H * head_dim]
+    float alpha;
+    int n, pos0, num_heads, num_kv_heads, head_dim, max_ctx;
+};
+cudaError_t launch_attn_prefill(Ctx *ctx, const AttnPrefillArgs &a);
+cudaError_t launch_embedding_rows(Ctx *ctx, const __half *table, const int *tokens, float *resid, int n, int E);
+cudaError_t launch_rmsnorm_rows_f32(Ctx *ctx, const float *x, const float *gamma, __half *y, int rows, int dim, float eps);
+cudaError_t launch_silu_mul_rows(Ctx *ctx, const __half *gu, __half *act, int rows, int F);
+
 // resid_f32[E] = (float) table[token][:]   (reference: CPU Embedding + float2half, cuda/Int4llamaDecoder.cu:62-69)
 cudaError_t launch_embedding(Ctx *ctx, const __half *table, const int *token, float *resid, int E, bool pdl);
 // argmax over fp32 logits -> int (first index of the maximum, like arg_max.cc)

@@ -142,6 +142,13 @@ LlamaDecoder::~LlamaDecoder() {
     cudaFree(d_logits_);
     cudaFree(d_tokpos_);
     cudaFree(d_next_);
+    cudaFree(pf_x_);
+    cudaFree(pf_xn_);
+    cudaFree(pf_qkv_);
+    cudaFree(pf_att_);
+    cudaFree(pf_gu_);
+    cudaFree(pf_act_);
+    cudaFree(pf_tok_);
     cudaFree(d_phases_);
     cudaFree(d_sync_);
     for (int p = 0; p < tp_; p++)
@@ -573,6 +580,103 @@ cudaError_t LlamaDecoder::decode_device(const int *tokpos_dev, std::string *err)
     }
     if (use_graphs_ && g_dev_) return cudaGraphLaunch(g_dev_, s);
     return enqueue_step(tokpos_dev, s, ctx_->use_pdl);
+}
+
+}  // namespace tce
+
+// ------------------------------------------------------------------------------------------------ prompt processing
+// n tokens at once (sqlen > 1 in the reference's Int4LlamaForCausalLM::forward): every linear runs as one tensor-core GEMM over the
+// [n][.] activation block (int4 weights expanded to fp16 once per GEMM), attention as one causal flash kernel over the KV cache.
+namespace tce {
+
+cudaError_t LlamaDecoder::prefill_reserve(int n) {
+    if (n <= pf_cap_) return cudaSuccess;
+    DCK(cudaStreamSynchronize(ctx_->stream));
+    cudaFree(pf_x_);
+    cudaFree(pf_xn_);
+    cudaFree(pf_qkv_);
+    cudaFree(pf_att_);
+    cudaFree(pf_gu_);
+    cudaFree(pf_act_);
+    cudaFree(pf_tok_);
+    pf_x_ = nullptr; pf_xn_ = nullptr; pf_qkv_ = nullptr; pf_att_ = nullptr; pf_gu_ = nullptr; pf_act_ = nullptr; pf_tok_ = nullptr;
+    pf_cap_ = 0;
+    const size_t E = cfg_.embed_dim, F = cfg_.hidden_dim, Q = (size_t)(cfg_.num_heads + 2 * cfg_.num_kv_heads) * cfg_.head_dim,
+                 A = (size_t)cfg_.num_heads * cfg_.head_dim;
+    DCK(cudaMalloc(&pf_x_, n * E * sizeof(float)));
+    DCK(cudaMalloc(&pf_xn_, n * E * sizeof(__half)));
+    DCK(cudaMalloc(&pf_qkv_, n * Q * sizeof(__half)));
+    DCK(cudaMalloc(&pf_att_, n * A * sizeof(__half)));
+    DCK(cudaMalloc(&pf_gu_, n * 2 * F * sizeof(__half)));
+    DCK(cudaMalloc(&pf_act_, n * F * sizeof(__half)));
+    DCK(cudaMalloc(&pf_tok_, n * sizeof(int)));
+    pf_cap_ = n;
+    return cudaSuccess;
+}
+
+// C[n][t.oc] (at column `col` of a row-major buffer with leading dimension ldc) = X[n][t.ic] * deq(t)^T
+cudaError_t LlamaDecoder::prefill_linear(const tce_w4_tensor &t, const __half *x, void *C, long long ldc, int n, bool add_f32) {
+    DCK(w4_scratch_reserve(ctx_, (size_t)t.oc * t.ic));
+    DCK(launch_w4_expand(ctx_, (const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, ctx_->w16_scratch, t.oc, t.ic));
+    return launch_gemm_f16_tc(ctx_, x, t.ic, ctx_->w16_scratch, t.ic, C, ldc, n, t.oc, t.ic, add_f32 ? 1 : 0);
+}
+
+cudaError_t LlamaDecoder::prefill(const int *tokens_host, int n, int pos0, float *logits_host, int *next_token, std::string *err) {
+    if (tp_ > 1) {
+        if (err) *err = "prefill is single-GPU in this build (tensor-parallel ranks process the prompt with decode steps)";
+        return cudaErrorNotSupported;
+    }
+    if (!tokens_host || n < 1 || pos0 < 0 || pos0 + n > cfg_.max_ctx) return cudaErrorInvalidValue;
+    for (int i = 0; i < n; i++)
+        if (tokens_host[i] < 0 || tokens_host[i] >= cfg_.vocab_size) return cudaErrorInvalidValue;
+    DCK(prefill_reserve(n));
+    cudaStream_t s = ctx_->stream;
+    const int E = cfg_.embed_dim, F = cfg_.hidden_dim, H = cfg_.num_heads, KVH = cfg_.num_kv_heads, hd = cfg_.head_dim;
+    const long long Q = (long long)(H + 2 * KVH) * hd;
+    DCK(cudaMemcpyAsync(pf_tok_, tokens_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    DCK(launch_embedding_rows(ctx_, (const __half *)w_.embed_f16, pf_tok_, pf_x_, n, E));
+    for (int l = 0; l < cfg_.num_layers; l++) {
+        const tce_llama_layer &L = layers_[l];
+        DCK(launch_rmsnorm_rows_f32(ctx_, pf_x_, L.input_norm, pf_xn_, n, E, cfg_.rms_eps));
+        DCK(prefill_linear(L.q, pf_xn_, pf_qkv_, Q, n, false));
+        DCK(prefill_linear(L.k, pf_xn_, pf_qkv_ + (size_t)H * hd, Q, n, false));
+        DCK(prefill_linear(L.v, pf_xn_, pf_qkv_ + (size_t)(H + KVH) * hd, Q, n, false));
+        AttnPrefillArgs a{};
+        a.qkv = pf_qkv_;
+        a.k_cache = (__half *)kv_cache(l, 0);
+        a.v_cache = (__half *)kv_cache(l, 1);
+        a.cos = d_cos_;
+        a.sin = d_sin_;
+        a.out = pf_att_;
+        a.alpha = cfg_.qk_alpha > 0 ? cfg_.qk_alpha : 1.0f / sqrtf((float)hd);
+        a.n = n;
+        a.pos0 = pos0;
+        a.num_heads = H;
+        a.num_kv_heads = KVH;
+        a.head_dim = hd;
+        a.max_ctx = cfg_.max_ctx;
+        DCK(launch_attn_prefill(ctx_, a));
+        DCK(prefill_linear(L.o, pf_att_, pf_x_, E, n, true));  // residual add in the GEMM epilogue
+        DCK(launch_rmsnorm_rows_f32(ctx_, pf_x_, L.post_norm, pf_xn_, n, E, cfg_.rms_eps));
+        DCK(prefill_linear(L.gate, pf_xn_, pf_gu_, 2LL * F, n, false));
+        DCK(prefill_linear(L.up, pf_xn_, pf_gu_ + F, 2LL * F, n, false));
+        DCK(launch_silu_mul_rows(ctx_, pf_gu_, pf_act_, n, F));
+        DCK(prefill_linear(L.down, pf_act_, pf_x_, E, n, true));
+    }
+    // only the last position feeds the sampler: final RMSNorm + lm_head as the decode step's last GEMV, then arg-max
+    DCK(cudaMemcpyAsync(d_resid_, pf_x_ + (size_t)(n - 1) * E, (size_t)E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    const StepOp *lm = nullptr;
+    for (const StepOp &op : ops_)
+        if (op.type == OP_GEMV) lm = &op;
+    if (!lm) return cudaErrorUnknown;
+    DCK(launch_w4a16_gemv(ctx_, lm->g));
+    DCK(launch_argmax(ctx_, d_logits_, cfg_.vocab_size, d_next_, false));
+    if (logits_host) DCK(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)cfg_.vocab_size * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DCK(cudaMemcpyAsync(h_next_, d_next_, sizeof(int), cudaMemcpyDeviceToHost, s));
+    DCK(cudaStreamSynchronize(s));
+    if (logits_host) memcpy(logits_host, h_logits_, (size_t)cfg_.vocab_size * sizeof(float));
+    if (next_token) *next_token = *h_next_;
+    return cudaSuccess;
 }
 
 }  // namespace tce

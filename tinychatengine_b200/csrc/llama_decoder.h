@@ -17,6 +17,8 @@ class LlamaDecoder {
     ~LlamaDecoder();
     cudaError_t decode_device(const int *tokpos_dev, std::string *err);
     cudaError_t decode_host(int token, int pos, float *logits_host, int *next_token, std::string *err);
+    // prompt processing: n tokens at positions pos0..pos0+n-1 in one pass (tensor-core GEMMs + causal flash attention)
+    cudaError_t prefill(const int *tokens_host, int n, int pos0, float *logits_host, int *next_token, std::string *err);
     const float *logits() const { return d_logits_; }
     void *kv_cache(int layer, int which) const;
     int kernels_per_step() const { return kernels_per_step_; }
@@ -35,6 +37,8 @@ class LlamaDecoder {
 
    private:
     LlamaDecoder() = default;
+    cudaError_t prefill_reserve(int n);
+    cudaError_t prefill_linear(const tce_w4_tensor &t, const __half *x, void *C, long long ldc, int n, bool add_f32);
     cudaError_t enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only = false);  // raw kernel sequence
     cudaError_t build_graphs(std::string *err);
     void build_ops();
@@ -80,6 +84,15 @@ class LlamaDecoder {
     int *d_next_ = nullptr;         // greedy arg-max
     float *d_cos_ = nullptr, *d_sin_ = nullptr;
     bool own_rope_ = false;
+    // prompt-processing activations, [pf_cap_] rows each (allocated on first use)
+    int pf_cap_ = 0;
+    float *pf_x_ = nullptr;         // fp32 residual stream [n][E]
+    __half *pf_xn_ = nullptr;       // RMSNorm output [n][E]
+    __half *pf_qkv_ = nullptr;      // [n][(H+2KVH)*hd]
+    __half *pf_att_ = nullptr;      // [n][H*hd]
+    __half *pf_gu_ = nullptr;       // [n][2F] gate | up
+    __half *pf_act_ = nullptr;      // [n][F]
+    int *pf_tok_ = nullptr;
     // pinned host staging for the end-to-end entry point
     int *h_tokpos_ = nullptr;
     float *h_logits_ = nullptr;
