@@ -79,6 +79,7 @@ int tce_ctx_create(int device, tce_ctx **out) {
     c.gemv_impl = env_int("TCE_GEMV_IMPL", 1);
     c.gemv_ctas_per_sm = env_int("TCE_GEMV_CTAS_PER_SM", 1);
     c.gemv_consumer_warps = env_int("TCE_GEMV_CONSUMER_WARPS", 8) == 16 ? 16 : 8;
+    c.pdl_early = env_int("TCE_PDL_EARLY", 0);
     c.use_pdl = env_int("TCE_USE_PDL", 0) != 0;  // measured slower than plain graph edges on B200 (profiles/README.md)
     ctx->attn_chunk = env_int("TCE_ATTN_CHUNK", 128);
     c.gemv_max_ctas = c.num_sms * 4;

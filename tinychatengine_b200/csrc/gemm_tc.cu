@@ -166,18 +166,32 @@ cudaError_t launch(Ctx *ctx, GemmArgs &a, const void *A, long long lda, const vo
     return cudaGetLastError();
 }
 
-// fewer idle SMs in the last wave decides between the 128x256 and the 128x128 tile
-bool prefer_n256(int M, int N, int sms) {
+// Tile width by wave quantisation: a persistent grid of `sms` CTAs needs ceil(tiles / sms) rounds, each costing ~BLOCK_N (the MMA
+// time of one tile) times a small penalty for the narrower tiles (the 128-row A tile is re-read once per N block).
+int pick_block_n(int M, int N, int sms) {
     const long long mb = (M + 127) / 128;
-    const long long t256 = mb * ((N + 255) / 256), t128 = mb * ((N + 127) / 128);
-    const double w256 = (double)((t256 + sms - 1) / sms) * 2.0, w128 = (double)((t128 + sms - 1) / sms) * 1.15;  // time in 128x128-tile units
-    return w256 <= w128;
+    const int bn[3] = {256, 192, 128};
+    const double pen[3] = {1.00, 1.04, 1.12};
+    int best = 256;
+    double best_cost = 1e30;
+    for (int i = 0; i < 3; i++) {
+        const long long tiles = mb * ((N + bn[i] - 1) / bn[i]);
+        const double cost = (double)((tiles + sms - 1) / sms) * bn[i] * pen[i];
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = bn[i];
+        }
+    }
+    return best;
 }
 
 template <class Epi, bool I8>
 cudaError_t dispatch(Ctx *ctx, GemmArgs &a, const void *A, long long lda, const void *B, long long ldb, long long K) {
-    if (prefer_n256(a.M, a.N, ctx->num_sms)) return launch<256, 4, I8, Epi>(ctx, a, A, lda, B, ldb, K);
-    return launch<128, 6, I8, Epi>(ctx, a, A, lda, B, ldb, K);
+    switch (pick_block_n(a.M, a.N, ctx->num_sms)) {
+        case 256: return launch<256, 4, I8, Epi>(ctx, a, A, lda, B, ldb, K);
+        case 192: return launch<192, 5, I8, Epi>(ctx, a, A, lda, B, ldb, K);
+        default: return launch<128, 6, I8, Epi>(ctx, a, A, lda, B, ldb, K);
+    }
 }
 
 }  // namespace

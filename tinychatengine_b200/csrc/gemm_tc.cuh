@@ -107,9 +107,9 @@ constexpr size_t smem_bytes() {
 // Epi::apply(args, row, col0, ncols_valid, v[32]) consumes 32 consecutive accumulator columns of one output row.
 template <int BLOCK_N, int STAGES, bool I8, class Epi>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs a) {
-    static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+    static_assert(BLOCK_N == 128 || BLOCK_N == 192 || BLOCK_N == 256, "BLOCK_N");
     constexpr int kBBytes = BLOCK_N * kAtomBytes;
-    constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+    constexpr uint32_t kTmemCols = BLOCK_N == 128 ? 256 : 512;  // two accumulators; allocations are powers of two
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;

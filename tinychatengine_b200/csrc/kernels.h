@@ -28,6 +28,7 @@ struct Ctx {
     int gemv_ctas_per_sm = 1;
     int gemv_consumer_warps = 8;   // 8 or 16 consumer warps per CTA
     bool use_pdl = false;
+    int pdl_early = 0;  // with use_pdl: 1 = dependents may become resident from the first instruction of each GEMV (2: and no 2-CTA/SM mode)
     // large-M (prefill) path: fp16 expansion of one int4 weight matrix, grown on demand; M >= gemm_min_m goes to the tcgen05 GEMM
     __half *w16_scratch = nullptr;
     size_t w16_scratch_elems = 0;

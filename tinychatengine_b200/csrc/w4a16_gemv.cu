@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
 
+    if (a.pdl_early) pdl_launch_dependents();
     if (tid == 0) {
         dbg_stamp(a, cta, 0);
         init_barriers<CW>(sm);
@@ -164,6 +165,7 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     a.partials = ctx->gemv_partials;
     a.counters = ctx->gemv_counters;
     a.dbg = ctx->gemv_dbg;
+    a.pdl_early = 0;
     a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
     a.aligned = 0;
     a.sg = a.NG < kStageGroups ? a.NG : kStageGroups;
@@ -195,7 +197,9 @@ cudaError_t launch_mma(Ctx *ctx, const KArgs &a_in, bool pdl) {
     // staging, which dominates small launches and long rows: only used when every CTA still gets >= 128 units and the
     // activation vector is short.  "gemv_ctas_per_sm" > 1 forces it.
     int per_sm = ctx->gemv_ctas_per_sm;
-    if (per_sm == 1 && NCOLS == 1 && CW == 8 && a.IC <= 8192 && U >= (long long)ctx->num_sms * 2 * 128) per_sm = 2;
+    a.pdl_early = (pdl && ctx->pdl_early) ? 1 : 0;
+    const bool allow2 = !(pdl && ctx->pdl_early == 2);  // an early-resident dependent needs the second CTA slot of every SM
+    if (allow2 && per_sm == 1 && NCOLS == 1 && CW == 8 && a.IC <= 8192 && U >= (long long)ctx->num_sms * 2 * 128) per_sm = 2;
     int nc = ctx->num_sms * per_sm;
     if (nc > ctx->gemv_max_ctas) nc = ctx->gemv_max_ctas;
     if ((long long)nc > U) nc = (int)U;

@@ -49,6 +49,7 @@ struct KArgs {
     int aligned;     // 1: CTA ranges are cut at row-tile boundaries (no split tiles, no fix-up)
     int atomic_add;  // 1: EPI_ADD_F32 partial tiles use RED.ADD.F32 instead of the ordered fix-up
     unsigned long long *dbg;  // optional per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
+    int pdl_early;   // 1: griddepcontrol.launch_dependents at kernel entry instead of after the last weight request
     // tensor parallel: see W4GemvParams
     int tp_size;
     const float *tp_in;

@@ -214,6 +214,14 @@ class LlamaModel:
         _lib.check(self.ctx.L.tce_llama_decode_host(self.h, int(token), int(pos), p, C.byref(nxt)), "tce_llama_decode_host")
         return nxt.value
 
+    def prefill(self, tokens, pos0: int = 0, logits_host=None) -> int:
+        """Prompt processing: all `tokens` (host ints) at positions pos0.. in one pass; returns the greedy next token."""
+        arr = (C.c_int * len(tokens))(*[int(t) for t in tokens])
+        nxt = C.c_int(-1)
+        p = None if logits_host is None else C.c_void_p(logits_host.data_ptr())
+        _lib.check(self.ctx.L.tce_llama_prefill(self.h, arr, len(tokens), int(pos0), p, C.byref(nxt)), "tce_llama_prefill")
+        return nxt.value
+
     def logits(self) -> torch.Tensor:
         """View of the device logits buffer (float32 [vocab])."""
         ptr = self.ctx.L.tce_llama_logits(self.h)
