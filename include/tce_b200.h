@@ -106,6 +106,13 @@ TCE_API int tce_attn_decode(tce_ctx *ctx, const void *qkv, void *k_cache, void *
                             const float *sin, const int *pos, void *out, float alpha, int num_heads, int num_kv_heads,
                             int head_dim, int max_ctx);
 
+/* Same module for sqlen = n > 1 (prompt processing): qkv half[n][(H + 2*KVH)*head_dim] holds the fused projections of n tokens at
+ * positions pos0..pos0+n-1; q is rotated IN PLACE, rotated k and v are appended to the caches, out half[n][H*head_dim] receives
+ * causal attention over cache rows 0..pos0+i for token i.  One flash kernel (mma.sync m16n8k16, fp32 softmax), no [n][T] score
+ * tensor in HBM.  head_dim == 128.                                                                                            */
+TCE_API int tce_attn_prefill(tce_ctx *ctx, void *qkv, void *k_cache, void *v_cache, const float *cos, const float *sin, void *out, float alpha,
+                             int n, int pos0, int num_heads, int num_kv_heads, int head_dim, int max_ctx);
+
 /* ---- small ops either side of the path -------------------------------------------------------------------
  * LlamaRMSNorm_cuda::forward (llm/src/ops/cuda/LlamaRMSNorm.cu:96-115): half in/out, fp32 gamma             */
 TCE_API int tce_rmsnorm_f16(tce_ctx *ctx, const void *x, const float *gamma, void *y, int rows, int dim, float eps);

@@ -251,3 +251,157 @@ def aligned_empty(shape, dtype, align: int = 64) -> np.ndarray:
     raw = np.empty(n + align, np.uint8)
     off = (-raw.ctypes.data) % align
     return raw[off:off + n].view(dtype).reshape(shape)
+
+
+# ----------------------------------------------------------------------------------------------
+# reference MODULE build (oracle/_ref/libtce_ref_modules.so: llm/src/nn_modules/Int8OPTAttention.cc + its ops, unmodified)
+# ----------------------------------------------------------------------------------------------
+def write_opt_attention_params(root, W, B, bo, a_qkv, b_qkv, qk_alpha, pv_alpha, a_out):
+    """The parameter tree Int8OPTAttention's constructor loads (load_W8A8B8O8Linear_params etc., llm/src/ops/*.cc:6-13).
+    W: dict q,k,v,o -> int8 [E][E]; B: dict q,k,v -> int8 [E]; bo: float32 [E]."""
+    import os
+
+    f32 = lambda v: np.array([v], np.float32)
+    for k in "qkv":
+        d = os.path.join(root, f"{k}_proj")
+        os.makedirs(d, exist_ok=True)
+        np.ascontiguousarray(W[k], np.int8).tofile(os.path.join(d, "weight.bin"))
+        np.ascontiguousarray(B[k], np.int8).tofile(os.path.join(d, "bias_int8.bin"))
+        f32(a_qkv).tofile(os.path.join(d, "alpha.bin"))
+        f32(b_qkv).tofile(os.path.join(d, "beta.bin"))
+    d = os.path.join(root, "out_proj")
+    os.makedirs(d, exist_ok=True)
+    np.ascontiguousarray(W["o"], np.int8).tofile(os.path.join(d, "weight.bin"))
+    np.ascontiguousarray(bo, np.float32).tofile(os.path.join(d, "bias.bin"))
+    f32(a_out).tofile(os.path.join(d, "alpha.bin"))
+    for name, v in (("qk_bmm", qk_alpha), ("pv_bmm", pv_alpha)):
+        d = os.path.join(root, name)
+        os.makedirs(d, exist_ok=True)
+        f32(v).tofile(os.path.join(d, "alpha.bin"))
+
+
+def ref_int8_opt_attention(param_root, hidden, E, H, prefill, decode_steps, max_sqlen=256):
+    """Runs the REFERENCE Int8OPTAttention::forward (prefill rows, then single-token steps).  Returns (out fp32 [T][E], K, V int8 [H][T][hd])."""
+    so = REF_DIR / "libtce_ref_modules.so"
+    if not so.exists():
+        raise FileNotFoundError(f"{so} not built (needs /root/reference; run `make -C oracle ref`)")
+    L = C.CDLL(str(so))
+    L.ref_int8_opt_attention.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    hidden = np.ascontiguousarray(hidden, np.int8)
+    T, hd = prefill + decode_steps, E // H
+    out = np.zeros((T, E), np.float32)
+    fk = np.zeros((H, T, hd), np.int8)
+    fv = np.zeros((H, T, hd), np.int8)
+    n = L.ref_int8_opt_attention(str(param_root).encode(), E, H, max_sqlen, hidden.ctypes.data, prefill, decode_steps, out.ctypes.data, fk.ctypes.data,
+                                 fv.ctypes.data)
+    assert n == T
+    return out, fk, fv
+
+
+def oracle_int8_opt_attention(hidden, W, B, bo, a_qkv, b_qkv, qk_alpha, pv_alpha, a_out, H, prefill, decode_steps):
+    """The same module flow composed from the oracle: projections (orc_int8_matmul), core, out_proj."""
+    E = hidden.shape[1]
+    hd = E // H
+    pk = pv = None
+    past = row = 0
+    outs = []
+    for call in range(1 + decode_steps):
+        s = prefill if call == 0 else 1
+        x = hidden[row:row + s]
+        q, k, v = (int8_matmul(0, x, W[n], B[n], None, a_qkv, b_qkv) for n in "qkv")
+        core, pk, pv = opt_int8_attention_core(q, k, v, pk, pv, causal_mask(s, past), qk_alpha, pv_alpha, H, hd)
+        outs.append(int8_matmul(4, core, W["o"], biasf=bo, alpha=a_out))
+        past += s
+        row += s
+    return np.concatenate(outs), pk, pv
+
+
+# ----------------------------------------------------------------------------------------------
+# reference Int4llamaAttention MODULE (CPU, the reference's own x86 flags): oracle/_ref/libtce_ref_llama.so
+# ----------------------------------------------------------------------------------------------
+def selection_matrix(rows: int, cols: int, rng):
+    """0/1 matrix picking `rows` distinct input channels: survives INT4 quantisation exactly, so the module's linears
+    become exact channel selections and the attention core can be compared at fp32 round-off."""
+    sel = rng.permutation(cols)[:rows]
+    W = np.zeros((rows, cols), np.float32)
+    W[np.arange(rows), sel] = 1.0
+    return W, sel
+
+
+def exact_w4a8_activations(shape, rng, unit=2.0 ** -6):
+    """fp32 activations that the reference's per-32 int8 activation quantiser (matmul_avx_int8_int4.cc:259-316) reproduces
+    exactly: integers in [-127, 127] times a power of two, every 32-block holding a +-127."""
+    xi = rng.integers(-127, 128, shape).astype(np.float32)
+    blocks = xi.reshape(shape[0], shape[1] // 32, 32)
+    blocks[:, :, 0] = 127 * np.sign(rng.standard_normal(blocks.shape[:2]))
+    return (xi * np.float32(unit)).astype(np.float32)
+
+
+def w4a8_activation_roundtrip(x):
+    """What an identity / selection Linear_FP_int4 returns on the x86 build: x quantised per 32-block to int8 and rescaled
+    (d = amax/127, id = 127/amax, round to nearest even) -- restates matmul_avx_int8_int4.cc:259-316 for the test harness."""
+    xb = np.ascontiguousarray(x, np.float32).reshape(-1, 32)
+    amax = np.abs(xb).max(1, keepdims=True)
+    d = (amax / np.float32(127)).astype(np.float32)
+    inv = np.where(amax != 0, np.float32(127) / np.where(amax != 0, amax, 1), 0).astype(np.float32)
+    q = np.rint((xb * inv).astype(np.float32))
+    return (q * d).astype(np.float32).reshape(np.shape(x))
+
+
+def write_llama_attention_params(root, W, cosb, sinb, alpha):
+    """Parameter tree of the CPU Int4llamaAttention (QM_x86): W dict q_proj/k_proj/v_proj/o_proj -> fp32 matrices."""
+    import os
+
+    from . import quant
+
+    for name, w in W.items():
+        d = os.path.join(root, name)
+        os.makedirs(d, exist_ok=True)
+        qs, sc = quant.quantize_q4_3(w)
+        qs.tofile(os.path.join(d, "weight_int4.bin"))
+        sc.astype(np.float32).tofile(os.path.join(d, "scaling_factor_int4.bin"))
+        np.array([8.0], np.float32).tofile(os.path.join(d, "zero_point_int4.bin"))
+    d = os.path.join(root, "rotary_emb")
+    os.makedirs(d, exist_ok=True)
+    np.ascontiguousarray(cosb, np.float32).tofile(os.path.join(d, "cos_cached.bin"))
+    np.ascontiguousarray(sinb, np.float32).tofile(os.path.join(d, "sin_cached.bin"))
+    d = os.path.join(root, "qk_bmm")
+    os.makedirs(d, exist_ok=True)
+    np.array([alpha], np.float32).tofile(os.path.join(d, "alpha.bin"))
+
+
+def ref_int4_llama_attention(param_root, hidden, E, H, KVH, prefill, decode_steps, max_sqlen):
+    """Runs the REFERENCE Int4llamaAttention::forward (CPU).  Returns (out fp32 [T][E], K, V fp32 [KVH][T][hd])."""
+    so = REF_DIR / "libtce_ref_llama.so"
+    if not so.exists():
+        raise FileNotFoundError(f"{so} not built (needs /root/reference; run `make -C oracle ref`)")
+    L = C.CDLL(str(so))
+    L.ref_int4_llama_attention.argtypes = [C.c_char_p] + [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    hidden = np.ascontiguousarray(hidden, np.float32)
+    T, hd = prefill + decode_steps, E // H
+    out = np.zeros((T, E), np.float32)
+    fk = np.zeros((KVH, T, hd), np.float32)
+    fv = np.zeros((KVH, T, hd), np.float32)
+    n = L.ref_int4_llama_attention(str(param_root).encode(), E, H, KVH, max_sqlen, hidden.ctypes.data, prefill, decode_steps, out.ctypes.data,
+                                   fk.ctypes.data, fv.ctypes.data)
+    assert n == T
+    return out, fk, fv
+
+
+def oracle_llama_attention_module(hidden, sel, cosb, sinb, alpha, H, KVH, prefill, decode_steps):
+    """Same flow from the oracle: selection projections (exact), orc_llama_attention_core, o_proj = selection of the
+    int8-round-tripped core output.  sel: dict q,k,v,o -> channel index arrays.  Returns (out, K, V, core)."""
+    E = hidden.shape[1]
+    hd = E // H
+    pk = pv = None
+    past = row = 0
+    outs, cores = [], []
+    for call in range(1 + decode_steps):
+        s = prefill if call == 0 else 1
+        x = hidden[row:row + s]
+        core, pk, pv = llama_attention_core(x[:, sel["q"]], x[:, sel["k"]], x[:, sel["v"]], pk, pv, causal_mask(s, past), cosb, sinb, alpha, H, KVH, hd)
+        cores.append(core)
+        outs.append(w4a8_activation_roundtrip(core)[:, sel["o"]])
+        past += s
+        row += s
+    return np.concatenate(outs), pk, pv, np.concatenate(cores)

@@ -1,0 +1,69 @@
+// ref_modules_shim.cc -- extern "C" doorway into the UNMODIFIED reference module Int8OPTAttention (compiled in place from
+// /root/reference/llm/src by oracle/Makefile into oracle/_ref/libtce_ref_modules.so).  TEST INFRASTRUCTURE ONLY.
+//
+// Nothing here re-implements arithmetic: the shim allocates the operator buffers the way the reference's own model code does
+// (llm/src/nn_modules/Int8OPTDecoderLayer.cc:130-170), lets the reference constructor load a synthetic parameter tree from
+// `param_path` (written by tests/golden/make_golden.py: q_proj|k_proj|v_proj/{weight,bias_int8,alpha,beta}.bin,
+// out_proj/{weight,bias,alpha}.bin, qk_bmm|pv_bmm/alpha.bin), and runs Int8OPTAttention::forward for a prefill followed by
+// single-token steps fed with the returned past_key_value.  It pins oracle/tce_oracle.c's restatement of the module.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nn_modules/Int8OPTAttention.h"
+#include "operators.h"
+#include "utils.h"
+
+int NUM_THREAD = 4;  // the reference applications define this global (llm/application/chat.cc)
+
+extern "C" {
+
+// hidden: int8 [total_tokens][E] (prefill rows first, then one row per decode step); masks built here as the reference's
+// Int8OPTDecoder::prepare_decoder_attention_mask does (0 / lowest float above the diagonal).
+// out_fp: float [total_tokens][E] attention outputs in call order; final_k/final_v: int8 [H][total_tokens][hd] after the last call.
+int ref_int8_opt_attention(const char *param_path, int E, int H, int max_sqlen, const int8_t *hidden, int prefill, int decode_steps, float *out_fp,
+                           int8_t *final_k, int8_t *final_v) {
+    struct model_config cfg(1, H, 1, max_sqlen, E, 4 * E, 50272, 1, 0);
+    Int8OPTAttention::initialized_memory(cfg);
+    const int hd = E / H;
+    std::vector<int8_t> wq((size_t)E * E), wk((size_t)E * E), wv((size_t)E * E), wo((size_t)E * E), bq(E), bk(E), bv(E);
+    std::vector<float> bo(E);
+    struct W8A8B8O8Linear_params pq, pk, pv;
+    pq.weight = Matrix3D<int8_t>(wq.data(), 1, E, E);
+    pq.bias = Matrix3D<int8_t>(bq.data(), 1, 1, E);
+    pk.weight = Matrix3D<int8_t>(wk.data(), 1, E, E);
+    pk.bias = Matrix3D<int8_t>(bk.data(), 1, 1, E);
+    pv.weight = Matrix3D<int8_t>(wv.data(), 1, E, E);
+    pv.bias = Matrix3D<int8_t>(bv.data(), 1, 1, E);
+    struct W8A8BFP32OFP32Linear_params po;
+    po.weight = Matrix3D<int8_t>(wo.data(), 1, E, E);
+    po.bias = Matrix3D<float>(bo.data(), 1, 1, E);
+    W8A8B8O8Linear q_proj(pq), k_proj(pk), v_proj(pv);
+    W8A8BFP32OFP32Linear out_proj(po);
+    BMM_S8T_S8N_F32T qk_bmm;
+    BMM_S8T_S8N_S8T pv_bmm;
+    Int8OPTAttention attn(std::string(param_path), cfg, qk_bmm, pv_bmm, k_proj, v_proj, q_proj, out_proj);
+
+    Matrix3D<int8_t> past_k, past_v;
+    int past = 0, row = 0;
+    for (int call = 0; call < 1 + decode_steps; call++) {
+        const int sqlen = call == 0 ? prefill : 1, tgz = past + sqlen;
+        std::vector<float> mask((size_t)sqlen * tgz, 0.f);
+        for (int i = 0; i < sqlen; i++)
+            for (int j = past + i + 1; j < tgz; j++) mask[(size_t)i * tgz + j] = -3.402823466e38f;
+        Matrix3D<int8_t> hs(const_cast<int8_t *>(hidden) + (size_t)row * E, 1, sqlen, E);
+        Matrix3D<float> m(mask.data(), 1, sqlen, tgz);
+        struct Int8OPTAttention_output out =
+            call == 0 ? attn.forward(Int8OPTAttention_input(hs, m, 0)) : attn.forward(Int8OPTAttention_input(hs, m, past_k, past_v, true, 0));
+        memcpy(out_fp + (size_t)row * E, out.attn_output.m_data, (size_t)sqlen * E * sizeof(float));
+        past_k = out.past_key_value.first;
+        past_v = out.past_key_value.second;
+        past = tgz;
+        row += sqlen;
+    }
+    memcpy(final_k, past_k.m_data, (size_t)H * past * hd);
+    memcpy(final_v, past_v.m_data, (size_t)H * past * hd);
+    return past;
+}
+}

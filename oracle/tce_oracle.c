@@ -385,7 +385,7 @@ ORC_API void orc_layernorm_q(const float *x, const float *weight, const float *b
 }
 
 /* llm/src/ops/softmax.cc:5-41 (dim 2).  NOTE the reference seeds max with input.m_data[0] (first element of
- * the whole tensor, softmax.cc:13), restated as-is via `seed`. */
+ * the whole tensor, softmax.cc:13), restated as-is via `seed`; the attention modules call it in place, see the callers. */
 static void softmax_row(const float *in, float *out, int n, float seed) {
     float max_value = seed;
     float sum = 0;
@@ -476,8 +476,9 @@ ORC_API int orc_llama_attention_core(const float *q_in, const float *k_in, const
                 *p = *p + mask[(size_t)i * tgz + j];
                 if (isinf(*p)) *p = lowest;
             }
-    float seed = S[0];
-    for (size_t r = 0; r < (size_t)H * sqlen; r++) softmax_row(&S[r * tgz], &S[r * tgz], tgz, seed);
+    /* the module runs softmax IN PLACE (attn_probs aliases attn_weights_arr), so `input.m_data[0]` read at the top of
+     * each row (softmax.cc:13) is the raw score only for the first row and p[0][0][0] afterwards */
+    for (size_t r = 0; r < (size_t)H * sqlen; r++) softmax_row(&S[r * tgz], &S[r * tgz], tgz, S[0]);
     memset(O, 0, sizeof(float) * H * sqlen * hd);
     for (int h = 0; h < H; h++) {
         const float *V = &final_v[(size_t)(h / n_rep) * tgz * hd];
@@ -534,8 +535,9 @@ ORC_API int orc_opt_int8_attention_core(const int8_t *q8, const int8_t *k8, cons
                 float s = (float)acc * qk_alpha;
                 S[((size_t)h * sqlen + i) * tgz + j] = s + mask[(size_t)i * tgz + j];
             }
-    float seed = S[0];
-    for (size_t r = 0; r < (size_t)H * sqlen; r++) softmax_row(&S[r * tgz], &S[r * tgz], tgz, seed);
+    /* the module runs softmax IN PLACE (attn_probs aliases attn_weights_arr), so `input.m_data[0]` read at the top of
+     * each row (softmax.cc:13) is the raw score only for the first row and p[0][0][0] afterwards */
+    for (size_t r = 0; r < (size_t)H * sqlen; r++) softmax_row(&S[r * tgz], &S[r * tgz], tgz, S[0]);
     for (size_t i = 0; i < (size_t)H * sqlen * tgz; i++) P[i] = (int8_t)(int32_t)roundf(S[i] * 127);
     for (int h = 0; h < H; h++)
         for (int i = 0; i < sqlen; i++)

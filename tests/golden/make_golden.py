@@ -130,6 +130,34 @@ def main():
     xs = capi.aligned_empty((M * IC // 32,), np.float32)
     X.ref_w4a8_avx(A.ctypes.data, Bq.ctypes.data, S.ctypes.data, Cx.ctypes.data, xi8.ctypes.data, xs.ctypes.data, M, IC, OC, 2)
     np.savez_compressed(OUT / "kernels_avx.npz", A=np.array(A), w=w, qs=qs3, d=d3, C=np.array(Cx))
+    # the reference MODULE Int8OPTAttention (compiled in place, oracle/ref_modules_shim.cc): prefill of 9 tokens + 3 decode steps
+    E, H, prefill, steps = 256, 4, 9, 3
+    par = dict(a_qkv=np.float32(0.0009), b_qkv=np.float32(0.9), qk_alpha=np.float32(0.0007), pv_alpha=np.float32(0.011), a_out=np.float32(0.0008))
+    W = {k: rng.integers(-127, 128, (E, E), dtype=np.int8) for k in "qkvo"}
+    Bq8 = {k: rng.integers(-127, 128, (E,), dtype=np.int8) for k in "qkv"}
+    bo = rng.standard_normal(E).astype(np.float32)
+    hidden = rng.integers(-127, 128, (prefill + steps, E), dtype=np.int8)
+    with tempfile.TemporaryDirectory() as d:
+        capi.write_opt_attention_params(d, W, Bq8, bo, **par)
+        out, fk, fv = capi.ref_int8_opt_attention(d, hidden, E, H, prefill, steps)
+    np.savez_compressed(OUT / "opt_attention_module.npz", hidden=hidden, wq=W["q"], wk=W["k"], wv=W["v"], wo=W["o"], bq=Bq8["q"], bk=Bq8["k"], bv=Bq8["v"],
+                        bo=bo, out=out, final_k=fk, final_v=fv, H=H, prefill=prefill, steps=steps, **par)
+    # the reference MODULE Int4llamaAttention (CPU build, GQA 4:2, head_dim 128): prefill of 7 tokens + 3 decode steps.  The four
+    # linears are 0/1 channel selections and the activations are exactly int8-representable, so the module output isolates the
+    # attention core (RoPE, KV concat, GQA repeat, mask, in-place softmax, PV) at fp32 round-off.
+    E, H, KVH, prefill, steps, max_sq = 512, 4, 2, 7, 3, 64
+    hd = E // H
+    Wsel, sel = {}, {}
+    for name, rows in (("q", E), ("k", KVH * hd), ("v", KVH * hd), ("o", E)):
+        Wsel[name + "_proj"], sel[name] = capi.selection_matrix(rows, E, rng)
+    cosb, sinb = capi.rope_tables(max_sq, hd, 10000.0)
+    alpha = np.float32(1.0 / np.sqrt(hd))
+    hidden = capi.exact_w4a8_activations((prefill + steps, E), rng)
+    with tempfile.TemporaryDirectory() as d:
+        capi.write_llama_attention_params(d, Wsel, cosb, sinb, alpha)
+        out, fk, fv = capi.ref_int4_llama_attention(d, hidden, E, H, KVH, prefill, steps, max_sq)
+    np.savez_compressed(OUT / "llama_attention_module.npz", hidden=hidden, sel_q=sel["q"], sel_k=sel["k"], sel_v=sel["v"], sel_o=sel["o"], out=out,
+                        final_k=fk, final_v=fv, H=H, KVH=KVH, prefill=prefill, steps=steps, max_sq=max_sq, alpha=alpha, theta=np.float32(10000.0))
     print("golden fixtures written to", OUT)
 
 

@@ -85,3 +85,74 @@ def test_multi_step_append_is_consistent(ctx):
         pk, pv = fk, fv
         got = out.float().cpu().numpy()
         assert np.abs(got - want[0]).max() / max(np.abs(want).max(), 1e-6) <= 3e-3, step
+
+
+@pytest.mark.parametrize("H,KVH,n,pos0", [(8, 2, 1, 0), (8, 2, 70, 0), (4, 4, 64, 0), (8, 1, 33, 100), (16, 8, 130, 61), (4, 2, 5, 1019)])
+def test_prefill_attention_matches_oracle(ctx, H, KVH, n, pos0):
+    """tce_attn_prefill (sqlen = n > 1, optional past): vs the fp32 GQA oracle; q rotated in place, K/V rows appended."""
+    from oracle import capi
+
+    max_ctx = 1024
+    rng = np.random.default_rng(7 * H + n + pos0)
+    cosb, sinb = capi.rope_tables(max_ctx, HD, 500000.0)
+    QKV = (H + 2 * KVH) * HD
+    qkv = rng.standard_normal((n, QKV)).astype(np.float16)
+    pk = (rng.standard_normal((KVH, pos0, HD)) * 0.7).astype(np.float16)
+    pv = rng.standard_normal((KVH, pos0, HD)).astype(np.float16)
+    alpha = 1.0 / np.sqrt(HD)
+    f = qkv.astype(np.float32)
+    want, fk, fv = capi.llama_attention_core(f[:, : H * HD], f[:, H * HD: (H + KVH) * HD], f[:, (H + KVH) * HD:], pk.astype(np.float32) if pos0 else None,
+                                             pv.astype(np.float32) if pos0 else None, capi.causal_mask(n, pos0), cosb, sinb, alpha, H, KVH, HD)
+    dev = torch.device("cuda", 0)
+    kc = torch.full((KVH, max_ctx, HD), float("nan"), dtype=torch.float16, device=dev)
+    vc = torch.full_like(kc, float("nan"))
+    if pos0:
+        kc[:, :pos0] = torch.from_numpy(pk).to(dev)
+        vc[:, :pos0] = torch.from_numpy(pv).to(dev)
+    out = torch.zeros((n, H * HD), dtype=torch.float16, device=dev)
+    dq = torch.from_numpy(qkv).to(dev)
+    ctx.attn_prefill(dq, kc, vc, torch.from_numpy(cosb).to(dev), torch.from_numpy(sinb).to(dev), out, alpha, n, pos0, H, KVH, HD, max_ctx)
+    torch.cuda.synchronize()
+    got = out.float().cpu().numpy()
+    assert np.all(np.isfinite(got))
+    assert np.abs(got - want).max() / max(np.abs(want).max(), 1e-6) <= 3e-3  # fp16 q/k/p operands of the tensor-core products
+    assert np.allclose(kc[:, pos0:pos0 + n].float().cpu().numpy(), fk[:, pos0:], atol=2e-3, rtol=1e-3)
+    assert np.array_equal(vc[:, pos0:pos0 + n].cpu().numpy(), fv[:, pos0:].astype(np.float16))
+    if pos0:
+        assert torch.equal(kc[:, :pos0].cpu(), torch.from_numpy(pk))
+    assert torch.isnan(kc[:, pos0 + n:]).all()  # rows past the new ones are never touched
+
+
+def test_attention_kernels_against_reference_module_fixture(ctx, golden_dir):
+    """The prefill kernel (7 tokens) followed by three decode-kernel steps on the inputs of tests/golden/llama_attention_module.npz:
+    compared directly with what the compiled reference Int4llamaAttention module returned.  Its o_proj is a channel selection of the
+    int8-round-tripped core output, so the comparison holds to half a quantisation step (amax/254 per 32-block) + fp16 rounding."""
+    g = np.load(golden_dir / "llama_attention_module.npz")
+    H, KVH, prefill, steps, max_sq = (int(g[k]) for k in ("H", "KVH", "prefill", "steps", "max_sq"))
+    from oracle import capi
+
+    hidden = g["hidden"]
+    E = hidden.shape[1]
+    assert E // H == HD
+    cosb, sinb = capi.rope_tables(max_sq, HD, float(g["theta"]))
+    dev = torch.device("cuda", 0)
+    dcos, dsin = torch.from_numpy(cosb).to(dev), torch.from_numpy(sinb).to(dev)
+    qkv_all = np.concatenate([hidden[:, g["sel_q"]], hidden[:, g["sel_k"]], hidden[:, g["sel_v"]]], axis=1).astype(np.float16)  # exact in fp16
+    kc = torch.zeros((KVH, max_sq, HD), dtype=torch.float16, device=dev)
+    vc = torch.zeros_like(kc)
+    outs = torch.zeros((prefill + steps, E), dtype=torch.float16, device=dev)
+    alpha = float(g["alpha"])
+    ctx.attn_prefill(torch.from_numpy(qkv_all[:prefill]).to(dev), kc, vc, dcos, dsin, outs[:prefill], alpha, prefill, 0, H, KVH, HD, max_sq)
+    for s in range(steps):
+        pos = torch.tensor([prefill + s], dtype=torch.int32, device=dev)
+        ctx.attn_decode(torch.from_numpy(qkv_all[prefill + s]).to(dev), kc, vc, dcos, dsin, pos, outs[prefill + s], alpha, H, KVH, HD, max_sq)
+    torch.cuda.synchronize()
+    T = prefill + steps
+    assert np.abs(kc[:, :T].float().cpu().numpy() - g["final_k"]).max() <= 2e-3 * np.abs(g["final_k"]).max()
+    assert np.array_equal(vc[:, :T].float().cpu().numpy(), g["final_v"])
+    core = outs.float().cpu().numpy()
+    ref_core = np.zeros_like(core)
+    ref_core[:, g["sel_o"]] = g["out"]  # undo the o_proj channel selection: out[:, j] = roundtrip(core)[:, sel_o[j]]
+    amax = np.abs(ref_core.reshape(T, -1, 32)).max(-1, keepdims=True)
+    tol = (amax / 254 * 1.05 + 2e-3 * np.abs(ref_core).max()) * np.ones((1, 1, 32), np.float32)
+    assert np.all(np.abs(core - ref_core).reshape(T, -1, 32) <= tol)

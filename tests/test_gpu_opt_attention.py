@@ -73,3 +73,32 @@ def test_rejects_bad_arguments(ctx):
         ctx.opt_int8_attention(q, q, q, None, None, ck, ck, None, 1.0, 1.0, 4, 1, 64)  # past > 0 without a past cache
     with pytest.raises(_lib.TceError):
         ctx.opt_int8_attention(q, q, q, ck, ck, ck, ck, None, 1.0, 1.0, 4, 1, 64)  # final stride too small for past + sqlen
+
+
+def test_module_golden_fixture(ctx, golden_dir):
+    """Projections (tce_w8a8_matmul) + core (tce_opt_int8_attention, in-place cache) + out_proj on the GPU == the outputs the compiled
+    reference Int8OPTAttention module produced (tests/golden/opt_attention_module.npz), bit for bit."""
+    g = np.load(golden_dir / "opt_attention_module.npz")
+    H, prefill, steps = int(g["H"]), int(g["prefill"]), int(g["steps"])
+    E = g["hidden"].shape[1]
+    hd = E // H
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    W = {k: dev(g["w" + k]) for k in "qkvo"}
+    B = {k: dev(g["b" + k]) for k in "qkv"}
+    bo = dev(g["bo"])
+    a_qkv, b_qkv, qk_alpha, pv_alpha, a_out = (float(g[k]) for k in ("a_qkv", "b_qkv", "qk_alpha", "pv_alpha", "a_out"))
+    ck = torch.zeros((H, 64, hd), dtype=torch.int8, device="cuda")
+    cv = torch.zeros_like(ck)
+    hidden = dev(g["hidden"])
+    outs, past, row = [], 0, 0
+    for call in range(1 + steps):
+        s = prefill if call == 0 else 1
+        x = hidden[row:row + s].contiguous()
+        q, k, v = (ctx.w8a8_matmul(0, x, W[n], B[n], a_qkv, b_qkv) for n in "qkv")
+        core = ctx.opt_int8_attention(q, k, v, ck, cv, ck, cv, None, qk_alpha, pv_alpha, past, H, hd)
+        outs.append(ctx.w8a8_matmul(2, core, W["o"], bo, a_out, 0.0))
+        past += s
+        row += s
+    got = torch.cat(outs).cpu().numpy()
+    assert np.array_equal(ck[:, :past].cpu().numpy(), g["final_k"]) and np.array_equal(cv[:, :past].cpu().numpy(), g["final_v"])
+    assert np.array_equal(got.view(np.uint32), g["out"].view(np.uint32))

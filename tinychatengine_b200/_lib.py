@@ -50,6 +50,7 @@ SIGNATURES = {
     "tce_w8a8_matmul": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_float, C.c_float, C.c_int, C.c_int]),
     "tce_opt_int8_attention": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong] + [C.c_void_p] * 2 + [C.c_longlong, C.c_void_p, C.c_float, C.c_float] + [C.c_int] * 4 + [C.c_void_p]),
+    "tce_attn_prefill": (C.c_int, [C.c_void_p] * 7 + [C.c_float] + [C.c_int] * 6),
     "tce_attn_decode": (C.c_int, [C.c_void_p] * 8 + [C.c_float] + [C.c_int] * 4),
     "tce_rmsnorm_f16": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float]),
     "tce_argmax_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

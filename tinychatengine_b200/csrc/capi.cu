@@ -79,6 +79,7 @@ int tce_ctx_create(int device, tce_ctx **out) {
     c.gemv_impl = env_int("TCE_GEMV_IMPL", 1);
     c.gemv_ctas_per_sm = env_int("TCE_GEMV_CTAS_PER_SM", 1);
     c.gemv_consumer_warps = env_int("TCE_GEMV_CONSUMER_WARPS", 8) == 16 ? 16 : 8;
+    c.gemv_stages = env_int("TCE_GEMV_STAGES", 4);
     c.pdl_early = env_int("TCE_PDL_EARLY", 0);
     c.use_pdl = env_int("TCE_USE_PDL", 0) != 0;  // measured slower than plain graph edges on B200 (profiles/README.md)
     ctx->attn_chunk = env_int("TCE_ATTN_CHUNK", 128);
@@ -138,6 +139,8 @@ int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
         ctx->c.gemv_ctas_per_sm = value < 1 ? 1 : (value > 4 ? 4 : value);
     else if (!strcmp(name, "gemv_consumer_warps"))
         ctx->c.gemv_consumer_warps = (value == 16) ? 16 : 8;
+    else if (!strcmp(name, "gemv_stages"))
+        ctx->c.gemv_stages = value < 0 ? 0 : value;
     else if (!strcmp(name, "gemv_debug")) {
         if (value && !ctx->c.gemv_dbg) {
             CK(cudaMalloc(&ctx->c.gemv_dbg, (size_t)ctx->c.gemv_max_ctas * 8 * sizeof(unsigned long long)), "cudaMalloc dbg");
@@ -315,6 +318,31 @@ int tce_attn_decode(tce_ctx *ctx, const void *qkv, void *k_cache, void *v_cache,
     a.max_ctx = max_ctx;
     a.chunk = ctx->attn_chunk;
     CK(launch_attn_decode(&ctx->c, a, false), "tce_attn_decode");
+    return TCE_OK;
+}
+
+int tce_attn_prefill(tce_ctx *ctx, void *qkv, void *k_cache, void *v_cache, const float *cosb, const float *sinb, void *out, float alpha, int n, int pos0,
+                     int num_heads, int num_kv_heads, int head_dim, int max_ctx) {
+    if (!ctx || !qkv || !k_cache || !v_cache || !cosb || !sinb || !out) return fail(TCE_ERR_INVALID, "tce_attn_prefill: null pointer");
+    if (head_dim != 128) return fail(TCE_ERR_UNSUPPORTED, "tce_attn_prefill: head_dim %d (only 128)", head_dim);
+    if (num_heads < 1 || num_kv_heads < 1 || num_heads % num_kv_heads || n < 1 || pos0 < 0 || pos0 + n > max_ctx)
+        return fail(TCE_ERR_INVALID, "tce_attn_prefill: bad shape n=%d pos0=%d max_ctx=%d", n, pos0, max_ctx);
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    AttnPrefillArgs a = {};
+    a.qkv = (__half *)qkv;
+    a.k_cache = (__half *)k_cache;
+    a.v_cache = (__half *)v_cache;
+    a.cos = cosb;
+    a.sin = sinb;
+    a.out = (__half *)out;
+    a.alpha = alpha;
+    a.n = n;
+    a.pos0 = pos0;
+    a.num_heads = num_heads;
+    a.num_kv_heads = num_kv_heads;
+    a.head_dim = head_dim;
+    a.max_ctx = max_ctx;
+    CK(launch_attn_prefill(&ctx->c, a), "tce_attn_prefill");
     return TCE_OK;
 }
 

@@ -204,6 +204,7 @@ cudaError_t megakernel_fill_gemv(Ctx *ctx, const W4GemvParams &p, MegaPhase *ph,
     a.counters = ctx->gemv_counters;
     a.dbg = nullptr;
     a.pdl_early = 0;
+    a.nst = kStages;
     a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
     a.aligned = (!a.atomic_add && a.num_tiles >= ncta) ? 1 : 0;
     a.sg = a.NG < kStageGroups ? a.NG : kStageGroups;

@@ -6,9 +6,11 @@
 //      round(p*127) -> P8 x V (exact int32) -> clamp(round(acc * pv_alpha)) -> unshape.  Replaces BMM_S8T_S8N_F32T, batch_Add,
 //      softmax, the int8 cast loop, transpose_1_2idx, BMM_S8T_S8N_S8T and unshape (:245-275) with no intermediate in HBM.
 // Bit-exactness with the CPU reference is the contract: integer parts are exact in any order; the float parts keep the
-// reference's evaluation order (max seeded with the first element of the whole score tensor, softmax.cc:13; serial float
-// sum over the row; p = float(double(e) / (double(sum) + 1e-10))), and exp() is evaluated in double and rounded to float,
-// which is what a correctly-rounded expf returns.
+// reference's evaluation order (serial float sum over the row; p = float(double(e) / (double(sum) + 1e-10))), and exp() is
+// evaluated in double and rounded to float, which is what a correctly-rounded expf returns.  The running max of every row
+// is seeded with element [0] of the score tensor (softmax.cc:13); the module runs softmax in place, so that element is the
+// raw score for row (head 0, query 0) and the PROBABILITY p[0][0][0] for every later row.  Reproduced literally: row (0,0)
+// runs first in a one-CTA launch that publishes p[0][0][0], then all other rows run seeded with it.
 #include "common.cuh"
 #include "kernels_w8a8.h"
 
@@ -48,9 +50,10 @@ TCE_DEVINL int dot_s8(const int8_t *__restrict__ a, const int8_t *__restrict__ b
 __global__ void __launch_bounds__(kThreads) opt_attn_rows_kernel(const int8_t *__restrict__ q8, const int8_t *__restrict__ final_k,
                                                                 const int8_t *__restrict__ final_v, long long hs, const float *__restrict__ mask,
                                                                 float qk_alpha, float pv_alpha, int sqlen, int past, int H, int hd,
-                                                                int8_t *__restrict__ out) {
+                                                                int8_t *__restrict__ out, float *seed_ws, int first_row_only) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int h = blockIdx.x, i = blockIdx.y, tgz = past + sqlen, tid = threadIdx.x;
+    if (!first_row_only && h == 0 && i == 0) return;  // done by the seed launch
     float *s = (float *)smem_raw;
     int8_t *p8 = (int8_t *)(s + tgz);
     int8_t *q = p8 + ((tgz + 15) & ~15);
@@ -65,12 +68,8 @@ __global__ void __launch_bounds__(kThreads) opt_attn_rows_kernel(const int8_t *_
     __syncthreads();
     const int8_t *K = final_k + h * hs, *V = final_v + h * hs;
     const float neg = -3.402823466e38f;
-    // softmax.cc:13 seeds the running max with element [0][0][0] of the masked score tensor
-    float mx;
-    {
-        const int a0 = dot_s8(q8, final_k, hd);  // head 0, row 0, key 0
-        mx = __fadd_rn(__fmul_rn((float)a0, qk_alpha), mask ? mask[0] : 0.f);
-    }
+    // softmax.cc:13: row (0,0) is seeded with its own first score (a member of the row: plain max), later rows with p[0][0][0]
+    float mx = first_row_only ? -INFINITY : *seed_ws;
     for (int j = tid; j < tgz; j += kThreads) {
         const int a = dot_s8(q, K + (size_t)j * hd, hd);
         const float m = mask ? mask[(size_t)i * tgz + j] : (j > past + i ? neg : 0.f);
@@ -95,6 +94,7 @@ __global__ void __launch_bounds__(kThreads) opt_attn_rows_kernel(const int8_t *_
     for (int j = tid; j < tgz; j += kThreads) {
         const float p = (float)((double)s[j] / denom);
         p8[j] = (int8_t)(int)roundf(__fmul_rn(p, 127.f));
+        if (first_row_only && j == 0) *seed_ws = p;
     }
     __syncthreads();
     // P8 x V: thread (g, c) walks rows t = g, g+G, ... and owns 4 consecutive d's
@@ -142,9 +142,14 @@ cudaError_t launch_opt_int8_attention(Ctx *ctx, const OptAttnParams &p) {
         e = cudaFuncSetAttribute(opt_attn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
+    float *seed_ws = ctx->attn_ws;  // one float of the attention workspace; same-stream ordering makes the reuse safe
+    opt_attn_rows_kernel<<<dim3(1, 1), kThreads, smem, ctx->stream>>>(p.q8, p.final_k, p.final_v, p.final_hs, p.mask, p.qk_alpha, p.pv_alpha, p.sqlen, p.past,
+                                                                      p.H, p.hd, p.out, seed_ws, 1);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || (p.H == 1 && p.sqlen == 1)) return e;
     dim3 g2(p.H, p.sqlen);
     opt_attn_rows_kernel<<<g2, kThreads, smem, ctx->stream>>>(p.q8, p.final_k, p.final_v, p.final_hs, p.mask, p.qk_alpha, p.pv_alpha, p.sqlen, p.past, p.H,
-                                                             p.hd, p.out);
+                                                             p.hd, p.out, seed_ws, 0);
     return cudaGetLastError();
 }
 

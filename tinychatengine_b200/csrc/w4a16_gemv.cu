@@ -17,7 +17,7 @@ template <int NCOLS, int CW>
 __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 && CW == 8) ? 2 : 1) w4a16_gemv_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     using L = Layout<NCOLS, CW>;
-    const Smem sm = carve<NCOLS, CW>(smem, a.IC);
+    const Smem sm = carve<NCOLS, CW>(smem, a.IC, a.nst);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
 
@@ -166,6 +166,7 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     a.counters = ctx->gemv_counters;
     a.dbg = ctx->gemv_dbg;
     a.pdl_early = 0;
+    a.nst = kStages;
     a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
     a.aligned = 0;
     a.sg = a.NG < kStageGroups ? a.NG : kStageGroups;
@@ -183,8 +184,7 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
 template <int NCOLS, int CW>
 cudaError_t launch_mma(Ctx *ctx, const KArgs &a_in, bool pdl) {
     KArgs a = a_in;
-    const size_t smem = Layout<NCOLS, CW>::bytes(a.IC);
-    if ((int)smem > ctx->smem_optin) return cudaErrorInvalidConfiguration;
+    if ((int)Layout<NCOLS, CW>::bytes(a.IC, kStages) > ctx->smem_optin) return cudaErrorInvalidConfiguration;
     static bool attr_set = false;  // per template instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(w4a16_gemv_kernel<NCOLS, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
@@ -207,6 +207,19 @@ cudaError_t launch_mma(Ctx *ctx, const KArgs &a_in, bool pdl) {
     // tiles altogether when there is at least one whole tile per CTA: the fix-up protocol costs ~2.5 us of tail per
     // launch (profiles/r01_gemv_phase_timeline.txt), more than the <= 1/tiles_per_cta imbalance it removes.
     a.aligned = (!a.atomic_add && a.num_tiles >= nc) ? 1 : 0;
+    // Ring depth = bytes in flight per SM.  HBM latency under load (~1.2 us) x 6.5 TB/s / 148 SMs = ~55 KB must be in flight per SM
+    // all the time, and a slot is only re-requested after it was consumed: the deepest ring that fits the per-CTA share of shared
+    // memory (1 KiB per CTA is reserved by the driver), at most kMaxStages and no more stages than the CTA has work for.
+    {
+        const int budget = ctx->smem_optin / per_sm - (per_sm > 1 ? 1024 : 0);
+        int nst = ctx->gemv_stages > 0 ? ctx->gemv_stages : kMaxStages;
+        if (nst > kMaxStages) nst = kMaxStages;
+        while (nst > 2 && (int)Layout<NCOLS, CW>::bytes(a.IC, nst) > budget) nst--;
+        const long long stages_per_cta = (U / nc + a.sg - 1) / a.sg + 1;
+        if (nst > stages_per_cta && stages_per_cta >= 2) nst = (int)stages_per_cta;
+        a.nst = nst;
+    }
+    const size_t smem = Layout<NCOLS, CW>::bytes(a.IC, a.nst);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nc);
     cfg.blockDim = dim3(32 * (kProducerWarps + 1 + CW));
@@ -223,8 +236,8 @@ cudaError_t launch_mma(Ctx *ctx, const KArgs &a_in, bool pdl) {
 }  // namespace
 
 size_t w4a16_gemv_smem_bytes(int ncols, int cw, int IC) {
-    if (ncols == 1) return cw == 16 ? Layout<1, 16>::bytes(IC) : Layout<1, 8>::bytes(IC);
-    return cw == 16 ? Layout<8, 16>::bytes(IC) : Layout<8, 8>::bytes(IC);
+    if (ncols == 1) return cw == 16 ? Layout<1, 16>::bytes(IC, kStages) : Layout<1, 8>::bytes(IC, kStages);
+    return cw == 16 ? Layout<8, 16>::bytes(IC, kStages) : Layout<8, 8>::bytes(IC, kStages);
 }
 
 cudaError_t launch_w4a16_gemv_simple(Ctx *ctx, const W4GemvParams &p) {

@@ -27,10 +27,11 @@ namespace gemv {
 
 constexpr int kStageGroups = 16;               // 128-k groups per pipeline stage (per row: up to 1024 B)
 constexpr int kStageBytes = 16 * kStageGroups * 64;  // 16 KiB: dense [16 rows][sg*64 B] box written by ONE 2-D TMA instruction
-constexpr int kStages = 4;
+constexpr int kStages = 4;         // default ring depth (persistent kernel); the per-op kernel picks the deepest ring that fits (KArgs::nst)
+constexpr int kMaxStages = 12;
 constexpr int kRedBufs = 3;
 constexpr int kProducerWarps = 1;        // a stage is one UTMALDG (two in gate/up pair mode): a single elected lane keeps up
-constexpr int kMetaSlots = kStages + 1;  // per-tile scales/zeros slabs in flight (a tile spans >= 1 stage)
+// per-tile scales/zeros slabs in flight: ring depth + 1 (a tile spans >= 1 stage)
 
 struct KArgs {
     W4Seg seg[3];
@@ -49,6 +50,7 @@ struct KArgs {
     int aligned;     // 1: CTA ranges are cut at row-tile boundaries (no split tiles, no fix-up)
     int atomic_add;  // 1: EPI_ADD_F32 partial tiles use RED.ADD.F32 instead of the ordered fix-up
     unsigned long long *dbg;  // optional per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
+    int nst;         // TMA ring depth of this launch (4..kMaxStages stages of 16 KiB)
     int pdl_early;   // 1: griddepcontrol.launch_dependents at kernel entry instead of after the last weight request
     // tensor parallel: see W4GemvParams
     int tp_size;
@@ -109,14 +111,14 @@ struct Layout {
     static __host__ __device__ int x_pitch(int IC) { return IC * 2 + kXPad; }
     // one meta slot = scales half[16][zeros_w*8] followed by zeros uint32[16][zeros_w] = 320 * zeros_w bytes
     static __host__ __device__ int meta_slot_bytes(int IC) { return 320 * (((IC / 128) + 7) / 8); }
-    static __host__ __device__ size_t off_meta() { return (size_t)kStages * kStageBytes; }
-    static __host__ __device__ size_t off_xs(int IC) { return off_meta() + (size_t)kMetaSlots * meta_slot_bytes(IC); }
-    static __host__ __device__ size_t off_gx(int IC) { return off_xs(IC) + (size_t)NCOLS * x_pitch(IC); }
+    static __host__ __device__ size_t off_meta(int nst) { return (size_t)nst * kStageBytes; }
+    static __host__ __device__ size_t off_xs(int IC, int nst) { return off_meta(nst) + (size_t)(nst + 1) * meta_slot_bytes(IC); }
+    static __host__ __device__ size_t off_gx(int IC, int nst) { return off_xs(IC, nst) + (size_t)NCOLS * x_pitch(IC); }
     // gx: float step[NCOLS][NG] followed by int gsum[NCOLS][NG]
-    static __host__ __device__ size_t off_red(int IC) { return off_gx(IC) + (size_t)2 * NCOLS * (IC / 128) * sizeof(float); }
-    static __host__ __device__ size_t off_rms(int IC) { return off_red(IC) + (size_t)kRedBufs * CW * kVals * sizeof(float); }
-    static __host__ __device__ size_t off_bar(int IC) { return (off_rms(IC) + (size_t)NCOLS * CW * sizeof(float) + 15) & ~(size_t)15; }
-    static __host__ __device__ size_t bytes(int IC) { return off_bar(IC) + (2 * kStages + 2 * kRedBufs) * sizeof(uint64_t) + 16; }
+    static __host__ __device__ size_t off_red(int IC, int nst) { return off_gx(IC, nst) + (size_t)2 * NCOLS * (IC / 128) * sizeof(float); }
+    static __host__ __device__ size_t off_rms(int IC, int nst) { return off_red(IC, nst) + (size_t)kRedBufs * CW * kVals * sizeof(float); }
+    static __host__ __device__ size_t off_bar(int IC, int nst) { return (off_rms(IC, nst) + (size_t)NCOLS * CW * sizeof(float) + 15) & ~(size_t)15; }
+    static __host__ __device__ size_t bytes(int IC, int nst = kStages) { return off_bar(IC, nst) + (2 * nst + 2 * kRedBufs) * sizeof(uint64_t) + 16; }
 };
 
 struct Smem {
@@ -126,23 +128,25 @@ struct Smem {
     float *red, *rms;
     uint64_t *full_bar, *empty_bar, *red_full, *red_empty;
     int meta_bytes;
+    int nst;  // ring depth
 };
 
 // `IC` here is the LARGEST IC the kernel will see (the persistent kernel carves once for all phases)
 template <int NCOLS, int CW>
-TCE_DEVINL Smem carve(uint8_t *base, int IC) {
+TCE_DEVINL Smem carve(uint8_t *base, int IC, int nst = kStages) {
     using L = Layout<NCOLS, CW>;
     Smem s;
+    s.nst = nst;
     s.stages = base;
-    s.meta = base + L::off_meta();
-    s.xs = base + L::off_xs(IC);
-    s.gx = reinterpret_cast<float *>(base + L::off_gx(IC));
+    s.meta = base + L::off_meta(nst);
+    s.xs = base + L::off_xs(IC, nst);
+    s.gx = reinterpret_cast<float *>(base + L::off_gx(IC, nst));
     s.gsum = reinterpret_cast<int *>(s.gx + (size_t)NCOLS * (IC / 128));
-    s.red = reinterpret_cast<float *>(base + L::off_red(IC));
-    s.rms = reinterpret_cast<float *>(base + L::off_rms(IC));
-    s.full_bar = reinterpret_cast<uint64_t *>(base + L::off_bar(IC));
-    s.empty_bar = s.full_bar + kStages;
-    s.red_full = s.empty_bar + kStages;
+    s.red = reinterpret_cast<float *>(base + L::off_red(IC, nst));
+    s.rms = reinterpret_cast<float *>(base + L::off_rms(IC, nst));
+    s.full_bar = reinterpret_cast<uint64_t *>(base + L::off_bar(IC, nst));
+    s.empty_bar = s.full_bar + nst;
+    s.red_full = s.empty_bar + nst;
     s.red_empty = s.red_full + kRedBufs;
     s.meta_bytes = L::meta_slot_bytes(IC);
     return s;
@@ -150,8 +154,7 @@ TCE_DEVINL Smem carve(uint8_t *base, int IC) {
 
 template <int CW>
 TCE_DEVINL void init_barriers(const Smem &sm) {  // one thread
-#pragma unroll
-    for (int s = 0; s < kStages; s++) {
+    for (int s = 0; s < sm.nst; s++) {
         mbar_init(&sm.full_bar[s], 1);
         mbar_init(&sm.empty_bar[s], CW);
     }
@@ -239,12 +242,12 @@ TCE_DEVINL void produce(const KArgs &a, const Smem &sm, RingState &rs, int cta, 
             }
             __syncwarp();
             first = false;
-            if (++rs.stage == kStages) {
+            if (++rs.stage == sm.nst) {
                 rs.stage = 0;
                 rs.phase ^= 1;
             }
         }
-        if (++rs.mslot == kMetaSlots) rs.mslot = 0;
+        if (++rs.mslot == sm.nst + 1) rs.mslot = 0;
         u += ge - gb;
         rt++;
         gb = 0;
@@ -634,7 +637,7 @@ TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty_bar[rs.stage]);
-            if (++rs.stage == kStages) {
+            if (++rs.stage == sm.nst) {
                 rs.stage = 0;
                 rs.phase ^= 1;
             }
@@ -660,7 +663,7 @@ TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState 
             cs.rb = 0;
             cs.rphase ^= 1;
         }
-        if (++rs.mslot == kMetaSlots) rs.mslot = 0;
+        if (++rs.mslot == sm.nst + 1) rs.mslot = 0;
         u += ge - gb;
         gb = 0;
     }

@@ -26,7 +26,7 @@ def alg_bytes(oc, ic):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=40)
-    ap.add_argument("--configs", default="16x1,8x1,8x2,simple")
+    ap.add_argument("--configs", default="8x1s4,8x1,16x1,8x2s4,8x2")
     ap.add_argument("--m", type=int, default=1)
     ap.add_argument("--shapes", default="", help="comma separated substrings to select shapes")
     args = ap.parse_args()
@@ -48,7 +48,9 @@ def main():
             if cfg == "simple":
                 ctx.set_option("gemv_impl", 0)
             else:
-                cw, cps = cfg.split("x")
+                base, _, st = cfg.partition("s")  # "8x1s4": 8 consumer warps, 1 CTA/SM, 4-stage ring ("s" omitted: deepest that fits)
+                cw, cps = base.split("x")
+                ctx.set_option("gemv_stages", int(st) if st else 0)
                 ctx.set_option("gemv_impl", 1)
                 ctx.set_option("gemv_consumer_warps", int(cw))
                 ctx.set_option("gemv_ctas_per_sm", int(cps))
@@ -77,6 +79,7 @@ def main():
         del bufs
         torch.cuda.empty_cache()
     ctx.set_option("gemv_impl", 1)
+    ctx.set_option("gemv_stages", 0)
 
 
 if __name__ == "__main__":
