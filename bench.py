@@ -304,7 +304,7 @@ def run_ours(args):
                        "mean_ctx": mean_ctx, "global_batch_note": "one sequence" if (tp or world == 1) else "one sequence per GPU",
                        "parallelism": (f"tp{world} (column/row sharded linears, 2 all-reduces per layer over NVLink peer memory)" if tp else
                                        ("1 sequence per GPU (replicas)" if world > 1 else "single GPU")),
-                       "l2": "inputs larger than L2: 3.9 GB of weights stream per step vs 126 MB L2", "pdl": bool(int(os.environ.get("TCE_USE_PDL", "0")))},
+                       "l2": "inputs larger than L2: 3.9 GB of weights stream per step vs 126 MB L2", "pdl": bool(int(os.environ.get("TCE_USE_PDL", "1")))},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 12, "d2h_bytes_per_step": gl.vocab_size * 4 + 4},
             "gpu_launches": K * model.kernels_per_step,

@@ -17,11 +17,13 @@ def ctx():
     c.close()
 
 
+@pytest.mark.parametrize("cluster", [16, 8, 0])  # CTAs per thread-block cluster (DSMEM merge); 0 = independent splits + global merge
 @pytest.mark.parametrize("H,KVH", [(8, 2), (4, 4), (8, 1), (16, 8)])
 @pytest.mark.parametrize("past", [0, 1, 5, 127, 128, 129, 300, 1023])
-def test_decode_attention_matches_oracle(ctx, H, KVH, past):
+def test_decode_attention_matches_oracle(ctx, H, KVH, past, cluster):
     from oracle import capi
 
+    ctx.set_option("attn_cluster", cluster)
     max_ctx = 1024
     rng = np.random.default_rng(1000 * H + past)
     cosb, sinb = capi.rope_tables(max_ctx, HD, 500000.0)
@@ -56,6 +58,7 @@ def test_decode_attention_matches_oracle(ctx, H, KVH, past):
     assert np.array_equal(vc[:, past].cpu().numpy(), fv[:, past].astype(np.float16))
     if past:
         assert torch.equal(kc[:, :past].cpu(), torch.from_numpy(pk))  # the cached prefix is untouched
+    ctx.set_option("attn_cluster", 0)
 
 
 def test_multi_step_append_is_consistent(ctx):
@@ -142,14 +145,20 @@ def test_attention_kernels_against_reference_module_fixture(ctx, golden_dir):
     vc = torch.zeros_like(kc)
     outs = torch.zeros((prefill + steps, E), dtype=torch.float16, device=dev)
     alpha = float(g["alpha"])
-    ctx.attn_prefill(torch.from_numpy(qkv_all[:prefill]).to(dev), kc, vc, dcos, dsin, outs[:prefill], alpha, prefill, 0, H, KVH, HD, max_sq)
+    dq_all = torch.from_numpy(qkv_all).to(dev)  # kept alive until the stream has consumed it (the caller owns every buffer it passes)
+    ctx.attn_prefill(dq_all[:prefill], kc, vc, dcos, dsin, outs[:prefill], alpha, prefill, 0, H, KVH, HD, max_sq)
+    torch.cuda.synchronize()
+    kerr0 = np.abs(kc[:, :prefill].float().cpu().numpy() - g["final_k"][:, :prefill]).max(axis=(0, 2))
+    assert kerr0.max() <= 2e-3 * np.abs(g["final_k"]).max(), f"K rows right after the prefill kernel: error per position {kerr0}"
     for s in range(steps):
         pos = torch.tensor([prefill + s], dtype=torch.int32, device=dev)
-        ctx.attn_decode(torch.from_numpy(qkv_all[prefill + s]).to(dev), kc, vc, dcos, dsin, pos, outs[prefill + s], alpha, H, KVH, HD, max_sq)
+        ctx.attn_decode(dq_all[prefill + s], kc, vc, dcos, dsin, pos, outs[prefill + s], alpha, H, KVH, HD, max_sq)
     torch.cuda.synchronize()
     T = prefill + steps
-    assert np.abs(kc[:, :T].float().cpu().numpy() - g["final_k"]).max() <= 2e-3 * np.abs(g["final_k"]).max()
-    assert np.array_equal(vc[:, :T].float().cpu().numpy(), g["final_v"])
+    kerr = np.abs(kc[:, :T].float().cpu().numpy() - g["final_k"]).max(axis=(0, 2))  # per position
+    assert kerr.max() <= 2e-3 * np.abs(g["final_k"]).max(), f"K cache error per position {kerr}"
+    verr = np.abs(vc[:, :T].float().cpu().numpy() - g["final_v"]).max(axis=(0, 2))
+    assert verr.max() == 0, f"V cache error per position {verr}"
     core = outs.float().cpu().numpy()
     ref_core = np.zeros_like(core)
     ref_core[:, g["sel_o"]] = g["out"]  # undo the o_proj channel selection: out[:, j] = roundtrip(core)[:, sel_o[j]]

@@ -78,11 +78,12 @@ int tce_ctx_create(int device, tce_ctx **out) {
     c.smem_optin = (int)prop.sharedMemPerBlockOptin;
     c.gemv_impl = env_int("TCE_GEMV_IMPL", 1);
     c.gemv_ctas_per_sm = env_int("TCE_GEMV_CTAS_PER_SM", 1);
-    c.gemv_consumer_warps = env_int("TCE_GEMV_CONSUMER_WARPS", 8) == 16 ? 16 : 8;
+    c.gemv_consumer_warps = env_int("TCE_GEMV_CONSUMER_WARPS", 0);  // 0 = per shape (16 for long rows), else 8 or 16
     c.gemv_stages = env_int("TCE_GEMV_STAGES", 4);
-    c.pdl_early = env_int("TCE_PDL_EARLY", 0);
-    c.use_pdl = env_int("TCE_USE_PDL", 0) != 0;  // measured slower than plain graph edges on B200 (profiles/README.md)
+    c.pdl_early = env_int("TCE_PDL_EARLY", 1);
+    c.use_pdl = env_int("TCE_USE_PDL", 1) != 0;  // programmatic dependent launch, dependents resident from kernel entry: +3 % (profiles/r01_pdl_matrix.txt)
     ctx->attn_chunk = env_int("TCE_ATTN_CHUNK", 128);
+    c.attn_cluster = env_int("TCE_ATTN_CLUSTER", 0);
     c.gemv_max_ctas = c.num_sms * 4;
     c.gemv_max_tiles = 32768;
     CK(cudaMalloc(&c.gemv_partials, (size_t)c.gemv_max_ctas * 2 * 16 * 8 * sizeof(float)), "cudaMalloc gemv partials");
@@ -138,7 +139,7 @@ int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "gemv_ctas_per_sm"))
         ctx->c.gemv_ctas_per_sm = value < 1 ? 1 : (value > 4 ? 4 : value);
     else if (!strcmp(name, "gemv_consumer_warps"))
-        ctx->c.gemv_consumer_warps = (value == 16) ? 16 : 8;
+        ctx->c.gemv_consumer_warps = (value == 16) ? 16 : (value == 8 ? 8 : 0);
     else if (!strcmp(name, "gemv_stages"))
         ctx->c.gemv_stages = value < 0 ? 0 : value;
     else if (!strcmp(name, "gemv_debug")) {
@@ -153,6 +154,8 @@ int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
         ctx->c.use_pdl = value != 0;
     else if (!strcmp(name, "gemm_min_m"))  // smallest M served by the tcgen05 GEMMs (W4A16 prefill slot, W8A8); below it the weight-streaming kernels run
         ctx->c.gemm_min_m = value < 1 ? 1 : value;
+    else if (!strcmp(name, "attn_cluster"))
+        ctx->c.attn_cluster = value;
     else if (!strcmp(name, "attn_chunk"))
         ctx->attn_chunk = value;
     else

@@ -208,6 +208,7 @@ cudaError_t megakernel_fill_gemv(Ctx *ctx, const W4GemvParams &p, MegaPhase *ph,
     a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
     a.aligned = (!a.atomic_add && a.num_tiles >= ncta) ? 1 : 0;
     a.sg = a.NG < kStageGroups ? a.NG : kStageGroups;
+    a.full = (a.NG % kStageGroups == 0) ? 1 : 0;
     a.tp_size = 1;
     a.tp_in = nullptr;
     a.tp_flags = nullptr;

@@ -23,10 +23,13 @@ struct Ctx {
     float *attn_ws = nullptr;
     size_t attn_ws_bytes = 0;
     unsigned *attn_counters = nullptr;
+    // decode attention: CTAs per thread-block cluster (one cluster per KV head, DSMEM merge); 0 = independent splits + global merge.
+    // Measured on B200: the cluster flavour is 2.2 us per layer SLOWER (cluster co-scheduling + two cluster barriers), so it is off.
+    int attn_cluster = 0;
     // tunables (env overridable, see ctx.cu)
     int gemv_impl = 1;      // 0 = simple warp-per-row, 1 = TMA + mma.sync stream-K
     int gemv_ctas_per_sm = 1;
-    int gemv_consumer_warps = 8;   // 8 or 16 consumer warps per CTA
+    int gemv_consumer_warps = 0;   // 8 or 16 consumer warps per CTA; 0 = chosen per shape
     int gemv_stages = 4;           // TMA ring depth (16 KiB stages); 0 = deepest that fits (measured: no gain over 4, profiles/)
     bool use_pdl = false;
     int pdl_early = 0;  // with use_pdl: 1 = dependents may become resident from the first instruction of each GEMV (2: and no 2-CTA/SM mode)
@@ -103,10 +106,15 @@ struct StreamK {
     int NG;        // groups per row tile
     int aligned = 0;  // cut at row-tile boundaries instead of unit boundaries
     int T = 0;        // row tiles (aligned mode)
+    int gran = 1;     // unaligned mode: cuts fall on multiples of `gran` units (16 = whole pipeline stages; U % gran == 0)
     __host__ __device__ long long start(int c) const {
-        return aligned ? (((long long)T * c) / nc) * NG : (U * (long long)c) / nc;
+        return aligned ? (((long long)T * c) / nc) * NG : (((U / gran) * (long long)c) / nc) * gran;
     }
-    __host__ __device__ int cta_of(long long u) const { return (int)(((u + 1) * nc + U - 1) / U - 1); }
+    // owner of unit u in unaligned mode: the largest c with start(c) <= u
+    __host__ __device__ int cta_of(long long u) const {
+        const long long Ug = U / gran, ug = u / gran;
+        return (int)(((ug + 1) * nc + Ug - 1) / Ug - 1);
+    }
 };
 
 }  // namespace tce

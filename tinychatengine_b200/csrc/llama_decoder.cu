@@ -452,7 +452,7 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
     Ctx *c = &local;
     bool first = true;
     for (const StepOp &op : ops_) {
-        const bool use_pdl = pdl && !first;
+        const bool use_pdl = pdl && !first && tp_ == 1;  // TP steps keep plain edges around the peer-flag kernels
         switch (op.type) {
             case OP_EMBED:
                 if (!gemv_only) DCK(launch_embedding(c, (const __half *)w_.embed_f16, tokpos, d_resid_, cfg_.embed_dim, false));  // residual buffer 0

@@ -170,6 +170,7 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     a.atomic_add = (p.atomic_residual && p.epi == EPI_ADD_F32 && !p.pair_mode) ? 1 : 0;
     a.aligned = 0;
     a.sg = a.NG < kStageGroups ? a.NG : kStageGroups;
+    a.full = (a.NG % kStageGroups == 0) ? 1 : 0;
     a.tp_size = p.tp_size;
     a.tp_in = p.tp_in;
     a.tp_flags = p.tp_flags;
@@ -202,7 +203,8 @@ cudaError_t launch_mma(Ctx *ctx, const KArgs &a_in, bool pdl) {
     if (allow2 && per_sm == 1 && NCOLS == 1 && CW == 8 && a.IC <= 8192 && U >= (long long)ctx->num_sms * 2 * 128) per_sm = 2;
     int nc = ctx->num_sms * per_sm;
     if (nc > ctx->gemv_max_ctas) nc = ctx->gemv_max_ctas;
-    if ((long long)nc > U) nc = (int)U;
+    const long long cuts = a.full ? U / kStageGroups : U;  // stream-K cuts fall on whole stages when every stage is full
+    if ((long long)nc > cuts) nc = (int)cuts;
     // Epilogues that need a single ordered writer per output (stores, SiLU*mul, deterministic residual) avoid split
     // tiles altogether when there is at least one whole tile per CTA: the fix-up protocol costs ~2.5 us of tail per
     // launch (profiles/r01_gemv_phase_timeline.txt), more than the <= 1/tiles_per_cta imbalance it removes.
@@ -261,7 +263,9 @@ cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p) {
         cudaError_t e = encode_w4_tmap(&a.tmap[i], p.seg[i].w, p.seg[i].rows, p.IC, a.sg, p.pair_mode ? 8 : 16);
         if (e != cudaSuccess) return e;
     }
-    const int cw = ctx->gemv_consumer_warps == 16 ? 16 : 8;
+    // 16 consumer warps pay off on long rows (down_proj, IC = 14336: 10.4 vs 12.1 us), where one CTA per SM stages a long activation
+    // vector and the 2-CTA mode is off; 8 warps (x 2 CTAs on large launches) everywhere else (profiles/r01_gemv_microbench_v5.jsonl)
+    const int cw = ctx->gemv_consumer_warps == 16 ? 16 : (ctx->gemv_consumer_warps == 8 ? 8 : (p.IC > 8192 && p.M == 1 ? 16 : 8));
     if (p.M > 1 && (int)w4a16_gemv_smem_bytes(8, cw, p.IC) > ctx->smem_optin) {
         // the 8-column activation tile does not fit next to the weight ring: one pass per activation row
         if (p.pair_mode && p.ldy == 0) return cudaErrorInvalidValue;

@@ -50,6 +50,7 @@ struct KArgs {
     int aligned;     // 1: CTA ranges are cut at row-tile boundaries (no split tiles, no fix-up)
     int atomic_add;  // 1: EPI_ADD_F32 partial tiles use RED.ADD.F32 instead of the ordered fix-up
     unsigned long long *dbg;  // optional per-CTA phase timestamps (globaltimer ns), 8 slots per CTA
+    int full;        // 1: every stage carries 16 whole groups (IC % 2048 == 0): the single-column consumer drops its bounds checks
     int nst;         // TMA ring depth of this launch (4..kMaxStages stages of 16 KiB)
     int pdl_early;   // 1: griddepcontrol.launch_dependents at kernel entry instead of after the last weight request
     // tensor parallel: see W4GemvParams
@@ -185,6 +186,7 @@ TCE_DEVINL StreamK make_sk(const KArgs &a, int ncta) {
     sk.NG = a.NG;
     sk.aligned = a.aligned;
     sk.T = a.num_tiles;
+    sk.gran = a.full ? kStageGroups : 1;  // whole 16-group stages per CTA: consume1<FULL> never sees a partial stage
     return sk;
 }
 
@@ -480,10 +482,23 @@ TCE_DEVINL void stage_activations(const KArgs &a, const Smem &sm, int x_pitch, i
             o.y = pack4(hi[1], hi[3], hi[5], hi[7]);
             o.z = pack4(lo[0], lo[2], lo[4], lo[6]);
             o.w = pack4(lo[1], lo[3], lo[5], lo[7]);
-            // units of a group are stored j-major so that the four t-lanes of one LDS.128 hit consecutive slots
             const int G = ui >> 4, tj = ui & 15;  // ui = G*16 + 4*t + j
-            const int pos = G * 16 + (tj & 3) * 4 + (tj >> 2);
-            if (valid) *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = o;
+            if (NCOLS == 1) {
+                // single-column layout (consume1): per group 256 B = [parity: even | odd nibble slots][t][plane: hi | lo][word j], so that
+                // one LDS.128 hands lane (t, plane) the B operands of both MMAs of a parity and the 8 (t, plane) chunks of a warp-wide
+                // load are 128 contiguous bytes (conflict free)
+                if (valid) {
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(xcol + (size_t)G * 256 + (size_t)(tj >> 2) * 32) + (tj & 3);
+                    dst[0] = o.x;       // even slots, hi plane
+                    dst[4] = o.z;       // even slots, lo plane
+                    dst[32] = o.y;      // odd slots, hi plane
+                    dst[36] = o.w;      // odd slots, lo plane
+                }
+            } else {
+                // units of a group are stored j-major so that the four t-lanes of one LDS.128 hit consecutive slots
+                const int pos = G * 16 + (tj & 3) * 4 + (tj >> 2);
+                if (valid) *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = o;
+            }
             sx += __shfl_xor_sync(0xffffffffu, sx, 8);
             sx += __shfl_xor_sync(0xffffffffu, sx, 4);
             sx += __shfl_xor_sync(0xffffffffu, sx, 2);
@@ -555,8 +570,100 @@ TCE_DEVINL void stage_activations(const KArgs &a, const Smem &sm, int x_pitch, i
 // ------------------------------------------------------------------------------------------------------------------
 // consumer main loop
 // ------------------------------------------------------------------------------------------------------------------
+// Single activation column (decode).  Per (16-row tile, 128-k group) a warp issues FOUR integer MMAs instead of eight:
+//   * the two activation planes ride in MMA columns 0 (hi) and 1 (lo): lane (g, t) supplies the B operand of column g, so lanes
+//     g = 0 load the hi plane and lanes g = 1 the lo plane, and thread t = 0 of every row pair receives both plane sums (c0, c1);
+//   * nibbles become bytes with ONE mask each: w & 0x0f0f0f0f (even slots) and w & 0xf0f0f0f0 (odd slots, = 16 x nibble, still
+//     u8).  Even and odd slots accumulate separately (accL, accH); accH is an exact multiple of 16 and is shifted back at the end.
+// Two MMAs per parity take words (0,1) and (2,3) of the lane's 16-byte weight load as their two k halves.
+template <int CW, bool FULL>
+TCE_DEVINL void consume1(const KArgs &a, const Smem &sm, RingState &rs, RedState &cs, int cta, int ncta, int cw, int lane) {
+    constexpr int GPW = kStageGroups / CW;
+    const int g = lane >> 2, t = lane & 3;
+    const StreamK sk = make_sk(a, ncta);
+    int u = (int)sk.start(cta);
+    const int uend = (int)sk.start(cta + 1);
+    int gb = u - (u / a.NG) * a.NG;
+    const int sg = FULL ? kStageGroups : a.sg;
+    const int rp = sg * 64;  // dense row pitch of the TMA box
+    // lane-constant offsets: weight rows g / g+8 of the group slot, activation chunk (t, plane = g & 1)
+    const uint32_t w_off = (uint32_t)(g * rp + t * 16);
+    const uint8_t *xlane = sm.xs + (size_t)(t * 2 + (g & 1)) * 16;
+    while (u < uend) {
+        const int ge = min(a.NG, gb + (uend - u));
+        const uint8_t *mbase = sm.meta + (size_t)rs.mslot * sm.meta_bytes;
+        const __half *msA = reinterpret_cast<const __half *>(mbase) + g * a.sf_w;
+        const __half *msB = msA + 8 * a.sf_w;
+        const uint32_t *mzA = reinterpret_cast<const uint32_t *>(mbase + 16 * a.sf_w * 2) + g * a.zeros_w;
+        const uint32_t *mzB = mzA + 8 * a.zeros_w;
+        float totA = 0.f, totB = 0.f;
+        for (int g0 = gb; g0 < ge; g0 += sg) {
+            const int n = FULL ? kStageGroups : min(sg, ge - g0);
+            mbar_wait(&sm.full_bar[rs.stage], rs.phase);
+            const uint8_t *sbase = sm.stages + (size_t)rs.stage * kStageBytes + w_off;
+#pragma unroll
+            for (int q = 0; q < GPW; q++) {
+                const int gi = cw + q * CW;
+                if (FULL || gi < n) {
+                    const int G = g0 + gi;
+                    const uint4 wa = *reinterpret_cast<const uint4 *>(sbase + gi * 64);
+                    const uint4 wb = *reinterpret_cast<const uint4 *>(sbase + gi * 64 + 8 * rp);
+                    const uint4 xe = *reinterpret_cast<const uint4 *>(xlane + (size_t)G * 256);
+                    const uint4 xo = *reinterpret_cast<const uint4 *>(xlane + (size_t)G * 256 + 128);
+                    const float sAq = __half2float(msA[G]), sBq = __half2float(msB[G]);
+                    const int zsh = (G & 7) * 4;
+                    const int zAq = (int)((mzA[G >> 3] >> zsh) & 0xFu);
+                    const int zBq = (int)((mzB[G >> 3] >> zsh) & 0xFu);
+                    constexpr uint32_t ML = 0x0f0f0f0fu, MH = 0xf0f0f0f0u;
+                    int accL[4], accH[4];
+                    mma_m16n8k32_u8s8_z(accL, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xe.x, xe.y);
+                    mma_m16n8k32_u8s8_z(accH, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xo.x, xo.y);
+                    mma_m16n8k32_u8s8(accL, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xe.z, xe.w);
+                    mma_m16n8k32_u8s8(accH, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xo.z, xo.w);
+                    // X = 128*hi + lo; odd slots carry 16 x nibble: exact integer group result sum_k q*X - z*sum_k X
+                    const int sxv = sm.gsum[G];
+                    const float st = sm.gx[G];
+                    const int vA = (accL[0] << 7) + accL[1] + (((accH[0] << 7) + accH[1]) >> 4) - zAq * sxv;
+                    const int vB = (accL[2] << 7) + accL[3] + (((accH[2] << 7) + accH[3]) >> 4) - zBq * sxv;
+                    totA += (sAq * st) * (float)vA;
+                    totB += (sBq * st) * (float)vB;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty_bar[rs.stage]);
+            if (++rs.stage == sm.nst) {
+                rs.stage = 0;
+                rs.phase ^= 1;
+            }
+        }
+        // ---- hand the tile partial to the epilogue warp (no consumer-to-consumer wait) ----
+        mbar_wait(&sm.red_empty[cs.rb], cs.rphase ^ 1);
+        float *rbuf = sm.red + ((size_t)cs.rb * CW + cw) * 16;
+        if (t == 0) {
+            rbuf[g] = totA;
+            rbuf[g + 8] = totB;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.red_full[cs.rb]);
+        if (++cs.rb == kRedBufs) {
+            cs.rb = 0;
+            cs.rphase ^= 1;
+        }
+        if (++rs.mslot == sm.nst + 1) rs.mslot = 0;
+        u += ge - gb;
+        gb = 0;
+    }
+}
+
 template <int NCOLS, int CW>
 TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState &cs, int x_pitch, int cta, int ncta, int cw, int lane) {
+    if constexpr (NCOLS == 1) {
+        if (a.full)
+            consume1<CW, true>(a, sm, rs, cs, cta, ncta, cw, lane);
+        else
+            consume1<CW, false>(a, sm, rs, cs, cta, ncta, cw, lane);
+        return;
+    }
     constexpr int kVals = 16 * NCOLS;
     constexpr int GPW = kStageGroups / CW;  // groups per consumer warp per stage
     const int g = lane >> 2, t = lane & 3;
