@@ -28,6 +28,15 @@ METRIC = "llama3_8b_awq_int4_batch1_decode_tokens_per_s"
 UNIT = "tok/s"
 
 
+def load_traffic():
+    """dram__bytes_read + dram__bytes_write per GEMV launch from the committed ncu capture (tools/ncu_launch_summary.py); None if absent."""
+    p = Path(__file__).resolve().parent / "profiles" / "roofline_traffic.json"
+    try:
+        return json.loads(p.read_text()).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -308,8 +317,8 @@ def run_ours(args):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 12, "d2h_bytes_per_step": gl.vocab_size * 4 + 4},
             "gpu_launches": K * model.kernels_per_step,
-            "roofline": {"bound": "hbm", "kernel": "w4a16_gemv_kernel<1> (161 launches/step: 4 per layer + lm_head)",
-                         "achieved": gemv_gbs, "peak": peak, "unit": "GB/s", "frac": None if tp else gemv_gbs / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": f"w4a16_gemv_kernel<1> ({n_gemv} launches/step: 4 per layer + lm_head)",
+                         "achieved": gemv_gbs, "peak": peak, "unit": "GB/s", "frac": None if tp else gemv_gbs / peak, "traffic": load_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": wbytes / n_gemv, "avg_launch_us": None if tp else ms_gemv_step * 1e3 / n_gemv,
                          "step": {"bytes_per_token": wbytes + kvbytes, "achieved": (wbytes + kvbytes) / (ms_dev / K * 1e-3) / 1e9,
                                   "frac": (wbytes + kvbytes) / (ms_dev / K * 1e-3) / 1e9 / peak}},

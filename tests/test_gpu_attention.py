@@ -19,7 +19,7 @@ def ctx():
 
 @pytest.mark.parametrize("cluster", [16, 8, 0])  # CTAs per thread-block cluster (DSMEM merge); 0 = independent splits + global merge
 @pytest.mark.parametrize("H,KVH", [(8, 2), (4, 4), (8, 1), (16, 8)])
-@pytest.mark.parametrize("past", [0, 1, 5, 127, 128, 129, 300, 1023])
+@pytest.mark.parametrize("past", [0, 1, 5, 127, 128, 129, 255, 256, 257, 300, 1023])
 def test_decode_attention_matches_oracle(ctx, H, KVH, past, cluster):
     from oracle import capi
 
@@ -140,7 +140,8 @@ def test_attention_kernels_against_reference_module_fixture(ctx, golden_dir):
     cosb, sinb = capi.rope_tables(max_sq, HD, float(g["theta"]))
     dev = torch.device("cuda", 0)
     dcos, dsin = torch.from_numpy(cosb).to(dev), torch.from_numpy(sinb).to(dev)
-    qkv_all = np.concatenate([hidden[:, g["sel_q"]], hidden[:, g["sel_k"]], hidden[:, g["sel_v"]]], axis=1).astype(np.float16)  # exact in fp16
+    # exact in fp16; fancy indexing yields column-major pieces, the kernels take row-major buffers
+    qkv_all = np.ascontiguousarray(np.concatenate([hidden[:, g["sel_q"]], hidden[:, g["sel_k"]], hidden[:, g["sel_v"]]], axis=1).astype(np.float16))
     kc = torch.zeros((KVH, max_sq, HD), dtype=torch.float16, device=dev)
     vc = torch.zeros_like(kc)
     outs = torch.zeros((prefill + steps, E), dtype=torch.float16, device=dev)

@@ -217,6 +217,9 @@ cudaError_t megakernel_fill_gemv(Ctx *ctx, const W4GemvParams &p, MegaPhase *ph,
     a.tp_per_step = 1;
     a.resid_out = nullptr;
     for (int i = 0; i < kMaxTP; i++) a.tp_out[i] = nullptr;
+    a.tp_sig_counter = nullptr;
+    for (int i = 0; i < kMaxTP; i++) a.tp_sig_flag[i] = nullptr;
+    a.tp_sig_k = 0;
     for (int i = 0; i < p.nseg; i++) {
         cudaError_t e = encode_w4_tmap(&a.tmap[i], p.seg[i].w, p.seg[i].rows, p.IC, a.sg, p.pair_mode ? 8 : 16);
         if (e != cudaSuccess) return e;

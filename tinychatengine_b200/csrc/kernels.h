@@ -29,7 +29,7 @@ struct Ctx {
     // tunables (env overridable, see ctx.cu)
     int gemv_impl = 1;      // 0 = simple warp-per-row, 1 = TMA + mma.sync stream-K
     int gemv_ctas_per_sm = 1;
-    int gemv_consumer_warps = 0;   // 8 or 16 consumer warps per CTA; 0 = chosen per shape
+    int gemv_consumer_warps = 8;   // 8 or 16 consumer warps per CTA; 0 = chosen per shape
     int gemv_stages = 4;           // TMA ring depth (16 KiB stages); 0 = deepest that fits (measured: no gain over 4, profiles/)
     bool use_pdl = false;
     int pdl_early = 0;  // with use_pdl: 1 = dependents may become resident from the first instruction of each GEMV (2: and no 2-CTA/SM mode)
@@ -84,6 +84,11 @@ struct W4GemvParams {
     float *resid_out = nullptr;
     // epilogue (EPI_TP_SCATTER_F32): the finished fp32 outputs are stored into slot `rank` of every peer's gather buffer
     float *tp_out[kMaxTP] = {};
+    // ... and, once every CTA of the launch has stored (local arrival counter), the last one release-stores the step-stamped flag
+    // into every peer's flag word: the collective needs no separate signal kernel
+    unsigned *tp_sig_counter = nullptr;
+    unsigned *tp_sig_flag[kMaxTP] = {};
+    int tp_sig_k = 0;
 };
 
 cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p);

@@ -227,8 +227,13 @@ void LlamaDecoder::build_ops() {
         cur ^= 1;
     };
     // send side: scatter epilogue + signal op
-    auto tp_send = [&](W4GemvParams &p, int buf) {
+    auto tp_send = [&](W4GemvParams &p, int buf, int k) {
         p.tp_size = P;
+        p.tp_sig_counter = flags_of(me, 0) + 32 + buf;  // spare words of the local flag block
+        for (int q = 0; q < P; q++) p.tp_sig_flag[q] = flags_of(q, buf) + me;
+        p.tp_sig_k = k;
+        p.tp_step = d_tokpos_ + 3;
+        p.tp_per_step = per_step;
         p.epi = EPI_TP_SCATTER_F32;
         p.atomic_residual = false;
         p.y = nullptr;
@@ -300,9 +305,8 @@ void LlamaDecoder::build_ops() {
             p.y = resid[cur];
             p.epi = EPI_ADD_F32;
             p.atomic_residual = atomic_residual_;
-            if (P > 1) tp_send(p, 0);
+            if (P > 1) tp_send(p, 0, 2 * l);
             ops_.push_back(op);
-            if (P > 1) push_signal(0, 2 * l);
         }
         {  // RMSNorm(post_attention_layernorm) + gate/up with SiLU(gate)*up epilogue
             StepOp op;
@@ -337,9 +341,8 @@ void LlamaDecoder::build_ops() {
             p.y = resid[cur];
             p.epi = EPI_ADD_F32;
             p.atomic_residual = atomic_residual_;
-            if (P > 1) tp_send(p, 1);
+            if (P > 1) tp_send(p, 1, 2 * l + 1);
             ops_.push_back(op);
-            if (P > 1) push_signal(1, 2 * l + 1);
         }
     }
     {  // final RMSNorm + lm_head -> fp32 logits (reference: lm_head GEMV + half2float, cuda/Int4llamaForCausalLM.cu:33-38)
@@ -614,11 +617,20 @@ cudaError_t LlamaDecoder::prefill_reserve(int n) {
     return cudaSuccess;
 }
 
-// C[n][t.oc] (at column `col` of a row-major buffer with leading dimension ldc) = X[n][t.ic] * deq(t)^T
-cudaError_t LlamaDecoder::prefill_linear(const tce_w4_tensor &t, const __half *x, void *C, long long ldc, int n, bool add_f32) {
-    DCK(w4_scratch_reserve(ctx_, (size_t)t.oc * t.ic));
-    DCK(launch_w4_expand(ctx_, (const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, ctx_->w16_scratch, t.oc, t.ic));
-    return launch_gemm_f16_tc(ctx_, x, t.ic, ctx_->w16_scratch, t.ic, C, ldc, n, t.oc, t.ic, add_f32 ? 1 : 0);
+// C[n][sum oc] (row-major, leading dimension ldc) = X[n][ic] * [deq(t0); deq(t1); ...]^T : the `count` weight matrices (same ic) are
+// expanded into consecutive row ranges of the fp16 scratch and multiplied by ONE GEMM (q|k|v and gate|up share their input)
+cudaError_t LlamaDecoder::prefill_linear(const tce_w4_tensor *const *ts, int count, const __half *x, void *C, long long ldc, int n, bool add_f32) {
+    const int ic = ts[0]->ic;
+    size_t rows = 0;
+    for (int i = 0; i < count; i++) rows += (size_t)ts[i]->oc;
+    DCK(w4_scratch_reserve(ctx_, rows * ic));
+    size_t r0 = 0;
+    for (int i = 0; i < count; i++) {
+        const tce_w4_tensor &t = *ts[i];
+        DCK(launch_w4_expand(ctx_, (const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, ctx_->w16_scratch + r0 * ic, t.oc, ic));
+        r0 += (size_t)t.oc;
+    }
+    return launch_gemm_f16_tc(ctx_, x, ic, ctx_->w16_scratch, ic, C, ldc, n, (int)rows, ic, add_f32 ? 1 : 0);
 }
 
 cudaError_t LlamaDecoder::prefill(const int *tokens_host, int n, int pos0, float *logits_host, int *next_token, std::string *err) {
@@ -638,9 +650,8 @@ cudaError_t LlamaDecoder::prefill(const int *tokens_host, int n, int pos0, float
     for (int l = 0; l < cfg_.num_layers; l++) {
         const tce_llama_layer &L = layers_[l];
         DCK(launch_rmsnorm_rows_f32(ctx_, pf_x_, L.input_norm, pf_xn_, n, E, cfg_.rms_eps));
-        DCK(prefill_linear(L.q, pf_xn_, pf_qkv_, Q, n, false));
-        DCK(prefill_linear(L.k, pf_xn_, pf_qkv_ + (size_t)H * hd, Q, n, false));
-        DCK(prefill_linear(L.v, pf_xn_, pf_qkv_ + (size_t)(H + KVH) * hd, Q, n, false));
+        const tce_w4_tensor *qkv[3] = {&L.q, &L.k, &L.v}, *gu[2] = {&L.gate, &L.up}, *o1[1] = {&L.o}, *d1[1] = {&L.down};
+        DCK(prefill_linear(qkv, 3, pf_xn_, pf_qkv_, Q, n, false));
         AttnPrefillArgs a{};
         a.qkv = pf_qkv_;
         a.k_cache = (__half *)kv_cache(l, 0);
@@ -656,12 +667,11 @@ cudaError_t LlamaDecoder::prefill(const int *tokens_host, int n, int pos0, float
         a.head_dim = hd;
         a.max_ctx = cfg_.max_ctx;
         DCK(launch_attn_prefill(ctx_, a));
-        DCK(prefill_linear(L.o, pf_att_, pf_x_, E, n, true));  // residual add in the GEMM epilogue
+        DCK(prefill_linear(o1, 1, pf_att_, pf_x_, E, n, true));  // residual add in the GEMM epilogue
         DCK(launch_rmsnorm_rows_f32(ctx_, pf_x_, L.post_norm, pf_xn_, n, E, cfg_.rms_eps));
-        DCK(prefill_linear(L.gate, pf_xn_, pf_gu_, 2LL * F, n, false));
-        DCK(prefill_linear(L.up, pf_xn_, pf_gu_ + F, 2LL * F, n, false));
+        DCK(prefill_linear(gu, 2, pf_xn_, pf_gu_, 2LL * F, n, false));
         DCK(launch_silu_mul_rows(ctx_, pf_gu_, pf_act_, n, F));
-        DCK(prefill_linear(L.down, pf_act_, pf_x_, E, n, true));
+        DCK(prefill_linear(d1, 1, pf_act_, pf_x_, E, n, true));
     }
     // only the last position feeds the sampler: final RMSNorm + lm_head as the decode step's last GEMV, then arg-max
     DCK(cudaMemcpyAsync(d_resid_, pf_x_ + (size_t)(n - 1) * E, (size_t)E * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -38,7 +38,7 @@ class LlamaDecoder {
    private:
     LlamaDecoder() = default;
     cudaError_t prefill_reserve(int n);
-    cudaError_t prefill_linear(const tce_w4_tensor &t, const __half *x, void *C, long long ldc, int n, bool add_f32);
+    cudaError_t prefill_linear(const tce_w4_tensor *const *ts, int count, const __half *x, void *C, long long ldc, int n, bool add_f32);
     cudaError_t enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only = false);  // raw kernel sequence
     cudaError_t build_graphs(std::string *err);
     void build_ops();

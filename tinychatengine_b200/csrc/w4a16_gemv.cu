@@ -179,6 +179,13 @@ KArgs make_kargs(Ctx *ctx, const W4GemvParams &p, int *total_rows) {
     a.tp_per_step = p.tp_per_step;
     a.resid_out = p.resid_out;
     for (int i = 0; i < kMaxTP; i++) a.tp_out[i] = p.tp_out[i];
+    a.tp_sig_counter = p.tp_sig_counter;
+    for (int i = 0; i < kMaxTP; i++) a.tp_sig_flag[i] = p.tp_sig_flag[i];
+    a.tp_sig_k = p.tp_sig_k;
+    if (p.tp_sig_counter) {  // the sender stamps its flags with the step counter too
+        a.tp_step = p.tp_step;
+        a.tp_per_step = p.tp_per_step;
+    }
     return a;
 }
 

@@ -61,6 +61,9 @@ struct KArgs {
     int tp_k, tp_per_step;
     float *resid_out;
     float *tp_out[kMaxTP];
+    unsigned *tp_sig_counter;     // fused signal (EPI_TP_SCATTER_F32): local arrival counter, peers' flag words, collective index
+    unsigned *tp_sig_flag[kMaxTP];
+    int tp_sig_k;
     // one 2-D tensor map per weight segment: uint32 [rows][IC/8], box = [16 (8 in pair mode) rows][sg*16 words]
     alignas(64) CUtensorMap tmap[3];
 };
@@ -386,6 +389,21 @@ TCE_DEVINL void epilogue(const KArgs &a, const Smem &sm, RedState &es, int cta, 
         u += ge - gb;
         rt++;
         gb = 0;
+    }
+    if (a.epi == EPI_TP_SCATTER_F32 && a.tp_sig_counter) {
+        // fused collective signal: this CTA's peer stores are fenced system-wide, then it checks in; the last CTA of the launch
+        // publishes the step-stamped flag to every rank (release), which the receiving prologue acquires
+        __threadfence_system();
+        __syncwarp();
+        unsigned last = 0;
+        if (lane == 0) last = (atomicAdd(a.tp_sig_counter, 1u) == (unsigned)(ncta - 1)) ? 1u : 0u;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence_system();
+            if (lane == 0) *a.tp_sig_counter = 0u;
+            const unsigned value = (unsigned)(*a.tp_step) * (unsigned)a.tp_per_step + (unsigned)a.tp_sig_k + 1u;
+            if (lane < a.tp_size) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.tp_sig_flag[lane]), "r"(value) : "memory");
+        }
     }
 }
 

@@ -13,7 +13,11 @@ from .formats import GROUP, zeros_width
 
 
 def _ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    if not t.is_contiguous():  # the C ABI takes dense row-major buffers; a strided view would be read as garbage
+        raise _lib.TceError(f"non-contiguous tensor passed to libtce_b200 (shape {tuple(t.shape)}, strides {t.stride()})")
+    return C.c_void_p(t.data_ptr())
 
 
 class Context:
