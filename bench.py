@@ -279,14 +279,21 @@ def run_ours(args):
         if tp:
             n_gemv, ms_gemv_step = 4 * geom.num_layers + 1, None  # the sharded GEMVs wait for their peers: not timed alone
         else:
-            n_gemv = ctx.L.tce_llama_enqueue_gemvs(model.h)
+            n_gemv = ctx.L.tce_llama_enqueue_gemvs(model.h)  # eager once: modules loaded, attributes set
             barrier()
             reps = 20
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record(stream)
-            for _ in range(reps):
-                ctx.L.tce_llama_enqueue_gemvs(model.h)
-            g1.record(stream)
+            # replayed from a CUDA graph like the real step (plain stream launches would add ~2 us of launch gap per kernel)
+            gemv_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gemv_graph, stream=stream):
+                for _ in range(reps):
+                    ctx.L.tce_llama_enqueue_gemvs(model.h)
+            with torch.cuda.stream(stream):
+                gemv_graph.replay()
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+                gemv_graph.replay()
+                g1.record(stream)
             barrier()
             ms_gemv_step = g0.elapsed_time(g1) / reps
 

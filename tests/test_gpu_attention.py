@@ -52,7 +52,7 @@ def test_decode_attention_matches_oracle(ctx, H, KVH, past, cluster):
     got = out.float().cpu().numpy()
     assert np.all(np.isfinite(got))
     scale = max(np.abs(want).max(), 1e-6)
-    assert np.abs(got - want[0]).max() / scale <= 2e-3  # fp16 output rounding + fp16 K row
+    assert np.abs(got - want[0]).max() / scale <= 3e-3  # fp16 q / K / P / V operands of the tensor-core products, fp16 output
     # the appended rows: rotated K (fp16 rounded) and V, bit-for-bit V
     assert np.allclose(kc[:, past].float().cpu().numpy(), fk[:, past], atol=2e-3, rtol=1e-3)
     assert np.array_equal(vc[:, past].cpu().numpy(), fv[:, past].astype(np.float16))

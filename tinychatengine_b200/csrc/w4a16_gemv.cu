@@ -25,13 +25,17 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
     if (tid == 0) {
         dbg_stamp(a, cta, 0);
         init_barriers<CW>(sm);
+    } else if (tid == 32) {
+        // the TMA unit's first use of a tensor map costs a descriptor fetch: start it while lane 0 initialises the barriers
+        for (int i = 0; i < a.nseg; i++) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmap[i]) : "memory");
     }
-    // warp 0 (which initialised the barriers) only signals; everyone else waits.  The first TMA copies therefore do
-    // not wait for 400+ threads to reach a CTA-wide barrier.
+    // Warp 0 (which initialised the barriers) only signals; the others wait where they first need the barriers: the epilogue warp
+    // right away, the consumers after they have staged the activations (staging touches no mbarrier), so that barrier set-up, the
+    // first weight copies and the activation staging all overlap.
     if (warp == 0) {
         __syncwarp();
         asm volatile("bar.arrive 3, %0;" ::"r"(32 * (kProducerWarps + 1 + CW)) : "memory");
-    } else {
+    } else if (warp == kProducerWarps) {
         asm volatile("bar.sync 3, %0;" ::"r"(32 * (kProducerWarps + 1 + CW)) : "memory");
     }
 
@@ -54,6 +58,7 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
     pdl_wait();  // activations belong to the previous kernel until here
     stage_activations<NCOLS, CW>(a, sm, L::x_pitch(a.IC), ctid, cw, lane);
     if (ctid == 0) dbg_stamp(a, cta, 2);
+    asm volatile("bar.sync 3, %0;" ::"r"(32 * (kProducerWarps + 1 + CW)) : "memory");
     RingState rs;
     RedState cs;
     consume<NCOLS, CW>(a, sm, rs, cs, L::x_pitch(a.IC), cta, ncta, cw, lane);
