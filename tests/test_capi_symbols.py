@@ -45,8 +45,60 @@ def test_sass_is_blackwell_native(built_lib):
 
     sass = subprocess.run(["cuobjdump", "-sass", str(built_lib)], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    assert "UBLKCP" in sass, "TMA bulk copies missing from the W4A16 GEMV / attention kernels"
-    assert "IMMA" in sass or "HMMA" in sass, "mma.sync path missing from the W4A16 GEMV"
+    assert "UBLKCP" in sass, "TMA bulk copies missing from the W4A16 GEMV"
+    assert "UTMALDG" in sass, "2-D TMA tensor copies missing (GEMV weight ring, tcgen05 GEMM operands)"
+    assert "IMMA" in sass and "HMMA" in sass, "mma.sync paths missing (integer GEMV, attention)"
+    assert "UTCHMMA" in sass and "UTCIMMA" in sass, "tcgen05.mma missing: the prefill / W8A8 GEMMs must run on the 5th-gen tensor cores"
+    assert "LDTM" in sass, "tcgen05.ld (TMEM epilogue) missing"
+
+
+def test_stream_k_partition_properties(tmp_path):
+    """The GEMV's stream-K partition (csrc/kernels.h StreamK, shared by host and device code) compiled for the host: CTA ranges tile
+    [0, U) exactly, are monotone, respect the cut granularity (whole stages / whole row tiles), and cta_of() inverts start()."""
+    import subprocess
+
+    src = tmp_path / "sk.cc"
+    src.write_text(r"""
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include "kernels.h"
+using tce::StreamK;
+static int check(long long tiles, int NG, int nc, int aligned, int gran) {
+    StreamK sk; sk.U = tiles * NG; sk.nc = nc; sk.NG = NG; sk.aligned = aligned; sk.T = (int)tiles; sk.gran = gran;
+    if (sk.start(0) != 0 || sk.start(nc) != sk.U) return 1;
+    for (int c = 0; c < nc; c++) {
+        const long long a = sk.start(c), b = sk.start(c + 1);
+        if (b < a) return 2;
+        if (aligned ? (a % NG) : (a % gran)) return 3;
+    }
+    if (!aligned)
+        for (long long u = 0; u < sk.U; u += (sk.U > 5000 ? 37 : 1)) {
+            const int c = sk.cta_of(u);
+            if (c < 0 || c >= nc || sk.start(c) > u || sk.start(c + 1) <= u) return 4;
+        }
+    return 0;
+}
+int main() {
+    const long long tiles[] = {1, 3, 64, 256, 384, 1792, 8016};
+    const int ngs[] = {1, 2, 16, 32, 86, 112}, ncs[] = {1, 7, 148, 296, 592};
+    for (long long t : tiles) for (int ng : ngs) for (int nc : ncs) {
+        const long long U = t * ng;
+        for (int gran : {1, 16}) {
+            if (U % gran) continue;
+            int n = nc; if (n > U / gran) n = (int)(U / gran);
+            if (int e = check(t, ng, n, 0, gran)) { printf("unaligned tiles=%lld NG=%d nc=%d gran=%d -> %d ", t, ng, n, gran, e); return 1; }
+        }
+        if (t >= nc) if (int e = check(t, ng, nc, 1, 1)) { printf("aligned tiles=%lld NG=%d nc=%d -> %d ", t, ng, nc, e); return 1; }
+    }
+    puts("ok");
+    return 0;
+}
+""")
+    exe = tmp_path / "sk"
+    inc = ROOT / "tinychatengine_b200" / "csrc"
+    subprocess.run(["g++", "-std=c++17", "-I/usr/local/cuda/include", f"-I{inc}", "-o", str(exe), str(src)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="this checks the no-GPU behaviour")
