@@ -24,7 +24,7 @@ def rnd8(shape, seed):
 ALPHA, BETA = 0.00050354, 0.0213013
 
 
-@pytest.mark.parametrize("M,N,K", [(1, 768, 768), (108, 768, 768), (1, 4096, 4096), (7, 1000, 136), (33, 64, 4096), (3, 40, 50)])
+@pytest.mark.parametrize("M,N,K", [(1, 768, 768), (108, 768, 768), (1, 4096, 4096), (7, 1000, 136), (33, 64, 4096), (3, 40, 50), (1, 1031, 11008), (3, 1000, 2064), (4, 64, 528), (2, 9, 16384)])
 def test_linear_variants_bit_exact(ctx, M, N, K):
     from oracle import capi
 

@@ -113,7 +113,9 @@ struct StreamK {
     int T = 0;        // row tiles (aligned mode)
     int gran = 1;     // unaligned mode: cuts fall on multiples of `gran` units (16 = whole pipeline stages; U % gran == 0)
     __host__ __device__ long long start(int c) const {
-        return aligned ? (((long long)T * c) / nc) * NG : (((U / gran) * (long long)c) / nc) * gran;
+        const long long n = aligned ? (long long)T : U / gran;  // cut positions are n * c / nc, in tiles or in `gran` units
+        const long long q = (n * nc < 0x7fffffffLL) ? (long long)(((unsigned)n * (unsigned)c) / (unsigned)nc) : (n * (long long)c) / nc;  // 32-bit divide when it fits
+        return q * (aligned ? NG : gran);
     }
     // owner of unit u in unaligned mode: the largest c with start(c) <= u
     __host__ __device__ int cta_of(long long u) const {

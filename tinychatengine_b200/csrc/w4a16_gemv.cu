@@ -22,9 +22,9 @@ __global__ void __launch_bounds__(32 * (kProducerWarps + 1 + CW), (NCOLS == 1 &&
     const int cta = blockIdx.x, ncta = gridDim.x;
 
     if (a.pdl_early) pdl_launch_dependents();
-    if (tid == 0) {
-        dbg_stamp(a, cta, 0);
-        init_barriers<CW>(sm);
+    if (warp == 0) {
+        if (lane == 0) dbg_stamp(a, cta, 0);
+        init_barriers_warp<CW>(sm, lane);
     } else if (tid == 32) {
         // the TMA unit's first use of a tensor map costs a descriptor fetch: start it while lane 0 initialises the barriers
         for (int i = 0; i < a.nseg; i++) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmap[i]) : "memory");

@@ -170,6 +170,20 @@ TCE_DEVINL void init_barriers(const Smem &sm) {  // one thread
     mbar_fence_init();
 }
 
+// same, spread over the lanes of one warp (one barrier pair per lane instead of ~14 dependent inits on one thread)
+template <int CW>
+TCE_DEVINL void init_barriers_warp(const Smem &sm, int lane) {
+    if (lane < sm.nst) {
+        mbar_init(&sm.full_bar[lane], 1);
+        mbar_init(&sm.empty_bar[lane], CW);
+    } else if (lane >= 16 && lane < 16 + kRedBufs) {
+        mbar_init(&sm.red_full[lane - 16], CW);
+        mbar_init(&sm.red_empty[lane - 16], 1);
+    }
+    mbar_fence_init();
+    __syncwarp();
+}
+
 // pipeline positions; every role keeps its own copy and all copies advance identically because every role walks the
 // same (tile, stage) sequence
 struct RingState {
