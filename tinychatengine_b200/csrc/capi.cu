@@ -79,7 +79,7 @@ int tce_ctx_create(int device, tce_ctx **out) {
     c.gemv_impl = env_int("TCE_GEMV_IMPL", 1);
     c.gemv_ctas_per_sm = env_int("TCE_GEMV_CTAS_PER_SM", 1);
     c.gemv_consumer_warps = env_int("TCE_GEMV_CONSUMER_WARPS", 8);  // 8, 16, or 0 = per shape (16 for long rows: faster alone, not in the step)
-    c.gemv_stages = env_int("TCE_GEMV_STAGES", 4);
+    c.gemv_stages = env_int("TCE_GEMV_STAGES", 8);  // 8 vs 4: +3 % on the decode step once the consumers outran HBM (profiles/README.md)
     c.pdl_early = env_int("TCE_PDL_EARLY", 1);
     c.use_pdl = env_int("TCE_USE_PDL", 1) != 0;  // programmatic dependent launch, dependents resident from kernel entry: +3 % (profiles/r01_pdl_matrix.txt)
     ctx->attn_chunk = env_int("TCE_ATTN_CHUNK", 256);  // cached rows per CTA: 256 measured best (64: -8 %, 128: -2 %; profiles/README.md)

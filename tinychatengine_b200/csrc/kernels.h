@@ -30,7 +30,7 @@ struct Ctx {
     int gemv_impl = 1;      // 0 = simple warp-per-row, 1 = TMA + mma.sync stream-K
     int gemv_ctas_per_sm = 1;
     int gemv_consumer_warps = 8;   // 8 or 16 consumer warps per CTA; 0 = chosen per shape
-    int gemv_stages = 4;           // TMA ring depth (16 KiB stages); 0 = deepest that fits (measured: no gain over 4, profiles/)
+    int gemv_stages = 8;           // TMA ring depth (16 KiB stages, capped by the per-CTA shared-memory share); 0 = deepest that fits
     bool use_pdl = false;
     int pdl_early = 0;  // with use_pdl: 1 = dependents may become resident from the first instruction of each GEMV (2: and no 2-CTA/SM mode)
     // large-M (prefill) path: fp16 expansion of one int4 weight matrix, grown on demand; M >= gemm_min_m goes to the tcgen05 GEMM
