@@ -20,3 +20,18 @@ def test_column_and_row_shards_dequantise_to_slices():
         w, z, s = shard_w4_rows(t, r, P)
         part = quant.dequant_qmcuda(w.numpy().view(np.uint32), s.numpy(), z.numpy().view(np.uint32))
         assert np.array_equal(part, full[r * oc // P:(r + 1) * oc // P])
+
+
+def test_tp_rank_keeps_the_full_embedding_table():
+    """A tensor-parallel rank shards lm_head over the vocabulary but looks up GLOBAL token ids: synthetic local weights must carry
+    an embedding table with all vocab_size * P rows (a local-size table made an 8-GPU run read far out of bounds)."""
+    from tinychatengine_b200.llama import GEOMETRIES, LlamaGeometry, make_random_weights, shard_weights
+
+    g = GEOMETRIES["tiny-gqa"]
+    P = 2
+    gl = LlamaGeometry(g.name, 1, g.num_heads // P, g.num_kv_heads // P, g.embed_dim, g.hidden_dim // P, g.vocab_size // P, g.rms_eps, g.rope_theta)
+    W = make_random_weights(gl, torch.device("cpu"), seed=3, embed_rows=gl.vocab_size * P)
+    assert W["embed"].shape == (g.vocab_size, g.embed_dim) and W["lm_head"][0].shape[0] == g.vocab_size // P
+    full = make_random_weights(LlamaGeometry(g.name, 1, g.num_heads, g.num_kv_heads, g.embed_dim, g.hidden_dim, g.vocab_size), torch.device("cpu"), seed=3)
+    Wl, gl2 = shard_weights(full, LlamaGeometry(g.name, 1, g.num_heads, g.num_kv_heads, g.embed_dim, g.hidden_dim, g.vocab_size), 1, P)
+    assert Wl["embed"].shape[0] == g.vocab_size and gl2.vocab_size == g.vocab_size // P

@@ -58,8 +58,10 @@ def kv_bytes_per_token(g: LlamaGeometry, ctx_len: int) -> int:
     return per_pos * ctx_len + per_pos
 
 
-def make_random_weights(geom: LlamaGeometry, dev, seed: int = 1234, random_zeros: bool = False):
-    """Synthetic AWQ-INT4 Llama weights (QM_CUDA layout) as a plain dict of torch tensors on `dev`."""
+def make_random_weights(geom: LlamaGeometry, dev, seed: int = 1234, random_zeros: bool = False, embed_rows: int | None = None):
+    """Synthetic AWQ-INT4 Llama weights (QM_CUDA layout) as a plain dict of torch tensors on `dev`.  `embed_rows`: rows of the
+    embedding table when it differs from geom.vocab_size (a tensor-parallel rank holds a vocabulary SHARD of lm_head but looks up
+    GLOBAL token ids, so its table has all the rows)."""
     g = geom
     hd = g.head_dim
     gen = torch.Generator(device=dev)
@@ -77,7 +79,7 @@ def make_random_weights(geom: LlamaGeometry, dev, seed: int = 1234, random_zeros
              "input_norm": (1.0 + 0.02 * torch.randn(g.embed_dim, device=dev, generator=gen)).float(),
              "post_norm": (1.0 + 0.02 * torch.randn(g.embed_dim, device=dev, generator=gen)).float()}
         W["layers"].append(L)
-    W["embed"] = (torch.randn((g.vocab_size, g.embed_dim), device=dev, generator=gen) * 0.5).to(torch.float16)
+    W["embed"] = (torch.randn((embed_rows or g.vocab_size, g.embed_dim), device=dev, generator=gen) * 0.5).to(torch.float16)
     W["final_norm"] = (1.0 + 0.02 * torch.randn(g.embed_dim, device=dev, generator=gen)).float()
     W["lm_head"] = random_w4(g.vocab_size, g.embed_dim, dev, seed * 1000 + 999983, 0.02, random_zeros)
     return W
@@ -139,7 +141,7 @@ class LlamaModel:
         dev = torch.device("cuda", ctx.device)
         g = geom
         hd = g.head_dim
-        W = weights if weights is not None else make_random_weights(geom, dev, seed, random_zeros)
+        W = weights if weights is not None else make_random_weights(geom, dev, seed, random_zeros, embed_rows=geom.vocab_size * max(1, tp_size))
         self.W = W
         self.tensors = []
 
