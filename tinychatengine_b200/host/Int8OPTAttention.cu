@@ -46,8 +46,8 @@ void Int8OPTAttention::initialized_memory(const struct model_config config) {
 
 Int8OPTAttention::Int8OPTAttention(const struct model_config config, BMM_S8T_S8N_F32T &qk_bmm_, BMM_S8T_S8N_S8T &pv_bmm_, W8A8B8O8Linear &k_proj_,
                                    W8A8B8O8Linear &v_proj_, W8A8B8O8Linear &q_proj_, W8A8BFP32OFP32Linear &out_proj_)
-    : embed_dim(config.embed_dim), num_heads(config.num_heads), head_dim(config.embed_dim / config.num_heads), qk_bmm(qk_bmm_), pv_bmm(pv_bmm_),
-      k_proj(k_proj_), v_proj(v_proj_), q_proj(q_proj_), out_proj(out_proj_) {
+    : embed_dim(config.embed_dim), num_heads(config.num_heads), head_dim(config.embed_dim / config.num_heads), q_proj(q_proj_), k_proj(k_proj_),
+      v_proj(v_proj_), out_proj(out_proj_), qk_bmm(qk_bmm_), pv_bmm(pv_bmm_) {
     assert(config.embed_dim % config.num_heads == 0);
 }
 
