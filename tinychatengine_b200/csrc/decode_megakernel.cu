@@ -4,8 +4,8 @@
 // library runs 5 kernels per layer, and measurements (profiles/README.md) show ~3.5 us per kernel during which HBM
 // idles (launch gap, cold start, first-byte latency, activation staging).  Here the whole token is ONE cooperative
 // kernel of one CTA per SM whose warp roles persist across all phases:
-//   * 4 producer warps stream the packed weights of phase after phase through the same 4-stage TMA ring.  They
-//     depend on nothing but the (static) weights, so they run ahead across phase boundaries: while the rest of the
+//   * 1 producer warp streams the packed weights of phase after phase through the same 4-stage TMA ring.  It
+//     depends on nothing but the (static) weights, so it runs ahead across phase boundaries: while the rest of the
 //     GPU synchronises, the first 64 KiB/SM of the next matrix are already landing in shared memory.
 //   * 8 consumer warps: per phase wait for the grid barrier (all earlier phases complete), stage + quantise the
 //     activations (fused RMSNorm), run the integer-MMA GEMV, or execute attention / embedding / arg-max work items.

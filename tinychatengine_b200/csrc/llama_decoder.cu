@@ -100,7 +100,7 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
         delete d;
         return nullptr;
     }
-    d->mega_ = getenv("TCE_MEGAKERNEL") ? atoi(getenv("TCE_MEGAKERNEL")) != 0 : false;  // measured: 2.42 vs 2.14 ms/token (profiles/)
+    d->mega_ = getenv("TCE_MEGAKERNEL") ? atoi(getenv("TCE_MEGAKERNEL")) != 0 : false;  // measured slower than the graph path (2.4 vs 1.7 ms/token, profiles/README.md)
     d->mega_attn_chunk_ = getenv("TCE_MEGA_ATTN_CHUNK") ? atoi(getenv("TCE_MEGA_ATTN_CHUNK")) : 64;
     d->tp_ = cfg.tp_size > 1 ? cfg.tp_size : 1;
     if (d->tp_ > 1) {

@@ -8,12 +8,15 @@
 //  * work unit = (16-row tile, one 128-k group) = 1 KiB of packed weights; the units of a launch are cut into equal
 //    contiguous per-CTA ranges (stream-K) or, for epilogues that need one ordered writer, at row-tile boundaries.
 //  * producer (1 warp, 1 elected lane): ONE 2-D TMA tensor copy (UTMALDG) per stage moves the [16 rows x <=16 groups]
-//    weight box into a 4-stage ring guarded by full/empty mbarriers, L2 evict-first; the tile's scales/zeros slabs
-//    (1-D bulk copies, UBLKCP) ride on the first stage's barrier.  Producers depend on nothing but the weights, so they may run ahead of everything else.
-//  * consumers (CW warps): 128-bit LDS of the packed nibbles; nibbles -> bytes with
-//    w & 0x0f0f0f0f / (w>>4) & 0x0f0f0f0f (3 ALU ops per 8 weights); mma.sync.m16n8k32 u8 x s8 -> s32 against the
-//    activations held as two int8 planes (15-bit block fixed point per 128-group, exact integer accumulation);
-//    per-group epilogue tot += (s * step) * (acc - z * sum_X).  The 8 MMA columns carry up to 8 activation rows.
+//    weight box into a ring of KArgs::nst stages (8 by default) guarded by full/empty mbarriers, L2 evict-first; the tile's
+//    scales/zeros slabs (1-D bulk copies, UBLKCP) ride on the first stage's barrier.  Producers depend on nothing but the weights,
+//    so they run ahead of everything else (in particular of the consumers' activation staging).
+//  * consumers (CW warps): 128-bit LDS of the packed nibbles; activations held as two int8 planes (15-bit block fixed point per
+//    128-group, exact integer accumulation); mma.sync.m16n8k32 u8 x s8 -> s32; per-group epilogue
+//    tot += (s * step) * (acc - z * sum_X).  One activation row (decode, consume1): the two planes ride in MMA columns 0/1 and
+//    nibbles become bytes with one mask each (even slots w & 0x0f0f0f0f, odd slots w & 0xf0f0f0f0 = 16 x nibble, shifted back
+//    after accumulation): 4 IMMAs per (16 rows x 128 k).  Up to 8 rows (consume<8>): the 8 MMA columns carry the rows, planes in
+//    separate MMAs, (w >> 4) & 0x0f0f0f0f for the odd slots.
 //  * tile partials go to the epilogue warp through a triple-buffered smem slot + mbarrier (consumers never wait for
 //    each other); the epilogue warp runs the fused epilogue (fp16/fp32 store, residual +=, SiLU(gate)*up), the
 //    RED.ADD residual path or the ordered stream-K fix-up.
