@@ -37,6 +37,18 @@ def load_traffic():
         return None
 
 
+def workload_config(geom, args, world: int, tp: bool) -> dict:
+    """The `config` object both arms report: names the workload, no model-architecture keys."""
+    return {
+        "workload": (f"{geom.name} AWQ-INT4 g128 batch-1 decode, timed steps spread over ctx 1->{args.max_ctx}" if args.ctx < 0
+                     else f"{geom.name} AWQ-INT4 g128 batch-1 decode at ctx {args.ctx}"),
+        "sequences": 1 if (world == 1 or tp) else world,
+        "max_ctx": args.max_ctx,
+        "parallelism": (f"tp{world}: one sequence, column/row sharded linears, 2 all-reduces per layer over NVLink peer memory" if tp else
+                        (f"{world} independent sequences, one per GPU (no collective)" if world > 1 else "single GPU")),
+    }
+
+
 def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -186,9 +198,12 @@ def run_reference(args):
         samples.append(cpu_reference_decode(geom, budget_s=max(4.0, 60.0 / max(1, min(args.steps, 3)))))
     best = max(samples, key=lambda d: d["value"])
     med = sorted(s["value"] for s in samples)[len(samples) // 2]
+    cfg = workload_config(geom, args, 1, False)  # the same workload as our arm; the reference has no multi-GPU path: rank 0's host cores
+    cfg["reference_path"] = "the reference's AVX W4A8 kernels (oracle/_ref, compiled in place) on all host threads; each step = a bounded sample"
+    cfg["sampled_steps"] = len(samples)
     line = {"impl": "reference", "metric": METRIC, "value": med, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 / med, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "w4a8 (int8 act x int4 weight, fp32 acc)",
-            "data": "synthetic", "config": {"workload": f"{geom.name} AWQ-INT4 batch-1 decode, reference AVX CPU path on host cores", "model": geom.name},
+            "ms_per_step": 1e3 / med, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "w4a8 (int8 act x int4 weight, fp32 acc)",
+            "data": "synthetic", "config": cfg,
             "cpu_baseline": dict(best, value=med),
             "e2e": {"value": med, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "wall_s": time.perf_counter() - t0}
@@ -315,12 +330,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
             "dtype": "w4a16 (int4 weights; activations fp16 -> 15-bit block fixed point; int32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": f"{geom.name} AWQ-INT4 g128 batch-1 decode, timed steps spread over ctx 1->{args.max_ctx}" if args.ctx < 0
-                       else f"{geom.name} AWQ-INT4 g128 batch-1 decode at ctx {args.ctx}", "model": geom.name, "global_batch": 1 if (world == 1 or tp) else world, "max_ctx": args.max_ctx,
-                       "mean_ctx": mean_ctx, "global_batch_note": "one sequence" if (tp or world == 1) else "one sequence per GPU",
-                       "parallelism": (f"tp{world} (column/row sharded linears, 2 all-reduces per layer over NVLink peer memory)" if tp else
-                                       ("1 sequence per GPU (replicas)" if world > 1 else "single GPU")),
-                       "l2": "inputs larger than L2: 3.9 GB of weights stream per step vs 126 MB L2", "pdl": bool(int(os.environ.get("TCE_USE_PDL", "1")))},
+            "config": dict(workload_config(geom, args, world, tp), mean_ctx=mean_ctx,
+                           l2="inputs larger than L2: 3.9 GB of weights stream per step vs 126 MB L2", pdl=bool(int(os.environ.get("TCE_USE_PDL", "1")))),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 12, "d2h_bytes_per_step": gl.vocab_size * 4 + 4},
             "gpu_launches": K * model.kernels_per_step,
