@@ -67,3 +67,25 @@ int ref_int8_opt_attention(const char *param_path, int E, int H, int max_sqlen, 
     return past;
 }
 }
+
+// ---- the small fp32 ops either side of the path, as the reference's CPU classes compute them (pins orc_rmsnorm / orc_layernorm_q) ----
+extern "C" {
+
+// LlamaRMSNorm::forward (llm/src/ops/LlamaRMSNorm.cc:7-38): x, out fp32 [rows][dim], weight fp32 [dim]
+void ref_llama_rmsnorm(const float *x, const float *weight, float *out, int rows, int dim, float eps) {
+    LlamaRMSNorm op(Matrix3D<float>(const_cast<float *>(weight), 1, 1, dim));
+    Matrix3D<float> X(const_cast<float *>(x), 1, rows, dim), Y(out, 1, rows, dim);
+    op.forward(X, Y, eps);
+}
+
+// LayerNormQ::forward (llm/src/ops/LayerNormQ.cc:11-51): fp32 in, int8 out = round(layernorm), eps fixed at 1e-5 by the reference
+void ref_layernorm_q(const float *x, const float *weight, const float *bias, int8_t *out, int rows, int dim) {
+    LayerNormQ_params p;
+    p.weight = Matrix3D<float>(const_cast<float *>(weight), 1, 1, dim);
+    p.bias = Matrix3D<float>(const_cast<float *>(bias), 1, 1, dim);
+    LayerNormQ op(p);
+    Matrix3D<float> X(const_cast<float *>(x), 1, rows, dim);
+    Matrix3D<int8_t> Y(out, 1, rows, dim);
+    op.forward(X, Y);
+}
+}

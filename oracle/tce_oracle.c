@@ -356,7 +356,8 @@ ORC_API void orc_rmsnorm(const float *x, const float *weight, float *out, int ro
         float var = 0;
         for (int k = 0; k < dim; k++) var += x[(size_t)j * dim + k] * x[(size_t)j * dim + k];
         var /= (float)dim;
-        float variance = (float)(1.0 / sqrt((double)(var + eps)));
+        /* `1.0 / sqrt(var + eps)` with a float argument: C++ picks the float overload of sqrt, the division is in double */
+        float variance = (float)(1.0 / (double)sqrtf(var + eps));
         for (int k = 0; k < dim; k++) {
             float value = x[(size_t)j * dim + k];
             out[(size_t)j * dim + k] = (value * variance) * weight[k];

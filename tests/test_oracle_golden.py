@@ -183,3 +183,27 @@ def test_llama_attention_module_live(E, H, KVH, prefill, steps, seed, tmp_path):
     diff = np.abs(got - want)
     assert (diff > 1e-5 * np.abs(want).max()).mean() <= 2e-3
     assert diff.max() <= np.abs(want).max() / 100
+
+
+@pytest.mark.skipif(not (capi.REF_DIR / "libtce_ref_modules.so").exists(), reason="reference module build (oracle/_ref) not present")
+def test_norms_match_the_compiled_reference_ops():
+    """orc_rmsnorm / orc_layernorm_q vs the reference's LlamaRMSNorm::forward / LayerNormQ::forward (compiled in place, strict IEEE
+    flags): RMSNorm bit-for-bit (it is the fused prologue of the decode GEMVs), LayerNormQ int8 outputs bit-for-bit."""
+    import ctypes as C
+
+    L = C.CDLL(str(capi.REF_DIR / "libtce_ref_modules.so"))
+    rng = np.random.default_rng(8)
+    for rows, dim in ((1, 4096), (5, 768), (3, 130)):
+        x = (rng.standard_normal((rows, dim)) * 3).astype(np.float32)
+        w = (1 + 0.1 * rng.standard_normal(dim)).astype(np.float32)
+        b = rng.standard_normal(dim).astype(np.float32)
+        want = np.zeros_like(x)
+        L.ref_llama_rmsnorm(x.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), rows, dim, C.c_float(1e-5))
+        got = capi.rmsnorm(x, w, 1e-5)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        want8 = np.zeros((rows, dim), np.int8)
+        x8 = (x * 20).astype(np.float32)
+        L.ref_layernorm_q(x8.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), want8.ctypes.data_as(C.c_void_p), rows, dim)
+        got8 = np.zeros((rows, dim), np.int8)
+        capi.lib().orc_layernorm_q(x8, w, b, got8, rows, dim)
+        assert np.array_equal(got8, want8)
