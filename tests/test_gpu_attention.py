@@ -61,6 +61,39 @@ def test_decode_attention_matches_oracle(ctx, H, KVH, past, cluster):
     ctx.set_option("attn_cluster", 0)
 
 
+@pytest.mark.parametrize("past", [1024, 2047, 3000, 4095])
+def test_decode_attention_benchmarked_geometry(ctx, past):
+    """The configuration bench.py times: Llama-3-8B heads (H = 32, KVH = 8), max_ctx = 4096, long contexts (the many-way
+    flash-decode split and its merge)."""
+    from oracle import capi
+
+    H, KVH, max_ctx = 32, 8, 4096
+    rng = np.random.default_rng(past)
+    cosb, sinb = capi.rope_tables(max_ctx, HD, 500000.0)
+    qkv = rng.standard_normal((H + 2 * KVH) * HD).astype(np.float16)
+    pk = (rng.standard_normal((KVH, past, HD)) * 0.7).astype(np.float16)
+    pv = rng.standard_normal((KVH, past, HD)).astype(np.float16)
+    alpha = 1.0 / np.sqrt(HD)
+    q = qkv[: H * HD].astype(np.float32)[None]
+    k = qkv[H * HD: (H + KVH) * HD].astype(np.float32)[None]
+    v = qkv[(H + KVH) * HD:].astype(np.float32)[None]
+    want, fk, fv = capi.llama_attention_core(q, k, v, pk.astype(np.float32), pv.astype(np.float32), capi.causal_mask(1, past), cosb, sinb, alpha, H, KVH, HD)
+    dev = torch.device("cuda", 0)
+    kc = torch.full((KVH, max_ctx, HD), float("nan"), dtype=torch.float16, device=dev)
+    vc = torch.full_like(kc, float("nan"))
+    kc[:, :past] = torch.from_numpy(pk).to(dev)
+    vc[:, :past] = torch.from_numpy(pv).to(dev)
+    out = torch.zeros(H * HD, dtype=torch.float16, device=dev)
+    pos = torch.tensor([past], dtype=torch.int32, device=dev)
+    ctx.attn_decode(torch.from_numpy(qkv).to(dev), kc, vc, torch.from_numpy(cosb).to(dev), torch.from_numpy(sinb).to(dev), pos, out, alpha, H, KVH, HD, max_ctx)
+    torch.cuda.synchronize()
+    got = out.float().cpu().numpy()
+    assert np.all(np.isfinite(got))
+    assert np.abs(got - want[0]).max() / max(np.abs(want).max(), 1e-6) <= 3e-3
+    assert np.allclose(kc[:, past].float().cpu().numpy(), fk[:, past], atol=2e-3, rtol=1e-3)
+    assert np.array_equal(vc[:, past].cpu().numpy(), fv[:, past].astype(np.float16))
+
+
 def test_multi_step_append_is_consistent(ctx):
     """decode 40 tokens one by one through the in-place cache and compare every step with the oracle fed by its
     own accumulated past (reference test: test_Int4llamaAttention sqlen 9 then 1 with past 9)."""

@@ -1,4 +1,4 @@
-"""Fused decode step (tce_llama_*: one CUDA graph per token) vs the oracle-composed step."""
+"""Fused decode step (tce_llama_*: one persistent kernel per token, or one kernel per op inside a CUDA graph) vs the oracle-composed step."""
 import numpy as np
 import pytest
 import torch
@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("mega", ["1", "0"])
 @pytest.mark.parametrize("geom", ["tiny-gqa", "tiny-mha"])
 def test_decode_steps_match_oracle(geom, mega, monkeypatch):
-    """mega=1: one persistent cooperative kernel per token; mega=0: one kernel per op inside a CUDA graph."""
-    monkeypatch.setenv("TCE_MEGAKERNEL", mega)
+    """mega=1: one persistent cooperative kernel per token (the default); mega=0: one kernel per op inside a CUDA graph."""
+    monkeypatch.setenv("TCE_PERSISTENT", mega)
     from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
     from tinychatengine_b200.runtime import Context
 
@@ -47,7 +47,7 @@ def test_graph_and_eager_paths_agree(monkeypatch):
     import os
 
     monkeypatch.setenv("TCE_DETERMINISTIC", "1")  # ordered stream-K fix-up instead of RED.ADD: bit-reproducible
-    monkeypatch.setenv("TCE_MEGAKERNEL", "0")
+    monkeypatch.setenv("TCE_PERSISTENT", "0")
 
     from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
     from tinychatengine_b200.runtime import Context
@@ -77,7 +77,7 @@ def test_persistent_kernel_long_context_matches_graph_path(monkeypatch):
     g = GEOMETRIES["tiny-gqa"]
     outs = {}
     for mega in ("1", "0"):
-        monkeypatch.setenv("TCE_MEGAKERNEL", mega)
+        monkeypatch.setenv("TCE_PERSISTENT", mega)
         ctx = Context(0)
         model = LlamaModel(ctx, g, max_ctx=256, seed=11)
         lg = torch.empty(g.vocab_size, dtype=torch.float32)
@@ -93,3 +93,61 @@ def test_persistent_kernel_long_context_matches_graph_path(monkeypatch):
         ctx.close()
     assert rel_err(outs["1"][0].numpy(), outs["0"][0].numpy()) <= 5e-3
     assert rel_err(outs["1"][1].numpy(), outs["0"][1].numpy()) <= 5e-3
+
+
+def test_persistent_kernel_is_deterministic_when_asked(monkeypatch):
+    """TCE_DETERMINISTIC=1: o_proj / down_proj are cut at tile boundaries (one writer per residual element): same bits every run."""
+    monkeypatch.setenv("TCE_DETERMINISTIC", "1")
+    monkeypatch.setenv("TCE_PERSISTENT", "1")
+    from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
+    from tinychatengine_b200.runtime import Context
+
+    outs = []
+    for _ in range(2):
+        ctx = Context(0)
+        model = LlamaModel(ctx, GEOMETRIES["tiny-gqa"], max_ctx=128, seed=3)
+        lg = torch.empty(model.geom.vocab_size, dtype=torch.float32)
+        seq = []
+        for pos, tok in enumerate([1, 2, 3, 4, 5, 6]):
+            model.decode_host(tok, pos, lg)
+            seq.append(lg.clone())
+        outs.append(torch.stack(seq))
+        model.close()
+        ctx.close()
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("mega", ["1", "0"])
+@pytest.mark.parametrize("pos", [0, 2048, 4095])
+def test_benchmarked_geometry_step_matches_oracle(pos, mega, monkeypatch):
+    """The configuration bench.py times -- Llama-3-8B widths (E 4096, F 14336, 32:8 heads, vocab 128256), max_ctx 4096 -- with two
+    layers, at the start, the middle and the end of the context window, against the oracle-composed step on a random-filled cache."""
+    monkeypatch.setenv("TCE_PERSISTENT", mega)
+    from tinychatengine_b200.llama import GEOMETRIES, LlamaGeometry, LlamaModel
+    from tinychatengine_b200.runtime import Context
+
+    g8 = GEOMETRIES["llama3-8b"]
+    g = LlamaGeometry("llama3-8b-2l", 2, g8.num_heads, g8.num_kv_heads, g8.embed_dim, g8.hidden_dim, g8.vocab_size, g8.rms_eps, g8.rope_theta)
+    ctx = Context(0)
+    model = LlamaModel(ctx, g, max_ctx=4096, seed=21, random_zeros=True)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(pos + 1)
+    past_k, past_v = [], []
+    for l in range(g.num_layers):
+        for which, store in ((0, past_k), (1, past_v)):
+            c = model.kv_cache(l, which)
+            c.copy_((torch.randn(c.shape, device="cuda", generator=gen) * 0.5).to(torch.float16))
+            store.append(c[:, :pos].float().cpu().numpy() if pos else None)
+    lg = torch.empty(g.vocab_size, dtype=torch.float32).pin_memory()
+    nxt = model.decode_host(4321, pos, lg)
+    want, fk, fv = oracle_decode_step(model, 4321, pos, past_k, past_v)
+    got = lg.numpy()
+    assert np.all(np.isfinite(got))
+    e = rel_err(got, want)
+    assert e <= 1e-2, (pos, e)
+    assert nxt == int(np.argmax(got))
+    for l in range(g.num_layers):
+        assert np.abs(model.kv_cache(l, 0)[:, pos].float().cpu().numpy() - fk[l][:, pos]).max() <= 2e-2 * max(1.0, np.abs(fk[l]).max())
+        assert np.array_equal(model.kv_cache(l, 1)[:, pos].cpu().numpy(), fv[l][:, pos].astype(np.float16))
+    model.close()
+    ctx.close()

@@ -15,7 +15,6 @@ def _tokens(n, vocab, seed):
 
 @pytest.mark.parametrize("geom,n", [("tiny-gqa", 70), ("tiny-mha", 33)])
 def test_prefill_matches_oracle(geom, n, monkeypatch):
-    monkeypatch.setenv("TCE_MEGAKERNEL", "0")
     from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
     from tinychatengine_b200.runtime import Context
 
@@ -42,7 +41,6 @@ def test_prefill_matches_oracle(geom, n, monkeypatch):
 
 
 def test_prefill_then_decode_agrees_with_decode_only(monkeypatch):
-    monkeypatch.setenv("TCE_MEGAKERNEL", "0")
     from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
     from tinychatengine_b200.runtime import Context
 
@@ -74,7 +72,6 @@ def test_prefill_then_decode_agrees_with_decode_only(monkeypatch):
 
 
 def test_chunked_prefill_equals_one_shot(monkeypatch):
-    monkeypatch.setenv("TCE_MEGAKERNEL", "0")
     from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
     from tinychatengine_b200.runtime import Context
 

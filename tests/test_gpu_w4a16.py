@@ -60,6 +60,64 @@ def test_gemv_small_batch(ctx, m):
         assert_w4_close(y.float().cpu().numpy(), oracle(x, w, z, s), f"M={m} {oc}x{ic}")
 
 
+def _per_element_err(y, ref):
+    """SURVEY.md 8(d) config 1, second criterion: relative error per element wherever |ref| > 1e-3 * max|ref|."""
+    y, ref = np.asarray(y, np.float64), np.asarray(ref, np.float64)
+    m = np.abs(ref) > 1e-3 * np.abs(ref).max()
+    return float(np.max(np.abs(y - ref)[m] / np.abs(ref)[m]))
+
+
+@pytest.mark.parametrize("m", [1, 3])
+@pytest.mark.parametrize("factor", [100.0, 1000.0])
+@pytest.mark.parametrize("kill", [False, True])
+def test_gemv_massive_activation_channels(ctx, m, factor, kill):
+    """AWQ exists because of massive-activation channels: one x`factor` outlier per 128-group.  The reference converts fp16
+    activations to fp32 exactly (gemv_cuda.cu:181-184); this kernel re-quantises each group to block fixed point, so the outlier
+    must not swamp the other 127 elements.  `kill`: the outlier channel's weights equal the zero point (it contributes nothing, the
+    result is made of the small elements only) -- the worst case for a block format.  Checked on the max-norm AND per element."""
+    oc, ic = 512, 4096
+    x, w, z, s = make_case(oc, ic, m, 4242, True)
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(7)
+    x = (x.float() * 0.05)
+    ch = torch.randint(0, 128, (ic // 128,), generator=gen) + torch.arange(ic // 128) * 128  # one outlier channel per group
+    x[:, ch] *= factor
+    x = x.to(torch.float16)
+    assert torch.isfinite(x).all()
+    if kill:
+        # nibble of channel c := zero point of its group, for every output row
+        wn = w.cpu().numpy().view(np.uint32).copy()
+        zn = z.cpu().numpy().view(np.uint32)
+        for g_, c in enumerate(ch.tolist()):
+            zg = (zn[:, g_ // 8] >> (4 * (g_ % 8))) & 0xF
+            word, sh = c // 8, 4 * (c % 8)
+            wn[:, word] = (wn[:, word] & ~np.uint32(0xF << sh)) | (zg.astype(np.uint32) << sh)
+        w = torch.from_numpy(wn.view(np.int32)).to(x.device)
+    y = ctx.w4a16_gemv(x, w, z, s)
+    torch.cuda.synchronize()
+    ref = oracle(x, w, z, s)
+    got = y.float().cpu().numpy()
+    assert_w4_close(got, ref, f"outliers x{factor} kill={kill}")
+    e = _per_element_err(got, ref)
+    assert e <= 1e-2, f"per-element rel err {e:.3e} (outliers x{factor}, kill={kill}, M={m})"
+
+
+def test_gemv_tiny_and_mixed_magnitudes(ctx):
+    """groups whose elements span the whole fp16 range, all-zero groups, and a denormal-only group"""
+    oc, ic = 64, 1024
+    x, w, z, s = make_case(oc, ic, 1, 99, True)
+    xf = x.float()
+    xf[:, 0:128] = 0.0
+    xf[:, 128:256] *= 6e-6          # fp16 subnormals
+    xf[:, 256:384] *= torch.logspace(-3, 3, 128, device=x.device)
+    x = xf.to(torch.float16)
+    y = ctx.w4a16_gemv(x, w, z, s)
+    torch.cuda.synchronize()
+    ref = oracle(x, w, z, s)
+    assert_w4_close(y.float().cpu().numpy(), ref, "mixed magnitudes")
+    assert _per_element_err(y.float().cpu().numpy(), ref) <= 1e-2
+
+
 def test_gemm_entry_point_same_contract(ctx):
     x, w, z, s = make_case(128, 1024, 24, 5, False)
     y = ctx.w4a16_gemv(x, w, z, s, gemm=True)

@@ -31,6 +31,31 @@ def test_naive_mat_mul_int4_bit_exact(golden_dir):
         assert np.array_equal(C.view(np.uint32), g[f"int4_{tag}_C"].view(np.uint32)), tag
 
 
+@pytest.mark.skipif(not capi.ref_available("generic"), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("M", [1, 16])
+def test_naive_mat_mul_int4_full_size_config1_live(M):
+    """BASELINE.json configs[0] at its full size (IC 4096 x OC 11008, group 128, M in {1, 16}): the oracle
+    restatement vs the reference's own naive_mat_mul_int4 (kernels/matmul_int4.cc:106-127) compiled in place -- bit for bit -- and
+    the QM_CUDA-layout oracle the GPU tests compare with vs both."""
+    rng = np.random.default_rng(1234)
+    IC, OC = 4096, 11008
+    w = (rng.standard_normal((OC, IC)) * 0.02).astype(np.float32)
+    qs, d, zp = quant.quantize_q4_6(w)
+    x = rng.standard_normal((M, IC)).astype(np.float16)
+    B = quant.qmcuda_to_sequential_bytes(qs)
+    sc = d[:, : IC // 128].astype(np.float32)
+    want = capi.ref_naive_mat_mul_int4(x.astype(np.float32), B, sc, 8.0, 128)
+    got = capi.naive_mat_mul_int4(x.astype(np.float32), B, sc, 8.0, 128)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    y = capi.w4a16_gemv(x, qs, zp, d)
+    assert np.array_equal(y.view(np.uint32), want.view(np.uint32))
+    # second weight set of config 1: random per-group zero points (the zero path), against float64
+    zp2 = rng.integers(0, 2**32, zp.shape, dtype=np.uint32)
+    y2 = capi.w4a16_gemv(x, qs, zp2, d)
+    ref = x.astype(np.float64) @ quant.dequant_qmcuda(qs, d, zp2).astype(np.float64).T
+    assert np.max(np.abs(y2 - ref)) <= 1e-5 * np.max(np.abs(ref))
+
+
 def test_w4a16_gemv_oracle_consistent_with_naive(golden_dir):
     """The QM_CUDA-layout oracle (per-group zeros, fp16 scales) equals naive_mat_mul_int4 when zeros == 8 and the
     scales/activations are exactly representable in fp16."""

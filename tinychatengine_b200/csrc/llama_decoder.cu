@@ -10,7 +10,7 @@
 #include "llama_decoder.h"
 
 #include "kernels_tp.h"
-#include "megakernel.h"
+#include "persistent.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -100,12 +100,10 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
         delete d;
         return nullptr;
     }
-    d->mega_ = getenv("TCE_MEGAKERNEL") ? atoi(getenv("TCE_MEGAKERNEL")) != 0 : false;  // measured slower than the graph path (2.4 vs 1.7 ms/token, profiles/README.md)
-    d->mega_attn_chunk_ = getenv("TCE_MEGA_ATTN_CHUNK") ? atoi(getenv("TCE_MEGA_ATTN_CHUNK")) : 64;
+    d->persistent_ = getenv("TCE_PERSISTENT") ? atoi(getenv("TCE_PERSISTENT")) != 0 : true;
     d->tp_ = cfg.tp_size > 1 ? cfg.tp_size : 1;
     if (d->tp_ > 1) {
         // tensor parallel: one peer-visible allocation [gather A|B: 2 x P x E fp32][flags: 3 x P u32 (256-B padded)][keys: P u64]
-        d->mega_ = false;
         d->tp_gather_floats_ = (size_t)2 * d->tp_ * E;
         d->tp_bytes_ = d->tp_gather_floats_ * sizeof(float) + 256 + (size_t)kMaxTP * sizeof(unsigned long long);
         if (cudaMalloc((void **)&d->tp_buf_, d->tp_bytes_) != cudaSuccess || cudaMemset(d->tp_buf_, 0, d->tp_bytes_) != cudaSuccess) {
@@ -114,19 +112,22 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
             return nullptr;
         }
         cudaDeviceSynchronize();
-        d->kernels_per_step_ = 1 + 7 * cfg.num_layers + 4;
+        d->kernels_per_step_ = d->persistent_ ? 1 : 1 + 7 * cfg.num_layers + 4;
         return d;  // the op list needs the peers' pointers: built in tp_connect()
     }
     d->build_ops();
-    if (d->mega_) {
-        cudaError_t me = d->build_megakernel();
-        if (me != cudaSuccess) {
-            *err = std::string("persistent kernel setup failed: ") + cudaGetErrorString(me);
+    if (d->persistent_) {
+        std::string why;
+        cudaError_t me = d->build_persistent(&why);
+        if (me == cudaErrorNotSupported) {
+            d->persistent_ = false;  // shape outside the persistent kernel's envelope: one kernel per op
+        } else if (me != cudaSuccess) {
+            *err = std::string("persistent kernel setup failed: ") + why + " " + cudaGetErrorString(me);
             delete d;
             return nullptr;
         }
     }
-    d->kernels_per_step_ = d->mega_ ? 1 : 1 + 5 * cfg.num_layers + 2;
+    d->kernels_per_step_ = d->persistent_ ? 1 : 1 + 5 * cfg.num_layers + 2;
     return d;
 }
 
@@ -149,8 +150,7 @@ LlamaDecoder::~LlamaDecoder() {
     cudaFree(pf_gu_);
     cudaFree(pf_act_);
     cudaFree(pf_tok_);
-    cudaFree(d_phases_);
-    cudaFree(d_sync_);
+    for (void *p : pk_allocs_) cudaFree(p);
     for (int p = 0; p < tp_; p++)
         if (p != cfg_.tp_rank && tp_peer_[p]) cudaIpcCloseMemHandle(tp_peer_[p]);
     cudaFree(tp_buf_);
@@ -194,6 +194,16 @@ cudaError_t LlamaDecoder::tp_connect(const void *handles) {
     }
     tp_connected_ = true;
     build_ops();
+    if (persistent_) {
+        std::string why;
+        cudaError_t e = build_persistent(&why);
+        if (e == cudaErrorNotSupported) {
+            persistent_ = false;
+            kernels_per_step_ = 1 + 7 * cfg_.num_layers + 4;
+        } else if (e != cudaSuccess) {
+            return e;
+        }
+    }
     return cudaSuccess;
 }
 
@@ -392,63 +402,179 @@ void LlamaDecoder::build_ops() {
     }
 }
 
-cudaError_t LlamaDecoder::build_megakernel() {
-    const int ncta = ctx_->num_sms;
-    std::vector<MegaPhase> ph(ops_.size());  // (operator new honours alignas(64) in C++17)
-    int max_ic = 0;
-    for (size_t i = 0; i < ops_.size(); i++) {
-        memset(&ph[i], 0, sizeof(MegaPhase));
-        switch (ops_[i].type) {
-            case OP_EMBED: ph[i].type = PH_EMBED; break;
-            case OP_ARGMAX: ph[i].type = PH_ARGMAX; break;
-            case OP_ATTN: {
-                ph[i].type = PH_ATTN;
-                AttnDecodeArgs a = ops_[i].at;
-                a.chunk = mega_attn_chunk_;
-                a.nsplit_max = (a.max_ctx + a.chunk - 1) / a.chunk;
-                a.ws = ctx_->attn_ws;
-                a.counters = ctx_->attn_counters;
-                if ((size_t)a.num_heads * a.nsplit_max * 130 * sizeof(float) > ctx_->attn_ws_bytes) return cudaErrorInvalidValue;
-                ph[i].at = a;
-                break;
-            }
-            default: return cudaErrorNotSupported;
-            case OP_GEMV:
-                DCK(megakernel_fill_gemv(ctx_, ops_[i].g, &ph[i], ncta));
-                if (ops_[i].g.IC > max_ic) max_ic = ops_[i].g.IC;
-                if (ph[i].g.num_tiles > ctx_->gemv_max_tiles) return cudaErrorInvalidValue;
-                break;
+// Everything the persistent decode kernel (decode_persistent.cu) needs beyond the caller's weights: one 2-D tensor map per packed
+// matrix, the per-stage scales|zeros records (a one-off repack of the QM_CUDA scales / zeros arrays into the order the TMA ring
+// consumes them: SURVEY.md 8(f)2 "repack once into the TMA-friendly interleave"), the layer table and the barrier counters.
+cudaError_t LlamaDecoder::build_persistent(std::string *err) {
+    const int E = cfg_.embed_dim, F = cfg_.hidden_dim, H = cfg_.num_heads, KVH = cfg_.num_kv_heads, hd = cfg_.head_dim, V = cfg_.vocab_size;
+    const int Lyr = cfg_.num_layers, ncta = ctx_->num_sms;
+    const int nrep = H / KVH;
+    auto no = [&](const char *m) {
+        if (err) *err = m;
+        return cudaErrorNotSupported;
+    };
+    if (hd != 128 || nrep > 4 || ncta < KVH || F % 8) return no("shape outside the persistent kernel's envelope");
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx_->device);
+    if (!coop) return no("device cannot launch cooperative kernels");
+    pk::Args a{};
+    auto mk = [&](int IC, int rows, int nseg, int pair, int rows0, int rows1, int x_mode, int epi, int aligned) {
+        pk::GemvOp o{};
+        o.IC = IC;
+        o.NG = IC / kW4Group;
+        o.sg = o.NG < 16 ? o.NG : 16;
+        o.S = (o.NG + 15) / 16;
+        o.num_tiles = rows / 16;
+        o.SU = o.num_tiles * o.S;
+        o.nseg = nseg;
+        o.pair = pair;
+        o.rows0 = rows0;
+        o.rows1 = rows1;
+        o.x_mode = x_mode;
+        o.epi = epi;
+        o.aligned = aligned;
+        o.box_bytes = 16 * o.sg * 64;
+        return o;
+    };
+    const bool tp = tp_ > 1;
+    const int add_epi = tp ? pk::PE_TP_SCATTER : pk::PE_ADD_F32;
+    a.op[pk::OPI_QKV] = mk(E, (H + 2 * KVH) * hd, 3, 0, H * hd, KVH * hd, pk::PX_RMS_F32, pk::PE_STORE_HALF, 1);
+    a.op[pk::OPI_O] = mk(H * hd, E, 1, 0, E, 0, pk::PX_HALF, add_epi, (tp || !atomic_residual_) ? 1 : 0);
+    a.op[pk::OPI_GATEUP] = mk(E, 2 * F, 2, 1, F, F, pk::PX_RMS_F32, pk::PE_SILU_MUL, 1);
+    a.op[pk::OPI_DOWN] = mk(F, E, 1, 0, E, 0, pk::PX_HALF, add_epi, (tp || !atomic_residual_) ? 1 : 0);
+    a.op[pk::OPI_LMHEAD] = mk(E, V, 1, 0, V, 0, pk::PX_RMS_F32, pk::PE_LOGITS, 1);
+    int max_ic = 0, max_ng = 0;
+    for (int i = 0; i < pk::OPI_COUNT; i++) {
+        if (a.op[i].IC > max_ic) max_ic = a.op[i].IC;
+        if (a.op[i].NG > max_ng) max_ng = a.op[i].NG;
+        if (a.op[i].IC % kW4Group || a.op[i].num_tiles < 1) return no("bad GEMV shape");
+    }
+    max_ng = (max_ng + 3) & ~3;
+    int xs = 3 * max_ic;
+    if (xs < pk::attn_scratch_bytes(nrep)) xs = pk::attn_scratch_bytes(nrep);
+    xs = (xs + 15) & ~15;
+    a.xs_bytes = xs;
+    a.max_ng = max_ng;
+    a.nst = pk::pick_stages(ctx_->smem_optin, xs, max_ng);
+    if (getenv("TCE_PK_STAGES")) {
+        const int want = atoi(getenv("TCE_PK_STAGES"));
+        if (want >= 2 && want < a.nst) a.nst = want;
+    }
+    if (a.nst < 3) return no("shared memory too small for the persistent kernel");
+
+    auto dalloc = [&](size_t bytes) -> void * {
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+        pk_allocs_.push_back(p);
+        return p;
+    };
+    cudaStream_t s = ctx_->stream;
+    // ---- tensor maps: [Lyr][7] + lm_head + KV cache ----
+    std::vector<CUtensorMap> maps((size_t)Lyr * 7 + 2);
+    std::vector<pk::LayerDesc> descs(Lyr);
+    const size_t per_kv = (size_t)KVH * cfg_.max_ctx;  // rows per (layer, K|V) slab
+    for (int l = 0; l < Lyr; l++) {
+        const tce_llama_layer &L = layers_[l];
+        const tce_w4_tensor *t7[7] = {&L.q, &L.k, &L.v, &L.o, &L.gate, &L.up, &L.down};
+        const int opi[7] = {pk::OPI_QKV, pk::OPI_QKV, pk::OPI_QKV, pk::OPI_O, pk::OPI_GATEUP, pk::OPI_GATEUP, pk::OPI_DOWN};
+        for (int i = 0; i < 7; i++) {
+            const pk::GemvOp &o = a.op[opi[i]];
+            DCK(encode_w4_tmap(&maps[(size_t)l * 7 + i], t7[i]->w, t7[i]->oc, t7[i]->ic, o.sg, o.pair ? 8 : 16));
+        }
+        pk::LayerDesc &D = descs[l];
+        memset(&D, 0, sizeof(D));
+        const W4Seg qkv[3] = {seg_of(L.q), seg_of(L.k), seg_of(L.v)}, o1[1] = {seg_of(L.o)}, gu[2] = {seg_of(L.gate), seg_of(L.up)}, d1[1] = {seg_of(L.down)};
+        const W4Seg *segs[4] = {qkv, o1, gu, d1};
+        const int nsegs[4] = {3, 1, 2, 1}, pairs[4] = {0, 0, 1, 0};
+        const int ops4[4] = {pk::OPI_QKV, pk::OPI_O, pk::OPI_GATEUP, pk::OPI_DOWN};
+        for (int i = 0; i < 4; i++) {
+            const pk::GemvOp &o = a.op[ops4[i]];
+            uint8_t *m = (uint8_t *)dalloc((size_t)o.SU * pk::kMetaBytes);
+            if (!m) return cudaErrorMemoryAllocation;
+            DCK(pk::repack_meta(ctx_, segs[i], nsegs[i], pairs[i], o.IC, m, s));
+            D.meta[i] = m;
+        }
+        D.input_norm = L.input_norm;
+        D.post_norm = L.post_norm;
+        D.k_cache = (__half *)kv_cache(l, 0);
+        D.v_cache = (__half *)kv_cache(l, 1);
+        D.k_row0 = (int)(((size_t)l * 2 + 0) * per_kv);
+        D.v_row0 = (int)(((size_t)l * 2 + 1) * per_kv);
+    }
+    {
+        const pk::GemvOp &o = a.op[pk::OPI_LMHEAD];
+        DCK(encode_w4_tmap(&maps[(size_t)Lyr * 7], w_.lm_head.w, w_.lm_head.oc, w_.lm_head.ic, o.sg, 16));
+        uint8_t *m = (uint8_t *)dalloc((size_t)o.SU * pk::kMetaBytes);
+        if (!m) return cudaErrorMemoryAllocation;
+        const W4Seg lm[1] = {seg_of(w_.lm_head)};
+        DCK(pk::repack_meta(ctx_, lm, 1, 0, o.IC, m, s));
+        a.lm_meta = m;
+        DCK(pk::encode_kv_tmap(&maps[(size_t)Lyr * 7 + 1], d_kv_, (long long)Lyr * 2 * per_kv));
+    }
+    CUtensorMap *dmaps = (CUtensorMap *)dalloc(maps.size() * sizeof(CUtensorMap));
+    pk::LayerDesc *ddesc = (pk::LayerDesc *)dalloc(descs.size() * sizeof(pk::LayerDesc));
+    const int NS = ncta / KVH;
+    float *ws = (float *)dalloc((size_t)H * NS * 130 * sizeof(float));
+    const size_t nsync = (size_t)5 * Lyr + 1;
+    // [arg-max cell u64][epoch u32][error i32][attn counters KVH u32][phase counters]
+    uint8_t *ctl = (uint8_t *)dalloc(16 + (size_t)KVH * 4 + nsync * 4);
+    if (!dmaps || !ddesc || !ws || !ctl) return cudaErrorMemoryAllocation;
+    DCK(cudaMemcpyAsync(dmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s));
+    DCK(cudaMemcpyAsync(ddesc, descs.data(), descs.size() * sizeof(pk::LayerDesc), cudaMemcpyHostToDevice, s));
+    DCK(cudaMemsetAsync(ctl, 0, 16 + (size_t)KVH * 4 + nsync * 4, s));
+    DCK(cudaStreamSynchronize(s));  // `maps` / `descs` are host temporaries
+    a.layers = ddesc;
+    a.num_layers = Lyr;
+    a.maps = dmaps;
+    a.final_norm = w_.final_norm;
+    a.embed = (const __half *)w_.embed_f16;
+    a.embed_rows = V * tp_;
+    a.resid = d_resid_;
+    a.qkv = d_qkv_;
+    a.attn = d_attn_;
+    a.act = d_act_;
+    a.logits = d_logits_;
+    a.tokpos = d_tokpos_;
+    a.next_token = d_next_;
+    a.argmax_cell = reinterpret_cast<unsigned long long *>(ctl);
+    a.epoch = reinterpret_cast<unsigned *>(ctl + 8);
+    a.error = reinterpret_cast<int *>(ctl + 12);
+    a.attn_cnt = reinterpret_cast<unsigned *>(ctl + 16);
+    a.sync = a.attn_cnt + KVH;
+    a.attn_ws = ws;
+    a.cos = d_cos_;
+    a.sin = d_sin_;
+    a.alpha = cfg_.qk_alpha > 0 ? cfg_.qk_alpha : 1.0f / sqrtf((float)hd);
+    a.eps = cfg_.rms_eps;
+    a.H = H;
+    a.KVH = KVH;
+    a.nrep = nrep;
+    a.max_ctx = cfg_.max_ctx;
+    a.E = E;
+    a.V = V;
+    a.tp_size = tp_;
+    a.tp_rank = tp ? cfg_.tp_rank : 0;
+    a.vocab_base = tp ? cfg_.tp_rank * V : 0;
+    if (tp) {
+        for (int q = 0; q < tp_; q++) {
+            uint8_t *base = tp_peer_[q];
+            a.tp_gather[q] = reinterpret_cast<float *>(base);
+            unsigned *words = reinterpret_cast<unsigned *>(base + tp_gather_floats_ * sizeof(float));
+            a.tp_arrive[q] = words;            // [0], [1]: the two gather buffers (adjacent words)
+            a.tp_key_arrive[q] = words + 32;   // own 128-byte line
+            a.tp_keys[q] = reinterpret_cast<unsigned long long *>(base + tp_gather_floats_ * sizeof(float) + 256);
         }
     }
-    DCK(cudaMalloc((void **)&d_phases_, ph.size() * sizeof(MegaPhase)));
-    DCK(cudaMemcpy(d_phases_, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
-    sync_bytes_ = ph.size() * sizeof(unsigned);
-    DCK(cudaMalloc((void **)&d_sync_, sizeof(unsigned long long) + sync_bytes_));
-    DCK(cudaMemset(d_sync_, 0, sizeof(unsigned long long) + sync_bytes_));
-    margs_ = MegaArgs{};
-    margs_.phases = d_phases_;
-    margs_.nphases = (int)ph.size();
-    margs_.argmax_cell = d_sync_;
-    margs_.sync = reinterpret_cast<unsigned *>(d_sync_ + 1);
-    margs_.embed = (const __half *)w_.embed_f16;
-    margs_.resid = d_resid_;
-    margs_.E = cfg_.embed_dim;
-    margs_.logits = d_logits_;
-    margs_.V = cfg_.vocab_size;
-    margs_.next_token = d_next_;
-    margs_.max_ic = max_ic;
-    margs_.attn_nrep = cfg_.num_heads / cfg_.num_kv_heads;
-    margs_.attn_chunk = mega_attn_chunk_;
-    if ((int)megakernel_smem_bytes(max_ic, margs_.attn_nrep, mega_attn_chunk_) > ctx_->smem_optin) return cudaErrorInvalidConfiguration;
+    if ((int)pk::smem_bytes(a) > ctx_->smem_optin) return no("shared memory");
+    pargs_ = a;
     return cudaSuccess;
 }
 
 cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only) {
-    if (mega_ && !gemv_only) {
-        DCK(cudaMemsetAsync(d_sync_ + 1, 0, sync_bytes_, s));
-        MegaArgs m = margs_;
+    if (persistent_ && !gemv_only) {
+        pk::Args m = pargs_;
         m.tokpos = tokpos;
-        return launch_megakernel(ctx_, m, s);
+        return pk::launch(ctx_, m, s);
     }
     Ctx local = *ctx_;  // same workspaces, but launch on `s`
     local.stream = s;
@@ -493,7 +619,9 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
 
 cudaError_t LlamaDecoder::build_graphs(std::string *err) {
     // one eager step first: loads the modules and sets the kernels' shared-memory attributes outside of capture
-    // (re-running a step at the same position is idempotent: the same K/V row is rewritten)
+    // (re-running a step at the same position is idempotent: the same K/V row is rewritten).  Work queued on the caller's stream
+    // (an asynchronous decode_device) touches the same buffers: drain it before switching to the capture stream.
+    DCK(cudaStreamSynchronize(ctx_->stream));
     DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 3 * sizeof(int), cudaMemcpyHostToDevice, cap_stream_));
     DCK(enqueue_step(d_tokpos_, cap_stream_, false));
     DCK(cudaStreamSynchronize(cap_stream_));

@@ -7,7 +7,7 @@
 #include "kernels.h"
 #include "kernels_attn.h"
 #include "kernels_tp.h"
-#include "megakernel.h"
+#include "persistent.h"
 
 namespace tce {
 
@@ -42,7 +42,7 @@ class LlamaDecoder {
     cudaError_t enqueue_step(const int *tokpos, cudaStream_t s, bool pdl, bool gemv_only = false);  // raw kernel sequence
     cudaError_t build_graphs(std::string *err);
     void build_ops();
-    cudaError_t build_megakernel();
+    cudaError_t build_persistent(std::string *err);
 
     enum OpType { OP_EMBED, OP_GEMV, OP_ATTN, OP_ARGMAX, OP_TP_SIGNAL, OP_TP_ARGMAX_SCATTER, OP_TP_ARGMAX_FINISH };
     struct StepOp {
@@ -61,12 +61,10 @@ class LlamaDecoder {
     uint8_t *tp_peer_[kMaxTP] = {};      // every rank's allocation as mapped into this process
     int step_index_ = 0;
     std::vector<StepOp> ops_;
-    bool mega_ = false;             // TCE_MEGAKERNEL=1: one persistent cooperative kernel per token instead of one kernel per op
-    int mega_attn_chunk_ = 64;
-    MegaPhase *d_phases_ = nullptr;
-    unsigned long long *d_sync_ = nullptr;  // [0] arg-max cell, then one 32-bit grid-barrier counter per phase
-    size_t sync_bytes_ = 0;
-    MegaArgs margs_{};
+    // persistent decode kernel (default; TCE_PERSISTENT=0 selects one kernel per op inside a CUDA graph)
+    bool persistent_ = false;
+    pk::Args pargs_{};
+    std::vector<void *> pk_allocs_;     // repacked scales|zeros, tensor maps, layer table, counters
 
     Ctx *ctx_ = nullptr;
     int attn_chunk_ = 128;

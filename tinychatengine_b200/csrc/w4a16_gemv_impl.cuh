@@ -11,9 +11,9 @@
 //    weight box into a ring of KArgs::nst stages (8 by default) guarded by full/empty mbarriers, L2 evict-first; the tile's
 //    scales/zeros slabs (1-D bulk copies, UBLKCP) ride on the first stage's barrier.  Producers depend on nothing but the weights,
 //    so they run ahead of everything else (in particular of the consumers' activation staging).
-//  * consumers (CW warps): 128-bit LDS of the packed nibbles; activations held as two int8 planes (15-bit block fixed point per
+//  * consumers (CW warps): 128-bit LDS of the packed nibbles; activations held as three int8 planes (22-bit block fixed point per
 //    128-group, exact integer accumulation); mma.sync.m16n8k32 u8 x s8 -> s32; per-group epilogue
-//    tot += (s * step) * (acc - z * sum_X).  One activation row (decode, consume1): the two planes ride in MMA columns 0/1 and
+//    tot += (s * step) * (acc - z * sum_X).  One activation row (decode, consume1): the three planes ride in MMA columns 0/1/2 and
 //    nibbles become bytes with one mask each (even slots w & 0x0f0f0f0f, odd slots w & 0xf0f0f0f0 = 16 x nibble, shifted back
 //    after accumulation): 4 IMMAs per (16 rows x 128 k).  Up to 8 rows (consume<8>): the 8 MMA columns carry the rows, planes in
 //    separate MMAs, (w >> 4) & 0x0f0f0f0f for the odd slots.
@@ -33,6 +33,7 @@ constexpr int kStageBytes = 16 * kStageGroups * 64;  // 16 KiB: dense [16 rows][
 constexpr int kStages = 4;         // default ring depth (persistent kernel); the per-op kernel picks the deepest ring that fits (KArgs::nst)
 constexpr int kMaxStages = 12;
 constexpr int kRedBufs = 3;
+constexpr float kActQ = 2080768.f;  // 127 * 2^14: activation fixed-point full scale (three int8 planes)
 constexpr int kProducerWarps = 1;        // a stage is one UTMALDG (two in gate/up pair mode): a single elected lane keeps up
 // per-tile scales/zeros slabs in flight: ring depth + 1 (a tile spans >= 1 stage)
 
@@ -115,14 +116,16 @@ template <int NCOLS, int CW>
 struct Layout {
     static constexpr int kXPad = (NCOLS > 1) ? 64 : 0;  // column pitch = 64 (mod 128) B for the per-column B loads
     static constexpr int kVals = 16 * NCOLS;
-    static __host__ __device__ int x_pitch(int IC) { return IC * 2 + kXPad; }
+    // three int8 planes per activation (22-bit block fixed point): planes (hi, mid) interleaved in region A (2 B per element),
+    // plane lo in region B (1 B per element) that follows region A of the same column
+    static __host__ __device__ int x_pitch(int IC) { return IC * 3 + kXPad; }
     // one meta slot = scales half[16][zeros_w*8] followed by zeros uint32[16][zeros_w] = 320 * zeros_w bytes
     static __host__ __device__ int meta_slot_bytes(int IC) { return 320 * (((IC / 128) + 7) / 8); }
     static __host__ __device__ size_t off_meta(int nst) { return (size_t)nst * kStageBytes; }
     static __host__ __device__ size_t off_xs(int IC, int nst) { return off_meta(nst) + (size_t)(nst + 1) * meta_slot_bytes(IC); }
     static __host__ __device__ size_t off_gx(int IC, int nst) { return off_xs(IC, nst) + (size_t)NCOLS * x_pitch(IC); }
-    // gx: float step[NCOLS][NG] followed by int gsum[NCOLS][NG]
-    static __host__ __device__ size_t off_red(int IC, int nst) { return off_gx(IC, nst) + (size_t)2 * NCOLS * (IC / 128) * sizeof(float); }
+    // gx: float step[NCOLS][NG] followed by int gsum[NCOLS][NG][2] = {128 * sum(hi) + sum(mid), sum(lo)}
+    static __host__ __device__ size_t off_red(int IC, int nst) { return off_gx(IC, nst) + (size_t)3 * NCOLS * (IC / 128) * sizeof(float); }
     static __host__ __device__ size_t off_rms(int IC, int nst) { return off_red(IC, nst) + (size_t)kRedBufs * CW * kVals * sizeof(float); }
     static __host__ __device__ size_t off_bar(int IC, int nst) { return (off_rms(IC, nst) + (size_t)NCOLS * CW * sizeof(float) + 15) & ~(size_t)15; }
     static __host__ __device__ size_t bytes(int IC, int nst = kStages) { return off_bar(IC, nst) + (2 * nst + 2 * kRedBufs) * sizeof(uint64_t) + 16; }
@@ -424,9 +427,80 @@ TCE_DEVINL void epilogue(const KArgs &a, const Smem &sm, RedState &es, int cta, 
     }
 }
 
+// quantise + stage one 8-element unit (v) of one activation column: xcol = the column's plane buffer, gx / gsum = the column's per-group
+// step and integer sums.  Must be called by all 32 lanes of a warp (half-warp shuffles); `valid` masks the stores.
+template <int NCOLS>
+TCE_DEVINL void emit_unit(uint8_t *xcol, int IC, float *gx, int *gsum, int ui, bool valid, const float (&v)[8], int lane) {
+    // Activations enter the integer tensor path as 22-bit block fixed point: per 128-group,
+    // X = rint(x * Q / max|x|), Q = 127 * 2^14, X = 2^14*hi + 2^7*mid + lo  (three int8 planes: hi in [-127,127],
+    // mid in [-64,64], lo in [-64,63]).  |x - step*X| <= max|x_group| * 2^-22: an element 2^11 times smaller than the largest
+    // of its group still keeps fp16's own 11 bits (the reference converts fp16 -> fp32 exactly, gemv_cuda.cu:181-184).  The
+    // integer dot products that follow are exact.  The third plane costs no MMA: the planes ride in MMA columns 0..2.
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    const float qinv = (amax > 0.f) ? (kActQ / amax) : 0.f;
+    int hi[8], mi[8], lo[8], sxh = 0, sxl = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int X = __float2int_rn(v[i] * qinv);
+        hi[i] = (X + 8192) >> 14;
+        const int r = X - (hi[i] << 14);
+        mi[i] = (r + 64) >> 7;
+        lo[i] = r - (mi[i] << 7);
+        sxh += (hi[i] << 7) + mi[i];
+        sxl += lo[i];
+    }
+    // B-fragment order of mma.m16n8k32: k-slots 4t..4t+3 <- elements (0,2,4,6) of the word (the bytes of
+    // w & 0x0f0f0f0f), k-slots 16+4t.. <- elements (1,3,5,7) (the bytes of (w>>4) & 0x0f0f0f0f).
+    auto pack4 = [](int b0, int b1, int b2, int b3) {
+        return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
+    };
+    const uint32_t oh0 = pack4(hi[0], hi[2], hi[4], hi[6]), oh1 = pack4(hi[1], hi[3], hi[5], hi[7]);
+    const uint32_t om0 = pack4(mi[0], mi[2], mi[4], mi[6]), om1 = pack4(mi[1], mi[3], mi[5], mi[7]);
+    const uint32_t ol0 = pack4(lo[0], lo[2], lo[4], lo[6]), ol1 = pack4(lo[1], lo[3], lo[5], lo[7]);
+    const int G = ui >> 4, tj = ui & 15;  // ui = G*16 + 4*t + j
+    if (NCOLS == 1) {
+        // single-column layout (consume1).  Region A, per group 256 B = [parity: even | odd nibble slots][t][plane: hi | mid][word j];
+        // region B (at byte IC*2), per group 128 B = [parity][t][word j] of plane lo.  One LDS.128 hands lane (t, plane) the
+        // B operands of both MMAs of a parity; the chunks a quarter-warp loads are contiguous (conflict free).
+        if (valid) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(xcol + (size_t)G * 256 + (size_t)(tj >> 2) * 32) + (tj & 3);
+            dst[0] = oh0;       // even slots, hi plane
+            dst[4] = om0;       // even slots, mid plane
+            dst[32] = oh1;      // odd slots, hi plane
+            dst[36] = om1;      // odd slots, mid plane
+            uint32_t *dl = reinterpret_cast<uint32_t *>(xcol + (size_t)IC * 2 + (size_t)G * 128 + (size_t)(tj >> 2) * 16) + (tj & 3);
+            dl[0] = ol0;        // even slots, lo plane
+            dl[16] = ol1;       // odd slots, lo plane
+        }
+    } else {
+        // units of a group are stored j-major so that the four t-lanes of one LDS.128 hit consecutive slots
+        const int pos = G * 16 + (tj & 3) * 4 + (tj >> 2);
+        if (valid) {
+            *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = make_uint4(oh0, oh1, om0, om1);
+            *reinterpret_cast<uint2 *>(xcol + (size_t)IC * 2 + (size_t)pos * 8) = make_uint2(ol0, ol1);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        sxh += __shfl_xor_sync(0xffffffffu, sxh, o);
+        sxl += __shfl_xor_sync(0xffffffffu, sxl, o);
+    }
+    if (valid && (lane & 15) == 0) {
+        gx[G] = (amax > 0.f) ? (amax / kActQ) : 0.f;  // step of the group
+        gsum[G * 2] = sxh;                            // 128 * sum(hi) + sum(mid) over the group
+        gsum[G * 2 + 1] = sxl;                        // sum(lo)
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// consumer prologue: activations -> (optional RMSNorm) -> two int8 planes per 128-group in MMA-B order, plus the
-// per-group step and integer sum.  Ends with a consumer-wide named barrier (id 1).
+// consumer prologue: activations -> (optional RMSNorm) -> three int8 planes per 128-group in MMA-B order, plus the
+// per-group step and integer sums.  Ends with a consumer-wide named barrier (id 1).
 // ------------------------------------------------------------------------------------------------------------------
 template <int NCOLS, int CW>
 TCE_DEVINL void stage_activations(const KArgs &a, const Smem &sm, int x_pitch, int ctid, int cw, int lane) {
@@ -485,63 +559,8 @@ TCE_DEVINL void stage_activations(const KArgs &a, const Smem &sm, int x_pitch, i
             for (int w = 0; w < CW; w++) tot += sm.rms[col * CW + w];
             inv = rsqrtf(tot / (float)a.IC + a.eps);
         }
-        // quantise + stage one 8-element unit (v) of activation column `col`
         auto emit = [&](int ui, bool valid, const float(&v)[8]) {
-            // Activations enter the integer tensor path as 15-bit block fixed point: per 128-group,
-            // X = rint(x * 16256 / max|x|) = 128*hi + lo with hi in [-127,127], lo in [-64,63] (two int8 planes).
-            // |x - step*X| <= max|x_group| / 32512, i.e. below fp16's own rounding for all but the smallest elements
-            // of a group; the integer dot products that follow are exact.
-            float amax = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            const float qinv = (amax > 0.f) ? (16256.f / amax) : 0.f;
-            int hi[8], lo[8], sx = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int X = __float2int_rn(v[i] * qinv);
-                hi[i] = (X + 64) >> 7;
-                lo[i] = X - (hi[i] << 7);
-                sx += X;
-            }
-            // B-fragment order of mma.m16n8k32: k-slots 4t..4t+3 <- elements (0,2,4,6) of the word (the bytes of
-            // w & 0x0f0f0f0f), k-slots 16+4t.. <- elements (1,3,5,7) (the bytes of (w>>4) & 0x0f0f0f0f).
-            auto pack4 = [](int b0, int b1, int b2, int b3) {
-                return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
-            };
-            uint4 o;
-            o.x = pack4(hi[0], hi[2], hi[4], hi[6]);
-            o.y = pack4(hi[1], hi[3], hi[5], hi[7]);
-            o.z = pack4(lo[0], lo[2], lo[4], lo[6]);
-            o.w = pack4(lo[1], lo[3], lo[5], lo[7]);
-            const int G = ui >> 4, tj = ui & 15;  // ui = G*16 + 4*t + j
-            if (NCOLS == 1) {
-                // single-column layout (consume1): per group 256 B = [parity: even | odd nibble slots][t][plane: hi | lo][word j], so that
-                // one LDS.128 hands lane (t, plane) the B operands of both MMAs of a parity and the 8 (t, plane) chunks of a warp-wide
-                // load are 128 contiguous bytes (conflict free)
-                if (valid) {
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(xcol + (size_t)G * 256 + (size_t)(tj >> 2) * 32) + (tj & 3);
-                    dst[0] = o.x;       // even slots, hi plane
-                    dst[4] = o.z;       // even slots, lo plane
-                    dst[32] = o.y;      // odd slots, hi plane
-                    dst[36] = o.w;      // odd slots, lo plane
-                }
-            } else {
-                // units of a group are stored j-major so that the four t-lanes of one LDS.128 hit consecutive slots
-                const int pos = G * 16 + (tj & 3) * 4 + (tj >> 2);
-                if (valid) *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = o;
-            }
-            sx += __shfl_xor_sync(0xffffffffu, sx, 8);
-            sx += __shfl_xor_sync(0xffffffffu, sx, 4);
-            sx += __shfl_xor_sync(0xffffffffu, sx, 2);
-            sx += __shfl_xor_sync(0xffffffffu, sx, 1);
-            if (valid && (lane & 15) == 0) {
-                sm.gx[col * a.NG + G] = (amax > 0.f) ? (amax / 16256.f) : 0.f;  // step of the group
-                sm.gsum[col * a.NG + G] = sx;                                     // sum of X over the group
-            }
+            emit_unit<NCOLS>(xcol, a.IC, sm.gx + (size_t)col * a.NG, sm.gsum + (size_t)col * a.NG * 2, ui, valid, v, lane);
         };
         // `units` is a multiple of 16, not of 32: trip counts are warp-uniform so that the half-warp shuffles in emit()
         // always run with all 32 lanes.  Loads of several iterations are issued before any is consumed.
@@ -605,12 +624,58 @@ TCE_DEVINL void stage_activations(const KArgs &a, const Smem &sm, int x_pitch, i
 // ------------------------------------------------------------------------------------------------------------------
 // consumer main loop
 // ------------------------------------------------------------------------------------------------------------------
-// Single activation column (decode).  Per (16-row tile, 128-k group) a warp issues FOUR integer MMAs instead of eight:
-//   * the two activation planes ride in MMA columns 0 (hi) and 1 (lo): lane (g, t) supplies the B operand of column g, so lanes
-//     g = 0 load the hi plane and lanes g = 1 the lo plane, and thread t = 0 of every row pair receives both plane sums (c0, c1);
+// Single activation column (decode).  Per (16-row tile, 128-k group) a warp issues FOUR integer MMAs instead of twelve:
+//   * the three activation planes ride in MMA columns 0 (hi), 1 (mid) and 2 (lo): lane (g, t) supplies the B operand of column g, so
+//     lanes g = 0 / 1 / 2 load the hi / mid / lo plane, thread t = 0 of every row pair receives the (hi, mid) plane sums (c0, c1) and
+//     thread t = 1 the lo plane sum (c0); columns 3..7 are don't-cares;
 //   * nibbles become bytes with ONE mask each: w & 0x0f0f0f0f (even slots) and w & 0xf0f0f0f0 (odd slots, = 16 x nibble, still
 //     u8).  Even and odd slots accumulate separately (accL, accH); accH is an exact multiple of 16 and is shifted back at the end.
 // Two MMAs per parity take words (0,1) and (2,3) of the lane's 16-byte weight load as their two k halves.
+struct Lane1 {  // lane-constant operands of the single-column consumer
+    const uint8_t *xlane;  // this lane's activation chunk of group 0
+    int xstride, xodd;     // bytes per group / offset of the odd-slot half
+    int wa, wb;            // integer weights of (c0, c1): t = 0: (128, 1) = 128*hi + mid, t = 1: (1, 0) = lo, else 0
+    float lscale;          // t = 0: 128 (the (hi, mid) sum counts in units of 2^7 lo steps), t = 1: 1, else 0
+    int gsel;              // which of the two group sums this lane subtracts (t & 1)
+};
+TCE_DEVINL Lane1 make_lane1(const uint8_t *xs, int IC, int g, int t) {
+    Lane1 L;
+    if (g == 2) {
+        L.xlane = xs + (size_t)IC * 2 + (size_t)t * 16;
+        L.xstride = 128;
+        L.xodd = 64;
+    } else {
+        L.xlane = xs + (size_t)(t * 2 + (g & 1)) * 16;
+        L.xstride = 256;
+        L.xodd = 128;
+    }
+    L.wa = (t == 0) ? 128 : (t == 1 ? 1 : 0);
+    L.wb = (t == 0) ? 1 : 0;
+    L.lscale = (t == 0) ? 128.f : (t == 1 ? 1.f : 0.f);
+    L.gsel = t & 1;
+    return L;
+}
+// one (16 rows x 128 k) unit: wa/wb = the lane's 16 B of rows g / g+8; returns the lane's share of the two row sums
+TCE_DEVINL void unit1(const Lane1 &L, const uint4 wa, const uint4 wb, int G, float sAq, float sBq, int zAq, int zBq, const float *gx, const int *gsum,
+                      float &totA, float &totB) {
+    const uint4 xe = *reinterpret_cast<const uint4 *>(L.xlane + (size_t)G * L.xstride);
+    const uint4 xo = *reinterpret_cast<const uint4 *>(L.xlane + (size_t)G * L.xstride + L.xodd);
+    constexpr uint32_t ML = 0x0f0f0f0fu, MH = 0xf0f0f0f0u;
+    int accL[4], accH[4];
+    mma_m16n8k32_u8s8_z(accL, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xe.x, xe.y);
+    mma_m16n8k32_u8s8_z(accH, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xo.x, xo.y);
+    mma_m16n8k32_u8s8(accL, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xe.z, xe.w);
+    mma_m16n8k32_u8s8(accH, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xo.z, xo.w);
+    // X = 2^14*hi + 2^7*mid + lo; odd slots carry 16 x nibble: exact integer group result sum_k q*X - z*sum_k X, held as a
+    // (hi,mid) part on t = 0 and a lo part on t = 1
+    const int sxv = gsum[2 * G + L.gsel];
+    const float st = gx[G] * L.lscale;
+    const int vA = L.wa * (accL[0] + (accH[0] >> 4)) + L.wb * (accL[1] + (accH[1] >> 4)) - zAq * sxv;
+    const int vB = L.wa * (accL[2] + (accH[2] >> 4)) + L.wb * (accL[3] + (accH[3] >> 4)) - zBq * sxv;
+    totA += (sAq * st) * (float)vA;
+    totB += (sBq * st) * (float)vB;
+}
+
 template <int CW, bool FULL>
 TCE_DEVINL void consume1(const KArgs &a, const Smem &sm, RingState &rs, RedState &cs, int cta, int ncta, int cw, int lane) {
     constexpr int GPW = kStageGroups / CW;
@@ -621,9 +686,9 @@ TCE_DEVINL void consume1(const KArgs &a, const Smem &sm, RingState &rs, RedState
     int gb = u - (u / a.NG) * a.NG;
     const int sg = FULL ? kStageGroups : a.sg;
     const int rp = sg * 64;  // dense row pitch of the TMA box
-    // lane-constant offsets: weight rows g / g+8 of the group slot, activation chunk (t, plane = g & 1)
+    // lane-constant offsets: weight rows g / g+8 of the group slot, activation chunk (t, plane = column g)
     const uint32_t w_off = (uint32_t)(g * rp + t * 16);
-    const uint8_t *xlane = sm.xs + (size_t)(t * 2 + (g & 1)) * 16;
+    const Lane1 L = make_lane1(sm.xs, a.IC, g, t);
     while (u < uend) {
         const int ge = min(a.NG, gb + (uend - u));
         const uint8_t *mbase = sm.meta + (size_t)rs.mslot * sm.meta_bytes;
@@ -643,25 +708,11 @@ TCE_DEVINL void consume1(const KArgs &a, const Smem &sm, RingState &rs, RedState
                     const int G = g0 + gi;
                     const uint4 wa = *reinterpret_cast<const uint4 *>(sbase + gi * 64);
                     const uint4 wb = *reinterpret_cast<const uint4 *>(sbase + gi * 64 + 8 * rp);
-                    const uint4 xe = *reinterpret_cast<const uint4 *>(xlane + (size_t)G * 256);
-                    const uint4 xo = *reinterpret_cast<const uint4 *>(xlane + (size_t)G * 256 + 128);
                     const float sAq = __half2float(msA[G]), sBq = __half2float(msB[G]);
                     const int zsh = (G & 7) * 4;
                     const int zAq = (int)((mzA[G >> 3] >> zsh) & 0xFu);
                     const int zBq = (int)((mzB[G >> 3] >> zsh) & 0xFu);
-                    constexpr uint32_t ML = 0x0f0f0f0fu, MH = 0xf0f0f0f0u;
-                    int accL[4], accH[4];
-                    mma_m16n8k32_u8s8_z(accL, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xe.x, xe.y);
-                    mma_m16n8k32_u8s8_z(accH, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xo.x, xo.y);
-                    mma_m16n8k32_u8s8(accL, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xe.z, xe.w);
-                    mma_m16n8k32_u8s8(accH, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xo.z, xo.w);
-                    // X = 128*hi + lo; odd slots carry 16 x nibble: exact integer group result sum_k q*X - z*sum_k X
-                    const int sxv = sm.gsum[G];
-                    const float st = sm.gx[G];
-                    const int vA = (accL[0] << 7) + accL[1] + (((accH[0] << 7) + accH[1]) >> 4) - zAq * sxv;
-                    const int vB = (accL[2] << 7) + accL[3] + (((accH[2] << 7) + accH[3]) >> 4) - zBq * sxv;
-                    totA += (sAq * st) * (float)vA;
-                    totB += (sBq * st) * (float)vB;
+                    unit1(L, wa, wb, G, sAq, sBq, zAq, zBq, sm.gx, sm.gsum, totA, totB);
                 }
             }
             __syncwarp();
@@ -672,6 +723,8 @@ TCE_DEVINL void consume1(const KArgs &a, const Smem &sm, RingState &rs, RedState
             }
         }
         // ---- hand the tile partial to the epilogue warp (no consumer-to-consumer wait) ----
+        totA += __shfl_xor_sync(0xffffffffu, totA, 1);  // (hi, mid) share of t = 0 + lo share of t = 1
+        totB += __shfl_xor_sync(0xffffffffu, totB, 1);
         mbar_wait(&sm.red_empty[cs.rb], cs.rphase ^ 1);
         float *rbuf = sm.red + ((size_t)cs.rb * CW + cw) * 16;
         if (t == 0) {
@@ -714,7 +767,7 @@ TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState 
         const __half *msB = msA + 8 * a.sf_w;
         const uint32_t *mzA = reinterpret_cast<const uint32_t *>(mbase + 16 * a.sf_w * 2) + g * a.zeros_w;
         const uint32_t *mzB = mzA + 8 * a.zeros_w;
-        constexpr int NT = (NCOLS == 1) ? 2 : 4;
+        constexpr int NT = 4;
         float tot[NT];
 #pragma unroll
         for (int i = 0; i < NT; i++) tot[i] = 0.f;
@@ -739,41 +792,41 @@ TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState 
                     const uint4 wb = *reinterpret_cast<const uint4 *>(sp + (g + 8) * rp);
                     const uint32_t wav[4] = {wa.x, wa.y, wa.z, wa.w};
                     const uint32_t wbv[4] = {wb.x, wb.y, wb.z, wb.w};
-                    const uint8_t *xp = sm.xs + ((NCOLS == 1) ? 0 : (size_t)g * x_pitch) + ((size_t)G * 16 + t) * 16;
+                    const uint8_t *xp = sm.xs + (size_t)g * x_pitch + ((size_t)G * 16 + t) * 16;
                     // nibbles -> bytes: w & 0x0f0f0f0f = (n0,n2,n4,n6), (w>>4) & 0x0f0f0f0f = (n1,n3,n5,n7): 3 ALU ops per
-                    // 8 weights.  Two independent accumulator chains per activation plane.
-                    int ch[2][4], cl[2][4];
+                    // 8 weights.  Two independent accumulator chains per activation plane (hi, mid, lo).
+                    const uint8_t *xl = sm.xs + (size_t)g * x_pitch + (size_t)a.IC * 2 + ((size_t)G * 16 + t) * 8;
+                    int ch[2][4], cm[2][4], cl[2][4];
 #pragma unroll
                     for (int e = 0; e < 2; e++)
 #pragma unroll
-                        for (int i = 0; i < 4; i++) ch[e][i] = cl[e][i] = 0;
+                        for (int i = 0; i < 4; i++) ch[e][i] = cm[e][i] = cl[e][i] = 0;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const uint4 xv = *reinterpret_cast<const uint4 *>(xp + j * 64);
+                        const uint2 xw = *reinterpret_cast<const uint2 *>(xl + j * 32);
                         const uint32_t a0 = wav[j] & 0x0f0f0f0fu, a2 = (wav[j] >> 4) & 0x0f0f0f0fu;
                         const uint32_t a1 = wbv[j] & 0x0f0f0f0fu, a3 = (wbv[j] >> 4) & 0x0f0f0f0fu;
                         mma_m16n8k32_u8s8(ch[j & 1], a0, a1, a2, a3, xv.x, xv.y);
-                        mma_m16n8k32_u8s8(cl[j & 1], a0, a1, a2, a3, xv.z, xv.w);
+                        mma_m16n8k32_u8s8(cm[j & 1], a0, a1, a2, a3, xv.z, xv.w);
+                        mma_m16n8k32_u8s8(cl[j & 1], a0, a1, a2, a3, xw.x, xw.y);
                     }
-                    // exact integer group result: sum_k q*X - z*sum_k X, X = 128*hi + lo
-                    if (NCOLS == 1) {
-                        const int sxv = sm.gsum[G];
-                        const float st = sm.gx[G];
-                        const int vA = ((ch[0][0] + ch[1][0]) << 7) + (cl[0][0] + cl[1][0]) - zAq * sxv;
-                        const int vB = ((ch[0][2] + ch[1][2]) << 7) + (cl[0][2] + cl[1][2]) - zBq * sxv;
-                        tot[0] += (sAq * st) * (float)vA;
-                        tot[1] += (sBq * st) * (float)vB;
-                    } else {
-                        const int sx0 = sm.gsum[(2 * t) * a.NG + G], sx1 = sm.gsum[(2 * t + 1) * a.NG + G];
+                    // exact integer group result: sum_k q*X - z*sum_k X, X = 2^14*hi + 2^7*mid + lo, kept as a (hi,mid) part in units of
+                    // 2^7 and a lo part (the full integer does not fit 32 bits)
+                    {
+                        const int *gs0 = sm.gsum + ((2 * t) * a.NG + G) * 2, *gs1 = sm.gsum + ((2 * t + 1) * a.NG + G) * 2;
                         const float st0 = sm.gx[(2 * t) * a.NG + G], st1 = sm.gx[(2 * t + 1) * a.NG + G];
-                        const int vA0 = ((ch[0][0] + ch[1][0]) << 7) + (cl[0][0] + cl[1][0]) - zAq * sx0;
-                        const int vA1 = ((ch[0][1] + ch[1][1]) << 7) + (cl[0][1] + cl[1][1]) - zAq * sx1;
-                        const int vB0 = ((ch[0][2] + ch[1][2]) << 7) + (cl[0][2] + cl[1][2]) - zBq * sx0;
-                        const int vB1 = ((ch[0][3] + ch[1][3]) << 7) + (cl[0][3] + cl[1][3]) - zBq * sx1;
-                        tot[0] += (sAq * st0) * (float)vA0;
-                        tot[1] += (sAq * st1) * (float)vA1;
-                        tot[2] += (sBq * st0) * (float)vB0;
-                        tot[3] += (sBq * st1) * (float)vB1;
+                        auto comb = [](int h, int m, int l, int z, const int *gs) {
+                            return 128.f * (float)((h << 7) + m - z * gs[0]) + (float)(l - z * gs[1]);
+                        };
+                        const float vA0 = comb(ch[0][0] + ch[1][0], cm[0][0] + cm[1][0], cl[0][0] + cl[1][0], zAq, gs0);
+                        const float vA1 = comb(ch[0][1] + ch[1][1], cm[0][1] + cm[1][1], cl[0][1] + cl[1][1], zAq, gs1);
+                        const float vB0 = comb(ch[0][2] + ch[1][2], cm[0][2] + cm[1][2], cl[0][2] + cl[1][2], zBq, gs0);
+                        const float vB1 = comb(ch[0][3] + ch[1][3], cm[0][3] + cm[1][3], cl[0][3] + cl[1][3], zBq, gs1);
+                        tot[0] += (sAq * st0) * vA0;
+                        tot[1] += (sAq * st1) * vA1;
+                        tot[2] += (sBq * st0) * vB0;
+                        tot[3] += (sBq * st1) * vB1;
                     }
                 }
             }
@@ -788,17 +841,10 @@ TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState 
         // ---- hand the tile partial to the epilogue warp (no consumer-to-consumer wait) ----
         mbar_wait(&sm.red_empty[cs.rb], cs.rphase ^ 1);
         float *rbuf = sm.red + ((size_t)cs.rb * CW + cw) * kVals;
-        if (NCOLS == 1) {
-            if (t == 0) {
-                rbuf[g] = tot[0];
-                rbuf[g + 8] = tot[1];
-            }
-        } else {
-            rbuf[g * NCOLS + 2 * t] = tot[0];
-            rbuf[g * NCOLS + 2 * t + 1] = tot[1];
-            rbuf[(g + 8) * NCOLS + 2 * t] = tot[2];
-            rbuf[(g + 8) * NCOLS + 2 * t + 1] = tot[3];
-        }
+        rbuf[g * NCOLS + 2 * t] = tot[0];
+        rbuf[g * NCOLS + 2 * t + 1] = tot[1];
+        rbuf[(g + 8) * NCOLS + 2 * t] = tot[2];
+        rbuf[(g + 8) * NCOLS + 2 * t + 1] = tot[3];
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.red_full[cs.rb]);
         if (++cs.rb == kRedBufs) {

@@ -31,7 +31,7 @@ def main():
     model.tp_connect()
     ref = None
     if rank == 0:
-        os.environ["TCE_MEGAKERNEL"] = "0"
+        os.environ["TCE_PERSISTENT"] = "0"  # the single-GPU reference runs one kernel per op
         ref = LlamaModel(ctx, g, max_ctx=256, weights=W)
     lg_local = torch.empty(gl.vocab_size, dtype=torch.float32)
     lg_ref = torch.empty(g.vocab_size, dtype=torch.float32)
