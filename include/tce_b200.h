@@ -117,6 +117,11 @@ TCE_API int tce_attn_prefill(tce_ctx *ctx, void *qkv, void *k_cache, void *v_cac
  * LlamaRMSNorm_cuda::forward (llm/src/ops/cuda/LlamaRMSNorm.cu:96-115): half in/out, fp32 gamma             */
 TCE_API int tce_rmsnorm_f16(tce_ctx *ctx, const void *x, const float *gamma, void *y, int rows, int dim, float eps);
 TCE_API int tce_argmax_f32(tce_ctx *ctx, const float *x, int n, int *out);
+/* LayerNormQ::forward (llm/src/ops/LayerNormQ.cc:12-52): fp32 [rows][dim] -> int8 [rows][dim], eps 1e-5, std::round.  Bit-exact: the two
+ * row sums run serially in the reference's order (the int8 result depends on their last bit near rounding ties).            */
+TCE_API int tce_layernorm_q(tce_ctx *ctx, const float *x, const float *weight, const float *bias, void *out_int8, int rows, int dim);
+/* out = a + b (fp32): the residual add of Int8OPTDecoderLayer::forward (llm/src/nn_modules/Int8OPTDecoderLayer.cc:10-22,38,56) */
+TCE_API int tce_add_f32(tce_ctx *ctx, const float *a, const float *b, float *out, long long n);
 
 /* ---- fused Llama decode step -----------------------------------------------------------------------------
  * The call sites of the path: Int4llamaDecoderLayer::forward / Int4llamaDecoder::forward /

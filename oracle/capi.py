@@ -219,6 +219,24 @@ def ref(kind: str = "generic") -> C.CDLL:
     return _REF[kind]
 
 
+_REF_CUDA = None
+
+
+def ref_cuda():
+    """oracle/_ref/libtce_ref_cuda.so: the reference's own kernels/cuda/gemv_cuda.cu compiled for sm_100a (GPU-side baseline and
+    second oracle).  Takes raw DEVICE pointers; launches on the legacy default stream like the reference."""
+    global _REF_CUDA
+    if _REF_CUDA is None:
+        so = REF_DIR / "libtce_ref_cuda.so"
+        if not so.exists():
+            raise FileNotFoundError(f"{so} not built (needs /root/reference and nvcc; run `make -C oracle ref`)")
+        L = C.CDLL(str(so))
+        L.ref_cuda_gemv.restype = C.c_int
+        L.ref_cuda_gemv.argtypes = [C.c_void_p] * 5 + [C.c_int] * 3
+        _REF_CUDA = L
+    return _REF_CUDA
+
+
 def ref_naive_mat_mul_int4(A, B, scales, zero_point=8.0, block_size=128, kind="generic"):
     A = np.ascontiguousarray(A, np.float32)
     M, IC = A.shape

@@ -49,3 +49,23 @@ def test_f32_transposed_golden_and_oracle(ctx, golden_dir):
     capi.lib().orc_mat_mul_transposed(A, B, want, 5, 129, 333)
     got = ctx.f32_matmul_transposed(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
     assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("rows,dim", [(1, 4096), (5, 768), (3, 130), (64, 4096)])
+def test_layernorm_q_bit_exact(ctx, rows, dim):
+    """tce_layernorm_q == LayerNormQ::forward (llm/src/ops/LayerNormQ.cc:12-52) as restated by the oracle (itself pinned bit-for-bit against
+    the compiled reference op, tests/test_oracle_golden.py): int8 outputs identical, including rounding ties."""
+    from oracle import capi
+
+    rng = np.random.default_rng(rows * 1000 + dim)
+    x = (rng.standard_normal((rows, dim)) * 60).astype(np.float32)
+    w = (1 + 0.1 * rng.standard_normal(dim)).astype(np.float32)
+    b = rng.standard_normal(dim).astype(np.float32)
+    want = np.zeros((rows, dim), np.int8)
+    capi.lib().orc_layernorm_q(x, w, b, want, rows, dim)
+    dev = torch.device("cuda", 0)
+    got = ctx.layernorm_q(torch.from_numpy(x).to(dev), torch.from_numpy(w).to(dev), torch.from_numpy(b).to(dev))
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), want)
+    a2 = torch.from_numpy(x).to(dev)
+    assert torch.equal(ctx.add_f32(a2, a2), a2 + a2)

@@ -118,6 +118,26 @@ def test_gemv_tiny_and_mixed_magnitudes(ctx):
     assert _per_element_err(y.float().cpu().numpy(), ref) <= 1e-2
 
 
+@pytest.mark.parametrize("oc,ic", [(4096, 4096), (1024, 14336), (11008, 4096)])
+def test_reference_cuda_kernel_on_this_gpu(ctx, oc, ic):
+    """The reference's own gemv_kernel_g128 (kernels/cuda/gemv_cuda.cu:140-194), compiled unchanged for sm_100a (oracle/_ref), on the
+    same device buffers: a second, independent oracle on the GPU.  Its arithmetic is fp32 FMA of exactly converted fp16 inputs."""
+    from oracle import capi
+
+    if not capi.ref_available("cuda"):
+        pytest.skip("oracle/_ref/libtce_ref_cuda.so not built")
+    x, w, z, s = make_case(oc, ic, 1, 5 + oc, True)
+    y = ctx.w4a16_gemv(x, w, z, s)
+    yr = torch.empty_like(y)
+    torch.cuda.synchronize()
+    rc = capi.ref_cuda().ref_cuda_gemv(x.data_ptr(), w.data_ptr(), z.data_ptr(), s.data_ptr(), yr.data_ptr(), 1, ic, oc)
+    torch.cuda.synchronize()
+    assert rc == 0
+    want = oracle(x, w, z, s)
+    assert_w4_close(yr.float().cpu().numpy(), want, "reference CUDA kernel vs oracle")
+    assert_w4_close(y.float().cpu().numpy(), yr.float().cpu().numpy(), "this kernel vs reference CUDA kernel")
+
+
 def test_gemm_entry_point_same_contract(ctx):
     x, w, z, s = make_case(128, 1024, 24, 5, False)
     y = ctx.w4a16_gemv(x, w, z, s, gemm=True)

@@ -54,6 +54,8 @@ SIGNATURES = {
     "tce_attn_decode": (C.c_int, [C.c_void_p] * 8 + [C.c_float] + [C.c_int] * 4),
     "tce_rmsnorm_f16": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float]),
     "tce_argmax_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "tce_layernorm_q": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int]),
+    "tce_add_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong]),
     "tce_llama_create": (C.c_int, [C.c_void_p, C.POINTER(LlamaConfig), C.POINTER(LlamaWeights), C.POINTER(C.c_void_p)]),
     "tce_llama_destroy": (C.c_int, [C.c_void_p]),
     "tce_llama_decode": (C.c_int, [C.c_void_p, C.c_void_p]),

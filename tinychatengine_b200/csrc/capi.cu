@@ -356,6 +356,20 @@ int tce_rmsnorm_f16(tce_ctx *ctx, const void *x, const float *gamma, void *y, in
     return TCE_OK;
 }
 
+int tce_layernorm_q(tce_ctx *ctx, const float *x, const float *weight, const float *bias, void *out_int8, int rows, int dim) {
+    if (!ctx || !x || !weight || !bias || !out_int8 || rows < 1 || dim < 1 || dim > 49000) return fail(TCE_ERR_INVALID, "tce_layernorm_q: bad argument");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    CK(launch_layernorm_q(&ctx->c, x, weight, bias, (int8_t *)out_int8, rows, dim), "tce_layernorm_q");
+    return TCE_OK;
+}
+
+int tce_add_f32(tce_ctx *ctx, const float *a, const float *b, float *out, long long n) {
+    if (!ctx || !a || !b || !out || n < 1) return fail(TCE_ERR_INVALID, "tce_add_f32: bad argument");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    CK(launch_add_f32(&ctx->c, a, b, out, n), "tce_add_f32");
+    return TCE_OK;
+}
+
 int tce_argmax_f32(tce_ctx *ctx, const float *x, int n, int *out) {
     if (!ctx || !x || !out || n < 1) return fail(TCE_ERR_INVALID, "tce_argmax_f32: bad argument");
     CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");

@@ -106,6 +106,45 @@ __global__ void rmsnorm_f16_kernel(const __half *__restrict__ x, const float *__
     for (int i = threadIdx.x; i < dim; i += blockDim.x) yr[i] = __float2half((__half2float(xr[i]) * inv) * gamma[i]);
 }
 
+// LayerNormQ::forward (llm/src/ops/LayerNormQ.cc:12-52): fp32 row -> int8 row, eps 1e-5.  The reference sums the row serially in fp32
+// (mean, then squared deviations), and the int8 result depends on those sums to the last bit near rounding ties, so the two reductions
+// are done by ONE thread in the reference's order (the loads are independent of the add chain and pipeline); the normalisation of the
+// row is spread over the block, with the reference's operation order and no FMA contraction.  One block per row.
+__global__ void layernorm_q_kernel(const float *__restrict__ x, const float *__restrict__ weight, const float *__restrict__ bias, int8_t *__restrict__ out,
+                                   int dim) {
+    extern __shared__ float srow[];  // [dim] + 2
+    const float *xr = x + (size_t)blockIdx.x * dim;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) srow[i] = xr[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mean = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < dim; k++) mean = __fadd_rn(mean, srow[k]);
+        mean = __fdiv_rn(mean, (float)dim);
+        float sq = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < dim; k++) {
+            const float d = __fsub_rn(srow[k], mean);
+            sq = __fadd_rn(sq, __fmul_rn(d, d));
+        }
+        const float var = __fdiv_rn(sq, (float)dim);
+        srow[dim] = mean;
+        srow[dim + 1] = __fsqrt_rn(__fadd_rn(var, 0.00001f));
+    }
+    __syncthreads();
+    const float mean = srow[dim], sd = srow[dim + 1];
+    int8_t *orow = out + (size_t)blockIdx.x * dim;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        const float fp = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(srow[i], mean), sd), weight[i]), bias[i]);
+        orow[i] = (int8_t)(int)roundf(fp);  // std::round: half away from zero, then the implementation's float -> int8 conversion
+    }
+}
+
+// fp32 residual add of the OPT decoder layer (Int8OPTDecoderLayer::add, llm/src/nn_modules/Int8OPTDecoderLayer.cc:10-22)
+__global__ void add_f32_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = __fadd_rn(a[i], b[i]);
+}
+
 // ---- row-wise versions for prompt processing (n tokens at once)
 __global__ void embedding_rows_kernel(const __half *__restrict__ table, const int *__restrict__ tokens, float *__restrict__ resid, int E) {
     const __half2 *row = reinterpret_cast<const __half2 *>(table + (size_t)tokens[blockIdx.x] * E);
@@ -182,6 +221,21 @@ cudaError_t launch_silu_mul_rows(Ctx *ctx, const __half *gu, __half *act, int ro
     const long long total = (long long)rows * F;
     const long long nb = (total + 255) / 256;
     silu_mul_rows_kernel<<<(unsigned)(nb < 4096 ? nb : 4096), 256, 0, ctx->stream>>>(gu, act, F, total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm_q(Ctx *ctx, const float *x, const float *weight, const float *bias, int8_t *out, int rows, int dim) {
+    const size_t smem = (size_t)(dim + 2) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(layernorm_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    layernorm_q_kernel<<<rows, 128, smem, ctx->stream>>>(x, weight, bias, out, dim);
+    return cudaGetLastError();
+}
+cudaError_t launch_add_f32(Ctx *ctx, const float *a, const float *b, float *out, long long n) {
+    const long long nb = (n + 255) / 256;
+    add_f32_kernel<<<(unsigned)(nb < 2368 ? nb : 2368), 256, 0, ctx->stream>>>(a, b, out, n);
     return cudaGetLastError();
 }
 

@@ -42,5 +42,8 @@ cudaError_t launch_embedding(Ctx *ctx, const __half *table, const int *token, fl
 cudaError_t launch_argmax(Ctx *ctx, const float *logits, int n, int *out, bool pdl);
 // standalone RMSNorm fp16 -> fp16 with fp32 gamma (reference LlamaRMSNorm_cuda, ops/cuda/LlamaRMSNorm.cu:68-115)
 cudaError_t launch_rmsnorm_f16(Ctx *ctx, const __half *x, const float *gamma, __half *y, int rows, int dim, float eps);
+// LayerNormQ::forward (llm/src/ops/LayerNormQ.cc:12-52), bit-exact (serial fp32 sums in the reference's order)
+cudaError_t launch_layernorm_q(Ctx *ctx, const float *x, const float *weight, const float *bias, int8_t *out, int rows, int dim);
+cudaError_t launch_add_f32(Ctx *ctx, const float *a, const float *b, float *out, long long n);
 
 }  // namespace tce

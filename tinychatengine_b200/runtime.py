@@ -118,6 +118,18 @@ class Context:
         _lib.check(self.L.tce_rmsnorm_f16(self.h, _ptr(x), _ptr(gamma), _ptr(out), x.shape[0], x.shape[1], eps), "tce_rmsnorm_f16")
         return out
 
+    def layernorm_q(self, x, weight, bias, out=None):
+        if out is None:
+            out = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+        _lib.check(self.L.tce_layernorm_q(self.h, _ptr(x), _ptr(weight), _ptr(bias), _ptr(out), x.shape[0], x.shape[1]), "tce_layernorm_q")
+        return out
+
+    def add_f32(self, a, b, out=None):
+        if out is None:
+            out = torch.empty_like(a)
+        _lib.check(self.L.tce_add_f32(self.h, _ptr(a), _ptr(b), _ptr(out), a.numel()), "tce_add_f32")
+        return out
+
     def argmax_f32(self, x, out=None):
         if out is None:
             out = torch.empty((1,), dtype=torch.int32, device=x.device)
