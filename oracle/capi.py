@@ -316,6 +316,79 @@ def ref_int8_opt_attention(param_root, hidden, E, H, prefill, decode_steps, max_
     return out, fk, fv
 
 
+def write_opt_decoder_layer_params(root, W, B, bo, ln, fc, scales):
+    """Parameter tree of Int8OPTDecoderLayer's constructor (llm/src/nn_modules/Int8OPTDecoderLayer.cc:60-90): self_attn/... (as above),
+    self_attn_layer_norm|final_layer_norm/{weight,bias}.bin, fc1/{weight,bias_int8,alpha,beta}.bin, fc2/{weight,bias,alpha}.bin.
+    ln: dict ln1w, ln1b, ln2w, ln2b (float32 [E]); fc: dict w1 int8 [F][E], b1 int8 [F], w2 int8 [E][F], b2 float32 [E];
+    scales: dict a_qkv, b_qkv, qk_alpha, pv_alpha, a_out, a1, b1, a2."""
+    import os
+
+    f32 = lambda v: np.array([v], np.float32)
+    write_opt_attention_params(os.path.join(root, "self_attn"), W, B, bo, scales["a_qkv"], scales["b_qkv"], scales["qk_alpha"], scales["pv_alpha"], scales["a_out"])
+    for name, w, b in (("self_attn_layer_norm", ln["ln1w"], ln["ln1b"]), ("final_layer_norm", ln["ln2w"], ln["ln2b"])):
+        d = os.path.join(root, name)
+        os.makedirs(d, exist_ok=True)
+        np.ascontiguousarray(w, np.float32).tofile(os.path.join(d, "weight.bin"))
+        np.ascontiguousarray(b, np.float32).tofile(os.path.join(d, "bias.bin"))
+    d = os.path.join(root, "fc1")
+    os.makedirs(d, exist_ok=True)
+    np.ascontiguousarray(fc["w1"], np.int8).tofile(os.path.join(d, "weight.bin"))
+    np.ascontiguousarray(fc["b1"], np.int8).tofile(os.path.join(d, "bias_int8.bin"))
+    f32(scales["a1"]).tofile(os.path.join(d, "alpha.bin"))
+    f32(scales["b1"]).tofile(os.path.join(d, "beta.bin"))
+    d = os.path.join(root, "fc2")
+    os.makedirs(d, exist_ok=True)
+    np.ascontiguousarray(fc["w2"], np.int8).tofile(os.path.join(d, "weight.bin"))
+    np.ascontiguousarray(fc["b2"], np.float32).tofile(os.path.join(d, "bias.bin"))
+    f32(scales["a2"]).tofile(os.path.join(d, "alpha.bin"))
+
+
+_MODLIBS = {}
+
+
+def modules_lib(kind: str = "ref_modules"):
+    """kind = "ref_modules": the reference's modules on the reference's own kernels/ref bodies (CPU).
+    kind = "callsites_cuda": the SAME reference call sites compiled unchanged with -DQM_CUDA on this repo's library (the drop-in proof)."""
+    if kind not in _MODLIBS:
+        so = REF_DIR / f"libtce_{kind}.so"
+        if not so.exists():
+            raise FileNotFoundError(f"{so} not built (run `make -C oracle ref` where /root/reference exists)")
+        L = C.CDLL(str(so))
+        L.ref_int8_opt_attention.restype = C.c_int
+        L.ref_int8_opt_attention.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, _i8p, C.c_int, C.c_int, _f32p, _i8p, _i8p]
+        L.ref_int8_opt_decoder_layer.restype = C.c_int
+        L.ref_int8_opt_decoder_layer.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, _i8p, _i8p]
+        if kind == "callsites_cuda":
+            L.ref_linear_half_int4.restype = C.c_int
+            L.ref_linear_half_int4.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, _u16p, _u16p]
+        _MODLIBS[kind] = L
+    return _MODLIBS[kind]
+
+
+def run_opt_decoder_layer(kind, param_root, hidden_f32, E, H, F, prefill, decode_steps, max_sqlen=256):
+    hidden = np.ascontiguousarray(hidden_f32, np.float32)
+    total = prefill + decode_steps
+    out = np.zeros((total, E), np.float32)
+    hd = E // H
+    fk = np.zeros((H, total, hd), np.int8)
+    fv = np.zeros((H, total, hd), np.int8)
+    n = modules_lib(kind).ref_int8_opt_decoder_layer(str(param_root).encode(), E, H, F, max_sqlen, hidden, prefill, decode_steps, out, fk, fv)
+    assert n == total
+    return out, fk, fv
+
+
+def run_opt_attention(kind, param_root, hidden_i8, E, H, prefill, decode_steps, max_sqlen=256):
+    hidden = np.ascontiguousarray(hidden_i8, np.int8)
+    total = prefill + decode_steps
+    out = np.zeros((total, E), np.float32)
+    hd = E // H
+    fk = np.zeros((H, total, hd), np.int8)
+    fv = np.zeros((H, total, hd), np.int8)
+    n = modules_lib(kind).ref_int8_opt_attention(str(param_root).encode(), E, H, max_sqlen, hidden, prefill, decode_steps, out, fk, fv)
+    assert n == total
+    return out, fk, fv
+
+
 def oracle_int8_opt_attention(hidden, W, B, bo, a_qkv, b_qkv, qk_alpha, pv_alpha, a_out, H, prefill, decode_steps):
     """The same module flow composed from the oracle: projections (orc_int8_matmul), core, out_proj."""
     E = hidden.shape[1]

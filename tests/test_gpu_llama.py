@@ -148,6 +148,7 @@ def test_benchmarked_geometry_step_matches_oracle(pos, mega, monkeypatch):
     assert nxt == int(np.argmax(got))
     for l in range(g.num_layers):
         assert np.abs(model.kv_cache(l, 0)[:, pos].float().cpu().numpy() - fk[l][:, pos]).max() <= 2e-2 * max(1.0, np.abs(fk[l]).max())
-        assert np.array_equal(model.kv_cache(l, 1)[:, pos].cpu().numpy(), fv[l][:, pos].astype(np.float16))
+        # (the appended V row is the GEMV's fp16 output: equal to the oracle's up to the GEMV tolerance, not bit for bit)
+        assert np.abs(model.kv_cache(l, 1)[:, pos].float().cpu().numpy() - fv[l][:, pos]).max() <= 5e-3 * max(1.0, np.abs(fv[l][:, pos]).max())
     model.close()
     ctx.close()

@@ -11,7 +11,7 @@
 //        on nothing but static data and the token position, so it runs ahead across every phase boundary: while the GPU synchronises or
 //        stages activations, up to nst x 16 KiB per SM of the NEXT matrices are already in flight, and HBM never goes idle.
 //   consumers (16 warps)  per phase: wait for the grid barrier of the previous phase, quantise the activation vector (fused RMSNorm,
-//        three int8 planes per 128-group), run the integer-MMA GEMV over this CTA's stage units (w4a16_gemv_impl.cuh: unit1), or
+//        four int8 planes per 128-group), run the integer-MMA GEMV over this CTA's stage units (w4a16_gemv_impl.cuh: unit1), or
 //        run flash-decoding attention straight out of the ring stages (mma.sync m16n8k16, ldmatrix on the swizzled K/V rows).
 //   epilogue (1 warp)  reduces the 16 consumer partials of every tile, applies the fused epilogue (fp16 store, RED.ADD into the fp32
 //        residual, SiLU(gate)*up, logits + running arg-max, tensor-parallel scatter to the peers) and signals the grid barrier.
@@ -86,6 +86,14 @@ TCE_DEVINL void sys_wait(const unsigned *ctr, unsigned target) {
     }
 }
 
+TCE_DEVINL void stamp(const Args &a, int cta, int nphase, int p, int k) {  // one thread
+    if (a.dbg) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.dbg[((size_t)cta * nphase + p) * 4 + k] = t;
+    }
+}
+
 TCE_DEVINL unsigned long long argmax_key(float v, int idx) {
     unsigned b = __float_as_uint(v);
     b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // monotone map float -> uint
@@ -94,7 +102,7 @@ TCE_DEVINL unsigned long long argmax_key(float v, int idx) {
 
 struct PSmem {
     uint8_t *ring;      // [nst][kStageBytes], 1024-B aligned
-    uint8_t *xs;        // activation planes (3 * IC bytes) | attention scratch
+    uint8_t *xs;        // activation planes (4 * IC bytes) | attention scratch
     float *gx;          // [max_ng] group steps
     int *gsum;          // [max_ng][2] group sums
     float *red;         // [kRedBufs][kCW][16] tile partials
@@ -743,7 +751,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             // everything this warp wrote in phase p is visible device-wide before the arrival
             __threadfence();
             __syncwarp();
-            if (lane == 0) red_release_gpu(a.sync + p);
+            if (lane == 0) {
+                red_release_gpu(a.sync + p);
+                stamp(a, cta, nphase, p, 3);
+            }
         }
         return;
     }
@@ -762,12 +773,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             if (ctid == 0) grid_wait(a.sync + p - 1, target);
             named_bar_sync(1, kConsumerThreads);
         }
+        if (ctid == 0) stamp(a, cta, nphase, p, 0);
         if (l < Lyr && k == 1) {
             // ---- RoPE + KV append + attention ----
             attention_phase(a, a.layers[l], sm, rs, cta, ncta, pos, ctid, cw, lane);
+            if (ctid == 0) stamp(a, cta, nphase, p, 2);
             __threadfence();
             named_bar_sync(1, kConsumerThreads);
-            if (ctid == 0) red_release_gpu(a.sync + p);
+            if (ctid == 0) {
+                red_release_gpu(a.sync + p);
+                stamp(a, cta, nphase, p, 3);
+            }
             continue;
         }
         const int oi = (l == Lyr) ? OPI_LMHEAD : ((k == 0) ? OPI_QKV : (k - 1));
@@ -802,7 +818,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             resid_cur = resid_alt;
             resid_alt = tmp;
         }
+        if (ctid == 0) stamp(a, cta, nphase, p, 1);
         consume_gemv(a.op[oi], sm, rs, cs, inv, cta, ncta, cw, lane);
+        if (ctid == 0) stamp(a, cta, nphase, p, 2);
     }
     // ---- greedy token: decoded once every CTA's epilogue has contributed its maximum ----
     if (cta == 0 && ctid == 0) {

@@ -450,7 +450,7 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         if (a.op[i].IC % kW4Group || a.op[i].num_tiles < 1) return no("bad GEMV shape");
     }
     max_ng = (max_ng + 3) & ~3;
-    int xs = 3 * max_ic;
+    int xs = 4 * max_ic;  // four int8 activation planes
     if (xs < pk::attn_scratch_bytes(nrep)) xs = pk::attn_scratch_bytes(nrep);
     xs = (xs + 15) & ~15;
     a.xs_bytes = xs;
@@ -564,6 +564,12 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
             a.tp_key_arrive[q] = words + 32;   // own 128-byte line
             a.tp_keys[q] = reinterpret_cast<unsigned long long *>(base + tp_gather_floats_ * sizeof(float) + 256);
         }
+    }
+    if (getenv("TCE_PK_DEBUG") && atoi(getenv("TCE_PK_DEBUG"))) {
+        const size_t n = (size_t)ncta * nsync * 4 * sizeof(unsigned long long);
+        a.dbg = (unsigned long long *)dalloc(n);
+        if (!a.dbg) return cudaErrorMemoryAllocation;
+        DCK(cudaMemset(a.dbg, 0, n));
     }
     if ((int)pk::smem_bytes(a) > ctx_->smem_optin) return no("shared memory");
     pargs_ = a;

@@ -28,6 +28,7 @@ class LlamaDecoder {
             case 1: return d_qkv_;
             case 2: return d_attn_;
             case 3: return d_act_;
+            case 4: return pargs_.dbg;  // persistent-kernel phase timestamps (TCE_PK_DEBUG=1), [#CTAs][5 * layers + 1][4] u64 ns
             default: return nullptr;
         }
     }

@@ -80,6 +80,7 @@ struct Args {
     unsigned long long *tp_keys[kMaxTP];  // every rank's arg-max key slots [P]
     unsigned *tp_key_arrive[kMaxTP];
     int vocab_base;              // global index of this rank's first vocabulary row
+    unsigned long long *dbg;     // optional (TCE_PK_DEBUG=1): globaltimer stamps [cta][phase][4] = barrier passed, staged, consumed, arrived
 };
 
 size_t smem_bytes(const Args &a);

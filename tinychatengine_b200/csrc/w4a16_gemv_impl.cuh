@@ -11,9 +11,9 @@
 //    weight box into a ring of KArgs::nst stages (8 by default) guarded by full/empty mbarriers, L2 evict-first; the tile's
 //    scales/zeros slabs (1-D bulk copies, UBLKCP) ride on the first stage's barrier.  Producers depend on nothing but the weights,
 //    so they run ahead of everything else (in particular of the consumers' activation staging).
-//  * consumers (CW warps): 128-bit LDS of the packed nibbles; activations held as three int8 planes (22-bit block fixed point per
+//  * consumers (CW warps): 128-bit LDS of the packed nibbles; activations held as four int8 planes (29-bit block fixed point per
 //    128-group, exact integer accumulation); mma.sync.m16n8k32 u8 x s8 -> s32; per-group epilogue
-//    tot += (s * step) * (acc - z * sum_X).  One activation row (decode, consume1): the three planes ride in MMA columns 0/1/2 and
+//    tot += (s * step) * (acc - z * sum_X).  One activation row (decode, consume1): the four planes ride in MMA columns 0..3 and
 //    nibbles become bytes with one mask each (even slots w & 0x0f0f0f0f, odd slots w & 0xf0f0f0f0 = 16 x nibble, shifted back
 //    after accumulation): 4 IMMAs per (16 rows x 128 k).  Up to 8 rows (consume<8>): the 8 MMA columns carry the rows, planes in
 //    separate MMAs, (w >> 4) & 0x0f0f0f0f for the odd slots.
@@ -33,7 +33,7 @@ constexpr int kStageBytes = 16 * kStageGroups * 64;  // 16 KiB: dense [16 rows][
 constexpr int kStages = 4;         // default ring depth (persistent kernel); the per-op kernel picks the deepest ring that fits (KArgs::nst)
 constexpr int kMaxStages = 12;
 constexpr int kRedBufs = 3;
-constexpr float kActQ = 2080768.f;  // 127 * 2^14: activation fixed-point full scale (three int8 planes)
+constexpr float kActQ = 266338304.f;  // 127 * 2^21: activation fixed-point full scale (four int8 planes)
 constexpr int kProducerWarps = 1;        // a stage is one UTMALDG (two in gate/up pair mode): a single elected lane keeps up
 // per-tile scales/zeros slabs in flight: ring depth + 1 (a tile spans >= 1 stage)
 
@@ -116,15 +116,15 @@ template <int NCOLS, int CW>
 struct Layout {
     static constexpr int kXPad = (NCOLS > 1) ? 64 : 0;  // column pitch = 64 (mod 128) B for the per-column B loads
     static constexpr int kVals = 16 * NCOLS;
-    // three int8 planes per activation (22-bit block fixed point): planes (hi, mid) interleaved in region A (2 B per element),
-    // plane lo in region B (1 B per element) that follows region A of the same column
-    static __host__ __device__ int x_pitch(int IC) { return IC * 3 + kXPad; }
+    // four int8 planes per activation (29-bit block fixed point): planes (p3, p2) interleaved in region A (2 B per element),
+    // planes (p1, p0) in region B that follows region A of the same column
+    static __host__ __device__ int x_pitch(int IC) { return IC * 4 + kXPad; }
     // one meta slot = scales half[16][zeros_w*8] followed by zeros uint32[16][zeros_w] = 320 * zeros_w bytes
     static __host__ __device__ int meta_slot_bytes(int IC) { return 320 * (((IC / 128) + 7) / 8); }
     static __host__ __device__ size_t off_meta(int nst) { return (size_t)nst * kStageBytes; }
     static __host__ __device__ size_t off_xs(int IC, int nst) { return off_meta(nst) + (size_t)(nst + 1) * meta_slot_bytes(IC); }
     static __host__ __device__ size_t off_gx(int IC, int nst) { return off_xs(IC, nst) + (size_t)NCOLS * x_pitch(IC); }
-    // gx: float step[NCOLS][NG] followed by int gsum[NCOLS][NG][2] = {128 * sum(hi) + sum(mid), sum(lo)}
+    // gx: float step[NCOLS][NG] followed by int gsum[NCOLS][NG][2] = {128 * sum(p3) + sum(p2), 128 * sum(p1) + sum(p0)}
     static __host__ __device__ size_t off_red(int IC, int nst) { return off_gx(IC, nst) + (size_t)3 * NCOLS * (IC / 128) * sizeof(float); }
     static __host__ __device__ size_t off_rms(int IC, int nst) { return off_red(IC, nst) + (size_t)kRedBufs * CW * kVals * sizeof(float); }
     static __host__ __device__ size_t off_bar(int IC, int nst) { return (off_rms(IC, nst) + (size_t)NCOLS * CW * sizeof(float) + 15) & ~(size_t)15; }
@@ -431,11 +431,12 @@ TCE_DEVINL void epilogue(const KArgs &a, const Smem &sm, RedState &es, int cta, 
 // step and integer sums.  Must be called by all 32 lanes of a warp (half-warp shuffles); `valid` masks the stores.
 template <int NCOLS>
 TCE_DEVINL void emit_unit(uint8_t *xcol, int IC, float *gx, int *gsum, int ui, bool valid, const float (&v)[8], int lane) {
-    // Activations enter the integer tensor path as 22-bit block fixed point: per 128-group,
-    // X = rint(x * Q / max|x|), Q = 127 * 2^14, X = 2^14*hi + 2^7*mid + lo  (three int8 planes: hi in [-127,127],
-    // mid in [-64,64], lo in [-64,63]).  |x - step*X| <= max|x_group| * 2^-22: an element 2^11 times smaller than the largest
-    // of its group still keeps fp16's own 11 bits (the reference converts fp16 -> fp32 exactly, gemv_cuda.cu:181-184).  The
-    // integer dot products that follow are exact.  The third plane costs no MMA: the planes ride in MMA columns 0..2.
+    // Activations enter the integer tensor path as 29-bit block fixed point: per 128-group,
+    // X = rint(x * Q / max|x|), Q = 127 * 2^21, X = 2^21*p3 + 2^14*p2 + 2^7*p1 + p0  (four int8 planes: p3 in [-127,127], the others in
+    // [-64,64]).  |x - step*X| <= max(|x| * 2^-24, max|x_group| * 2^-29): every fp16 activation whose magnitude is within 2^17 of the
+    // largest of its group keeps all of its 11 significand bits, i.e. the planes carry what the reference's exact fp16 -> fp32
+    // conversion carries (gemv_cuda.cu:181-184) unless a group spans more than 5 decades.  The integer dot products that follow are
+    // exact.  The extra planes cost no MMA: the four planes ride in MMA columns 0..3 of the same instruction.
     float amax = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
@@ -444,46 +445,51 @@ TCE_DEVINL void emit_unit(uint8_t *xcol, int IC, float *gx, int *gsum, int ui, b
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
     const float qinv = (amax > 0.f) ? (kActQ / amax) : 0.f;
-    int hi[8], mi[8], lo[8], sxh = 0, sxl = 0;
+    int p3[8], p2[8], p1[8], p0[8], sxh = 0, sxl = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int X = __float2int_rn(v[i] * qinv);
-        hi[i] = (X + 8192) >> 14;
-        const int r = X - (hi[i] << 14);
-        mi[i] = (r + 64) >> 7;
-        lo[i] = r - (mi[i] << 7);
-        sxh += (hi[i] << 7) + mi[i];
-        sxl += lo[i];
+        p3[i] = (X + (1 << 20)) >> 21;
+        const int r = X - (p3[i] << 21);
+        p2[i] = (r + (1 << 13)) >> 14;
+        const int r2 = r - (p2[i] << 14);
+        p1[i] = (r2 + 64) >> 7;
+        p0[i] = r2 - (p1[i] << 7);
+        sxh += (p3[i] << 7) + p2[i];
+        sxl += (p1[i] << 7) + p0[i];
     }
     // B-fragment order of mma.m16n8k32: k-slots 4t..4t+3 <- elements (0,2,4,6) of the word (the bytes of
     // w & 0x0f0f0f0f), k-slots 16+4t.. <- elements (1,3,5,7) (the bytes of (w>>4) & 0x0f0f0f0f).
     auto pack4 = [](int b0, int b1, int b2, int b3) {
         return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
     };
-    const uint32_t oh0 = pack4(hi[0], hi[2], hi[4], hi[6]), oh1 = pack4(hi[1], hi[3], hi[5], hi[7]);
-    const uint32_t om0 = pack4(mi[0], mi[2], mi[4], mi[6]), om1 = pack4(mi[1], mi[3], mi[5], mi[7]);
-    const uint32_t ol0 = pack4(lo[0], lo[2], lo[4], lo[6]), ol1 = pack4(lo[1], lo[3], lo[5], lo[7]);
+    const uint32_t o3e = pack4(p3[0], p3[2], p3[4], p3[6]), o3o = pack4(p3[1], p3[3], p3[5], p3[7]);
+    const uint32_t o2e = pack4(p2[0], p2[2], p2[4], p2[6]), o2o = pack4(p2[1], p2[3], p2[5], p2[7]);
+    const uint32_t o1e = pack4(p1[0], p1[2], p1[4], p1[6]), o1o = pack4(p1[1], p1[3], p1[5], p1[7]);
+    const uint32_t o0e = pack4(p0[0], p0[2], p0[4], p0[6]), o0o = pack4(p0[1], p0[3], p0[5], p0[7]);
     const int G = ui >> 4, tj = ui & 15;  // ui = G*16 + 4*t + j
     if (NCOLS == 1) {
-        // single-column layout (consume1).  Region A, per group 256 B = [parity: even | odd nibble slots][t][plane: hi | mid][word j];
-        // region B (at byte IC*2), per group 128 B = [parity][t][word j] of plane lo.  One LDS.128 hands lane (t, plane) the
-        // B operands of both MMAs of a parity; the chunks a quarter-warp loads are contiguous (conflict free).
+        // single-column layout (consume1).  Region A (planes p3 | p2) and region B (at byte IC*2, planes p1 | p0), each per group
+        // 256 B = [parity: even | odd nibble slots][t][plane][word j].  One LDS.128 hands lane (t, plane) the B operands of both MMAs of a
+        // parity; the chunks a quarter-warp loads are contiguous (conflict free).
         if (valid) {
             uint32_t *dst = reinterpret_cast<uint32_t *>(xcol + (size_t)G * 256 + (size_t)(tj >> 2) * 32) + (tj & 3);
-            dst[0] = oh0;       // even slots, hi plane
-            dst[4] = om0;       // even slots, mid plane
-            dst[32] = oh1;      // odd slots, hi plane
-            dst[36] = om1;      // odd slots, mid plane
-            uint32_t *dl = reinterpret_cast<uint32_t *>(xcol + (size_t)IC * 2 + (size_t)G * 128 + (size_t)(tj >> 2) * 16) + (tj & 3);
-            dl[0] = ol0;        // even slots, lo plane
-            dl[16] = ol1;       // odd slots, lo plane
+            dst[0] = o3e;       // even slots, p3
+            dst[4] = o2e;       // even slots, p2
+            dst[32] = o3o;      // odd slots, p3
+            dst[36] = o2o;      // odd slots, p2
+            uint32_t *dl = reinterpret_cast<uint32_t *>(xcol + (size_t)IC * 2 + (size_t)G * 256 + (size_t)(tj >> 2) * 32) + (tj & 3);
+            dl[0] = o1e;
+            dl[4] = o0e;
+            dl[32] = o1o;
+            dl[36] = o0o;
         }
     } else {
         // units of a group are stored j-major so that the four t-lanes of one LDS.128 hit consecutive slots
         const int pos = G * 16 + (tj & 3) * 4 + (tj >> 2);
         if (valid) {
-            *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = make_uint4(oh0, oh1, om0, om1);
-            *reinterpret_cast<uint2 *>(xcol + (size_t)IC * 2 + (size_t)pos * 8) = make_uint2(ol0, ol1);
+            *reinterpret_cast<uint4 *>(xcol + (size_t)pos * 16) = make_uint4(o3e, o3o, o2e, o2o);
+            *reinterpret_cast<uint4 *>(xcol + (size_t)IC * 2 + (size_t)pos * 16) = make_uint4(o1e, o1o, o0e, o0o);
         }
     }
 #pragma unroll
@@ -493,13 +499,13 @@ TCE_DEVINL void emit_unit(uint8_t *xcol, int IC, float *gx, int *gsum, int ui, b
     }
     if (valid && (lane & 15) == 0) {
         gx[G] = (amax > 0.f) ? (amax / kActQ) : 0.f;  // step of the group
-        gsum[G * 2] = sxh;                            // 128 * sum(hi) + sum(mid) over the group
-        gsum[G * 2 + 1] = sxl;                        // sum(lo)
+        gsum[G * 2] = sxh;                            // 128 * sum(p3) + sum(p2) over the group
+        gsum[G * 2 + 1] = sxl;                        // 128 * sum(p1) + sum(p0)
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// consumer prologue: activations -> (optional RMSNorm) -> three int8 planes per 128-group in MMA-B order, plus the
+// consumer prologue: activations -> (optional RMSNorm) -> four int8 planes per 128-group in MMA-B order, plus the
 // per-group step and integer sums.  Ends with a consumer-wide named barrier (id 1).
 // ------------------------------------------------------------------------------------------------------------------
 template <int NCOLS, int CW>
@@ -625,53 +631,41 @@ TCE_DEVINL void stage_activations(const KArgs &a, const Smem &sm, int x_pitch, i
 // consumer main loop
 // ------------------------------------------------------------------------------------------------------------------
 // Single activation column (decode).  Per (16-row tile, 128-k group) a warp issues FOUR integer MMAs instead of twelve:
-//   * the three activation planes ride in MMA columns 0 (hi), 1 (mid) and 2 (lo): lane (g, t) supplies the B operand of column g, so
-//     lanes g = 0 / 1 / 2 load the hi / mid / lo plane, thread t = 0 of every row pair receives the (hi, mid) plane sums (c0, c1) and
-//     thread t = 1 the lo plane sum (c0); columns 3..7 are don't-cares;
+//   * the four activation planes ride in MMA columns 0..3: lane (g, t) supplies the B operand of column g, so lanes g = 0..3 load planes
+//     p3..p0, thread t = 0 of every row pair receives the (p3, p2) plane sums (c0, c1) and thread t = 1 the (p1, p0) sums; columns
+//     4..7 are don't-cares;
 //   * nibbles become bytes with ONE mask each: w & 0x0f0f0f0f (even slots) and w & 0xf0f0f0f0 (odd slots, = 16 x nibble, still
 //     u8).  Even and odd slots accumulate separately (accL, accH); accH is an exact multiple of 16 and is shifted back at the end.
 // Two MMAs per parity take words (0,1) and (2,3) of the lane's 16-byte weight load as their two k halves.
 struct Lane1 {  // lane-constant operands of the single-column consumer
-    const uint8_t *xlane;  // this lane's activation chunk of group 0
-    int xstride, xodd;     // bytes per group / offset of the odd-slot half
-    int wa, wb;            // integer weights of (c0, c1): t = 0: (128, 1) = 128*hi + mid, t = 1: (1, 0) = lo, else 0
-    float lscale;          // t = 0: 128 (the (hi, mid) sum counts in units of 2^7 lo steps), t = 1: 1, else 0
+    const uint8_t *xlane;  // this lane's activation chunk of group 0 (256 B per group)
+    float lscale;          // t = 0: 2^14 (columns 0,1 = planes p3,p2), t = 1: 1 (columns 2,3 = planes p1,p0), else 0 (don't-care columns)
     int gsel;              // which of the two group sums this lane subtracts (t & 1)
 };
 TCE_DEVINL Lane1 make_lane1(const uint8_t *xs, int IC, int g, int t) {
     Lane1 L;
-    if (g == 2) {
-        L.xlane = xs + (size_t)IC * 2 + (size_t)t * 16;
-        L.xstride = 128;
-        L.xodd = 64;
-    } else {
-        L.xlane = xs + (size_t)(t * 2 + (g & 1)) * 16;
-        L.xstride = 256;
-        L.xodd = 128;
-    }
-    L.wa = (t == 0) ? 128 : (t == 1 ? 1 : 0);
-    L.wb = (t == 0) ? 1 : 0;
-    L.lscale = (t == 0) ? 128.f : (t == 1 ? 1.f : 0.f);
+    L.xlane = xs + (size_t)((g >> 1) & 1) * IC * 2 + (size_t)(t * 2 + (g & 1)) * 16;  // column g & 3 supplies plane 3 - (g & 3)
+    L.lscale = (t == 0) ? 16384.f : (t == 1 ? 1.f : 0.f);
     L.gsel = t & 1;
     return L;
 }
 // one (16 rows x 128 k) unit: wa/wb = the lane's 16 B of rows g / g+8; returns the lane's share of the two row sums
 TCE_DEVINL void unit1(const Lane1 &L, const uint4 wa, const uint4 wb, int G, float sAq, float sBq, int zAq, int zBq, const float *gx, const int *gsum,
                       float &totA, float &totB) {
-    const uint4 xe = *reinterpret_cast<const uint4 *>(L.xlane + (size_t)G * L.xstride);
-    const uint4 xo = *reinterpret_cast<const uint4 *>(L.xlane + (size_t)G * L.xstride + L.xodd);
+    const uint4 xe = *reinterpret_cast<const uint4 *>(L.xlane + (size_t)G * 256);
+    const uint4 xo = *reinterpret_cast<const uint4 *>(L.xlane + (size_t)G * 256 + 128);
     constexpr uint32_t ML = 0x0f0f0f0fu, MH = 0xf0f0f0f0u;
     int accL[4], accH[4];
     mma_m16n8k32_u8s8_z(accL, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xe.x, xe.y);
     mma_m16n8k32_u8s8_z(accH, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xo.x, xo.y);
     mma_m16n8k32_u8s8(accL, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xe.z, xe.w);
     mma_m16n8k32_u8s8(accH, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xo.z, xo.w);
-    // X = 2^14*hi + 2^7*mid + lo; odd slots carry 16 x nibble: exact integer group result sum_k q*X - z*sum_k X, held as a
-    // (hi,mid) part on t = 0 and a lo part on t = 1
+    // X = 2^21*p3 + 2^14*p2 + 2^7*p1 + p0; odd slots carry 16 x nibble: exact integer group result sum_k q*X - z*sum_k X, held as a
+    // (p3,p2) part on t = 0 (in units of 2^14) and a (p1,p0) part on t = 1
     const int sxv = gsum[2 * G + L.gsel];
     const float st = gx[G] * L.lscale;
-    const int vA = L.wa * (accL[0] + (accH[0] >> 4)) + L.wb * (accL[1] + (accH[1] >> 4)) - zAq * sxv;
-    const int vB = L.wa * (accL[2] + (accH[2] >> 4)) + L.wb * (accL[3] + (accH[3] >> 4)) - zBq * sxv;
+    const int vA = ((accL[0] + (accH[0] >> 4)) << 7) + (accL[1] + (accH[1] >> 4)) - zAq * sxv;
+    const int vB = ((accL[2] + (accH[2] >> 4)) << 7) + (accL[3] + (accH[3] >> 4)) - zBq * sxv;
     totA += (sAq * st) * (float)vA;
     totB += (sBq * st) * (float)vB;
 }
@@ -723,7 +717,7 @@ TCE_DEVINL void consume1(const KArgs &a, const Smem &sm, RingState &rs, RedState
             }
         }
         // ---- hand the tile partial to the epilogue warp (no consumer-to-consumer wait) ----
-        totA += __shfl_xor_sync(0xffffffffu, totA, 1);  // (hi, mid) share of t = 0 + lo share of t = 1
+        totA += __shfl_xor_sync(0xffffffffu, totA, 1);  // (p3, p2) share of t = 0 + (p1, p0) share of t = 1
         totB += __shfl_xor_sync(0xffffffffu, totB, 1);
         mbar_wait(&sm.red_empty[cs.rb], cs.rphase ^ 1);
         float *rbuf = sm.red + ((size_t)cs.rb * CW + cw) * 16;
@@ -794,39 +788,34 @@ TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState 
                     const uint32_t wbv[4] = {wb.x, wb.y, wb.z, wb.w};
                     const uint8_t *xp = sm.xs + (size_t)g * x_pitch + ((size_t)G * 16 + t) * 16;
                     // nibbles -> bytes: w & 0x0f0f0f0f = (n0,n2,n4,n6), (w>>4) & 0x0f0f0f0f = (n1,n3,n5,n7): 3 ALU ops per
-                    // 8 weights.  Two independent accumulator chains per activation plane (hi, mid, lo).
-                    const uint8_t *xl = sm.xs + (size_t)g * x_pitch + (size_t)a.IC * 2 + ((size_t)G * 16 + t) * 8;
-                    int ch[2][4], cm[2][4], cl[2][4];
+                    // 8 weights.  One accumulator set per activation plane (p3..p0).
+                    const uint8_t *xl = xp + (size_t)a.IC * 2;
+                    int c3[4], c2[4], c1[4], c0[4];
 #pragma unroll
-                    for (int e = 0; e < 2; e++)
-#pragma unroll
-                        for (int i = 0; i < 4; i++) ch[e][i] = cm[e][i] = cl[e][i] = 0;
+                    for (int i = 0; i < 4; i++) c3[i] = c2[i] = c1[i] = c0[i] = 0;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const uint4 xv = *reinterpret_cast<const uint4 *>(xp + j * 64);
-                        const uint2 xw = *reinterpret_cast<const uint2 *>(xl + j * 32);
+                        const uint4 xw = *reinterpret_cast<const uint4 *>(xl + j * 64);
                         const uint32_t a0 = wav[j] & 0x0f0f0f0fu, a2 = (wav[j] >> 4) & 0x0f0f0f0fu;
                         const uint32_t a1 = wbv[j] & 0x0f0f0f0fu, a3 = (wbv[j] >> 4) & 0x0f0f0f0fu;
-                        mma_m16n8k32_u8s8(ch[j & 1], a0, a1, a2, a3, xv.x, xv.y);
-                        mma_m16n8k32_u8s8(cm[j & 1], a0, a1, a2, a3, xv.z, xv.w);
-                        mma_m16n8k32_u8s8(cl[j & 1], a0, a1, a2, a3, xw.x, xw.y);
+                        mma_m16n8k32_u8s8(c3, a0, a1, a2, a3, xv.x, xv.y);
+                        mma_m16n8k32_u8s8(c2, a0, a1, a2, a3, xv.z, xv.w);
+                        mma_m16n8k32_u8s8(c1, a0, a1, a2, a3, xw.x, xw.y);
+                        mma_m16n8k32_u8s8(c0, a0, a1, a2, a3, xw.z, xw.w);
                     }
-                    // exact integer group result: sum_k q*X - z*sum_k X, X = 2^14*hi + 2^7*mid + lo, kept as a (hi,mid) part in units of
-                    // 2^7 and a lo part (the full integer does not fit 32 bits)
+                    // exact integer group result: sum_k q*X - z*sum_k X, X = 2^21*p3 + 2^14*p2 + 2^7*p1 + p0, kept as a (p3,p2) part in
+                    // units of 2^14 and a (p1,p0) part (the full integer does not fit 32 bits)
                     {
                         const int *gs0 = sm.gsum + ((2 * t) * a.NG + G) * 2, *gs1 = sm.gsum + ((2 * t + 1) * a.NG + G) * 2;
                         const float st0 = sm.gx[(2 * t) * a.NG + G], st1 = sm.gx[(2 * t + 1) * a.NG + G];
-                        auto comb = [](int h, int m, int l, int z, const int *gs) {
-                            return 128.f * (float)((h << 7) + m - z * gs[0]) + (float)(l - z * gs[1]);
+                        auto comb = [](int h3, int h2, int l1, int l0, int z, const int *gs) {
+                            return 16384.f * (float)((h3 << 7) + h2 - z * gs[0]) + (float)((l1 << 7) + l0 - z * gs[1]);
                         };
-                        const float vA0 = comb(ch[0][0] + ch[1][0], cm[0][0] + cm[1][0], cl[0][0] + cl[1][0], zAq, gs0);
-                        const float vA1 = comb(ch[0][1] + ch[1][1], cm[0][1] + cm[1][1], cl[0][1] + cl[1][1], zAq, gs1);
-                        const float vB0 = comb(ch[0][2] + ch[1][2], cm[0][2] + cm[1][2], cl[0][2] + cl[1][2], zBq, gs0);
-                        const float vB1 = comb(ch[0][3] + ch[1][3], cm[0][3] + cm[1][3], cl[0][3] + cl[1][3], zBq, gs1);
-                        tot[0] += (sAq * st0) * vA0;
-                        tot[1] += (sAq * st1) * vA1;
-                        tot[2] += (sBq * st0) * vB0;
-                        tot[3] += (sBq * st1) * vB1;
+                        tot[0] += (sAq * st0) * comb(c3[0], c2[0], c1[0], c0[0], zAq, gs0);
+                        tot[1] += (sAq * st1) * comb(c3[1], c2[1], c1[1], c0[1], zAq, gs1);
+                        tot[2] += (sBq * st0) * comb(c3[2], c2[2], c1[2], c0[2], zBq, gs0);
+                        tot[3] += (sBq * st1) * comb(c3[3], c2[3], c1[3], c0[3], zBq, gs1);
                     }
                 }
             }

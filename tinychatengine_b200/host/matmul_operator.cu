@@ -4,8 +4,20 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <cuda_runtime.h>
+
 #include "../../include/tce_b200.h"
+// Built against this package's mirror of the operator header by default; the drop-in proof (oracle/Makefile, target callsites) builds
+// the same file against the reference's own kernels/matmul.h (-DTCE_REFERENCE_MATMUL_H='"<path>"' -DQM_CUDA) so that the reference's
+// unchanged call sites and these definitions share ONE declaration of matmul::MatmulOperator.
+#ifdef TCE_REFERENCE_MATMUL_H
+#include TCE_REFERENCE_MATMUL_H
+struct tce_ctx;
+extern "C" tce_ctx *tce_host_ctx(void);
+extern "C" void tce_host_set_stream(void *cuda_stream);
+#else
 #include "matmul.h"
+#endif
 
 static tce_ctx *g_ctx = nullptr;
 
@@ -19,6 +31,62 @@ extern "C" tce_ctx *tce_host_ctx(void) {
     return g_ctx;
 }
 extern "C" void tce_host_set_stream(void *s) { tce_ctx_set_stream(tce_host_ctx(), s); }
+
+// ---- operands that live in plain host memory ------------------------------------------------------------------------------------
+// The reference's CUDA build keeps the W8A8 operators' buffers in posix_memalign host memory (llm/src/utils.cc:205-220; only the W4
+// path uses cudaMallocManaged, cuda/utils.cu:93-96) and its "CUDA" int8 kernels are host loops (kernels/cuda/matmul_ref_int8.cc).  A
+// drop-in therefore has to accept host pointers: operands the device cannot reach are staged through grow-only device scratch (one
+// slot per operand role) and results are copied back before the call returns, which also preserves the synchronous contract of those
+// operators.  Device-reachable pointers (cudaMalloc / cudaMallocManaged / pinned) are passed through untouched.
+namespace {
+struct Scratch {
+    void *dev = nullptr;
+    size_t cap = 0;
+};
+Scratch g_scratch[4];  // 0 A, 1 B, 2 bias, 3 C
+
+bool device_reachable(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged || (at.type == cudaMemoryTypeHost && at.devicePointer != nullptr);
+}
+void *scratch(int slot, size_t bytes) {
+    Scratch &s = g_scratch[slot];
+    if (s.cap < bytes) {
+        if (s.dev) cudaFree(s.dev);
+        if (cudaMalloc(&s.dev, bytes) != cudaSuccess) {
+            fprintf(stderr, "libtce_b200: staging allocation of %zu bytes failed\n", bytes);
+            abort();
+        }
+        s.cap = bytes;
+    }
+    return s.dev;
+}
+// input operand: device-reachable pointer to the same bytes
+const void *in_dev(const void *p, size_t bytes, int slot) {
+    if (!p || device_reachable(p)) return p;
+    void *d = scratch(slot, bytes);
+    if (cudaMemcpy(d, p, bytes, cudaMemcpyHostToDevice) != cudaSuccess) abort();
+    return d;
+}
+struct OutStage {
+    void *host = nullptr, *dev = nullptr;
+    size_t bytes = 0;
+    void *begin(void *p, size_t n, int slot) {
+        if (device_reachable(p)) return p;
+        host = p;
+        bytes = n;
+        dev = scratch(slot, n);
+        return dev;
+    }
+    void finish() {  // results in the caller's buffer when the call returns, like the host loops this replaces
+        if (host && cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) abort();
+    }
+};
+}  // namespace
 
 static void must(int rc, const char *what) {
     if (rc != TCE_OK) {
@@ -69,9 +137,14 @@ void MatmulOperator::mat_mul_accelerator_int4_fast_no_offset(const struct matmul
 static void w8(const struct matmul_params *p, int variant, int batch, const void *bias, void *C, const char *who) {
     const int M = p->A.row, K = p->A.column, N = p->B.column;
     assert(p->A.column == p->B.row && p->C.row == M && p->C.column == N);
-    must(tce_w8a8_matmul(tce_host_ctx(), variant, batch, p->A.int8_data_ptr, p->B.int8_data_ptr, bias, C, M, N, K, p->alpha, p->beta,
-                         p->C.qparams.q_min, p->C.qparams.q_max),
-         who);
+    const size_t cel = (variant < 2) ? 1 : 4, bel = (variant == 0) ? 1 : 4;
+    const void *A = in_dev(p->A.int8_data_ptr, (size_t)M * K, 0);
+    const void *B = in_dev(p->B.int8_data_ptr, (size_t)(batch ? M : 1) * N * K, 1);
+    const void *bs = bias ? in_dev(bias, (size_t)N * bel, 2) : nullptr;
+    OutStage out;
+    void *Cd = out.begin(C, (size_t)M * N * cel, 3);
+    must(tce_w8a8_matmul(tce_host_ctx(), variant, batch, A, B, bs, Cd, M, N, K, p->alpha, p->beta, p->C.qparams.q_min, p->C.qparams.q_max), who);
+    out.finish();
 }
 void MatmulOperator::mat_mul_accelerator_int8_fast_2x2_32unroll(const struct matmul_params *p) {
     w8(p, 0, 0, p->bias.int8_data_ptr, p->C.int8_data_ptr, "int8_fast_2x2_32unroll");
