@@ -1,15 +1,17 @@
 #!/usr/bin/env python
-"""bench.py -- Llama-3-8B AWQ-INT4 batch-1 decode on B200 (BASELINE.json configs[1]), the reference CPU path beside it.
+"""bench.py -- Llama-3-8B AWQ-INT4 batch-1 decode on B200 (BASELINE.json configs[1] at N = 1, configs[4] = tensor-parallel decode at
+N > 1), the reference's own CPU path beside it.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own AVX CPU path (rank 0 only)
 
-A "step" is one decode token of the synthetic Llama-3-8B (random AWQ-INT4 weights in the reference's QM_CUDA
-layout, random-filled fp16 KV cache).  The K timed steps are spread evenly over context lengths 1 -> max_ctx, so
-ms_per_step estimates the mean cost per token of a 1 -> 4096 generation.  `value` = tokens/s with token ids already
-in HBM (tce_llama_decode); `e2e` = the same through the host entry point (tce_llama_decode_host): token id/position
-copied from pinned host memory and the fp32 logits row + greedy token copied back, every step, inside the timed
-region.  One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the roofline arithmetic.
+A "step" is one decode token of the synthetic Llama-3-8B (random AWQ-INT4 weights in the reference's QM_CUDA layout, random-filled
+fp16 KV cache).  The K timed steps are spread evenly over context lengths 1 -> max_ctx, so ms_per_step estimates the mean cost per
+token of a 1 -> 4096 generation.  `value` = tokens/s with token ids already in HBM (tce_llama_decode); `e2e` = the same through the host
+entry point (tce_llama_decode_host): token id/position copied from pinned host memory and the fp32 logits row + greedy token copied
+back, every step, inside the timed region.  N > 1 defaults to tensor-parallel decode of ONE sequence (column/row sharded linears,
+two all-reduces per layer over NVLink peer memory inside the persistent kernel); `tp_parity_rel_err` compares its logits with a
+single-GPU run of the same weights before timing.  One JSON line on stdout (rank 0).  See DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
@@ -29,16 +31,18 @@ UNIT = "tok/s"
 
 
 def load_traffic():
-    """dram__bytes_read + dram__bytes_write per GEMV launch from the committed ncu capture (tools/ncu_launch_summary.py); None if absent."""
-    p = Path(__file__).resolve().parent / "profiles" / "roofline_traffic.json"
+    """dram__bytes_read + dram__bytes_write of one decode_persistent_kernel launch from this round's `ncu --set full` capture
+    (profiles/roofline_traffic.json, written by tools/ncu_launch_summary.py); None if absent."""
+    p = ROOT / "profiles" / "roofline_traffic.json"
     try:
-        return json.loads(p.read_text()).get("dram_bytes_per_launch")
+        d = json.loads(p.read_text())
+        return d.get("dram_bytes_per_launch"), d.get("source")
     except Exception:
-        return None
+        return None, None
 
 
 def workload_config(geom, args, world: int, tp: bool) -> dict:
-    """The `config` object both arms report: names the workload, no model-architecture keys."""
+    """The `config` object both arms report (identical keys and values): names the workload, no model-architecture keys."""
     return {
         "workload": (f"{geom.name} AWQ-INT4 g128 batch-1 decode, timed steps spread over ctx 1->{args.max_ctx}" if args.ctx < 0
                      else f"{geom.name} AWQ-INT4 g128 batch-1 decode at ctx {args.ctx}"),
@@ -85,7 +89,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv:
@@ -107,34 +111,41 @@ def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return d, float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return {}, 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's AVX W4A8 path (oracle/_ref/libtce_ref_avx.so) on the host cores
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_decode(geom, budget_s: float = 20.0):
-    """Time Linear_FP_int4::forward's kernel (mat_mul_accelerator_int8_int4_fast_no_offset, QM_x86 g32 format) over
-    the linears of ONE decoder layer + lm_head at `geom` shapes with all host threads, extrapolate to a token:
-    t_token = L * t_layer + t_lm_head.  Returns dict(value tok/s, cores, kind, sample)."""
-    import numpy as np
+class CpuReferenceDecode:
+    """The linears of one decode token driven through the reference's own CPU kernel (Linear_FP_int4::forward's
+    mat_mul_accelerator_int8_int4_fast_no_offset, QM_x86 g32 format, oracle/ref_shim.cc fills matmul_params like
+    llm/src/ops/linear.cc:171-236) with all host threads.  `token()` runs EVERY linear of a token once -- num_layers x (q k v o gate up
+    down) + lm_head -- cycling over `distinct` separately allocated layers so that the weights do not stay cache resident; attention
+    and norms are not included (they are < 1 % of the reference's CPU time at batch 1)."""
 
-    from oracle import capi
+    def __init__(self, geom, distinct: int = 4):
+        import numpy as np
 
-    cores = os.cpu_count() or 1
-    if capi.ref_available("avx"):
-        kind = "reference"
-        X = capi.ref("avx")
-    else:
-        kind = "port"
-        X = None
-    hd = geom.head_dim
-    E, F = geom.embed_dim, geom.hidden_dim
-    layer_shapes = [(geom.num_heads * hd, E), (geom.num_kv_heads * hd, E), (geom.num_kv_heads * hd, E), (E, geom.num_heads * hd), (F, E), (F, E), (E, F)]
-    rng = np.random.default_rng(0)
+        from oracle import capi
 
-    def make(oc, ic):
+        self.np, self.capi, self.geom = np, capi, geom
+        self.cores = os.cpu_count() or 1
+        if capi.ref_available("avx"):
+            self.kind, self.X = "reference", capi.ref("avx")
+        else:
+            self.kind, self.X, self.cores = "port", None, 1
+        hd, E, F = geom.head_dim, geom.embed_dim, geom.hidden_dim
+        shapes = [(geom.num_heads * hd, E), (geom.num_kv_heads * hd, E), (geom.num_kv_heads * hd, E), (E, geom.num_heads * hd), (F, E), (F, E), (E, F)]
+        rng = np.random.default_rng(0)
+        self.distinct = max(1, min(distinct, geom.num_layers))
+        self.layers = [[(self._make(oc, ic, rng), oc, ic) for oc, ic in shapes] for _ in range(self.distinct)]
+        self.lm = (self._make(geom.vocab_size, E, rng), geom.vocab_size, E)
+        self.token()  # warm-up (also creates the reference's static thread pool with `cores` threads)
+
+    def _make(self, oc, ic, rng):
+        np, capi = self.np, self.capi
         B = capi.aligned_empty((oc, ic // 2), np.uint8)
         B[:] = rng.integers(0, 256, (oc, ic // 2), dtype=np.uint8)
         S = capi.aligned_empty((oc, ic // 32), np.float32)
@@ -146,41 +157,35 @@ def cpu_reference_decode(geom, budget_s: float = 20.0):
         xs = capi.aligned_empty((ic // 32,), np.float32)
         return A, B, S, Cc, xi8, xs
 
-    def run(t, oc, ic):
+    def _run(self, t, oc, ic):
         A, B, S, Cc, xi8, xs = t
-        if X is not None:
-            X.ref_w4a8_avx(A.ctypes.data, B.ctypes.data, S.ctypes.data, Cc.ctypes.data, xi8.ctypes.data, xs.ctypes.data, 1, ic, oc, cores)
+        if self.X is not None:
+            self.X.ref_w4a8_avx(A.ctypes.data, B.ctypes.data, S.ctypes.data, Cc.ctypes.data, xi8.ctypes.data, xs.ctypes.data, 1, ic, oc, self.cores)
         else:  # oracle port of the naive path (scalar, 1 core): only when oracle/_ref could not be built
-            capi.naive_mat_mul_int4(np.asarray(A), np.asarray(B), np.asarray(S), 8.0, 32)
+            self.capi.naive_mat_mul_int4(self.np.asarray(A), self.np.asarray(B), self.np.asarray(S), 8.0, 32)
 
-    if X is None:
-        cores = 1
-    mats = [(make(oc, ic), oc, ic) for oc, ic in layer_shapes]
-    for t, oc, ic in mats:
-        run(t, oc, ic)  # warm-up (also creates the reference's static thread pool with `cores` threads)
+    def token(self) -> float:
+        t0 = time.perf_counter()
+        for l in range(self.geom.num_layers):
+            for t, oc, ic in self.layers[l % self.distinct]:
+                self._run(t, oc, ic)
+        self._run(*self.lm)
+        return time.perf_counter() - t0
+
+    def describe(self, n):
+        g = self.geom
+        return (f"{n} full tokens: every linear of a {g.name} decode step ({g.num_layers} layers x 7 + lm_head) through the reference's W4A8 AVX kernel "
+                f"(g32 CPU format), {self.distinct} distinct layers' weights cycled; attention/norms not included")
+
+
+def cpu_baseline(geom, budget_s: float):
+    ref = CpuReferenceDecode(geom)
+    times = []
     t0 = time.perf_counter()
-    reps = 0
-    while True:
-        for t, oc, ic in mats:
-            run(t, oc, ic)
-        reps += 1
-        if time.perf_counter() - t0 > budget_s * 0.6 or reps >= 20:
-            break
-    t_layer = (time.perf_counter() - t0) / reps
-    lm = make(geom.vocab_size, E)
-    run(lm, geom.vocab_size, E)
-    t1 = time.perf_counter()
-    lm_reps = 0
-    while True:
-        run(lm, geom.vocab_size, E)
-        lm_reps += 1
-        if time.perf_counter() - t1 > budget_s * 0.3 or lm_reps >= 10:
-            break
-    t_lm = (time.perf_counter() - t1) / lm_reps
-    t_token = geom.num_layers * t_layer + t_lm
-    return {"value": 1.0 / t_token, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"linears of 1 decoder layer x{reps} + lm_head x{lm_reps} at {geom.name} shapes (W4A8 g32, the reference's CPU format), "
-                      f"extrapolated t_token = {geom.num_layers}*t_layer + t_lm_head = {t_token * 1e3:.1f} ms; attention/norms not included"}
+    while not times or (time.perf_counter() - t0 < budget_s and len(times) < 16):
+        times.append(ref.token())
+    med = sorted(times)[len(times) // 2]
+    return {"value": 1.0 / med, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.describe(len(times))}
 
 
 def run_reference(args):
@@ -190,24 +195,87 @@ def run_reference(args):
     from tinychatengine_b200.llama import GEOMETRIES
 
     geom = GEOMETRIES[args.model]
-    samples = []
-    for _ in range(max(1, args.warmup // 3)):
-        cpu_reference_decode(geom, budget_s=4.0)
+    ref = CpuReferenceDecode(geom)
+    for _ in range(args.warmup):
+        ref.token()
     t0 = time.perf_counter()
-    for _ in range(max(1, min(args.steps, 3))):
-        samples.append(cpu_reference_decode(geom, budget_s=max(4.0, 60.0 / max(1, min(args.steps, 3)))))
-    best = max(samples, key=lambda d: d["value"])
-    med = sorted(s["value"] for s in samples)[len(samples) // 2]
-    cfg = workload_config(geom, args, 1, False)  # the same workload as our arm; the reference has no multi-GPU path: rank 0's host cores
-    cfg["reference_path"] = "the reference's AVX W4A8 kernels (oracle/_ref, compiled in place) on all host threads; each step = a bounded sample"
-    cfg["sampled_steps"] = len(samples)
-    line = {"impl": "reference", "metric": METRIC, "value": med, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 / med, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "w4a8 (int8 act x int4 weight, fp32 acc)",
-            "data": "synthetic", "config": cfg,
-            "cpu_baseline": dict(best, value=med),
-            "e2e": {"value": med, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
-            "wall_s": time.perf_counter() - t0}
+    times = [ref.token() for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    tok_s = args.steps / sum(times)
+    tp = args.gpus > 1 and args.parallel == "tp"
+    line = {"impl": "reference", "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
+            "dtype": "w4a8 (int8 act x int4 weight, fp32 acc)", "data": "synthetic",
+            "config": workload_config(geom, args, args.gpus, tp),  # the same workload as our arm; the reference has no GPU path here: rank 0's host cores
+            "reference_path": "the reference's AVX W4A8 kernels (oracle/_ref, compiled in place) on all host threads; each step = one full token's linears",
+            "cpu_baseline": {"value": tok_s, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.describe(args.steps)},
+            "e2e": {"value": tok_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, "wall_s": wall}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# secondary configs measured in the same run (BASELINE.json configs[2], configs[3]) and the reference's CUDA kernel on this GPU
+# ------------------------------------------------------------------------------------------------------------------
+def gpu_reference_gemv(model, geom, dev):
+    """The reference's own gemv_kernel_g128 (kernels/cuda/gemv_cuda.cu, compiled unchanged for sm_100a into oracle/_ref) over every
+    GEMV of one decode step on the model's real weights: the GPU-side baseline SURVEY.md 8(d) config 2 names."""
+    import torch
+
+    from oracle import capi
+
+    if not capi.ref_available("cuda"):
+        return None
+    L = capi.ref_cuda()
+    hd = geom.head_dim
+    xs = {ic: torch.randn((1, ic), device=dev).to(torch.float16) for ic in (geom.embed_dim, geom.num_heads * hd, geom.hidden_dim)}
+    ys = {}
+
+    def run_all():
+        for l in range(geom.num_layers):
+            T = model.layer_tensors(l)
+            for name in ("q", "k", "v", "o", "gate", "up", "down"):
+                w, z, s = T[name]
+                oc, ic = w.shape[0], w.shape[1] * 8
+                y = ys.setdefault(oc, torch.empty((1, oc), dtype=torch.float16, device=dev))
+                L.ref_cuda_gemv(xs[ic].data_ptr(), w.data_ptr(), z.data_ptr(), s.data_ptr(), y.data_ptr(), 1, ic, oc)
+        w, z, s = model.tensors[-1]
+        oc, ic = w.shape[0], w.shape[1] * 8
+        y = ys.setdefault(oc, torch.empty((1, oc), dtype=torch.float16, device=dev))
+        L.ref_cuda_gemv(xs[ic].data_ptr(), w.data_ptr(), z.data_ptr(), s.data_ptr(), y.data_ptr(), 1, ic, oc)
+
+    ds = torch.cuda.default_stream(dev)  # the reference launches on the legacy default stream
+    torch.cuda.synchronize(dev)
+    with torch.cuda.stream(ds):
+        run_all()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record(ds)
+        for _ in range(reps):
+            run_all()
+        e1.record(ds)
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    return {"kernel": "reference gemv_kernel_g128 (kernels/cuda/gemv_cuda.cu:140-194) built for sm_100a, all GEMVs of one step, eager launches",
+            "ms_per_token_gemvs_only": ms, "tok_s_gemvs_only": 1e3 / ms}
+
+
+def run_extras(ctx, dev, stream, peaks):
+    """configs[3] (Llama-2-13B 2048-token prefill) and configs[2] (Llama-2-7B-shaped W8A8 decoder layer) on this GPU, CUDA events."""
+    out = {}
+    try:
+        from tools.prefill_bench import prefill_once
+
+        out["prefill_13b_2048"] = prefill_once(ctx, dev, stream, "llama2-13b", 2048, peaks)
+    except Exception as ex:  # a secondary number must never hide the headline
+        out["prefill_13b_2048"] = {"error": repr(ex)}
+    try:
+        from tools.w8a8_layer_bench import w8a8_layer
+
+        out["w8a8_7b"] = w8a8_layer(ctx, dev, stream, peaks)
+    except Exception as ex:
+        out["w8a8_7b"] = {"error": repr(ex)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -229,25 +297,10 @@ def run_ours(args):
 
     geom = LL.GEOMETRIES[args.model]
     stream = torch.cuda.Stream(dev)
+    tp = world > 1 and args.parallel == "tp"
+    extra = {}
     with torch.cuda.stream(stream):
         ctx = Context(local_rank, stream)
-        tp = world > 1 and args.parallel == "tp"
-        if tp:
-            # tensor-parallel decode of ONE sequence: every rank holds a 1/N shard of every matrix (random shards of the
-            # right shapes), all-reduce over NVLink peer memory inside the GEMV kernels
-            if geom.num_kv_heads % world or geom.num_heads % world:
-                raise SystemExit(f"{geom.name}: heads do not split over {world} ranks")
-            gl = LL.LlamaGeometry(geom.name, geom.num_layers, geom.num_heads // world, geom.num_kv_heads // world, geom.embed_dim,
-                                  geom.hidden_dim // world, geom.vocab_size // world, geom.rms_eps, geom.rope_theta, geom.head_dim)
-            model = LL.LlamaModel(ctx, gl, max_ctx=args.max_ctx, seed=1234 + rank, tp_rank=rank, tp_size=world)
-            model.tp_connect()
-        else:
-            gl = geom
-            model = LL.LlamaModel(ctx, geom, max_ctx=args.max_ctx, seed=1234 + rank)
-        # random-filled KV cache so every context length is "already generated"
-        for l in range(geom.num_layers):
-            model.kv_cache(l, 0).normal_(0, 0.5)
-            model.kv_cache(l, 1).normal_(0, 0.5)
         K, W = args.steps, args.warmup
         gen = torch.Generator(device="cpu")
         gen.manual_seed(99)
@@ -256,100 +309,150 @@ def run_ours(args):
         pos_list = [args.max_ctx // 2] * W + [min(args.max_ctx - 1, int(round(i * (args.max_ctx - 1) / max(1, K - 1)))) for i in range(K)]
         if args.ctx >= 0:
             pos_list = [args.ctx] * (W + K)
-        tokpos_all = torch.tensor(list(zip(toks, pos_list)), dtype=torch.int32, device=dev)
-        tokpos = torch.zeros(2, dtype=torch.int32, device=dev)
-        logits_pinned = torch.empty(gl.vocab_size, dtype=torch.float32).pin_memory()
 
         def barrier():
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize(dev)
 
-        # ---- value: token ids resident in HBM ----
-        for i in range(W):
-            tokpos.copy_(tokpos_all[i])
-            model.decode(tokpos)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clk:
-            e0.record(stream)
-            for i in range(W, W + K):
+        def fill_cache(m, g):
+            # random-filled KV cache so every context length is "already generated"
+            for l in range(g.num_layers):
+                m.kv_cache(l, 0).normal_(0, 0.5)
+                m.kv_cache(l, 1).normal_(0, 0.5)
+
+        def timed(m, vocab_local):
+            """(device-resident ms, host entry point ms, clocks) over the K timed steps of model m"""
+            tokpos_all = torch.tensor(list(zip(toks, pos_list)), dtype=torch.int32, device=dev)
+            tokpos = torch.zeros(2, dtype=torch.int32, device=dev)
+            logits_pinned = torch.empty(vocab_local, dtype=torch.float32).pin_memory()
+            for i in range(W):
                 tokpos.copy_(tokpos_all[i])
-                model.decode(tokpos)
-            e1.record(stream)
+                m.decode(tokpos)
             barrier()
-        ms_dev = e0.elapsed_time(e1)
-        # ---- e2e: host entry point, H2D + D2H inside ----
-        for i in range(W):
-            model.decode_host(toks[i], pos_list[i], logits_pinned)
-        barrier()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record(stream)
-        for i in range(W, W + K):
-            model.decode_host(toks[i], pos_list[i], logits_pinned)
-        e3.record(stream)
-        barrier()
-        ms_e2e = e2.elapsed_time(e3)
-        # ---- dominant kernel: the W4A16 GEMV launches of one step, timed alone with events ----
-        if tp:
-            n_gemv, ms_gemv_step = 4 * geom.num_layers + 1, None  # the sharded GEMVs wait for their peers: not timed alone
-        else:
-            n_gemv = ctx.L.tce_llama_enqueue_gemvs(model.h)  # eager once: modules loaded, attributes set
-            barrier()
-            reps = 20
-            # replayed from a CUDA graph like the real step (plain stream launches would add ~2 us of launch gap per kernel)
-            gemv_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gemv_graph, stream=stream):
-                for _ in range(reps):
-                    ctx.L.tce_llama_enqueue_gemvs(model.h)
-            with torch.cuda.stream(stream):
-                gemv_graph.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with ClockSampler(local_rank) as clk:
+                e0.record(stream)
+                for i in range(W, W + K):
+                    tokpos.copy_(tokpos_all[i])
+                    m.decode(tokpos)
+                e1.record(stream)
                 barrier()
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                g0.record(stream)
-                gemv_graph.replay()
-                g1.record(stream)
+            ms_dev = e0.elapsed_time(e1)
+            for i in range(W):
+                m.decode_host(toks[i], pos_list[i], logits_pinned)
             barrier()
-            ms_gemv_step = g0.elapsed_time(g1) / reps
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record(stream)
+            for i in range(W, W + K):
+                m.decode_host(toks[i], pos_list[i], logits_pinned)
+            e3.record(stream)
+            barrier()
+            return ms_dev, e2.elapsed_time(e3), clk.summary()
+
+        if tp:
+            # tensor-parallel decode of ONE sequence: every rank generates the same full weights (same seed) and keeps its 1/N shard
+            if geom.num_kv_heads % world or geom.num_heads % world or (geom.hidden_dim // world) % 128:
+                raise SystemExit(f"{geom.name}: does not split over {world} ranks on head / 128-channel group boundaries")
+            Wfull = LL.make_random_weights(geom, dev, seed=1234)
+            Wl, gl = LL.shard_weights(Wfull, geom, rank, world)
+            model = LL.LlamaModel(ctx, gl, max_ctx=args.max_ctx, weights=Wl, tp_rank=rank, tp_size=world)
+            model.tp_connect()
+            # ---- parity: 4 steps against a single-GPU run of the same weights (rank 0), before any timing ----
+            ptoks, ppos = [11, 4242, 77777, 5], [0, 1, 2, 3]
+            lg_local = torch.empty(gl.vocab_size, dtype=torch.float32)
+            full_logits = []
+            for tkn, ps in zip(ptoks, ppos):
+                model.decode_host(tkn, ps, lg_local)
+                shards = [torch.empty(gl.vocab_size, dtype=torch.float32, device=dev) for _ in range(world)]
+                dist.all_gather(shards, lg_local.to(dev))
+                full_logits.append(torch.cat(shards).cpu())
+            single = LL.LlamaModel(ctx, geom, max_ctx=args.max_ctx, weights=Wfull) if (rank == 0 or args.replicas_too) else None
+            parity = None
+            if rank == 0:
+                lg = torch.empty(geom.vocab_size, dtype=torch.float32)
+                parity = 0.0
+                for (tkn, ps), got in zip(zip(ptoks, ppos), full_logits):
+                    single.decode_host(tkn, ps, lg)
+                    parity = max(parity, float((got - lg).abs().max() / lg.abs().max()))
+                extra["tp_parity_rel_err"] = parity
+                extra["tp_parity_note"] = "max |logits_tp - logits_1gpu| / max |logits_1gpu| over 4 decode steps of the same weights (rank 0 runs the single-GPU model)"
+            fill_cache(model, gl)
+            ms_dev, ms_e2e, clocks = timed(model, gl.vocab_size)
+            if args.replicas_too:
+                fill_cache(single, geom)
+                r_dev, _, _ = timed(single, geom.vocab_size)
+                rt = torch.tensor([r_dev], dtype=torch.float64, device=dev)
+                dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+                extra["replicas_tok_s"] = world * K / (rt.item() * 1e-3)
+            if single is not None:
+                single.close()
+            vocab_local = gl.vocab_size
+        else:
+            gl = geom
+            model = LL.LlamaModel(ctx, geom, max_ctx=args.max_ctx, seed=1234 + rank)
+            fill_cache(model, geom)
+            ms_dev, ms_e2e, clocks = timed(model, geom.vocab_size)
+            vocab_local = geom.vocab_size
+        kernels_per_step = model.kernels_per_step
+        if rank == 0 and world == 1 and not args.no_extras:
+            peaks, _, _ = load_peaks()
+            try:
+                extra["gpu_reference"] = gpu_reference_gemv(model, geom, dev)
+            except Exception as ex:
+                extra["gpu_reference"] = {"error": repr(ex)}
+        model.close()
+        if rank == 0 and world == 1 and not args.no_extras:
+            extra.update(run_extras(ctx, dev, stream, peaks))
 
     times = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = times.tolist()
     if rank == 0:
-        peak, peak_src = load_peaks()
+        _, peak, peak_src = load_peaks()
         wbytes = LL.weight_bytes_per_token(geom)
         mean_ctx = sum(pos_list[W:]) / K
         kvbytes = LL.kv_bytes_per_token(geom, int(mean_ctx))
-        seqs = 1 if tp else world
+        seqs = 1 if (tp or world == 1) else world
         tok_s = seqs * K / (ms_dev * 1e-3)
         e2e_tok_s = seqs * K / (ms_e2e * 1e-3)
-        gemv_gbs = None if tp else wbytes / (ms_gemv_step * 1e-3) / 1e9
+        per_gpu_bytes = (wbytes + kvbytes) / (world if tp else 1)
+        achieved = per_gpu_bytes / (ms_dev / K * 1e-3) / 1e9
+        traffic, traffic_src = load_traffic()
+        persistent = kernels_per_step == 1
         line = {
             "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
             "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
-            "dtype": "w4a16 (int4 weights; activations fp16 -> 15-bit block fixed point; int32 accumulate)",
+            "dtype": "w4a16 (int4 weights; activations fp16 -> 22-bit block fixed point, three int8 planes; int32 accumulate)",
             "data": "synthetic",
-            "config": dict(workload_config(geom, args, world, tp), mean_ctx=mean_ctx,
-                           l2="inputs larger than L2: 3.9 GB of weights stream per step vs 126 MB L2", pdl=bool(int(os.environ.get("TCE_USE_PDL", "1")))),
-            "clocks": clk.summary(),
-            "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 12, "d2h_bytes_per_step": gl.vocab_size * 4 + 4},
-            "gpu_launches": K * model.kernels_per_step,
-            "roofline": {"bound": "hbm", "kernel": f"w4a16_gemv_kernel<1> ({n_gemv} launches/step: 4 per layer + lm_head)",
-                         "achieved": gemv_gbs, "peak": peak, "unit": "GB/s", "frac": None if tp else gemv_gbs / peak, "traffic": load_traffic(), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": wbytes / n_gemv, "avg_launch_us": None if tp else ms_gemv_step * 1e3 / n_gemv,
-                         "step": {"bytes_per_token": wbytes + kvbytes, "achieved": (wbytes + kvbytes) / (ms_dev / K * 1e-3) / 1e9,
-                                  "frac": (wbytes + kvbytes) / (ms_dev / K * 1e-3) / 1e9 / peak}},
+            "config": workload_config(geom, args, world, tp),
+            "mean_ctx": mean_ctx,
+            "l2": "inputs larger than L2: 3.9 GB of weights stream per step vs 126 MB L2",
+            "clocks": clocks,
+            "e2e": {"value": e2e_tok_s, "unit": UNIT, "h2d_bytes_per_step": 12, "d2h_bytes_per_step": vocab_local * 4 + 4},
+            "gpu_launches": K * kernels_per_step,
+            "roofline": {"bound": "hbm",
+                         "kernel": ("decode_persistent_kernel (1 launch per step: every weight, scale/zero and KV byte of the token streams through its TMA ring)"
+                                    if persistent else f"{kernels_per_step} kernels per step (kernel-per-op graph path)"),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic if (persistent and world == 1) else None, "traffic_source": traffic_src if (persistent and world == 1) else None,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": per_gpu_bytes / (1 if persistent else kernels_per_step),
+                         "avg_launch_us": ms_dev / K * 1e3 / kernels_per_step,
+                         "note": "per GPU; algorithmic bytes = packed weights + fp16 scales + 4-bit zeros (SURVEY.md 8d: 3.899 GB) + KV rows at the mean context"
+                                 + (", divided by the tensor-parallel degree" if tp else "")},
         }
+        line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_reference_decode(geom, budget_s=args.cpu_budget)
+                line["cpu_baseline"] = cpu_baseline(geom, args.cpu_budget)
             except Exception as ex:  # the baseline must never hide the GPU number
                 line["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)
-    model.close()
     ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -362,17 +465,19 @@ def main():
     ap.add_argument("--model", default="llama3-8b")
     ap.add_argument("--max-ctx", type=int, default=4096)
     ap.add_argument("--ctx", type=int, default=-1, help="fixed context length for every step (default: sweep 1 -> max_ctx)")
-    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    # N > 1 default = one independent batch-1 sequence per GPU (no data-path collective, weak scaling): the throughput configuration.
-    # --parallel tp = tensor-parallel decode of ONE sequence over NVLink peer memory (BASELINE config 5, strong scaling): implemented
-    # and parity-tested at 2 GPUs, measured 464 / 427 tok/s at 2 / 4 GPUs vs 566 on one (profiles/README.md) -- batch-1 latency is
-    # bound by per-launch cost, not bandwidth, so sharding the weights does not pay yet; not verified at 8 GPUs this round.
-    ap.add_argument("--parallel", default="replicas", choices=["tp", "replicas"], help="N>1: one sequence per GPU (default), or tensor-parallel decode of one sequence")
+    ap.add_argument("--no-extras", action="store_true", help="skip gpu_reference / prefill_13b_2048 / w8a8_7b (N = 1 only)")
+    # N > 1 default = tensor-parallel decode of ONE sequence (BASELINE config 5, strong scaling); "replicas" = one independent batch-1
+    # sequence per GPU (no data-path collective, weak scaling), also reported as `replicas_tok_s` beside the tensor-parallel value
+    ap.add_argument("--parallel", default="tp", choices=["tp", "replicas"])
+    ap.add_argument("--no-replicas", dest="replicas_too", action="store_false", help="N>1 tp: skip the secondary replicas measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
+        if args.steps == 128:
+            args.steps = 8  # a full token costs seconds on the host: keep the default invocation within minutes
         run_reference(args)
     else:
         run_ours(args)

@@ -138,6 +138,21 @@ def test_reference_cuda_kernel_on_this_gpu(ctx, oc, ic):
     assert_w4_close(y.float().cpu().numpy(), yr.float().cpu().numpy(), "this kernel vs reference CUDA kernel")
 
 
+@pytest.mark.parametrize("oc,ic,m", [(64, 1024, 1), (48, 4096, 2), (256, 192, 1)])
+def test_group_64_path(ctx, oc, ic, m):
+    """gemv_kernel_g64 (kernels/cuda/gemv_cuda.cu:68-123): one scale / zero per 64 channels, zeros_width(IC, 64) padded rows."""
+    from oracle import capi
+    from tinychatengine_b200.runtime import random_w4
+
+    dev = torch.device("cuda", 0)
+    w, z, s = random_w4(oc, ic, dev, 9 + oc, random_zeros=True, group=64)
+    x = torch.randn((m, ic), device=dev).to(torch.float16)
+    y = ctx.w4a16_gemv(x, w, z, s, group=64)
+    torch.cuda.synchronize()
+    ref = capi.w4a16_gemv(x.cpu().numpy(), w.cpu().numpy().view(np.uint32), z.cpu().numpy().view(np.uint32), s.cpu().numpy(), group=64)
+    assert_w4_close(y.float().cpu().numpy(), ref, f"g64 {oc}x{ic}")
+
+
 def test_gemm_entry_point_same_contract(ctx):
     x, w, z, s = make_case(128, 1024, 24, 5, False)
     y = ctx.w4a16_gemv(x, w, z, s, gemm=True)
@@ -186,8 +201,8 @@ def test_error_behaviour(ctx):
     from tinychatengine_b200 import _lib
 
     x, w, z, s = make_case(16, 256, 1, 1, False)
-    with pytest.raises(_lib.TceError):  # reference: printf + exit(1) on a group size it was not compiled for
-        ctx.w4a16_gemv(x, w, z, s, group=64)
+    with pytest.raises(_lib.TceError):  # reference: printf + exit(1) on a group size other than 64 / 128 (gemv_cuda.cu:253-257)
+        ctx.w4a16_gemv(x, w, z, s, group=32)
     y = torch.empty((1, 16), dtype=torch.float16, device=x.device)
     rc = ctx.L.tce_w4a16_gemv(ctx.h, None, None, None, None, None, 1, 256, 16, 128)
     assert rc == -1

@@ -106,6 +106,7 @@ int tce_ctx_destroy(tce_ctx *ctx) {
     cudaFree(ctx->c.attn_ws);
     cudaFree(ctx->c.attn_counters);
     cudaFree(ctx->c.w16_scratch);
+    cudaFree(ctx->c.gemv_dbg_keep);
     delete ctx;
     return TCE_OK;
 }
@@ -143,11 +144,14 @@ int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "gemv_stages"))
         ctx->c.gemv_stages = value < 0 ? 0 : value;
     else if (!strcmp(name, "gemv_debug")) {
+        // the buffer is never freed before the context dies: CUDA graphs captured while the option was on keep writing to it
         if (value && !ctx->c.gemv_dbg) {
-            CK(cudaMalloc(&ctx->c.gemv_dbg, (size_t)ctx->c.gemv_max_ctas * 8 * sizeof(unsigned long long)), "cudaMalloc dbg");
-            CK(cudaMemset(ctx->c.gemv_dbg, 0, (size_t)ctx->c.gemv_max_ctas * 8 * sizeof(unsigned long long)), "cudaMemset");
-        } else if (!value && ctx->c.gemv_dbg) {
-            cudaFree(ctx->c.gemv_dbg);
+            if (!ctx->c.gemv_dbg_keep) {
+                CK(cudaMalloc(&ctx->c.gemv_dbg_keep, (size_t)ctx->c.gemv_max_ctas * 8 * sizeof(unsigned long long)), "cudaMalloc dbg");
+                CK(cudaMemset(ctx->c.gemv_dbg_keep, 0, (size_t)ctx->c.gemv_max_ctas * 8 * sizeof(unsigned long long)), "cudaMemset");
+            }
+            ctx->c.gemv_dbg = ctx->c.gemv_dbg_keep;
+        } else if (!value) {
             ctx->c.gemv_dbg = nullptr;
         }
     } else if (!strcmp(name, "use_pdl"))
@@ -168,7 +172,13 @@ static int w4a16_common(tce_ctx *ctx, const void *x, const void *w, const void *
                         int OC, int group, const char *who) {
     if (!ctx || !x || !w || !zeros || !scales || !y) return fail(TCE_ERR_INVALID, "%s: null pointer", who);
     // the reference exits on any group size but 64/128 (gemv_cuda.cu:253-257) and is compiled with QK=128
-    if (group != kW4Group) return fail(TCE_ERR_INVALID, "%s: unsupported group size %d (QM_CUDA uses 128)", who, group);
+    if (group == 64) {  // gemv_kernel_g64 (gemv_cuda.cu:68-123)
+        if (M < 1 || IC < 64 || IC % 64 || OC < 1) return fail(TCE_ERR_INVALID, "%s: bad shape M=%d IC=%d OC=%d", who, M, IC, OC);
+        CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+        CK(launch_w4a16_gemv_g64(&ctx->c, (const __half *)x, (const uint32_t *)w, (const uint32_t *)zeros, (const __half *)scales, (__half *)y, M, IC, OC), who);
+        return TCE_OK;
+    }
+    if (group != kW4Group) return fail(TCE_ERR_INVALID, "%s: unsupported group size %d (the reference supports 64 and 128)", who, group);
     if (M < 1 || IC < kW4Group || IC % kW4Group || OC < 1) return fail(TCE_ERR_INVALID, "%s: bad shape M=%d IC=%d OC=%d", who, M, IC, OC);
     CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
     const int zw = zeros_width(IC, group);

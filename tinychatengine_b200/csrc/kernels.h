@@ -19,6 +19,7 @@ struct Ctx {
     int gemv_max_ctas = 0;
     int gemv_max_tiles = 0;
     unsigned long long *gemv_dbg = nullptr;  // optional phase timestamps (option "gemv_debug")
+    unsigned long long *gemv_dbg_keep = nullptr;  // its allocation (kept until the context is destroyed)
     // flash-decode workspace (partial m, l, o per (head, split))
     float *attn_ws = nullptr;
     size_t attn_ws_bytes = 0;
@@ -93,6 +94,7 @@ struct W4GemvParams {
 
 cudaError_t launch_w4a16_gemv(Ctx *ctx, const W4GemvParams &p);
 cudaError_t launch_w4a16_gemv_simple(Ctx *ctx, const W4GemvParams &p);
+cudaError_t launch_w4a16_gemv_g64(Ctx *ctx, const __half *x, const uint32_t *w, const uint32_t *zeros, const __half *scales, __half *y, int M, int IC, int OC);
 size_t w4a16_gemv_smem_bytes(int ncols, int consumer_warps, int IC);
 cudaError_t encode_w4_tmap(CUtensorMap *out, const void *w, int rows, int IC, int sg, int box_rows);
 

@@ -118,7 +118,47 @@ __global__ void w4a16_gemv_simple_kernel(const KArgs a, int total_rows) {
     }
 }
 
+// Group size 64 (reference gemv_kernel_g64, kernels/cuda/gemv_cuda.cu:68-123): same QM_CUDA layout with zeros_w = zeros_width(IC, 64) and one
+// scale / zero point per 64 input channels.  One warp per output row, 128-bit loads, fp32 accumulation like the reference; kept simple
+// (QM_CUDA models are quantised with group 128, this slot exists for interface completeness).
+__global__ void w4a16_gemv_g64_kernel(const __half *__restrict__ x, const uint32_t *__restrict__ w, const uint32_t *__restrict__ zeros,
+                                      const __half *__restrict__ scales, __half *__restrict__ y, int M, int IC, int OC, int zeros_w) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= OC) return;
+    const uint4 *wrow = reinterpret_cast<const uint4 *>(w + (size_t)row * (IC / 8));
+    const uint32_t *zrow = zeros + (size_t)row * zeros_w;
+    const __half *srow = scales + (size_t)row * zeros_w * 8;
+    for (int m = 0; m < M; m++) {
+        const __half *xr = x + (size_t)m * IC;
+        float acc = 0.f;
+        for (int c = lane; c < IC / 32; c += 32) {  // 32 nibbles per uint4: two uint4 per group
+            const uint4 wv = wrow[c];
+            const int G = c >> 1;
+            const float sc = __half2float(srow[G]);
+            const float z = (float)((zrow[G >> 3] >> ((G & 7) * 4)) & 0xF);
+            const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float q = (float)((words[j] >> (4 * i)) & 0xF);
+                    acc += (sc * (q - z)) * __half2float(xr[c * 32 + j * 8 + i]);
+                }
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) y[(size_t)m * OC + row] = __float2half(acc);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_w4a16_gemv_g64(Ctx *ctx, const __half *x, const uint32_t *w, const uint32_t *zeros, const __half *scales, __half *y, int M, int IC, int OC) {
+    const int warps = 8;
+    w4a16_gemv_g64_kernel<<<(OC + warps - 1) / warps, warps * 32, 0, ctx->stream>>>(x, w, zeros, scales, y, M, IC, OC, zeros_width(IC, 64));
+    return cudaGetLastError();
+}
 
 // 2-D tensor map of one packed weight segment: uint32 [rows][IC/8], box = [box_rows][sg*16 words], no swizzle.
 // cuTensorMapEncodeTiled is a pure host-side encoder; it is reached through the runtime's driver entry point so the
