@@ -6,18 +6,21 @@
 // token is ONE kernel of one CTA per SM whose warp roles persist across all phases (5 per layer + lm_head):
 //
 //   producer (1 warp, 1 elected lane)  walks the phases in order and keeps a ring of `nst` TMA stages full.  A stage is either
-//        [16 rows x <=16 groups] of packed int4 weights (ONE 2-D UTMALDG, 16 KiB) + the stage's repacked scales|zeros record (one 640 B
-//        UBLKCP), or 64 cached K rows or 64 cached V rows of the attention phase (two 128B-swizzled 2-D boxes, 16 KiB).  It depends
-//        on nothing but static data and the token position, so it runs ahead across every phase boundary: while the GPU synchronises or
-//        stages activations, up to nst x 16 KiB per SM of the NEXT matrices are already in flight, and HBM never goes idle.
-//   consumers (16 warps)  per phase: wait for the grid barrier of the previous phase, quantise the activation vector (fused RMSNorm,
-//        four int8 planes per 128-group), run the integer-MMA GEMV over this CTA's stage units (w4a16_gemv_impl.cuh: unit1), or
-//        run flash-decoding attention straight out of the ring stages (mma.sync m16n8k16, ldmatrix on the swizzled K/V rows).
-//   epilogue (1 warp)  reduces the 16 consumer partials of every tile, applies the fused epilogue (fp16 store, RED.ADD into the fp32
-//        residual, SiLU(gate)*up, logits + running arg-max, tensor-parallel scatter to the peers) and signals the grid barrier.
+//        [16 rows x <=32 groups] of packed int4 weights (two 2-D UTMALDG boxes of 16 KiB) + the stage's repacked scales|zeros record (one
+//        1280 B UBLKCP), or 64 cached K rows + 64 cached V rows of the attention phase (four 128B-swizzled 2-D boxes).  It depends on
+//        nothing but static data and the token position, so it runs ahead across every phase boundary.
+//   consumers (16 warps)  per phase: spin on the flag-carrying words of their input vector, quantise it (fused RMSNorm, four int8 planes
+//        per 128-group), run the integer-MMA GEMV over this CTA's tiles (two 128-k groups per warp and stage), or run flash-decoding
+//        attention straight out of the ring stages (mma.sync m16n8k16, ldmatrix on the swizzled K/V rows).
+//   epilogue (1 warp)  reduces the 16 consumer partials of every tile and publishes the results as {value, phase tag} words.
 //
-// Grid barrier = one monotonic arrival counter per phase (red.release.gpu / ld.acquire.gpu); counters are never reset, the target of
-// launch e is (e + 1) * #CTAs.  Data produced by other CTAs inside the kernel is read with ld.global.cg (L2), never through L1.
+// There is NO grid barrier between phases.  Every vector that crosses CTAs (q|k|v, attention partials and outputs, SiLU*mul
+// activations, the o_proj / down_proj outputs) is an array of 8-byte words {payload, tag} written with one 8-byte store and read with
+// 8/16-byte loads: a reader spins until the tag of the phase it waits for appears, so the hand-off costs one L2 write + one L2 read
+// instead of fence + arrive + poll + fence.  The fp32 residual stream never leaves the SM: every CTA keeps its own copy in shared
+// memory and adds the (identical) o_proj / down_proj outputs to it in the same order -- which is also the tensor-parallel
+// all-reduce: with P ranks every rank stores its partial outputs into slot `rank` of every rank's buffer (NVLink peer stores of
+// 8-byte words, flag included) and every reader sums the P slots in rank order.
 // All waits are bounded: a protocol bug surfaces as a launch failure within seconds, not as a hung GPU.
 #include <stdio.h>
 
@@ -30,61 +33,96 @@ namespace pk {
 
 namespace {
 
-using gemv::Lane1;
-using gemv::make_lane1;
-using gemv::unit1;
-
 // ------------------------------------------------------------------------------------------------------------ small helpers
 TCE_DEVINL unsigned ld_acquire_gpu(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-TCE_DEVINL unsigned ld_acquire_sys(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 TCE_DEVINL void red_release_gpu(unsigned *p) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
-TCE_DEVINL void red_release_sys(unsigned *p) { asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
-TCE_DEVINL uint4 ldcg_u4(const void *p) {
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-TCE_DEVINL float4 ldcg_f4(const void *p) {
-    float4 r;
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-TCE_DEVINL float ldcg_f32(const void *p) {
-    float r;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
-}
-TCE_DEVINL unsigned short ldcg_u16(const void *p) {
-    unsigned short r;
-    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p));
-    return r;
-}
-TCE_DEVINL float ldcg_half(const __half *p) { return __half2float(__ushort_as_half(ldcg_u16(p))); }
 
-// wait until *ctr has reached `target` (wrap-safe); one thread
-TCE_DEVINL void grid_wait(const unsigned *ctr, unsigned target) {
-    if ((int)(ld_acquire_gpu(ctr) - target) >= 0) return;
+// {payload, tag} words.  8-byte aligned 8-byte accesses are single transactions: payload and tag always travel together.
+TCE_DEVINL void st_ll(uint2 *p, uint32_t data, uint32_t tag, bool sys) {
+    if (sys)
+        asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
+    else
+        asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
+}
+TCE_DEVINL uint4 ld_ll2(const uint2 *p, bool sys) {  // two consecutive words (16-byte aligned)
+    uint4 r;
+    if (sys)
+        asm volatile("ld.relaxed.sys.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    else
+        asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+TCE_DEVINL uint2 ld_ll1(const uint2 *p, bool sys) {
+    uint2 r;
+    if (sys)
+        asm volatile("ld.relaxed.sys.global.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    else
+        asm volatile("ld.relaxed.gpu.global.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
+constexpr long long kSpinLimit = 20000000000LL;  // ~10 s: a peer rank may legitimately start its kernel later
+// spin until both words of the pair carry `tag`
+TCE_DEVINL uint4 wait_ll2(const uint2 *p, uint32_t tag, bool sys) {
+    uint4 r = ld_ll2(p, sys);
+    if (r.y == tag && r.w == tag) return r;
     const long long t0 = clock64();
-    while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
-        if (clock64() - t0 > 8000000000LL) __trap();
+    while (true) {
+        r = ld_ll2(p, sys);
+        if (r.y == tag && r.w == tag) return r;
+        if (clock64() - t0 > kSpinLimit) __trap();
     }
 }
-// same for a counter peers arrive on over NVLink; a peer may legitimately lag (separate launch), so the bound is generous
-TCE_DEVINL void sys_wait(const unsigned *ctr, unsigned target) {
-    if ((int)(ld_acquire_sys(ctr) - target) >= 0) return;
+TCE_DEVINL uint32_t wait_ll1(const uint2 *p, uint32_t tag, bool sys) {
+    uint2 r = ld_ll1(p, sys);
+    if (r.y == tag) return r.x;
     const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(ctr) - target) < 0) {
-        if (clock64() - t0 > 60000000000LL) __trap();
+    while (true) {
+        r = ld_ll1(p, sys);
+        if (r.y == tag) return r.x;
+        if (clock64() - t0 > kSpinLimit) __trap();
     }
 }
+TCE_DEVINL float2 h2_to_f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2 *>(&u)); }
+
+// shared-memory accesses by 32-bit shared address (no generic-address conversion inside the hot loops)
+TCE_DEVINL uint4 lds_u4(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+    return r;
+}
+TCE_DEVINL uint2 lds_u2(uint32_t a) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a) : "memory");
+    return r;
+}
+TCE_DEVINL uint32_t lds_u32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+    return r;
+}
+TCE_DEVINL float lds_f32(uint32_t a) { return __uint_as_float(lds_u32(a)); }
+TCE_DEVINL float lds_h16(uint32_t a) {
+    unsigned short r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a) : "memory");
+    return __half2float(__ushort_as_half(r));
+}
+TCE_DEVINL bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+TCE_DEVINL void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_u32(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_u32(bar, parity)) {
+        if (clock64() - t0 > kSpinLimit) __trap();
+    }
+}
+TCE_DEVINL void mbar_arrive_u32(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 TCE_DEVINL void stamp(const Args &a, int cta, int nphase, int p, int k) {  // one thread
     if (a.dbg) {
@@ -103,12 +141,13 @@ TCE_DEVINL unsigned long long argmax_key(float v, int idx) {
 struct PSmem {
     uint8_t *ring;      // [nst][kStageBytes], 1024-B aligned
     uint8_t *xs;        // activation planes (4 * IC bytes) | attention scratch
+    float *resid;       // [E] this CTA's copy of the fp32 residual stream
     float *gx;          // [max_ng] group steps
     int *gsum;          // [max_ng][2] group sums
     float *red;         // [kRedBufs][kCW][16] tile partials
-    float *rms;         // [kCW] + misc
+    float *rms;         // [kCW]
     uint64_t *full, *empty, *red_full, *red_empty;
-    int *aflag;
+    uint32_t ring_u32, xs_u32, gx_u32, gsum_u32, full_u32, empty_u32, redfull_u32, redempty_u32;
     int nst;
 };
 
@@ -120,6 +159,8 @@ TCE_DEVINL PSmem carve(uint8_t *raw, const Args &a) {
     uint8_t *p = base + (size_t)a.nst * kStageBytes;
     s.xs = p;
     p += a.xs_bytes;
+    s.resid = reinterpret_cast<float *>(p);
+    p += (size_t)a.E * 4;
     s.gx = reinterpret_cast<float *>(p);
     p += (size_t)a.max_ng * 4;
     s.gsum = reinterpret_cast<int *>(p);
@@ -132,7 +173,14 @@ TCE_DEVINL PSmem carve(uint8_t *raw, const Args &a) {
     s.empty = s.full + a.nst;
     s.red_full = s.empty + a.nst;
     s.red_empty = s.red_full + kRedBufs;
-    s.aflag = reinterpret_cast<int *>(s.red_empty + kRedBufs);
+    s.ring_u32 = smem_u32(s.ring);
+    s.xs_u32 = smem_u32(s.xs);
+    s.gx_u32 = smem_u32(s.gx);
+    s.gsum_u32 = smem_u32(s.gsum);
+    s.full_u32 = smem_u32(s.full);
+    s.empty_u32 = smem_u32(s.empty);
+    s.redfull_u32 = smem_u32(s.red_full);
+    s.redempty_u32 = smem_u32(s.red_empty);
     return s;
 }
 
@@ -157,21 +205,15 @@ struct Red {
     }
 };
 
-// this CTA's stage-unit range [su0, su1) of one GEMV op
-TCE_DEVINL void partition(const GemvOp &op, int cta, int ncta, int &su0, int &su1) {
-    if (op.aligned) {
-        const unsigned T = (unsigned)op.num_tiles;
-        su0 = (int)((T * (unsigned)cta) / (unsigned)ncta) * op.S;
-        su1 = (int)((T * (unsigned)(cta + 1)) / (unsigned)ncta) * op.S;
-    } else {
-        const unsigned U = (unsigned)op.SU;
-        su0 = (int)(((unsigned long long)U * (unsigned)cta) / (unsigned)ncta);
-        su1 = (int)(((unsigned long long)U * (unsigned)(cta + 1)) / (unsigned)ncta);
-    }
+// this CTA's tile range of one GEMV op: cut at tile boundaries (every output has exactly one writer)
+TCE_DEVINL void partition(const GemvOp &op, int cta, int ncta, int &t0, int &t1) {
+    const unsigned T = (unsigned)op.num_tiles;
+    t0 = (int)((T * (unsigned)cta) / (unsigned)ncta);
+    t1 = (int)((T * (unsigned)(cta + 1)) / (unsigned)ncta);
 }
 
 // attention work split: the visible positions [0, T) in chunks of kKvChunk; every KV head gets NS = #CTAs / KVH consecutive CTAs,
-// each takes `cps` consecutive chunks
+// each takes `cps` consecutive chunks (at least kAttnCps when the context has them: fewer splits to merge, same latency per CTA)
 struct AttnSplit {
     int kvh, split, ch0, ch1, nsplit;  // ch0 >= ch1: nothing to do
 };
@@ -181,7 +223,10 @@ TCE_DEVINL AttnSplit attn_split(int cta, int ncta, int KVH, int pos) {
     const int nch = (T + kKvChunk - 1) / kKvChunk;
     int NS = ncta / KVH;
     if (NS < 1) NS = 1;
-    const int cps = (nch + NS - 1) / NS;
+    int cps = (nch + NS - 1) / NS;
+    const int want = nch < kAttnCps ? nch : kAttnCps;
+    if (cps < want) cps = want;
+    if (cps * 32 < nch) cps = (nch + 31) / 32;  // the split merge keeps one split per lane
     s.nsplit = (nch + cps - 1) / cps;
     s.kvh = cta / NS;
     s.split = cta - s.kvh * NS;
@@ -198,37 +243,39 @@ TCE_DEVINL AttnSplit attn_split(int cta, int ncta, int KVH, int pos) {
 // ------------------------------------------------------------------------------------------------------------ producer
 TCE_DEVINL void produce_gemv(const GemvOp &op, const CUtensorMap *m0, const uint8_t *meta, const PSmem &sm, Ring &rs, int cta, int ncta, uint32_t leader,
                              uint64_t policy) {
-    int su, su1;
-    partition(op, cta, ncta, su, su1);
-    int tile = su / op.S;
-    int s = su - tile * op.S;
-    for (; su < su1; su++) {
-        mbar_wait(&sm.empty[rs.stage], rs.phase ^ 1);
-        uint64_t *bar = &sm.full[rs.stage];
-        uint8_t *dst = sm.ring + (size_t)rs.stage * kStageBytes;
-        mbar_arrive_expect_tx_pred(bar, (uint32_t)op.box_bytes + kMetaBytes, leader);
-        if (op.pair) {
-            tma_load_2d_pred(dst, m0, s * 256, tile * 8, bar, policy, leader);
-            tma_load_2d_pred(dst + 8 * op.sg * 64, m0 + 1, s * 256, tile * 8, bar, policy, leader);
-        } else {
-            int row = tile * 16;
-            const CUtensorMap *m = m0;
-            if (op.nseg > 1 && row >= op.rows0) {
-                row -= op.rows0;
-                m = m0 + 1;
-                if (op.nseg > 2 && row >= op.rows1) {
-                    row -= op.rows1;
-                    m = m0 + 2;
+    int t0, t1;
+    partition(op, cta, ncta, t0, t1);
+    for (int tile = t0; tile < t1; tile++) {
+        for (int s = 0; s < op.S; s++) {
+            const bool two = (kStageGroups * s + 16) < op.NG;  // the stage carries a second box of 16 groups
+            mbar_wait(&sm.empty[rs.stage], rs.phase ^ 1);
+            uint64_t *bar = &sm.full[rs.stage];
+            uint8_t *dst = sm.ring + (size_t)rs.stage * kStageBytes;
+            mbar_arrive_expect_tx_pred(bar, (uint32_t)op.box_bytes * (two ? 2u : 1u) + kMetaBytes, leader);
+#pragma unroll 1
+            for (int h = 0; h < (two ? 2 : 1); h++) {
+                const int xw = (kStageGroups * s + 16 * h) * 16;  // first 32-bit word of the box within the row
+                uint8_t *d = dst + h * kHalfBytes;
+                if (op.pair) {
+                    tma_load_2d_pred(d, m0, xw, tile * 8, bar, policy, leader);
+                    tma_load_2d_pred(d + 8 * op.sg * 64, m0 + 1, xw, tile * 8, bar, policy, leader);
+                } else {
+                    int row = tile * 16;
+                    const CUtensorMap *m = m0;
+                    if (op.nseg > 1 && row >= op.rows0) {
+                        row -= op.rows0;
+                        m = m0 + 1;
+                        if (op.nseg > 2 && row >= op.rows1) {
+                            row -= op.rows1;
+                            m = m0 + 2;
+                        }
+                    }
+                    tma_load_2d_pred(d, m, xw, row, bar, policy, leader);
                 }
             }
-            tma_load_2d_pred(dst, m, s * 256, row, bar, policy, leader);
-        }
-        bulk_g2s_pred(dst + kMetaOff, meta + (size_t)su * kMetaBytes, kMetaBytes, bar, policy, leader);
-        __syncwarp();
-        rs.advance(sm.nst);
-        if (++s == op.S) {
-            s = 0;
-            tile++;
+            bulk_g2s_pred(dst + kMetaOff, meta + ((size_t)tile * op.S + s) * kMetaBytes, kMetaBytes, bar, policy, leader);
+            __syncwarp();
+            rs.advance(sm.nst);
         }
     }
 }
@@ -237,68 +284,72 @@ TCE_DEVINL void produce_attn(const Args &a, const LayerDesc &L, const CUtensorMa
                              uint32_t leader, uint64_t policy) {
     const AttnSplit sp = attn_split(cta, ncta, a.KVH, pos);
     for (int c = sp.ch0; c < sp.ch1; c++) {
-#pragma unroll 1
-        for (int kv = 0; kv < 2; kv++) {
-            const int row = (kv ? L.v_row0 : L.k_row0) + sp.kvh * a.max_ctx + c * kKvChunk;
-            mbar_wait(&sm.empty[rs.stage], rs.phase ^ 1);
-            uint64_t *bar = &sm.full[rs.stage];
-            uint8_t *dst = sm.ring + (size_t)rs.stage * kStageBytes;
-            mbar_arrive_expect_tx_pred(bar, 16384u, leader);
-            tma_load_2d_pred(dst, kvmap, 0, row, bar, policy, leader);
-            tma_load_2d_pred(dst + 8192, kvmap, 64, row, bar, policy, leader);
-            __syncwarp();
-            rs.advance(sm.nst);
-        }
+        mbar_wait(&sm.empty[rs.stage], rs.phase ^ 1);
+        uint64_t *bar = &sm.full[rs.stage];
+        uint8_t *dst = sm.ring + (size_t)rs.stage * kStageBytes;
+        mbar_arrive_expect_tx_pred(bar, 2u * kHalfBytes, leader);
+        const int krow = L.k_row0 + sp.kvh * a.max_ctx + c * kKvChunk, vrow = L.v_row0 + sp.kvh * a.max_ctx + c * kKvChunk;
+        tma_load_2d_pred(dst, kvmap, 0, krow, bar, policy, leader);
+        tma_load_2d_pred(dst + 8192, kvmap, 64, krow, bar, policy, leader);
+        tma_load_2d_pred(dst + kHalfBytes, kvmap, 0, vrow, bar, policy, leader);
+        tma_load_2d_pred(dst + kHalfBytes + 8192, kvmap, 64, vrow, bar, policy, leader);
+        __syncwarp();
+        rs.advance(sm.nst);
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------ consumers: GEMV
-// Quantise the activation vector of one GEMV phase into the plane buffer.  Returns the factor the tile sums must be multiplied by
-// (1/rms for the fused RMSNorm: y = inv * W (x . gamma), so the normalisation needs no second pass over x).
-TCE_DEVINL float stage_x(const Args &a, const GemvOp &op, int x_mode, const PSmem &sm, const void *xsrc, const float *gamma, const float *tp_in, float *resid_out,
-                         int token, int cta, int ctid, int cw, int lane) {
-    const int units = op.IC / 8;
-    float ss = 0.f;
-    if (x_mode == PX_HALF) {
-        constexpr int PRE = 4;
-        for (int ui0 = 0; ui0 < units; ui0 += PRE * kConsumerThreads) {
-            uint4 raw[PRE];
-#pragma unroll
-            for (int k = 0; k < PRE; k++) {
-                const int ui = ui0 + k * kConsumerThreads + ctid;
-                raw[k] = make_uint4(0u, 0u, 0u, 0u);
-                if (ui < units) raw[k] = ldcg_u4(reinterpret_cast<const __half *>(xsrc) + (size_t)ui * 8);
-            }
-#pragma unroll
-            for (int k = 0; k < PRE; k++) {
-                if (ui0 + k * kConsumerThreads >= units) break;  // warp-uniform
-                const int ui = ui0 + k * kConsumerThreads + ctid;
-                const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw[k]);
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float2 f = __half22float2(h2[i]);
-                    v[2 * i] = f.x;
-                    v[2 * i + 1] = f.y;
-                }
-                gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, ui, ui < units, v, lane);
-            }
-        }
-        named_bar_sync(1, kConsumerThreads);
-        return 1.f;
-    }
-    // fp32 residual stream (or the embedding row of the token) with fused RMSNorm
+// ------------------------------------------------------------------------------------------------------------ consumers: staging
+// unit rotation: CTA c starts its walk over the input vector `rot` groups further on, so that the 148 CTAs do not all pull the same
+// L2 lines at the same moment.  Whole groups (16 units) keep the half-warp amax shuffles of emit_unit intact.
+TCE_DEVINL int rot_unit(int u, int units, int cta) {
+    const int ng = units >> 4;
+    int g = (u >> 4) + (cta % ng);
+    if (g >= ng) g -= ng;
+    return (g << 4) | (u & 15);
+}
+
+// fp16 input vector (attention output / SiLU*mul activations) published as {half2, tag} words -> activation planes
+TCE_DEVINL void stage_half(const GemvOp &op, const PSmem &sm, const uint2 *src, uint32_t tag, int cta, int ctid, int lane) {
+    const int units = op.IC / 8;  // 8 halfs = 4 words = 32 B per unit
     for (int ui0 = 0; ui0 < units; ui0 += kConsumerThreads) {  // warp-uniform trip count
-        const int ui = ui0 + ctid;
-        const bool valid = ui < units;
+        const int u = ui0 + ctid;
+        const bool valid = u < units;
+        const int ui = valid ? rot_unit(u, units, cta) : 0;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = 0.f;
+        if (valid) {
+            const uint4 w0 = wait_ll2(src + (size_t)ui * 4, tag, false);
+            const uint4 w1 = wait_ll2(src + (size_t)ui * 4 + 2, tag, false);
+            const float2 f0 = h2_to_f2(w0.x), f1 = h2_to_f2(w0.z), f2 = h2_to_f2(w1.x), f3 = h2_to_f2(w1.z);
+            v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+            v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+        }
+        gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, ui, valid, v, lane);
+    }
+    named_bar_sync(1, kConsumerThreads);
+}
+
+// fp32 residual stream with fused RMSNorm.  Every CTA holds the stream in shared memory; `delta` (o_proj or down_proj outputs of all
+// tensor-parallel ranks, {float, tag} words) is added to it here by every CTA in the same (rank) order.  Returns 1/rms: y = inv * W (x . gamma).
+TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, const uint2 *delta, uint32_t tag, const float *gamma, int token, bool first,
+                           bool emit, int cta, int ctid, int cw, int lane) {
+    const int units = op.IC / 8;
+    const bool sys = a.tp_size > 1;
+    float ss = 0.f;
+    for (int ui0 = 0; ui0 < units; ui0 += kConsumerThreads) {  // warp-uniform trip count
+        const int u = ui0 + ctid;
+        const bool valid = u < units;
+        const int ui = valid ? rot_unit(u, units, cta) : 0;
         float x[8], v[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) x[i] = 0.f;
         float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
         if (valid) {
-            g0 = *reinterpret_cast<const float4 *>(gamma + (size_t)ui * 8);
+            g0 = *reinterpret_cast<const float4 *>(gamma + (size_t)ui * 8);  // static: requested before the spin
             g1 = *reinterpret_cast<const float4 *>(gamma + (size_t)ui * 8 + 4);
-            if (x_mode == PX_EMBED_RMS) {
+            if (first) {
+                // the token's embedding row is the residual stream (reference: CPU Embedding, cuda/Int4llamaDecoder.cu:62-69)
                 const uint4 raw = *reinterpret_cast<const uint4 *>(a.embed + (size_t)token * a.E + (size_t)ui * 8);
                 const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
 #pragma unroll
@@ -308,31 +359,29 @@ TCE_DEVINL float stage_x(const Args &a, const GemvOp &op, int x_mode, const PSme
                     x[2 * i + 1] = f.y;
                 }
             } else {
-                const float4 r0 = ldcg_f4(reinterpret_cast<const float *>(xsrc) + (size_t)ui * 8);
-                const float4 r1 = ldcg_f4(reinterpret_cast<const float *>(xsrc) + (size_t)ui * 8 + 4);
+                const float4 r0 = *reinterpret_cast<const float4 *>(sm.resid + (size_t)ui * 8);
+                const float4 r1 = *reinterpret_cast<const float4 *>(sm.resid + (size_t)ui * 8 + 4);
                 x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; x[3] = r0.w;
                 x[4] = r1.x; x[5] = r1.y; x[6] = r1.z; x[7] = r1.w;
-                if (tp_in) {
-                    // tensor-parallel all-reduce, receive side: residual += sum over ranks, in rank order (bit-identical everywhere)
-                    for (int pr = 0; pr < a.tp_size; pr++) {
-                        const float4 q0 = ldcg_f4(tp_in + (size_t)pr * a.E + (size_t)ui * 8);
-                        const float4 q1 = ldcg_f4(tp_in + (size_t)pr * a.E + (size_t)ui * 8 + 4);
-                        x[0] += q0.x; x[1] += q0.y; x[2] += q0.z; x[3] += q0.w;
-                        x[4] += q1.x; x[5] += q1.y; x[6] += q1.z; x[7] += q1.w;
-                    }
+                for (int pr = 0; pr < a.tp_size; pr++) {  // residual += sum over ranks, in rank order (bit-identical everywhere)
+                    const uint2 *d = delta + (size_t)pr * a.E + (size_t)ui * 8;
+                    const uint4 w0 = wait_ll2(d, tag, sys), w1 = wait_ll2(d + 2, tag, sys), w2 = wait_ll2(d + 4, tag, sys), w3 = wait_ll2(d + 6, tag, sys);
+                    x[0] += __uint_as_float(w0.x); x[1] += __uint_as_float(w0.z); x[2] += __uint_as_float(w1.x); x[3] += __uint_as_float(w1.z);
+                    x[4] += __uint_as_float(w2.x); x[5] += __uint_as_float(w2.z); x[6] += __uint_as_float(w3.x); x[7] += __uint_as_float(w3.z);
                 }
             }
-            if (resid_out && cta == 0) {  // the embedding row / the reduced residual becomes the residual stream (one writer)
-                *reinterpret_cast<float4 *>(resid_out + (size_t)ui * 8) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4 *>(resid_out + (size_t)ui * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
-            }
+            *reinterpret_cast<float4 *>(sm.resid + (size_t)ui * 8) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4 *>(sm.resid + (size_t)ui * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
         }
+        if (emit) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) ss += x[i] * x[i];
-        v[0] = x[0] * g0.x; v[1] = x[1] * g0.y; v[2] = x[2] * g0.z; v[3] = x[3] * g0.w;
-        v[4] = x[4] * g1.x; v[5] = x[5] * g1.y; v[6] = x[6] * g1.z; v[7] = x[7] * g1.w;
-        gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, ui, valid, v, lane);
+            for (int i = 0; i < 8; i++) ss += x[i] * x[i];
+            v[0] = x[0] * g0.x; v[1] = x[1] * g0.y; v[2] = x[2] * g0.z; v[3] = x[3] * g0.w;
+            v[4] = x[4] * g1.x; v[5] = x[5] * g1.y; v[6] = x[6] * g1.z; v[7] = x[7] * g1.w;
+            gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, ui, valid, v, lane);
+        }
     }
+    if (!emit) return 1.f;
     ss = warp_sum(ss);
     if (lane == 0) sm.rms[cw] = ss;
     named_bar_sync(1, kConsumerThreads);
@@ -342,69 +391,80 @@ TCE_DEVINL float stage_x(const Args &a, const GemvOp &op, int x_mode, const PSme
     return rsqrtf(tot / (float)op.IC + a.eps);  // LlamaRMSNorm (llm/src/ops/LlamaRMSNorm.cc): x / sqrt(mean(x^2) + eps) * weight
 }
 
+// ------------------------------------------------------------------------------------------------------------ consumers: GEMV
+// one (16 rows x 128 k) unit; see gemv::unit1 (w4a16_gemv_impl.cuh) for the arithmetic.  All operands by shared address.
+TCE_DEVINL void unit_pk(uint32_t w_addr, uint32_t rp8, uint32_t x_addr, uint32_t meta_addr, int gi, int g, int G, uint32_t gx_u32, uint32_t gsum_u32,
+                        float lscale, int gsel, float &totA, float &totB) {
+    const uint4 wa = lds_u4(w_addr), wb = lds_u4(w_addr + rp8);
+    const uint4 xe = lds_u4(x_addr + (uint32_t)G * 256u), xo = lds_u4(x_addr + (uint32_t)G * 256u + 128u);
+    const float sAq = lds_h16(meta_addr + (uint32_t)(gi * 16 + g) * 2u), sBq = lds_h16(meta_addr + (uint32_t)(gi * 16 + g + 8) * 2u);
+    const uint2 z = lds_u2(meta_addr + 1024u + (uint32_t)gi * 8u);
+    const int sxv = (int)lds_u32(gsum_u32 + (uint32_t)(2 * G + gsel) * 4u);
+    const float st = lds_f32(gx_u32 + (uint32_t)G * 4u) * lscale;
+    constexpr uint32_t ML = 0x0f0f0f0fu, MH = 0xf0f0f0f0u;
+    int accL[4], accH[4];
+    mma_m16n8k32_u8s8_z(accL, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xe.x, xe.y);
+    mma_m16n8k32_u8s8_z(accH, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xo.x, xo.y);
+    mma_m16n8k32_u8s8(accL, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xe.z, xe.w);
+    mma_m16n8k32_u8s8(accH, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xo.z, xo.w);
+    const int zAq = (int)((z.x >> (4 * g)) & 0xFu), zBq = (int)((z.y >> (4 * g)) & 0xFu);
+    const int vA = ((accL[0] + (accH[0] >> 4)) << 7) + (accL[1] + (accH[1] >> 4)) - zAq * sxv;
+    const int vB = ((accL[2] + (accH[2] >> 4)) << 7) + (accL[3] + (accH[3] >> 4)) - zBq * sxv;
+    totA += (sAq * st) * (float)vA;
+    totB += (sBq * st) * (float)vB;
+}
+
 TCE_DEVINL void consume_gemv(const GemvOp &op, const PSmem &sm, Ring &rs, Red &cs, float inv, int cta, int ncta, int cw, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    int su, su1;
-    partition(op, cta, ncta, su, su1);
-    const int rp = op.sg * 64;  // dense row pitch of the TMA box
-    const uint32_t w_off = (uint32_t)(g * rp + t * 16 + cw * 64);
-    const Lane1 L = make_lane1(sm.xs, op.IC, g, t);
-    int tile = su / op.S;
-    int sb = su - tile * op.S;
-    while (su < su1) {
-        const int se = min(op.S, sb + (su1 - su));
+    int t0, t1;
+    partition(op, cta, ncta, t0, t1);
+    const uint32_t rp = (uint32_t)op.sg * 64u;  // dense row pitch of a TMA box
+    const uint32_t w_off = (uint32_t)g * rp + (uint32_t)t * 16u + (uint32_t)cw * 64u;
+    // lane-constant activation operands: MMA column g & 3 supplies plane 3 - (g & 3)
+    const uint32_t x_lane = sm.xs_u32 + (uint32_t)((g >> 1) & 1) * (uint32_t)op.IC * 2u + (uint32_t)(t * 2 + (g & 1)) * 16u;
+    const float lscale = (t == 0) ? 16384.f : (t == 1 ? 1.f : 0.f);
+    const int gsel = t & 1;
+    for (int tile = t0; tile < t1; tile++) {
         float totA = 0.f, totB = 0.f;
-        for (int s = sb; s < se; s++) {
-            const int n = min(16, op.NG - 16 * s);  // groups this stage carries
-            mbar_wait(&sm.full[rs.stage], rs.phase);
-            if (cw < n) {
-                const uint8_t *base = sm.ring + (size_t)rs.stage * kStageBytes;
-                const uint4 wa = *reinterpret_cast<const uint4 *>(base + w_off);
-                const uint4 wb = *reinterpret_cast<const uint4 *>(base + w_off + 8 * rp);
-                const __half *sc = reinterpret_cast<const __half *>(base + kMetaOff) + cw * 16 + g;
-                const uint2 z = *reinterpret_cast<const uint2 *>(base + kMetaOff + 512 + cw * 8);
-                const float sAq = __half2float(sc[0]), sBq = __half2float(sc[8]);
-                const int zAq = (int)((z.x >> (4 * g)) & 0xFu), zBq = (int)((z.y >> (4 * g)) & 0xFu);
-                unit1(L, wa, wb, 16 * s + cw, sAq, sBq, zAq, zBq, sm.gx, sm.gsum, totA, totB);
-            }
+        for (int s = 0; s < op.S; s++) {
+            const int n = min(kStageGroups, op.NG - kStageGroups * s);  // groups this stage carries
+            mbar_wait_u32(sm.full_u32 + (uint32_t)rs.stage * 8u, rs.phase);
+            const uint32_t base = sm.ring_u32 + (uint32_t)rs.stage * (uint32_t)kStageBytes;
+            if (cw < n) unit_pk(base + w_off, 8u * rp, x_lane, base + kMetaOff, cw, g, kStageGroups * s + cw, sm.gx_u32, sm.gsum_u32, lscale, gsel, totA, totB);
+            if (cw + 16 < n)
+                unit_pk(base + kHalfBytes + w_off, 8u * rp, x_lane, base + kMetaOff, cw + 16, g, kStageGroups * s + cw + 16, sm.gx_u32, sm.gsum_u32, lscale, gsel,
+                        totA, totB);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[rs.stage]);
+            if (lane == 0) mbar_arrive_u32(sm.empty_u32 + (uint32_t)rs.stage * 8u);
             rs.advance(sm.nst);
         }
-        // ---- hand the (possibly partial) tile sums to the epilogue warp ----
-        totA += __shfl_xor_sync(0xffffffffu, totA, 1);  // (hi, mid) share of t = 0 + lo share of t = 1
+        // ---- hand the tile sums to the epilogue warp ----
+        totA += __shfl_xor_sync(0xffffffffu, totA, 1);  // (p3, p2) share of t = 0 + (p1, p0) share of t = 1
         totB += __shfl_xor_sync(0xffffffffu, totB, 1);
-        mbar_wait(&sm.red_empty[cs.rb], cs.rphase ^ 1);
+        mbar_wait_u32(sm.redempty_u32 + (uint32_t)cs.rb * 8u, cs.rphase ^ 1);
         float *rbuf = sm.red + ((size_t)cs.rb * kCW + cw) * 16;
         if (t == 0) {
             rbuf[g] = totA * inv;
             rbuf[g + 8] = totB * inv;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.red_full[cs.rb]);
+        if (lane == 0) mbar_arrive_u32(sm.redfull_u32 + (uint32_t)cs.rb * 8u);
         cs.advance();
-        su += se - sb;
-        sb = 0;
-        tile++;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------ epilogue warp
-struct EpiOut {
-    void *y;                 // fp16 / fp32 output vector, or the fp32 residual for PE_ADD_F32
-    float *logits;
+struct EpiState {
     unsigned long long best;  // PE_LOGITS: running arg-max key of this warp
-    int index_base;
 };
 
-TCE_DEVINL void epilogue_gemv(const Args &a, const GemvOp &op, const PSmem &sm, Red &es, EpiOut &o, int tp_buf, int cta, int ncta, int lane) {
-    int su, su1;
-    partition(op, cta, ncta, su, su1);
-    int tile = su / op.S;
-    int sb = su - tile * op.S;
-    while (su < su1) {
-        const int se = min(op.S, sb + (su1 - su));
-        mbar_wait(&sm.red_full[es.rb], es.rphase);
+TCE_DEVINL void epilogue_gemv(const Args &a, const GemvOp &op, const PSmem &sm, Red &es, EpiState &st, uint2 *out_ll, int which, uint32_t tag, int cta, int ncta,
+                              int lane) {
+    int t0, t1;
+    partition(op, cta, ncta, t0, t1);
+    const bool tp = a.tp_size > 1;
+    for (int tile = t0; tile < t1; tile++) {
+        mbar_wait_u32(sm.redfull_u32 + (uint32_t)es.rb * 8u, es.rphase);
         const float *rbuf = sm.red + (size_t)es.rb * kCW * 16;
         // lane l < 16 sums consumer warps 0..7 of row l, lane l + 16 warps 8..15
         float v = 0.f;
@@ -415,251 +475,246 @@ TCE_DEVINL void epilogue_gemv(const Args &a, const GemvOp &op, const PSmem &sm, 
         }
         v += __shfl_down_sync(0xffffffffu, v, 16);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.red_empty[es.rb]);
+        if (lane == 0) mbar_arrive_u32(sm.redempty_u32 + (uint32_t)es.rb * 8u);
         es.advance();
         switch (op.epi) {
-            case PE_ADD_F32:
-                // residual accumulate: RED.ADD of the tile sum (a split tile's contributors each add their part; fire and forget)
-                if (lane < 16) atomicAdd(reinterpret_cast<float *>(o.y) + (size_t)tile * 16 + lane, v);
+            case PE_DELTA_LL:
+                // o_proj / down_proj output rows: one {float, tag} word each, into slot `rank` of every rank's buffer (NVLink peer stores
+                // when tensor parallel) -- the residual add happens in every reader (stage_rms)
+                if (lane < 16) {
+                    const size_t o = (size_t)a.tp_rank * a.E + (size_t)tile * 16 + lane;
+                    if (tp) {
+                        for (int pr = 0; pr < a.tp_size; pr++) st_ll(a.tp_delta[which][pr] + o, __float_as_uint(v), tag, true);
+                    } else {
+                        st_ll(out_ll + o, __float_as_uint(v), tag, false);
+                    }
+                }
                 break;
-            case PE_STORE_HALF:
-                if (lane < 16) reinterpret_cast<__half *>(o.y)[(size_t)tile * 16 + lane] = __float2half(v);
+            case PE_HALF_LL: {
+                const float hi = __shfl_down_sync(0xffffffffu, v, 1);
+                if (lane < 16 && !(lane & 1)) st_ll(out_ll + (size_t)tile * 8 + (lane >> 1), pack_half2(v, hi), tag, false);
                 break;
-            case PE_SILU_MUL: {
+            }
+            case PE_SILU_LL: {
                 // rows 0-7 = gate, rows 8-15 = up of the same output channels: y = SiLU(gate) * up
                 // (reference SiLuMul_half, llm/src/nn_modules/cuda/Int4llamaDecoderLayer.cu:21-30; fp32 here)
                 const float up = __shfl_down_sync(0xffffffffu, v, 8);
-                if (lane < 8) reinterpret_cast<__half *>(o.y)[(size_t)tile * 8 + lane] = __float2half(v / (1.f + __expf(-v)) * up);
+                const float y = v / (1.f + __expf(-v)) * up;
+                const float yhi = __shfl_down_sync(0xffffffffu, y, 1);
+                if (lane < 8 && !(lane & 1)) st_ll(out_ll + (size_t)tile * 4 + (lane >> 1), pack_half2(y, yhi), tag, false);
                 break;
             }
             case PE_LOGITS:
                 if (lane < 16) {
                     const int idx = tile * 16 + lane;
-                    o.logits[idx] = v;
-                    const unsigned long long key = argmax_key(v, o.index_base + idx);
-                    o.best = key > o.best ? key : o.best;
-                }
-                break;
-            case PE_TP_SCATTER:
-                // fused collective: the finished outputs go straight into slot `rank` of every rank's gather buffer over NVLink
-                if (lane < 16) {
-                    for (int pr = 0; pr < a.tp_size; pr++)
-                        a.tp_gather[pr][((size_t)tp_buf * a.tp_size + a.tp_rank) * a.E + (size_t)tile * 16 + lane] = v;
+                    a.logits[idx] = v;
+                    const unsigned long long key = argmax_key(v, a.vocab_base + idx);
+                    st.best = key > st.best ? key : st.best;
                 }
                 break;
         }
-        su += se - sb;
-        sb = 0;
-        tile++;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------ consumers: attention
-// byte offset of (row r, 16-byte chunk c of the 256-byte row) inside a K or V stage: two [64 rows][128 B] boxes, 128B-swizzled
+// byte offset of (row r, 16-byte chunk c of the 256-byte row) inside the K or V half of a stage: two [64 rows][128 B] boxes, 128B-swizzled
 TCE_DEVINL uint32_t kv_off(int r, int c) { return (uint32_t)((c >> 3) * 8192 + r * 128 + (((c & 7) ^ (r & 7)) << 4)); }
 
-TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &sm, Ring &rs, int cta, int ncta, int pos, int ctid, int cw, int lane) {
+// RoPE (llm/src/ops/RotaryPosEmb.cc:7-69, rotate-half) of one {half2, tag} word pair: word j holds dims (2j, 2j+1), its partner word j +- 32
+TCE_DEVINL float2 rope_pair(const uint2 *vec, int j, uint32_t tag, const float *cosr, const float *sinr) {
+    const float2 x = h2_to_f2(wait_ll1(vec + j, tag, false));
+    const float2 xp = h2_to_f2(wait_ll1(vec + (j < 32 ? j + 32 : j - 32), tag, false));
+    const float sgn = (j < 32) ? -1.f : 1.f;
+    const int d = 2 * j;
+    return make_float2(x.x * cosr[d] + sgn * xp.x * sinr[d], x.y * cosr[d + 1] + sgn * xp.y * sinr[d + 1]);
+}
+
+TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &sm, Ring &rs, uint32_t tag_qkv, uint32_t tag_part, uint32_t tag_out, int cta,
+                                int ncta, int pos, int ctid, int cw, int lane) {
     const AttnSplit sp = attn_split(cta, ncta, a.KVH, pos);
-    if (sp.ch0 >= sp.ch1) return;
     const int nrep = a.nrep;
     const int g = lane >> 2, t = lane & 3;
-    // scratch (the activation-plane buffer is idle during this phase)
-    __half *sQ = reinterpret_cast<__half *>(sm.xs);                        // [8][136] q * alpha after RoPE, rows >= nrep zero
-    float *sO = reinterpret_cast<float *>(sm.xs + 8 * 136 * 2);            // [kCW][nrep][128] per-warp unnormalised outputs
-    float *sML = sO + (size_t)kCW * nrep * 128;                            // [kCW][nrep][2] per-warp (max, sum)
-    const float *cosr = a.cos + (size_t)pos * 128, *sinr = a.sin + (size_t)pos * 128;
-    // ---- RoPE (llm/src/ops/RotaryPosEmb.cc:7-69, rotate-half) on the nrep query heads of this KV head; fp32 math ----
-    for (int i = ctid; i < 8 * 128; i += kConsumerThreads) {
-        const int r = i >> 7, j = i & 127;
-        float v = 0.f;
-        if (r < nrep) {
-            const __half *q = a.qkv + (size_t)(sp.kvh * nrep + r) * 128;
-            const float x = ldcg_half(q + j);
-            const float xr = (j < 64) ? -ldcg_half(q + j + 64) : ldcg_half(q + j - 64);
-            v = (x * cosr[j] + xr * sinr[j]) * a.alpha;
+    if (sp.ch0 < sp.ch1) {
+        // scratch (the activation-plane buffer is idle during this phase)
+        __half *sQ = reinterpret_cast<__half *>(sm.xs);                        // [8][136] q * alpha after RoPE, rows >= nrep zero
+        float *sO = reinterpret_cast<float *>(sm.xs + 8 * 136 * 2);            // [kCW][nrep][128] per-warp unnormalised outputs
+        float *sML = sO + (size_t)kCW * nrep * 128;                            // [kCW][nrep][2] per-warp (max, sum)
+        const float *cosr = a.cos + (size_t)pos * 128, *sinr = a.sin + (size_t)pos * 128;
+        // ---- RoPE on the nrep query heads of this KV head (fp32), one {half2} word per thread and pass ----
+        for (int i = ctid; i < 8 * 64; i += kConsumerThreads) {
+            const int r = i >> 6, j = i & 63;
+            float2 v = make_float2(0.f, 0.f);
+            if (r < nrep) {
+                v = rope_pair(a.qkv_ll + (size_t)(sp.kvh * nrep + r) * 64, j, tag_qkv, cosr, sinr);
+                v.x *= a.alpha;
+                v.y *= a.alpha;
+            }
+            *reinterpret_cast<__half2 *>(sQ + r * 136 + 2 * j) = __floats2half2_rn(v.x, v.y);
         }
-        sQ[r * 136 + j] = __float2half(v);
-    }
-    named_bar_sync(1, kConsumerThreads);
-    uint32_t qa[8][2];  // A operand: q[head g][dims], all 8 k-steps (rows 8..15 of the MMA tile are zero)
+        named_bar_sync(1, kConsumerThreads);
+        uint32_t qa[8][2];  // A operand: q[head g][dims], all 8 k-steps (rows 8..15 of the MMA tile are zero)
 #pragma unroll
-    for (int ks = 0; ks < 8; ks++) {
-        qa[ks][0] = *reinterpret_cast<const uint32_t *>(sQ + g * 136 + ks * 16 + t * 2);
-        qa[ks][1] = *reinterpret_cast<const uint32_t *>(sQ + g * 136 + ks * 16 + 8 + t * 2);
-    }
-    float m_run = -INFINITY, l_run = 0.f;  // of head row g (replicated over t)
-    bool have = false;
-    float *myO = sO + (size_t)cw * nrep * 128;
-    const int kb = cw & 3;  // 16-key block of the chunk this warp owns
-    for (int c = sp.ch0; c < sp.ch1; c++) {
-        const bool mine = (((c - sp.ch0) & 3) == (cw >> 2)) && (c * kKvChunk + kb * 16 <= pos);
-        const int kbase = c * kKvChunk + kb * 16;          // first key of the block
-        const bool has_new = mine && pos >= kbase && pos < kbase + 16;
-        // ================= K stage: scores =================
-        mbar_wait(&sm.full[rs.stage], rs.phase);
-        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-        if (mine) {
-            uint8_t *kst = sm.ring + (size_t)rs.stage * kStageBytes;
-            if (has_new) {
-                // the token's own key: RoPE, round to fp16, append to the cache and patch the (stale) row of the stage
-                const __half *k = a.qkv + (size_t)a.H * 128 + (size_t)sp.kvh * 128;
-                const int r = pos - c * kKvChunk;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int j = lane * 4 + i;
-                    const float x = ldcg_half(k + j);
-                    const float xr = (j < 64) ? -ldcg_half(k + j + 64) : ldcg_half(k + j - 64);
-                    const __half kh = __float2half(x * cosr[j] + xr * sinr[j]);
-                    *reinterpret_cast<__half *>(kst + kv_off(r, j >> 3) + (j & 7) * 2) = kh;
-                    L.k_cache[((size_t)sp.kvh * a.max_ctx + pos) * 128 + j] = kh;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes into a stage the TMA unit will refill
-                __syncwarp();
-            }
-            const int lr = (lane & 7) + ((lane >> 4) << 3);  // ldmatrix row supplied by this lane (key within the block)
-            const int lc = (lane >> 3) & 1;                  // ... and which 8-dim half of the k-step
-#pragma unroll
-            for (int ks = 0; ks < 8; ks++) {
-                uint32_t b0, b1, b2, b3;
-                attn::ldmatrix_x4(b0, b1, b2, b3, kst + kv_off(kb * 16 + lr, 2 * ks + lc));
-                mma_m16n8k16(s0, qa[ks][0], 0u, qa[ks][1], 0u, b0, b1);  // keys 0..7 of the block
-                mma_m16n8k16(s1, qa[ks][0], 0u, qa[ks][1], 0u, b2, b3);  // keys 8..15
-            }
+        for (int ks = 0; ks < 8; ks++) {
+            qa[ks][0] = *reinterpret_cast<const uint32_t *>(sQ + g * 136 + ks * 16 + t * 2);
+            qa[ks][1] = *reinterpret_cast<const uint32_t *>(sQ + g * 136 + ks * 16 + 8 + t * 2);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[rs.stage]);
-        rs.advance(sm.nst);
-        // ================= V stage: softmax + P.V =================
-        mbar_wait(&sm.full[rs.stage], rs.phase);
-        if (mine) {
-            uint8_t *vst = sm.ring + (size_t)rs.stage * kStageBytes;
-            if (has_new) {
-                const __half *v = a.qkv + (size_t)(a.H + a.KVH) * 128 + (size_t)sp.kvh * 128;
-                const int r = pos - c * kKvChunk;
+        float m_run = -INFINITY, l_run = 0.f;  // of head row g (replicated over t)
+        bool have = false;
+        float *myO = sO + (size_t)cw * nrep * 128;
+        const int kb = cw & 3;  // 16-key block of the chunk this warp owns
+        for (int c = sp.ch0; c < sp.ch1; c++) {
+            const int kbase = c * kKvChunk + kb * 16;  // first key of the block
+            const bool mine = (((c - sp.ch0) & 3) == (cw >> 2)) && (kbase <= pos);
+            const bool has_new = mine && pos < kbase + 16;
+            mbar_wait_u32(sm.full_u32 + (uint32_t)rs.stage * 8u, rs.phase);
+            if (mine) {
+                uint8_t *kst = sm.ring + (size_t)rs.stage * kStageBytes, *vst = kst + kHalfBytes;
+                if (has_new) {
+                    // the token's own key / value: RoPE(k), round to fp16, append to the cache and patch the (stale) rows of the stage
+                    const uint2 *kw = a.qkv_ll + (size_t)a.H * 64 + (size_t)sp.kvh * 64, *vw = a.qkv_ll + (size_t)(a.H + a.KVH) * 64 + (size_t)sp.kvh * 64;
+                    const int r = pos - c * kKvChunk;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int j = lane * 4 + i;
-                    const __half vh = __ushort_as_half(ldcg_u16(v + j));
-                    *reinterpret_cast<__half *>(vst + kv_off(r, j >> 3) + (j & 7) * 2) = vh;
-                    L.v_cache[((size_t)sp.kvh * a.max_ctx + pos) * 128 + j] = vh;
+                    for (int i = 0; i < 2; i++) {
+                        const int j = lane * 2 + i;  // word j = dims 2j, 2j+1
+                        const float2 kr = rope_pair(kw, j, tag_qkv, cosr, sinr);
+                        const __half2 kh = __floats2half2_rn(kr.x, kr.y);
+                        const uint32_t vv = wait_ll1(vw + j, tag_qkv, false);
+                        *reinterpret_cast<__half2 *>(kst + kv_off(r, j >> 2) + (j & 3) * 4) = kh;
+                        *reinterpret_cast<uint32_t *>(vst + kv_off(r, j >> 2) + (j & 3) * 4) = vv;
+                        *reinterpret_cast<__half2 *>(L.k_cache + ((size_t)sp.kvh * a.max_ctx + pos) * 128 + 2 * j) = kh;
+                        *reinterpret_cast<uint32_t *>(L.v_cache + ((size_t)sp.kvh * a.max_ctx + pos) * 128 + 2 * j) = vv;
+                    }
+                    // V rows of the block beyond the token were never written for this sequence: finite zeros (0 * garbage must not be NaN)
+                    for (int rr = r + 1; rr < kb * 16 + 16; rr++)
+                        *reinterpret_cast<uint2 *>(vst + kv_off(rr, lane >> 1) + (lane & 1) * 8) = make_uint2(0u, 0u);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes into a stage the TMA unit will refill
+                    __syncwarp();
                 }
-                // rows of the block beyond the token were never written for this sequence: finite zeros (0 * garbage must not be NaN)
-                for (int rr = r + 1; rr < kb * 16 + 16; rr++)
-                    *reinterpret_cast<uint2 *>(vst + kv_off(rr, lane >> 1) + (lane & 1) * 8) = make_uint2(0u, 0u);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-            }
-            // thread (g, t): head row g, keys kbase + {2t, 2t+1} (s0) and kbase + 8 + {2t, 2t+1} (s1)
-            const int k0 = kbase + 2 * t;
-            float e0 = (k0 <= pos) ? s0[0] : -INFINITY, e1 = (k0 + 1 <= pos) ? s0[1] : -INFINITY;
-            float e2 = (k0 + 8 <= pos) ? s1[0] : -INFINITY, e3 = (k0 + 9 <= pos) ? s1[1] : -INFINITY;
-            float mb = fmaxf(fmaxf(e0, e1), fmaxf(e2, e3));
-            mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
-            mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
-            const float m_new = fmaxf(m_run, mb);  // finite: key kbase is visible
-            e0 = __expf(e0 - m_new);
-            e1 = __expf(e1 - m_new);
-            e2 = __expf(e2 - m_new);
-            e3 = __expf(e3 - m_new);
-            float lb = (e0 + e1) + (e2 + e3);
-            lb += __shfl_xor_sync(0xffffffffu, lb, 1);
-            lb += __shfl_xor_sync(0xffffffffu, lb, 2);
-            const float sc_old = have ? __expf(m_run - m_new) : 0.f;
-            l_run = l_run * sc_old + lb;
-            m_run = m_new;
-            const uint32_t pa0 = pack_half2(e0, e1), pa2 = pack_half2(e2, e3);  // A operand: P[head g][keys], rows 8..15 zero
-            const int lr = (lane & 7) + (((lane >> 3) & 1) << 3);  // ldmatrix.trans row = key within the block
-            const int lc = lane >> 4;                                // ... which of the two 8-dim n-tiles
+                // ---- scores: S[head][key] = q . K ----
+                float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+                {
+                    const int lr = (lane & 7) + ((lane >> 4) << 3);  // ldmatrix row supplied by this lane (key within the block)
+                    const int lc = (lane >> 3) & 1;                  // ... and which 8-dim half of the k-step
 #pragma unroll
-            for (int h = 0; h < 2; h++) {  // dims 64h .. 64h + 63
-                float oacc[8][4];
-#pragma unroll
-                for (int j = 0; j < 8; j++) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
-#pragma unroll
-                for (int jp = 0; jp < 4; jp++) {
-                    uint32_t b0, b1, b2, b3;
-                    attn::ldmatrix_x4_t(b0, b1, b2, b3, vst + kv_off(kb * 16 + lr, 8 * h + 2 * jp + lc));
-                    mma_m16n8k16(oacc[2 * jp], pa0, 0u, pa2, 0u, b0, b1);
-                    mma_m16n8k16(oacc[2 * jp + 1], pa0, 0u, pa2, 0u, b2, b3);
-                }
-                if (g < nrep) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float2 *dst = reinterpret_cast<float2 *>(myO + g * 128 + 64 * h + 8 * j + 2 * t);
-                        float2 nv = make_float2(oacc[j][0], oacc[j][1]);
-                        if (have) {
-                            const float2 old = *dst;
-                            nv.x += old.x * sc_old;
-                            nv.y += old.y * sc_old;
-                        }
-                        *dst = nv;
+                    for (int ks = 0; ks < 8; ks++) {
+                        uint32_t b0, b1, b2, b3;
+                        attn::ldmatrix_x4(b0, b1, b2, b3, kst + kv_off(kb * 16 + lr, 2 * ks + lc));
+                        mma_m16n8k16(s0, qa[ks][0], 0u, qa[ks][1], 0u, b0, b1);  // keys 0..7 of the block
+                        mma_m16n8k16(s1, qa[ks][0], 0u, qa[ks][1], 0u, b2, b3);  // keys 8..15
                     }
                 }
+                // thread (g, t): head row g, keys kbase + {2t, 2t+1} (s0) and kbase + 8 + {2t, 2t+1} (s1)
+                const int k0 = kbase + 2 * t;
+                float e0 = (k0 <= pos) ? s0[0] : -INFINITY, e1 = (k0 + 1 <= pos) ? s0[1] : -INFINITY;
+                float e2 = (k0 + 8 <= pos) ? s1[0] : -INFINITY, e3 = (k0 + 9 <= pos) ? s1[1] : -INFINITY;
+                float mb = fmaxf(fmaxf(e0, e1), fmaxf(e2, e3));
+                mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+                mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+                const float m_new = fmaxf(m_run, mb);  // finite: key kbase is visible
+                e0 = __expf(e0 - m_new);
+                e1 = __expf(e1 - m_new);
+                e2 = __expf(e2 - m_new);
+                e3 = __expf(e3 - m_new);
+                float lb = (e0 + e1) + (e2 + e3);
+                lb += __shfl_xor_sync(0xffffffffu, lb, 1);
+                lb += __shfl_xor_sync(0xffffffffu, lb, 2);
+                const float sc_old = have ? __expf(m_run - m_new) : 0.f;
+                l_run = l_run * sc_old + lb;
+                m_run = m_new;
+                const uint32_t pa0 = pack_half2(e0, e1), pa2 = pack_half2(e2, e3);  // A operand: P[head g][keys], rows 8..15 zero
+                const int lr = (lane & 7) + (((lane >> 3) & 1) << 3);  // ldmatrix.trans row = key within the block
+                const int lc = lane >> 4;                                // ... which of the two 8-dim n-tiles
+#pragma unroll
+                for (int h = 0; h < 2; h++) {  // dims 64h .. 64h + 63
+                    float oacc[8][4];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+#pragma unroll
+                    for (int jp = 0; jp < 4; jp++) {
+                        uint32_t b0, b1, b2, b3;
+                        attn::ldmatrix_x4_t(b0, b1, b2, b3, vst + kv_off(kb * 16 + lr, 8 * h + 2 * jp + lc));
+                        mma_m16n8k16(oacc[2 * jp], pa0, 0u, pa2, 0u, b0, b1);
+                        mma_m16n8k16(oacc[2 * jp + 1], pa0, 0u, pa2, 0u, b2, b3);
+                    }
+                    if (g < nrep) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float2 *dst = reinterpret_cast<float2 *>(myO + g * 128 + 64 * h + 8 * j + 2 * t);
+                            float2 nv = make_float2(oacc[j][0], oacc[j][1]);
+                            if (have) {
+                                const float2 old = *dst;
+                                nv.x += old.x * sc_old;
+                                nv.y += old.y * sc_old;
+                            }
+                            *dst = nv;
+                        }
+                    }
+                }
+                have = true;
             }
-            have = true;
+            __syncwarp();
+            if (lane == 0) mbar_arrive_u32(sm.empty_u32 + (uint32_t)rs.stage * 8u);
+            rs.advance(sm.nst);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[rs.stage]);
-        rs.advance(sm.nst);
-    }
-    if (t == 0 && g < nrep) {
-        sML[(cw * nrep + g) * 2] = have ? m_run : -INFINITY;
-        sML[(cw * nrep + g) * 2 + 1] = have ? l_run : 0.f;
-    }
-    named_bar_sync(1, kConsumerThreads);
-    // ---- merge the 16 warp partials of this CTA: thread i < nrep * 128 owns (head r, dim d) ----
-    float o = 0.f, M = -INFINITY, Lsum = 0.f;
-    const int r = ctid >> 7, d = ctid & 127;
-    const bool owner = ctid < nrep * 128;
-    if (owner) {
-        for (int w = 0; w < kCW; w++) M = fmaxf(M, sML[(w * nrep + r) * 2]);
-        for (int w = 0; w < kCW; w++) {
-            const float mw = sML[(w * nrep + r) * 2];
-            if (mw != -INFINITY) {
-                const float wt = __expf(mw - M);
-                Lsum += wt * sML[(w * nrep + r) * 2 + 1];
-                o += wt * sO[((size_t)w * nrep + r) * 128 + d];
+        if (t == 0 && g < nrep) {
+            sML[(cw * nrep + g) * 2] = have ? m_run : -INFINITY;
+            sML[(cw * nrep + g) * 2 + 1] = have ? l_run : 0.f;
+        }
+        named_bar_sync(1, kConsumerThreads);
+        // ---- merge the 16 warp partials of this CTA: thread i < nrep * 128 owns (head r, dim d) ----
+        const int r = ctid >> 7, d = ctid & 127;
+        if (ctid < nrep * 128) {  // whole warps: nrep * 128 is a multiple of 32
+            float o = 0.f, M = -INFINITY, Lsum = 0.f;
+            for (int w = 0; w < kCW; w++) M = fmaxf(M, sML[(w * nrep + r) * 2]);
+            for (int w = 0; w < kCW; w++) {
+                const float mw = sML[(w * nrep + r) * 2];
+                if (mw != -INFINITY) {
+                    const float wt = __expf(mw - M);
+                    Lsum += wt * sML[(w * nrep + r) * 2 + 1];
+                    o += wt * sO[((size_t)w * nrep + r) * 128 + d];
+                }
+            }
+            const int head = sp.kvh * nrep + r;
+            if (sp.nsplit == 1) {
+                const float y = o / Lsum;
+                const float yhi = __shfl_down_sync(0xffffffffu, y, 1);
+                if (!(d & 1)) st_ll(a.attn_ll + (size_t)head * 64 + (d >> 1), pack_half2(y, yhi), tag_out, false);
+            } else {
+                uint2 *rec = a.part_ll + ((size_t)head * a.nsplit_max + sp.split) * 130;
+                st_ll(rec + d, __float_as_uint(o), tag_part, false);
+                if (d == 0) {
+                    st_ll(rec + 128, __float_as_uint(M), tag_part, false);
+                    st_ll(rec + 129, __float_as_uint(Lsum), tag_part, false);
+                }
             }
         }
     }
-    const int head = sp.kvh * nrep + r;
-    if (sp.nsplit == 1) {
-        if (owner) a.attn[(size_t)head * 128 + d] = __float2half(o / Lsum);
-        return;
-    }
-    int NS = ncta / a.KVH;
-    if (NS < 1) NS = 1;
-    if (owner) {
-        float *rec = a.attn_ws + ((size_t)head * NS + sp.split) * 130;
-        rec[d] = o;
-        if (d == 0) {
-            rec[128] = M;
-            rec[129] = Lsum;
+    if (sp.nsplit == 1) return;
+    // ---- split merge, spread over the grid: task = (head, block of 32 dims), one warp each ----
+    const int ntask = a.H * 4;
+    for (int task = cta + cw * ncta; task < ntask; task += ncta * kCW) {
+        const int head = task >> 2, d = ((task & 3) << 5) + lane;
+        const uint2 *base = a.part_ll + (size_t)head * a.nsplit_max * 130;
+        // lane s < nsplit fetches (m, l) of split s; the maximum and the weights are formed with shuffles
+        float ms = -INFINITY, ls = 0.f;
+        if (lane < sp.nsplit) {
+            ms = __uint_as_float(wait_ll1(base + (size_t)lane * 130 + 128, tag_part, false));
+            ls = __uint_as_float(wait_ll1(base + (size_t)lane * 130 + 129, tag_part, false));
         }
-    }
-    // ---- the last split of this KV head to arrive combines all of them in split order ----
-    __threadfence();
-    named_bar_sync(1, kConsumerThreads);
-    if (ctid == 0) {
-        const unsigned prev = atomicAdd(&a.attn_cnt[sp.kvh], 1u);
-        const int last = (prev == (unsigned)(sp.nsplit - 1)) ? 1 : 0;
-        if (last) a.attn_cnt[sp.kvh] = 0;
-        *sm.aflag = last;
-    }
-    named_bar_sync(1, kConsumerThreads);
-    if (*sm.aflag == 0) return;
-    __threadfence();
-    if (owner) {
-        const float *base = a.attn_ws + (size_t)head * NS * 130;
-        float m = -INFINITY;
-        for (int s = 0; s < sp.nsplit; s++) m = fmaxf(m, ldcg_f32(base + (size_t)s * 130 + 128));
-        float l = 0.f, acc = 0.f;
-        for (int s = 0; s < sp.nsplit; s++) {
-            const float w = __expf(ldcg_f32(base + (size_t)s * 130 + 128) - m);
-            l += w * ldcg_f32(base + (size_t)s * 130 + 129);
-            acc += w * ldcg_f32(base + (size_t)s * 130 + d);
+        const float M = warp_max(ms);
+        const float wgt = (lane < sp.nsplit) ? __expf(ms - M) : 0.f;
+        const float Lt = warp_sum(wgt * ls);
+        float acc = 0.f;
+        for (int s0 = 0; s0 < sp.nsplit; s0 += 4) {
+            float ov[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) ov[i] = (s0 + i < sp.nsplit) ? __uint_as_float(wait_ll1(base + (size_t)(s0 + i) * 130 + d, tag_part, false)) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc += __shfl_sync(0xffffffffu, wgt, (s0 + i) & 31) * ov[i];
         }
-        a.attn[(size_t)head * 128 + d] = __float2half(acc / l);
+        const float y = acc / Lt;
+        const float yhi = __shfl_down_sync(0xffffffffu, y, 1);
+        if (!(lane & 1)) st_ll(a.attn_ll + (size_t)head * 64 + (d >> 1), pack_half2(y, yhi), tag_out, false);
     }
 }
 
@@ -689,15 +744,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
         mbar_fence_init();
     }
     __syncthreads();
-    const unsigned epoch = *a.epoch;
-    const unsigned target = (epoch + 1u) * (unsigned)ncta;  // every phase counter reaches this when all CTAs have arrived in this launch
-    const bool tp = a.tp_size > 1;
-    // tensor-parallel arrival counters advance by tp_size * ncta per collective, num_layers collectives per launch on each of the two
-    const unsigned tp_per = (unsigned)a.tp_size * (unsigned)ncta;
-    const unsigned tp_base = epoch * (unsigned)Lyr * tp_per;
-
     // phase p = 5 * layer + k, k: 0 RMSNorm + q|k|v, 1 attention, 2 o_proj, 3 RMSNorm + gate|up, 4 down_proj; p = 5 * Lyr: lm_head
     const int nphase = 5 * Lyr + 1;
+    const unsigned epoch = *a.epoch;
+    const uint32_t tag_base = epoch * (uint32_t)(2 * nphase + 2) + 1u;  // tag of (phase p, sub-result s) = tag_base + 2p + s: unique over launches, never 0
+
     if (warp == 0) {
         // ================= producer: every byte this CTA needs from HBM, in consumption order =================
         Ring rs;
@@ -722,40 +773,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
     if (warp == 1) {
         // ================= epilogue warp =================
         Red es;
-        EpiOut o;
-        o.logits = a.logits;
-        o.best = 0ull;
-        o.index_base = a.vocab_base;
+        EpiState st;
+        st.best = 0ull;
 #pragma unroll 1
         for (int p = 0; p < nphase; p++) {
             const int l = p / 5, k = p - 5 * l;
-            if (l < Lyr && k == 1) continue;  // attention: the consumers signal the barrier themselves
+            if (l < Lyr && k == 1) continue;  // attention publishes its own results
             const int oi = (l == Lyr) ? OPI_LMHEAD : ((k == 0) ? OPI_QKV : (k - 1));
-            o.y = (oi == OPI_QKV) ? (void *)a.qkv : (oi == OPI_GATEUP ? (void *)a.act : (void *)a.resid);
-            epilogue_gemv(a, a.op[oi], sm, es, o, (oi == OPI_DOWN) ? 1 : 0, cta, ncta, lane);
-            if (tp && (oi == OPI_O || oi == OPI_DOWN)) {
-                // this CTA's peer stores are fenced system-wide, then it checks in with every rank
-                __threadfence_system();
-                __syncwarp();
-                if (lane < a.tp_size) red_release_sys(a.tp_arrive[lane] + (oi == OPI_DOWN ? 1 : 0));
-            }
-            if (oi == OPI_LMHEAD) {
-                unsigned long long key = o.best;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, off);
-                    key = other > key ? other : key;
-                }
-                if (lane == 0 && key) atomicMax(a.argmax_cell, key);
-            }
-            // everything this warp wrote in phase p is visible device-wide before the arrival
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                red_release_gpu(a.sync + p);
-                stamp(a, cta, nphase, p, 3);
-            }
+            uint2 *out = (oi == OPI_QKV) ? a.qkv_ll : (oi == OPI_GATEUP ? a.act_ll : (oi == OPI_O ? a.delta_ll[0] : a.delta_ll[1]));
+            epilogue_gemv(a, a.op[oi], sm, es, st, out, (oi == OPI_DOWN) ? 1 : 0, tag_base + 2u * (uint32_t)p, cta, ncta, lane);
+            if (lane == 0) stamp(a, cta, nphase, p, 3);
         }
+        unsigned long long key = st.best;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, off);
+            key = other > key ? other : key;
+        }
+        if (lane == 0 && key) atomicMax(a.argmax_cell, key);
+        // the logits and the arg-max contribution of this CTA are visible device-wide before the arrival
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) red_release_gpu(a.done);
         return;
     }
 
@@ -764,77 +803,58 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
     const int cw = warp - 2;
     Ring rs;
     Red cs;
-    // tensor parallel: residual buffers ping-pong (every rank reduces the same gathered partials into the other buffer)
-    float *resid_cur = a.resid, *resid_alt = a.resid + a.E;
 #pragma unroll 1
     for (int p = 0; p < nphase; p++) {
         const int l = p / 5, k = p - 5 * l;
-        if (p > 0) {  // all CTAs have completed phase p - 1
-            if (ctid == 0) grid_wait(a.sync + p - 1, target);
-            named_bar_sync(1, kConsumerThreads);
-        }
+        const uint32_t tag_in = tag_base + 2u * (uint32_t)(p - 1);  // primary result of the previous phase
         if (ctid == 0) stamp(a, cta, nphase, p, 0);
         if (l < Lyr && k == 1) {
             // ---- RoPE + KV append + attention ----
-            attention_phase(a, a.layers[l], sm, rs, cta, ncta, pos, ctid, cw, lane);
+            attention_phase(a, a.layers[l], sm, rs, tag_in, tag_base + 2u * (uint32_t)p + 1u, tag_base + 2u * (uint32_t)p, cta, ncta, pos, ctid, cw, lane);
             if (ctid == 0) stamp(a, cta, nphase, p, 2);
-            __threadfence();
-            named_bar_sync(1, kConsumerThreads);
-            if (ctid == 0) {
-                red_release_gpu(a.sync + p);
-                stamp(a, cta, nphase, p, 3);
-            }
+            named_bar_sync(1, kConsumerThreads);  // the scratch aliases the activation planes of the next phase
             continue;
         }
         const int oi = (l == Lyr) ? OPI_LMHEAD : ((k == 0) ? OPI_QKV : (k - 1));
-        int x_mode = a.op[oi].x_mode;
-        const void *xsrc = resid_cur;
-        const float *gamma = nullptr, *tin = nullptr;
-        float *rout = nullptr;
+        const GemvOp &op = a.op[oi];
+        int t0, t1;
+        partition(op, cta, ncta, t0, t1);
+        const bool work = t1 > t0;
+        float inv = 1.f;
         if (oi == OPI_O) {
-            xsrc = a.attn;
+            if (work) stage_half(op, sm, a.attn_ll, tag_in, cta, ctid, lane);
         } else if (oi == OPI_DOWN) {
-            xsrc = a.act;
+            if (work) stage_half(op, sm, a.act_ll, tag_in, cta, ctid, lane);
         } else {
-            gamma = (oi == OPI_LMHEAD) ? a.final_norm : (oi == OPI_QKV ? a.layers[l].input_norm : a.layers[l].post_norm);
-            if (p == 0) {
-                // the token's embedding row is the residual stream (reference: CPU Embedding, cuda/Int4llamaDecoder.cu:62-69)
-                x_mode = PX_EMBED_RMS;
-                rout = resid_cur;
-            } else if (tp) {
-                // tensor-parallel all-reduce, receive side: the collective that feeds this RMSNorm (o_proj of this layer for gate|up,
-                // down_proj of the previous layer otherwise) has landed in the local gather buffer once every CTA of every rank arrived
-                const int buf = (oi == OPI_GATEUP) ? 0 : 1;
-                const unsigned done = (oi == OPI_GATEUP) ? (unsigned)(l + 1) : (unsigned)l;  // collectives completed on that buffer this launch
-                if (ctid == 0) sys_wait(a.tp_arrive[a.tp_rank] + buf, tp_base + done * tp_per);
-                named_bar_sync(1, kConsumerThreads);
-                tin = a.tp_gather[a.tp_rank] + (size_t)buf * a.tp_size * a.E;
-                rout = resid_alt;
-            }
-        }
-        const float inv = stage_x(a, a.op[oi], x_mode, sm, xsrc, gamma, tin, rout, token, cta, ctid, cw, lane);
-        if (tin) {
-            float *tmp = resid_cur;
-            resid_cur = resid_alt;
-            resid_alt = tmp;
+            // the residual copy of this CTA must see every o_proj / down_proj output, whether or not the CTA owns tiles of this phase
+            const float *gamma = (oi == OPI_LMHEAD) ? a.final_norm : (oi == OPI_QKV ? a.layers[l].input_norm : a.layers[l].post_norm);
+            const uint2 *delta = (oi == OPI_GATEUP) ? a.delta_ll[0] : a.delta_ll[1];
+            inv = stage_rms(a, op, sm, delta, tag_in, gamma, token, p == 0, work, cta, ctid, cw, lane);
         }
         if (ctid == 0) stamp(a, cta, nphase, p, 1);
-        consume_gemv(a.op[oi], sm, rs, cs, inv, cta, ncta, cw, lane);
+        if (work) consume_gemv(op, sm, rs, cs, inv, cta, ncta, cw, lane);
         if (ctid == 0) stamp(a, cta, nphase, p, 2);
+        named_bar_sync(1, kConsumerThreads);  // every warp is done with the planes before the next phase overwrites them
     }
     // ---- greedy token: decoded once every CTA's epilogue has contributed its maximum ----
     if (cta == 0 && ctid == 0) {
-        grid_wait(a.sync + 5 * Lyr, target);
+        const unsigned target = (epoch + 1u) * (unsigned)ncta;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_gpu(a.done) - target) < 0) {
+            if (clock64() - t0 > kSpinLimit) __trap();
+        }
         unsigned long long key = *reinterpret_cast<volatile unsigned long long *>(a.argmax_cell);
-        if (tp) {
-            // vocabulary shards: scatter the local key to every rank, wait for all of them, take the global maximum
-            for (int pr = 0; pr < a.tp_size; pr++) *reinterpret_cast<volatile unsigned long long *>(a.tp_keys[pr] + a.tp_rank) = key;
-            __threadfence_system();
-            for (int pr = 0; pr < a.tp_size; pr++) red_release_sys(a.tp_key_arrive[pr]);
-            sys_wait(a.tp_key_arrive[a.tp_rank], (epoch + 1u) * (unsigned)a.tp_size);
+        if (a.tp_size > 1) {
+            // vocabulary shards: publish the local key to every rank as two tagged words, take the global maximum
+            const uint32_t tag = tag_base + 2u * (uint32_t)nphase;
+            for (int pr = 0; pr < a.tp_size; pr++) {
+                st_ll(a.tp_keys[pr] + (size_t)a.tp_rank * 2, (uint32_t)(key >> 32), tag, true);
+                st_ll(a.tp_keys[pr] + (size_t)a.tp_rank * 2 + 1, (uint32_t)key, tag, true);
+            }
             key = 0ull;
             for (int pr = 0; pr < a.tp_size; pr++) {
-                const unsigned long long k2 = *reinterpret_cast<volatile unsigned long long *>(a.tp_keys[a.tp_rank] + pr);
+                const uint32_t hi = wait_ll1(a.tp_keys[a.tp_rank] + (size_t)pr * 2, tag, true), lo = wait_ll1(a.tp_keys[a.tp_rank] + (size_t)pr * 2 + 1, tag, true);
+                const unsigned long long k2 = ((unsigned long long)hi << 32) | lo;
                 key = k2 > key ? k2 : key;
             }
         }
@@ -845,15 +865,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
 }
 
 // ------------------------------------------------------------------------------------------------------------ repack kernel
-// scales half[rows][sf_w] + zeros u32[rows][zeros_w] (QM_CUDA, llm/tools/quantize_methods.py:370-442) -> one 640-byte record per
-// (16-row tile, 16-group stage): scales half[16 groups][16 rows], zeros u64[16 groups] (nibble r = zero point of row r).
+// scales half[rows][sf_w] + zeros u32[rows][zeros_w] (QM_CUDA, llm/tools/quantize_methods.py:370-442) -> one 1280-byte record per
+// (16-row tile, 32-group stage): scales half[32 groups][16 rows], zeros u64[32 groups] (nibble r = zero point of row r).
 __global__ void repack_meta_kernel(W4Seg s0, W4Seg s1, W4Seg s2, int nseg, int pair, int NG, int zeros_w, int sf_w, int S, int num_tiles, uint8_t *out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tile, s, gi)
-    if (idx >= num_tiles * S * 16) return;
-    const int gi = idx & 15, su = idx >> 4;
+    if (idx >= num_tiles * S * kStageGroups) return;
+    const int gi = idx % kStageGroups, su = idx / kStageGroups;
     const int tile = su / S, s = su - tile * S;
-    const int G = 16 * s + gi;
-    __half sc[16];
+    const int G = kStageGroups * s + gi;
+    uint8_t *rec = out + (size_t)su * kMetaBytes;
+    __half *so = reinterpret_cast<__half *>(rec) + gi * 16;
     unsigned long long z = 0ull;
     for (int r = 0; r < 16; r++) {
         const W4Seg *seg = &s0;
@@ -873,40 +894,44 @@ __global__ void repack_meta_kernel(W4Seg s0, W4Seg s1, W4Seg s2, int nseg, int p
             }
         }
         if (G < NG) {
-            sc[r] = seg->scales[(size_t)row * sf_w + G];
+            so[r] = seg->scales[(size_t)row * sf_w + G];
             z |= (unsigned long long)((seg->zeros[(size_t)row * zeros_w + (G >> 3)] >> ((G & 7) * 4)) & 0xFu) << (4 * r);
         } else {
-            sc[r] = __float2half(0.f);
+            so[r] = __float2half(0.f);
         }
     }
-    uint8_t *rec = out + (size_t)su * kMetaBytes;
-    __half *so = reinterpret_cast<__half *>(rec) + gi * 16;
-    for (int r = 0; r < 16; r++) so[r] = sc[r];
-    reinterpret_cast<unsigned long long *>(rec + 512)[gi] = z;
+    reinterpret_cast<unsigned long long *>(rec + 1024)[gi] = z;
 }
 
 }  // namespace
 
 int attn_scratch_bytes(int nrep) { return 8 * 136 * 2 + kCW * nrep * 128 * 4 + kCW * nrep * 2 * 4; }
 
-static size_t fixed_bytes(int xs_bytes, int max_ng) {
-    return (size_t)xs_bytes + (size_t)max_ng * 12 + (size_t)kRedBufs * kCW * 16 * 4 + 32 * 4 + (size_t)(2 * kMaxStages + 2 * kRedBufs) * 8 + 16 + 1024;
+int attn_nsplit_max(int ncta, int KVH, int max_ctx) {
+    int NS = ncta / KVH;
+    if (NS < 1) NS = 1;
+    const int nch = (max_ctx + kKvChunk - 1) / kKvChunk;
+    return NS < nch ? NS : nch;
 }
-int pick_stages(int smem_optin, int xs_bytes, int max_ng) {
-    const long long avail = (long long)smem_optin - (long long)fixed_bytes(xs_bytes, max_ng);
+
+static size_t fixed_bytes(int xs_bytes, int max_ng, int E) {
+    return (size_t)xs_bytes + (size_t)E * 4 + (size_t)max_ng * 12 + (size_t)kRedBufs * kCW * 16 * 4 + 32 * 4 + (size_t)(2 * kMaxStages + 2 * kRedBufs) * 8 + 16 + 1024;
+}
+int pick_stages(int smem_optin, int xs_bytes, int max_ng, int E) {
+    const long long avail = (long long)smem_optin - (long long)fixed_bytes(xs_bytes, max_ng, E);
     long long n = avail / kStageBytes;
     if (n > kMaxStages) n = kMaxStages;
     return n < 2 ? 0 : (int)n;
 }
-size_t smem_bytes(const Args &a) { return fixed_bytes(a.xs_bytes, a.max_ng) + (size_t)a.nst * kStageBytes; }
+size_t smem_bytes(const Args &a) { return fixed_bytes(a.xs_bytes, a.max_ng, a.E) + (size_t)a.nst * kStageBytes; }
 
 cudaError_t repack_meta(Ctx *ctx, const W4Seg *segs, int nseg, int pair, int IC, uint8_t *out, cudaStream_t stream) {
-    const int NG = IC / kW4Group, S = (NG + 15) / 16;
+    const int NG = IC / kW4Group, S = (NG + kStageGroups - 1) / kStageGroups;
     int rows = 0;
     for (int i = 0; i < nseg; i++) rows += segs[i].rows;
     const int num_tiles = rows / 16;
     const int zw = zeros_width(IC, kW4Group);
-    const int total = num_tiles * S * 16;
+    const int total = num_tiles * S * kStageGroups;
     if (total == 0) return cudaSuccess;
     repack_meta_kernel<<<(total + 127) / 128, 128, 0, stream>>>(segs[0], segs[nseg > 1 ? 1 : 0], segs[nseg > 2 ? 2 : 0], nseg, pair, NG, zw, zw * 8, S, num_tiles, out);
     (void)ctx;
@@ -941,7 +966,7 @@ cudaError_t launch(Ctx *ctx, const Args &a, cudaStream_t stream) {
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident: the kernel synchronises grid-wide
+    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident: they wait for each other's results
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;

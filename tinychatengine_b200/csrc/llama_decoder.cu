@@ -106,6 +106,9 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
         // tensor parallel: one peer-visible allocation [gather A|B: 2 x P x E fp32][flags: 3 x P u32 (256-B padded)][keys: P u64]
         d->tp_gather_floats_ = (size_t)2 * d->tp_ * E;
         d->tp_bytes_ = d->tp_gather_floats_ * sizeof(float) + 256 + (size_t)kMaxTP * sizeof(unsigned long long);
+        // persistent kernel layout: two delta buffers of P x E {float, tag} words + P x 2 key words
+        const size_t pk_bytes = ((size_t)2 * d->tp_ * E + (size_t)2 * d->tp_) * sizeof(uint2);
+        if (d->tp_bytes_ < pk_bytes) d->tp_bytes_ = pk_bytes;
         if (cudaMalloc((void **)&d->tp_buf_, d->tp_bytes_) != cudaSuccess || cudaMemset(d->tp_buf_, 0, d->tp_bytes_) != cudaSuccess) {
             *err = "tensor-parallel buffer allocation failed";
             delete d;
@@ -404,7 +407,7 @@ void LlamaDecoder::build_ops() {
 
 // Everything the persistent decode kernel (decode_persistent.cu) needs beyond the caller's weights: one 2-D tensor map per packed
 // matrix, the per-stage scales|zeros records (a one-off repack of the QM_CUDA scales / zeros arrays into the order the TMA ring
-// consumes them: SURVEY.md 8(f)2 "repack once into the TMA-friendly interleave"), the layer table and the barrier counters.
+// consumes them: SURVEY.md 8(f)2 "repack once into the TMA-friendly interleave"), the layer table and the tagged hand-off buffers.
 cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     const int E = cfg_.embed_dim, F = cfg_.hidden_dim, H = cfg_.num_heads, KVH = cfg_.num_kv_heads, hd = cfg_.head_dim, V = cfg_.vocab_size;
     const int Lyr = cfg_.num_layers, ncta = ctx_->num_sms;
@@ -413,36 +416,33 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         if (err) *err = m;
         return cudaErrorNotSupported;
     };
-    if (hd != 128 || nrep > 4 || ncta < KVH || F % 8) return no("shape outside the persistent kernel's envelope");
+    if (hd != 128 || nrep > 4 || ncta < KVH || F % 16 || V % 16) return no("shape outside the persistent kernel's envelope");
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx_->device);
     if (!coop) return no("device cannot launch cooperative kernels");
     pk::Args a{};
-    auto mk = [&](int IC, int rows, int nseg, int pair, int rows0, int rows1, int x_mode, int epi, int aligned) {
+    auto mk = [&](int IC, int rows, int nseg, int pair, int rows0, int rows1, int x_mode, int epi) {
         pk::GemvOp o{};
         o.IC = IC;
         o.NG = IC / kW4Group;
         o.sg = o.NG < 16 ? o.NG : 16;
-        o.S = (o.NG + 15) / 16;
+        o.S = (o.NG + pk::kStageGroups - 1) / pk::kStageGroups;
         o.num_tiles = rows / 16;
-        o.SU = o.num_tiles * o.S;
         o.nseg = nseg;
         o.pair = pair;
         o.rows0 = rows0;
         o.rows1 = rows1;
         o.x_mode = x_mode;
         o.epi = epi;
-        o.aligned = aligned;
         o.box_bytes = 16 * o.sg * 64;
         return o;
     };
     const bool tp = tp_ > 1;
-    const int add_epi = tp ? pk::PE_TP_SCATTER : pk::PE_ADD_F32;
-    a.op[pk::OPI_QKV] = mk(E, (H + 2 * KVH) * hd, 3, 0, H * hd, KVH * hd, pk::PX_RMS_F32, pk::PE_STORE_HALF, 1);
-    a.op[pk::OPI_O] = mk(H * hd, E, 1, 0, E, 0, pk::PX_HALF, add_epi, (tp || !atomic_residual_) ? 1 : 0);
-    a.op[pk::OPI_GATEUP] = mk(E, 2 * F, 2, 1, F, F, pk::PX_RMS_F32, pk::PE_SILU_MUL, 1);
-    a.op[pk::OPI_DOWN] = mk(F, E, 1, 0, E, 0, pk::PX_HALF, add_epi, (tp || !atomic_residual_) ? 1 : 0);
-    a.op[pk::OPI_LMHEAD] = mk(E, V, 1, 0, V, 0, pk::PX_RMS_F32, pk::PE_LOGITS, 1);
+    a.op[pk::OPI_QKV] = mk(E, (H + 2 * KVH) * hd, 3, 0, H * hd, KVH * hd, pk::PX_RMS_F32, pk::PE_HALF_LL);
+    a.op[pk::OPI_O] = mk(H * hd, E, 1, 0, E, 0, pk::PX_HALF, pk::PE_DELTA_LL);
+    a.op[pk::OPI_GATEUP] = mk(E, 2 * F, 2, 1, F, F, pk::PX_RMS_F32, pk::PE_SILU_LL);
+    a.op[pk::OPI_DOWN] = mk(F, E, 1, 0, E, 0, pk::PX_HALF, pk::PE_DELTA_LL);
+    a.op[pk::OPI_LMHEAD] = mk(E, V, 1, 0, V, 0, pk::PX_RMS_F32, pk::PE_LOGITS);
     int max_ic = 0, max_ng = 0;
     for (int i = 0; i < pk::OPI_COUNT; i++) {
         if (a.op[i].IC > max_ic) max_ic = a.op[i].IC;
@@ -455,12 +455,13 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     xs = (xs + 15) & ~15;
     a.xs_bytes = xs;
     a.max_ng = max_ng;
-    a.nst = pk::pick_stages(ctx_->smem_optin, xs, max_ng);
+    a.E = E;
+    a.nst = pk::pick_stages(ctx_->smem_optin, xs, max_ng, E);
     if (getenv("TCE_PK_STAGES")) {
         const int want = atoi(getenv("TCE_PK_STAGES"));
         if (want >= 2 && want < a.nst) a.nst = want;
     }
-    if (a.nst < 3) return no("shared memory too small for the persistent kernel");
+    if (a.nst < 2) return no("shared memory too small for the persistent kernel");
 
     auto dalloc = [&](size_t bytes) -> void * {
         void *p = nullptr;
@@ -489,7 +490,7 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         const int ops4[4] = {pk::OPI_QKV, pk::OPI_O, pk::OPI_GATEUP, pk::OPI_DOWN};
         for (int i = 0; i < 4; i++) {
             const pk::GemvOp &o = a.op[ops4[i]];
-            uint8_t *m = (uint8_t *)dalloc((size_t)o.SU * pk::kMetaBytes);
+            uint8_t *m = (uint8_t *)dalloc((size_t)o.num_tiles * o.S * pk::kMetaBytes);
             if (!m) return cudaErrorMemoryAllocation;
             DCK(pk::repack_meta(ctx_, segs[i], nsegs[i], pairs[i], o.IC, m, s));
             D.meta[i] = m;
@@ -504,7 +505,7 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     {
         const pk::GemvOp &o = a.op[pk::OPI_LMHEAD];
         DCK(encode_w4_tmap(&maps[(size_t)Lyr * 7], w_.lm_head.w, w_.lm_head.oc, w_.lm_head.ic, o.sg, 16));
-        uint8_t *m = (uint8_t *)dalloc((size_t)o.SU * pk::kMetaBytes);
+        uint8_t *m = (uint8_t *)dalloc((size_t)o.num_tiles * o.S * pk::kMetaBytes);
         if (!m) return cudaErrorMemoryAllocation;
         const W4Seg lm[1] = {seg_of(w_.lm_head)};
         DCK(pk::repack_meta(ctx_, lm, 1, 0, o.IC, m, s));
@@ -513,15 +514,18 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     }
     CUtensorMap *dmaps = (CUtensorMap *)dalloc(maps.size() * sizeof(CUtensorMap));
     pk::LayerDesc *ddesc = (pk::LayerDesc *)dalloc(descs.size() * sizeof(pk::LayerDesc));
-    const int NS = ncta / KVH;
-    float *ws = (float *)dalloc((size_t)H * NS * 130 * sizeof(float));
-    const size_t nsync = (size_t)5 * Lyr + 1;
-    // [arg-max cell u64][epoch u32][error i32][attn counters KVH u32][phase counters]
-    uint8_t *ctl = (uint8_t *)dalloc(16 + (size_t)KVH * 4 + nsync * 4);
-    if (!dmaps || !ddesc || !ws || !ctl) return cudaErrorMemoryAllocation;
+    a.nsplit_max = pk::attn_nsplit_max(ncta, KVH, cfg_.max_ctx);
+    // hand-off buffers ({payload, tag} words; tag 0 = never written)
+    const size_t n_qkv = (size_t)(H + 2 * KVH) * 64, n_attn = (size_t)H * 64, n_act = (size_t)F / 2, n_part = (size_t)H * a.nsplit_max * 130;
+    const size_t ll_words = n_qkv + n_attn + n_act + n_part + (tp ? 0 : (size_t)2 * E);
+    uint2 *ll = (uint2 *)dalloc(ll_words * sizeof(uint2));
+    // [arg-max cell u64][epoch u32][error i32][done u32]
+    uint8_t *ctl = (uint8_t *)dalloc(32);
+    if (!dmaps || !ddesc || !ll || !ctl) return cudaErrorMemoryAllocation;
     DCK(cudaMemcpyAsync(dmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s));
     DCK(cudaMemcpyAsync(ddesc, descs.data(), descs.size() * sizeof(pk::LayerDesc), cudaMemcpyHostToDevice, s));
-    DCK(cudaMemsetAsync(ctl, 0, 16 + (size_t)KVH * 4 + nsync * 4, s));
+    DCK(cudaMemsetAsync(ll, 0, ll_words * sizeof(uint2), s));
+    DCK(cudaMemsetAsync(ctl, 0, 32, s));
     DCK(cudaStreamSynchronize(s));  // `maps` / `descs` are host temporaries
     a.layers = ddesc;
     a.num_layers = Lyr;
@@ -529,19 +533,17 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     a.final_norm = w_.final_norm;
     a.embed = (const __half *)w_.embed_f16;
     a.embed_rows = V * tp_;
-    a.resid = d_resid_;
-    a.qkv = d_qkv_;
-    a.attn = d_attn_;
-    a.act = d_act_;
+    a.qkv_ll = ll;
+    a.attn_ll = a.qkv_ll + n_qkv;
+    a.act_ll = a.attn_ll + n_attn;
+    a.part_ll = a.act_ll + n_act;
     a.logits = d_logits_;
     a.tokpos = d_tokpos_;
     a.next_token = d_next_;
     a.argmax_cell = reinterpret_cast<unsigned long long *>(ctl);
     a.epoch = reinterpret_cast<unsigned *>(ctl + 8);
     a.error = reinterpret_cast<int *>(ctl + 12);
-    a.attn_cnt = reinterpret_cast<unsigned *>(ctl + 16);
-    a.sync = a.attn_cnt + KVH;
-    a.attn_ws = ws;
+    a.done = reinterpret_cast<unsigned *>(ctl + 16);
     a.cos = d_cos_;
     a.sin = d_sin_;
     a.alpha = cfg_.qk_alpha > 0 ? cfg_.qk_alpha : 1.0f / sqrtf((float)hd);
@@ -550,23 +552,27 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     a.KVH = KVH;
     a.nrep = nrep;
     a.max_ctx = cfg_.max_ctx;
-    a.E = E;
     a.V = V;
+    a.F = F;
     a.tp_size = tp_;
     a.tp_rank = tp ? cfg_.tp_rank : 0;
     a.vocab_base = tp ? cfg_.tp_rank * V : 0;
     if (tp) {
+        // peer-visible allocation of every rank: [delta 0: P x E words][delta 1: P x E words][keys: P x 2 words]
         for (int q = 0; q < tp_; q++) {
-            uint8_t *base = tp_peer_[q];
-            a.tp_gather[q] = reinterpret_cast<float *>(base);
-            unsigned *words = reinterpret_cast<unsigned *>(base + tp_gather_floats_ * sizeof(float));
-            a.tp_arrive[q] = words;            // [0], [1]: the two gather buffers (adjacent words)
-            a.tp_key_arrive[q] = words + 32;   // own 128-byte line
-            a.tp_keys[q] = reinterpret_cast<unsigned long long *>(base + tp_gather_floats_ * sizeof(float) + 256);
+            uint2 *base = reinterpret_cast<uint2 *>(tp_peer_[q]);
+            a.tp_delta[0][q] = base;
+            a.tp_delta[1][q] = base + (size_t)tp_ * E;
+            a.tp_keys[q] = base + (size_t)2 * tp_ * E;
         }
+        a.delta_ll[0] = a.tp_delta[0][a.tp_rank];
+        a.delta_ll[1] = a.tp_delta[1][a.tp_rank];
+    } else {
+        a.delta_ll[0] = a.part_ll + n_part;
+        a.delta_ll[1] = a.delta_ll[0] + E;
     }
     if (getenv("TCE_PK_DEBUG") && atoi(getenv("TCE_PK_DEBUG"))) {
-        const size_t n = (size_t)ncta * nsync * 4 * sizeof(unsigned long long);
+        const size_t n = (size_t)ncta * ((size_t)5 * Lyr + 1) * 4 * sizeof(unsigned long long);
         a.dbg = (unsigned long long *)dalloc(n);
         if (!a.dbg) return cudaErrorMemoryAllocation;
         DCK(cudaMemset(a.dbg, 0, n));
