@@ -23,6 +23,7 @@
 // 8-byte words, flag included) and every reader sums the P slots in rank order.
 // All waits are bounded: a protocol bug surfaces as a launch failure within seconds, not as a hung GPU.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "attention_impl.cuh"
 #include "persistent.h"
@@ -86,6 +87,22 @@ TCE_DEVINL uint32_t wait_ll1(const uint2 *p, uint32_t tag, bool sys) {
         if (clock64() - t0 > kSpinLimit) __trap();
     }
 }
+// N consecutive 16-byte pairs: all loads are issued before the first tag is examined (one L2 round trip when the data is there)
+template <int N>
+TCE_DEVINL void wait_ll2xN(const uint2 *p, uint32_t tag, bool sys, uint4 (&r)[N]) {
+    long long t0 = 0;
+    while (true) {
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < N; i++) r[i] = ld_ll2(p + 2 * i, sys);
+#pragma unroll
+        for (int i = 0; i < N; i++) ok = ok && (r[i].y == tag) && (r[i].w == tag);
+        if (ok) return;
+        if (t0 == 0) t0 = clock64();
+        if (clock64() - t0 > kSpinLimit) __trap();
+    }
+}
+
 TCE_DEVINL float2 h2_to_f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2 *>(&u)); }
 
 // shared-memory accesses by 32-bit shared address (no generic-address conversion inside the hot loops)
@@ -105,10 +122,10 @@ TCE_DEVINL uint32_t lds_u32(uint32_t a) {
     return r;
 }
 TCE_DEVINL float lds_f32(uint32_t a) { return __uint_as_float(lds_u32(a)); }
-TCE_DEVINL float lds_h16(uint32_t a) {
+TCE_DEVINL uint32_t lds_u16(uint32_t a) {
     unsigned short r;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a) : "memory");
-    return __half2float(__ushort_as_half(r));
+    return (uint32_t)r;
 }
 TCE_DEVINL bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -124,11 +141,27 @@ TCE_DEVINL void mbar_wait_u32(uint32_t bar, uint32_t parity) {
 }
 TCE_DEVINL void mbar_arrive_u32(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
+// L2 prefetch of a TMA box / of a byte range: HBM -> L2 only, no shared-memory slot, no barrier
+TCE_DEVINL void tma_prefetch_2d_pred(const void *tmap, int x, int y, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t}" ::"l"(tmap), "r"(x), "r"(y),
+                 "r"(pred)
+                 : "memory");
+}
+TCE_DEVINL void bulk_prefetch_pred(const void *src, uint32_t bytes, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}" ::"l"(src), "r"(bytes), "r"(pred) : "memory");
+}
+TCE_DEVINL int lds_volatile_i32(const int *p) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+TCE_DEVINL void sts_volatile_i32(int *p, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
+
 TCE_DEVINL void stamp(const Args &a, int cta, int nphase, int p, int k) {  // one thread
     if (a.dbg) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        a.dbg[((size_t)cta * nphase + p) * 4 + k] = t;
+        a.dbg[((size_t)cta * nphase + p) * 8 + k] = t;
     }
 }
 
@@ -146,7 +179,9 @@ struct PSmem {
     int *gsum;          // [max_ng][2] group sums
     float *red;         // [kRedBufs][kCW][16] tile partials
     float *rms;         // [kCW]
+    float *rope;        // cos[128] | sin[128] of the token position
     uint64_t *full, *empty, *red_full, *red_empty;
+    int *issued;        // stages the loader has issued so far (read by the L2 prefetch warp)
     uint32_t ring_u32, xs_u32, gx_u32, gsum_u32, full_u32, empty_u32, redfull_u32, redempty_u32;
     int nst;
 };
@@ -169,10 +204,13 @@ TCE_DEVINL PSmem carve(uint8_t *raw, const Args &a) {
     p += (size_t)kRedBufs * kCW * 16 * 4;
     s.rms = reinterpret_cast<float *>(p);
     p += 32 * 4;
+    s.rope = reinterpret_cast<float *>(p);
+    p += 256 * 4;
     s.full = reinterpret_cast<uint64_t *>(p);
     s.empty = s.full + a.nst;
     s.red_full = s.empty + a.nst;
     s.red_empty = s.red_full + kRedBufs;
+    s.issued = reinterpret_cast<int *>(s.red_empty + kRedBufs);
     s.ring_u32 = smem_u32(s.ring);
     s.xs_u32 = smem_u32(s.xs);
     s.gx_u32 = smem_u32(s.gx);
@@ -213,7 +251,7 @@ TCE_DEVINL void partition(const GemvOp &op, int cta, int ncta, int &t0, int &t1)
 }
 
 // attention work split: the visible positions [0, T) in chunks of kKvChunk; every KV head gets NS = #CTAs / KVH consecutive CTAs,
-// each takes `cps` consecutive chunks (at least kAttnCps when the context has them: fewer splits to merge, same latency per CTA)
+// each takes `cps` consecutive chunks (the fewest that cover the context: see kAttnCps)
 struct AttnSplit {
     int kvh, split, ch0, ch1, nsplit;  // ch0 >= ch1: nothing to do
 };
@@ -241,60 +279,136 @@ TCE_DEVINL AttnSplit attn_split(int cta, int ncta, int KVH, int pos) {
 }
 
 // ------------------------------------------------------------------------------------------------------------ producer
-TCE_DEVINL void produce_gemv(const GemvOp &op, const CUtensorMap *m0, const uint8_t *meta, const PSmem &sm, Ring &rs, int cta, int ncta, uint32_t leader,
+// The same walk over (tile, stage, box) serves two warps: the loader (PF = false) moves stages into the ring as slots free up; the
+// prefetcher (PF = true) runs `kPrefetchAhead` stages ahead of it and only asks L2 for the same boxes, so that the bytes in flight
+// towards HBM are not bounded by the ring (4 x 32 KiB per SM x ~3 us loaded HBM latency = ~40 GB/s per SM, the ceiling measured without
+// it, profiles/README.md) and a ring slot waits one L2 round trip instead of one DRAM round trip.
+constexpr int kPrefetchAhead = 10;
+struct ProdState {
+    Ring rs;
+    int count = 0;  // stages issued (loader) / prefetched (prefetcher) so far
+};
+template <bool PF>
+TCE_DEVINL void prod_throttle_or_slot(const PSmem &sm, ProdState &ps) {
+    if (PF) {
+        if (ps.count >= lds_volatile_i32(sm.issued) + kPrefetchAhead) {
+            const long long t0 = clock64();
+            while (ps.count >= lds_volatile_i32(sm.issued) + kPrefetchAhead) {
+                __nanosleep(64);
+                if (clock64() - t0 > kSpinLimit) __trap();
+            }
+        }
+    } else {
+        mbar_wait(&sm.empty[ps.rs.stage], ps.rs.phase ^ 1);
+    }
+}
+template <bool PF>
+TCE_DEVINL void prod_done(const PSmem &sm, ProdState &ps, uint32_t leader) {
+    ps.count++;
+    if (!PF) {
+        if (leader) sts_volatile_i32(sm.issued, ps.count);
+        __syncwarp();
+        ps.rs.advance(sm.nst);
+    }
+}
+
+template <bool PF>
+TCE_DEVINL void produce_gemv(const GemvOp &op, const CUtensorMap *m0, const uint8_t *meta, const PSmem &sm, ProdState &ps, int cta, int ncta, uint32_t leader,
                              uint64_t policy) {
     int t0, t1;
     partition(op, cta, ncta, t0, t1);
+    const bool ragged = (op.NG % kStageGroups) != 0;
     for (int tile = t0; tile < t1; tile++) {
         for (int s = 0; s < op.S; s++) {
-            const bool two = (kStageGroups * s + 16) < op.NG;  // the stage carries a second box of 16 groups
-            mbar_wait(&sm.empty[rs.stage], rs.phase ^ 1);
-            uint64_t *bar = &sm.full[rs.stage];
-            uint8_t *dst = sm.ring + (size_t)rs.stage * kStageBytes;
-            mbar_arrive_expect_tx_pred(bar, (uint32_t)op.box_bytes * (two ? 2u : 1u) + kMetaBytes, leader);
+            const BoxPlan &pl = op.plan[(ragged && s == op.S - 1) ? 1 : 0];
+            prod_throttle_or_slot<PF>(sm, ps);
+            uint64_t *bar = &sm.full[ps.rs.stage];
+            uint8_t *dst = sm.ring + (size_t)ps.rs.stage * kStageBytes;
+            if (!PF) mbar_arrive_expect_tx_pred(bar, (uint32_t)pl.bytes + kMetaBytes, leader);
 #pragma unroll 1
-            for (int h = 0; h < (two ? 2 : 1); h++) {
-                const int xw = (kStageGroups * s + 16 * h) * 16;  // first 32-bit word of the box within the row
-                uint8_t *d = dst + h * kHalfBytes;
-                if (op.pair) {
-                    tma_load_2d_pred(d, m0, xw, tile * 8, bar, policy, leader);
-                    tma_load_2d_pred(d + 8 * op.sg * 64, m0 + 1, xw, tile * 8, bar, policy, leader);
+            for (int b = 0; b < pl.nbox; b++) {
+                const int xw = (kStageGroups * s + pl.b0[b]) * 16;  // first 32-bit word of the box within the row
+                uint8_t *d = dst + pl.off[b];
+                if (op.pair) {  // matrices of an op are kMapsPerMat maps apart
+                    if (PF) {
+                        tma_prefetch_2d_pred(m0 + pl.map[b], xw, tile * 8, leader);
+                        tma_prefetch_2d_pred(m0 + kMapsPerMat + pl.map[b], xw, tile * 8, leader);
+                    } else {
+                        tma_load_2d_pred(d, m0 + pl.map[b], xw, tile * 8, bar, policy, leader);
+                        tma_load_2d_pred(d + 8 * pl.bw[b] * 64, m0 + kMapsPerMat + pl.map[b], xw, tile * 8, bar, policy, leader);
+                    }
                 } else {
                     int row = tile * 16;
                     const CUtensorMap *m = m0;
                     if (op.nseg > 1 && row >= op.rows0) {
                         row -= op.rows0;
-                        m = m0 + 1;
+                        m = m0 + kMapsPerMat;
                         if (op.nseg > 2 && row >= op.rows1) {
                             row -= op.rows1;
-                            m = m0 + 2;
+                            m = m0 + 2 * kMapsPerMat;
                         }
                     }
-                    tma_load_2d_pred(d, m, xw, row, bar, policy, leader);
+                    if (PF)
+                        tma_prefetch_2d_pred(m + pl.map[b], xw, row, leader);
+                    else
+                        tma_load_2d_pred(d, m + pl.map[b], xw, row, bar, policy, leader);
                 }
             }
-            bulk_g2s_pred(dst + kMetaOff, meta + ((size_t)tile * op.S + s) * kMetaBytes, kMetaBytes, bar, policy, leader);
-            __syncwarp();
-            rs.advance(sm.nst);
+            const uint8_t *mrec = meta + ((size_t)tile * op.S + s) * kMetaBytes;
+            if (PF)
+                bulk_prefetch_pred(mrec, kMetaBytes, leader);
+            else
+                bulk_g2s_pred(dst + kMetaOff, mrec, kMetaBytes, bar, policy, leader);
+            prod_done<PF>(sm, ps, leader);
         }
     }
 }
 
-TCE_DEVINL void produce_attn(const Args &a, const LayerDesc &L, const CUtensorMap *kvmap, const PSmem &sm, Ring &rs, int cta, int ncta, int pos,
+template <bool PF>
+TCE_DEVINL void produce_attn(const Args &a, const LayerDesc &L, const CUtensorMap *kvmap, const PSmem &sm, ProdState &ps, int cta, int ncta, int pos,
                              uint32_t leader, uint64_t policy) {
     const AttnSplit sp = attn_split(cta, ncta, a.KVH, pos);
     for (int c = sp.ch0; c < sp.ch1; c++) {
-        mbar_wait(&sm.empty[rs.stage], rs.phase ^ 1);
-        uint64_t *bar = &sm.full[rs.stage];
-        uint8_t *dst = sm.ring + (size_t)rs.stage * kStageBytes;
-        mbar_arrive_expect_tx_pred(bar, 2u * kHalfBytes, leader);
+        prod_throttle_or_slot<PF>(sm, ps);
+        uint64_t *bar = &sm.full[ps.rs.stage];
+        uint8_t *dst = sm.ring + (size_t)ps.rs.stage * kStageBytes;
         const int krow = L.k_row0 + sp.kvh * a.max_ctx + c * kKvChunk, vrow = L.v_row0 + sp.kvh * a.max_ctx + c * kKvChunk;
-        tma_load_2d_pred(dst, kvmap, 0, krow, bar, policy, leader);
-        tma_load_2d_pred(dst + 8192, kvmap, 64, krow, bar, policy, leader);
-        tma_load_2d_pred(dst + kHalfBytes, kvmap, 0, vrow, bar, policy, leader);
-        tma_load_2d_pred(dst + kHalfBytes + 8192, kvmap, 64, vrow, bar, policy, leader);
-        __syncwarp();
-        rs.advance(sm.nst);
+        if (PF) {
+            tma_prefetch_2d_pred(kvmap, 0, krow, leader);
+            tma_prefetch_2d_pred(kvmap, 64, krow, leader);
+            tma_prefetch_2d_pred(kvmap, 0, vrow, leader);
+            tma_prefetch_2d_pred(kvmap, 64, vrow, leader);
+        } else {
+            mbar_arrive_expect_tx_pred(bar, 2u * kHalfBytes, leader);
+            tma_load_2d_pred(dst, kvmap, 0, krow, bar, policy, leader);
+            tma_load_2d_pred(dst + 8192, kvmap, 64, krow, bar, policy, leader);
+            tma_load_2d_pred(dst + kHalfBytes, kvmap, 0, vrow, bar, policy, leader);
+            tma_load_2d_pred(dst + kHalfBytes + 8192, kvmap, 64, vrow, bar, policy, leader);
+        }
+        prod_done<PF>(sm, ps, leader);
+    }
+}
+
+// the producer role: PF = false on warp 0 (loader), PF = true on warp 2 (L2 prefetcher)
+template <bool PF>
+TCE_DEVINL void producer_walk(const Args &a, const PSmem &sm, int cta, int ncta, int pos, int lane) {
+    ProdState ps;
+    const uint64_t policy = l2_policy_evict_first();
+    const uint32_t leader = (lane == 0) ? 1u : 0u;
+    const int Lyr = a.num_layers, nphase = 5 * Lyr + 1;
+    const CUtensorMap *kvmap = a.maps + ((size_t)Lyr * 7 + 1) * kMapsPerMat;
+#pragma unroll 1
+    for (int p = 0; p < nphase; p++) {
+        const int l = p / 5, k = p - 5 * l;
+        if (l == Lyr) {
+            produce_gemv<PF>(a.op[OPI_LMHEAD], a.maps + (size_t)Lyr * 7 * kMapsPerMat, a.lm_meta, sm, ps, cta, ncta, leader, policy);
+        } else if (k == 1) {
+            produce_attn<PF>(a, a.layers[l], kvmap, sm, ps, cta, ncta, pos, leader, policy);
+        } else {
+            const int oi = (k == 0) ? OPI_QKV : (k - 1);       // k = 2,3,4 -> OPI_O, OPI_GATEUP, OPI_DOWN
+            const int mi = (k == 0) ? 0 : (k == 2 ? 3 : (k == 3 ? 4 : 6));  // first tensor map of the op within the layer's seven
+            produce_gemv<PF>(a.op[oi], a.maps + ((size_t)l * 7 + mi) * kMapsPerMat, a.layers[l].meta[oi], sm, ps, cta, ncta, leader, policy);
+        }
     }
 }
 
@@ -319,9 +433,9 @@ TCE_DEVINL void stage_half(const GemvOp &op, const PSmem &sm, const uint2 *src, 
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = 0.f;
         if (valid) {
-            const uint4 w0 = wait_ll2(src + (size_t)ui * 4, tag, false);
-            const uint4 w1 = wait_ll2(src + (size_t)ui * 4 + 2, tag, false);
-            const float2 f0 = h2_to_f2(w0.x), f1 = h2_to_f2(w0.z), f2 = h2_to_f2(w1.x), f3 = h2_to_f2(w1.z);
+            uint4 w[2];
+            wait_ll2xN<2>(src + (size_t)ui * 4, tag, false, w);
+            const float2 f0 = h2_to_f2(w[0].x), f1 = h2_to_f2(w[0].z), f2 = h2_to_f2(w[1].x), f3 = h2_to_f2(w[1].z);
             v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
             v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
         }
@@ -364,10 +478,10 @@ TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, con
                 x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; x[3] = r0.w;
                 x[4] = r1.x; x[5] = r1.y; x[6] = r1.z; x[7] = r1.w;
                 for (int pr = 0; pr < a.tp_size; pr++) {  // residual += sum over ranks, in rank order (bit-identical everywhere)
-                    const uint2 *d = delta + (size_t)pr * a.E + (size_t)ui * 8;
-                    const uint4 w0 = wait_ll2(d, tag, sys), w1 = wait_ll2(d + 2, tag, sys), w2 = wait_ll2(d + 4, tag, sys), w3 = wait_ll2(d + 6, tag, sys);
-                    x[0] += __uint_as_float(w0.x); x[1] += __uint_as_float(w0.z); x[2] += __uint_as_float(w1.x); x[3] += __uint_as_float(w1.z);
-                    x[4] += __uint_as_float(w2.x); x[5] += __uint_as_float(w2.z); x[6] += __uint_as_float(w3.x); x[7] += __uint_as_float(w3.z);
+                    uint4 w[4];
+                    wait_ll2xN<4>(delta + (size_t)pr * a.E + (size_t)ui * 8, tag, sys, w);
+                    x[0] += __uint_as_float(w[0].x); x[1] += __uint_as_float(w[0].z); x[2] += __uint_as_float(w[1].x); x[3] += __uint_as_float(w[1].z);
+                    x[4] += __uint_as_float(w[2].x); x[5] += __uint_as_float(w[2].z); x[6] += __uint_as_float(w[3].x); x[7] += __uint_as_float(w[3].z);
                 }
             }
             *reinterpret_cast<float4 *>(sm.resid + (size_t)ui * 8) = make_float4(x[0], x[1], x[2], x[3]);
@@ -392,48 +506,158 @@ TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, con
 }
 
 // ------------------------------------------------------------------------------------------------------------ consumers: GEMV
-// one (16 rows x 128 k) unit; see gemv::unit1 (w4a16_gemv_impl.cuh) for the arithmetic.  All operands by shared address.
-TCE_DEVINL void unit_pk(uint32_t w_addr, uint32_t rp8, uint32_t x_addr, uint32_t meta_addr, int gi, int g, int G, uint32_t gx_u32, uint32_t gsum_u32,
-                        float lscale, int gsel, float &totA, float &totB) {
-    const uint4 wa = lds_u4(w_addr), wb = lds_u4(w_addr + rp8);
-    const uint4 xe = lds_u4(x_addr + (uint32_t)G * 256u), xo = lds_u4(x_addr + (uint32_t)G * 256u + 128u);
-    const float sAq = lds_h16(meta_addr + (uint32_t)(gi * 16 + g) * 2u), sBq = lds_h16(meta_addr + (uint32_t)(gi * 16 + g + 8) * 2u);
-    const uint2 z = lds_u2(meta_addr + 1024u + (uint32_t)gi * 8u);
-    const int sxv = (int)lds_u32(gsum_u32 + (uint32_t)(2 * G + gsel) * 4u);
-    const float st = lds_f32(gx_u32 + (uint32_t)G * 4u) * lscale;
+// one (16 rows x 128 k) unit; see gemv::unit1 (w4a16_gemv_impl.cuh) for the arithmetic.  All operands by shared address; the loads
+// of both units of a stage are issued before either is consumed.
+struct UnitRegs {
+    uint4 wa, wb, xe, xo;
+    uint32_t z;   // zero points of rows g (bits 0..7) and g + 8 (bits 8..15)
+    uint32_t sc;  // half2: scales of rows g, g + 8
+    int sxv;
+    float st;
+};
+TCE_DEVINL void unit_load(UnitRegs &u, uint32_t w_addr, uint32_t rp8, uint32_t x_addr, uint32_t meta_addr, int gi, int g, int G, uint32_t gx_u32,
+                          uint32_t gsum_u32, int gsel) {
+    u.wa = lds_u4(w_addr);
+    u.wb = lds_u4(w_addr + rp8);
+    u.xe = u.xo = make_uint4(0u, 0u, 0u, 0u);
+    if (g < 4) {  // MMA columns 4..7 are don't-cares: half of the warp skips the activation loads (half the shared-memory wavefronts)
+        u.xe = lds_u4(x_addr + (uint32_t)G * 256u);
+        u.xo = lds_u4(x_addr + (uint32_t)G * 256u + 128u);
+    }
+    u.sc = lds_u32(meta_addr + (uint32_t)(gi * 8 + g) * 4u);
+    u.z = lds_u16(meta_addr + 1024u + (uint32_t)(gi * 8 + g) * 2u);
+    u.sxv = (int)lds_u32(gsum_u32 + (uint32_t)(2 * G + gsel) * 4u);
+    u.st = lds_f32(gx_u32 + (uint32_t)G * 4u);
+}
+TCE_DEVINL void unit_compute(const UnitRegs &u, float lscale, float &totA, float &totB) {
     constexpr uint32_t ML = 0x0f0f0f0fu, MH = 0xf0f0f0f0u;
     int accL[4], accH[4];
-    mma_m16n8k32_u8s8_z(accL, wa.x & ML, wb.x & ML, wa.y & ML, wb.y & ML, xe.x, xe.y);
-    mma_m16n8k32_u8s8_z(accH, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xo.x, xo.y);
-    mma_m16n8k32_u8s8(accL, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xe.z, xe.w);
-    mma_m16n8k32_u8s8(accH, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xo.z, xo.w);
-    const int zAq = (int)((z.x >> (4 * g)) & 0xFu), zBq = (int)((z.y >> (4 * g)) & 0xFu);
-    const int vA = ((accL[0] + (accH[0] >> 4)) << 7) + (accL[1] + (accH[1] >> 4)) - zAq * sxv;
-    const int vB = ((accL[2] + (accH[2] >> 4)) << 7) + (accL[3] + (accH[3] >> 4)) - zBq * sxv;
-    totA += (sAq * st) * (float)vA;
-    totB += (sBq * st) * (float)vB;
+    mma_m16n8k32_u8s8_z(accL, u.wa.x & ML, u.wb.x & ML, u.wa.y & ML, u.wb.y & ML, u.xe.x, u.xe.y);
+    mma_m16n8k32_u8s8_z(accH, u.wa.x & MH, u.wb.x & MH, u.wa.y & MH, u.wb.y & MH, u.xo.x, u.xo.y);
+    mma_m16n8k32_u8s8(accL, u.wa.z & ML, u.wb.z & ML, u.wa.w & ML, u.wb.w & ML, u.xe.z, u.xe.w);
+    mma_m16n8k32_u8s8(accH, u.wa.z & MH, u.wb.z & MH, u.wa.w & MH, u.wb.w & MH, u.xo.z, u.xo.w);
+    const float2 sc = h2_to_f2(u.sc);
+    const float st = u.st * lscale;
+    const int zAq = (int)(u.z & 0xFFu), zBq = (int)(u.z >> 8);
+    // X = 2^24*p3 + 2^16*p2 + 2^8*p1 + p0; odd slots carry 16 x nibble (exact multiple of 16): c0 * 256 + c1 per parity, then q*X - z*sum X
+    const int vA = (accL[0] << 8) + accL[1] + (((accH[0] << 8) + accH[1]) >> 4) - zAq * u.sxv;
+    const int vB = (accL[2] << 8) + accL[3] + (((accH[2] << 8) + accH[3]) >> 4) - zBq * u.sxv;
+    totA += (sc.x * st) * (float)vA;
+    totB += (sc.y * st) * (float)vB;
+}
+
+// where group `gi` of a stage lives: byte offset of (row g, this lane's 16-byte chunk) and the distance to row g + 8
+TCE_DEVINL void locate(const BoxPlan &pl, int gi, int g, int t, uint32_t &off, uint32_t &rp8) {
+    int b = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxBoxes; i++)
+        if (i < pl.nbox && gi >= pl.b0[i]) b = i;
+    const uint32_t rp = (uint32_t)pl.bw[b] * 64u;
+    off = (uint32_t)pl.off[b] + (uint32_t)g * rp + (uint32_t)(gi - pl.b0[b]) * 64u + (uint32_t)t * 16u;
+    rp8 = 8u * rp;
+}
+
+// Fast path for dense boxes of 16 groups (NG >= 16: every Llama width): within a stage every operand address is a per-lane constant
+// plus the slot base, and the second unit of a warp sits at fixed distances (+16 KiB weights, +4 KiB planes, +512 B scales ...), so the
+// inner loop carries almost no address arithmetic (the ALU pipe is what bounds this loop, profiles/README.md).
+TCE_DEVINL void consume_gemv_dense(const GemvOp &op, const PSmem &sm, Ring &rs, Red &cs, float inv, int cta, int ncta, int cw, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    int t0, t1;
+    partition(op, cta, ncta, t0, t1);
+    const int NG = op.NG, S = op.S;
+    const uint32_t w_lane = (uint32_t)g * 1024u + (uint32_t)t * 16u + (uint32_t)cw * 64u;               // row g of group cw, this lane's 16-byte chunk
+    const uint32_t m_lane = (uint32_t)kMetaOff + (uint32_t)(cw * 8 + g) * 4u;                            // scales of rows g, g + 8 of group cw
+    const uint32_t z_lane = (uint32_t)kMetaOff + 1024u + (uint32_t)(cw * 8 + g) * 2u;
+    const uint32_t x_lane = sm.xs_u32 + (uint32_t)((g >> 1) & 1) * (uint32_t)op.IC * 2u + (uint32_t)(t * 2 + (g & 1)) * 16u + (uint32_t)cw * 256u;
+    const uint32_t s_lane = sm.gsum_u32 + (uint32_t)(2 * cw + (t & 1)) * 4u;
+    const uint32_t q_lane = sm.gx_u32 + (uint32_t)cw * 4u;
+    const float lscale = (t == 0) ? 65536.f : (t == 1 ? 1.f : 0.f);
+    const bool xl = g < 4;  // MMA columns 4..7 are don't-cares
+    for (int tile = t0; tile < t1; tile++) {
+        float totA = 0.f, totB = 0.f;
+        for (int s = 0; s < S; s++) {
+            const bool two = kStageGroups * s + 16 < NG;  // the stage carries groups 16..31 as well (warp-uniform)
+            mbar_wait_u32(sm.full_u32 + (uint32_t)rs.stage * 8u, rs.phase);
+            const uint32_t base = sm.ring_u32 + (uint32_t)rs.stage * (uint32_t)kStageBytes;
+            const uint32_t wb_ = base + w_lane, mb_ = base + m_lane, zb_ = base + z_lane;
+            const uint32_t xb_ = x_lane + (uint32_t)s * (kStageGroups * 256u), sb_ = s_lane + (uint32_t)s * (kStageGroups * 8u), qb_ = q_lane + (uint32_t)s * (kStageGroups * 4u);
+            UnitRegs u0, u1;
+            u0.wa = lds_u4(wb_);
+            u0.wb = lds_u4(wb_ + 8192u);
+            u0.xe = u0.xo = u1.xe = u1.xo = make_uint4(0u, 0u, 0u, 0u);
+            if (xl) {
+                u0.xe = lds_u4(xb_);
+                u0.xo = lds_u4(xb_ + 128u);
+            }
+            u0.sc = lds_u32(mb_);
+            u0.z = lds_u16(zb_);
+            u0.sxv = (int)lds_u32(sb_);
+            u0.st = lds_f32(qb_);
+            if (two) {
+                u1.wa = lds_u4(wb_ + 16384u);
+                u1.wb = lds_u4(wb_ + 16384u + 8192u);
+                if (xl) {
+                    u1.xe = lds_u4(xb_ + 4096u);
+                    u1.xo = lds_u4(xb_ + 4096u + 128u);
+                }
+                u1.sc = lds_u32(mb_ + 512u);
+                u1.z = lds_u16(zb_ + 256u);
+                u1.sxv = (int)lds_u32(sb_ + 128u);
+                u1.st = lds_f32(qb_ + 64u);
+            }
+            unit_compute(u0, lscale, totA, totB);
+            if (two) unit_compute(u1, lscale, totA, totB);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_u32(sm.empty_u32 + (uint32_t)rs.stage * 8u);
+            rs.advance(sm.nst);
+        }
+        // ---- hand the tile sums to the epilogue warp ----
+        totA += __shfl_xor_sync(0xffffffffu, totA, 1);  // (p3, p2) share of t = 0 + (p1, p0) share of t = 1
+        totB += __shfl_xor_sync(0xffffffffu, totB, 1);
+        mbar_wait_u32(sm.redempty_u32 + (uint32_t)cs.rb * 8u, cs.rphase ^ 1);
+        float *rbuf = sm.red + ((size_t)cs.rb * kCW + cw) * 16;
+        if (t == 0) {
+            rbuf[g] = totA * inv;
+            rbuf[g + 8] = totB * inv;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(sm.redfull_u32 + (uint32_t)cs.rb * 8u);
+        cs.advance();
+    }
 }
 
 TCE_DEVINL void consume_gemv(const GemvOp &op, const PSmem &sm, Ring &rs, Red &cs, float inv, int cta, int ncta, int cw, int lane) {
     const int g = lane >> 2, t = lane & 3;
     int t0, t1;
     partition(op, cta, ncta, t0, t1);
-    const uint32_t rp = (uint32_t)op.sg * 64u;  // dense row pitch of a TMA box
-    const uint32_t w_off = (uint32_t)g * rp + (uint32_t)t * 16u + (uint32_t)cw * 64u;
+    const int NG = op.NG, S = op.S;
+    const bool ragged = (NG % kStageGroups) != 0;
+    // lane-constant weight operands of this warp's two groups (cw, cw + 16), for a full stage and for the ragged last stage of a tile
+    uint32_t wf0, rf0, wf1, rf1, wl0 = 0, rl0 = 0, wl1 = 0, rl1 = 0;
+    locate(op.plan[0], cw, g, t, wf0, rf0);
+    locate(op.plan[0], cw + 16, g, t, wf1, rf1);
+    if (ragged) {
+        locate(op.plan[1], cw, g, t, wl0, rl0);
+        locate(op.plan[1], cw + 16, g, t, wl1, rl1);
+    }
     // lane-constant activation operands: MMA column g & 3 supplies plane 3 - (g & 3)
     const uint32_t x_lane = sm.xs_u32 + (uint32_t)((g >> 1) & 1) * (uint32_t)op.IC * 2u + (uint32_t)(t * 2 + (g & 1)) * 16u;
-    const float lscale = (t == 0) ? 16384.f : (t == 1 ? 1.f : 0.f);
+    const float lscale = (t == 0) ? 65536.f : (t == 1 ? 1.f : 0.f);
     const int gsel = t & 1;
+    const uint32_t gx_u32 = sm.gx_u32, gsum_u32 = sm.gsum_u32;
     for (int tile = t0; tile < t1; tile++) {
         float totA = 0.f, totB = 0.f;
-        for (int s = 0; s < op.S; s++) {
-            const int n = min(kStageGroups, op.NG - kStageGroups * s);  // groups this stage carries
+        for (int s = 0; s < S; s++) {
+            const int n = min(kStageGroups, NG - kStageGroups * s);  // groups this stage carries
+            const bool last = ragged && s == S - 1;
             mbar_wait_u32(sm.full_u32 + (uint32_t)rs.stage * 8u, rs.phase);
             const uint32_t base = sm.ring_u32 + (uint32_t)rs.stage * (uint32_t)kStageBytes;
-            if (cw < n) unit_pk(base + w_off, 8u * rp, x_lane, base + kMetaOff, cw, g, kStageGroups * s + cw, sm.gx_u32, sm.gsum_u32, lscale, gsel, totA, totB);
-            if (cw + 16 < n)
-                unit_pk(base + kHalfBytes + w_off, 8u * rp, x_lane, base + kMetaOff, cw + 16, g, kStageGroups * s + cw + 16, sm.gx_u32, sm.gsum_u32, lscale, gsel,
-                        totA, totB);
+            UnitRegs u0, u1;
+            const bool has0 = cw < n, has1 = cw + 16 < n;
+            if (has0) unit_load(u0, base + (last ? wl0 : wf0), last ? rl0 : rf0, x_lane, base + kMetaOff, cw, g, kStageGroups * s + cw, gx_u32, gsum_u32, gsel);
+            if (has1) unit_load(u1, base + (last ? wl1 : wf1), last ? rl1 : rf1, x_lane, base + kMetaOff, cw + 16, g, kStageGroups * s + cw + 16, gx_u32, gsum_u32, gsel);
+            if (has0) unit_compute(u0, lscale, totA, totB);
+            if (has1) unit_compute(u1, lscale, totA, totB);
             __syncwarp();
             if (lane == 0) mbar_arrive_u32(sm.empty_u32 + (uint32_t)rs.stage * 8u);
             rs.advance(sm.nst);
@@ -522,15 +746,18 @@ TCE_DEVINL uint32_t kv_off(int r, int c) { return (uint32_t)((c >> 3) * 8192 + r
 
 // RoPE (llm/src/ops/RotaryPosEmb.cc:7-69, rotate-half) of one {half2, tag} word pair: word j holds dims (2j, 2j+1), its partner word j +- 32
 TCE_DEVINL float2 rope_pair(const uint2 *vec, int j, uint32_t tag, const float *cosr, const float *sinr) {
-    const float2 x = h2_to_f2(wait_ll1(vec + j, tag, false));
-    const float2 xp = h2_to_f2(wait_ll1(vec + (j < 32 ? j + 32 : j - 32), tag, false));
+    const uint2 *pa = vec + j, *pb = vec + (j < 32 ? j + 32 : j - 32);
+    uint2 wa = ld_ll1(pa, false), wb = ld_ll1(pb, false);  // both requests in flight before either tag is examined
+    if (wa.y != tag) wa.x = wait_ll1(pa, tag, false);
+    if (wb.y != tag) wb.x = wait_ll1(pb, tag, false);
+    const float2 x = h2_to_f2(wa.x), xp = h2_to_f2(wb.x);
     const float sgn = (j < 32) ? -1.f : 1.f;
     const int d = 2 * j;
     return make_float2(x.x * cosr[d] + sgn * xp.x * sinr[d], x.y * cosr[d + 1] + sgn * xp.y * sinr[d + 1]);
 }
 
 TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &sm, Ring &rs, uint32_t tag_qkv, uint32_t tag_part, uint32_t tag_out, int cta,
-                                int ncta, int pos, int ctid, int cw, int lane) {
+                                int ncta, int pos, int ctid, int cw, int lane, int p, int nphase) {
     const AttnSplit sp = attn_split(cta, ncta, a.KVH, pos);
     const int nrep = a.nrep;
     const int g = lane >> 2, t = lane & 3;
@@ -539,7 +766,7 @@ TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &
         __half *sQ = reinterpret_cast<__half *>(sm.xs);                        // [8][136] q * alpha after RoPE, rows >= nrep zero
         float *sO = reinterpret_cast<float *>(sm.xs + 8 * 136 * 2);            // [kCW][nrep][128] per-warp unnormalised outputs
         float *sML = sO + (size_t)kCW * nrep * 128;                            // [kCW][nrep][2] per-warp (max, sum)
-        const float *cosr = a.cos + (size_t)pos * 128, *sinr = a.sin + (size_t)pos * 128;
+        const float *cosr = sm.rope, *sinr = sm.rope + 128;  // the position's table rows, staged once per kernel
         // ---- RoPE on the nrep query heads of this KV head (fp32), one {half2} word per thread and pass ----
         for (int i = ctid; i < 8 * 64; i += kConsumerThreads) {
             const int r = i >> 6, j = i & 63;
@@ -552,6 +779,7 @@ TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &
             *reinterpret_cast<__half2 *>(sQ + r * 136 + 2 * j) = __floats2half2_rn(v.x, v.y);
         }
         named_bar_sync(1, kConsumerThreads);
+        if (ctid == 0) stamp(a, cta, nphase, p, 4);
         uint32_t qa[8][2];  // A operand: q[head g][dims], all 8 k-steps (rows 8..15 of the MMA tile are zero)
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {
@@ -656,6 +884,7 @@ TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &
             if (lane == 0) mbar_arrive_u32(sm.empty_u32 + (uint32_t)rs.stage * 8u);
             rs.advance(sm.nst);
         }
+        if (ctid == 0) stamp(a, cta, nphase, p, 5);
         if (t == 0 && g < nrep) {
             sML[(cw * nrep + g) * 2] = have ? m_run : -INFINITY;
             sML[(cw * nrep + g) * 2 + 1] = have ? l_run : 0.f;
@@ -689,6 +918,7 @@ TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &
             }
         }
     }
+    if (ctid == 0) stamp(a, cta, nphase, p, 6);
     if (sp.nsplit == 1) return;
     // ---- split merge, spread over the grid: task = (head, block of 32 dims), one warp each ----
     const int ntask = a.H * 4;
@@ -705,12 +935,15 @@ TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &
         const float wgt = (lane < sp.nsplit) ? __expf(ms - M) : 0.f;
         const float Lt = warp_sum(wgt * ls);
         float acc = 0.f;
-        for (int s0 = 0; s0 < sp.nsplit; s0 += 4) {
-            float ov[4];
+        for (int s0 = 0; s0 < sp.nsplit; s0 += 8) {
+            uint2 ow[8];
 #pragma unroll
-            for (int i = 0; i < 4; i++) ov[i] = (s0 + i < sp.nsplit) ? __uint_as_float(wait_ll1(base + (size_t)(s0 + i) * 130 + d, tag_part, false)) : 0.f;
+            for (int i = 0; i < 8; i++) ow[i] = (s0 + i < sp.nsplit) ? ld_ll1(base + (size_t)(s0 + i) * 130 + d, false) : make_uint2(0u, tag_part);
 #pragma unroll
-            for (int i = 0; i < 4; i++) acc += __shfl_sync(0xffffffffu, wgt, (s0 + i) & 31) * ov[i];
+            for (int i = 0; i < 8; i++) {
+                if (ow[i].y != tag_part) ow[i].x = wait_ll1(base + (size_t)(s0 + i) * 130 + d, tag_part, false);
+                acc += __shfl_sync(0xffffffffu, wgt, (s0 + i) & 31) * __uint_as_float(ow[i].x);
+            }
         }
         const float y = acc / Lt;
         const float yhi = __shfl_down_sync(0xffffffffu, y, 1);
@@ -741,6 +974,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             mbar_init(&sm.red_full[lane - 16], kCW);
             mbar_init(&sm.red_empty[lane - 16], 1);
         }
+        if (lane == 31) *sm.issued = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -749,27 +983,21 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
     const unsigned epoch = *a.epoch;
     const uint32_t tag_base = epoch * (uint32_t)(2 * nphase + 2) + 1u;  // tag of (phase p, sub-result s) = tag_base + 2p + s: unique over launches, never 0
 
-    if (warp == 0) {
-        // ================= producer: every byte this CTA needs from HBM, in consumption order =================
-        Ring rs;
-        const uint64_t policy = l2_policy_evict_first();
-        const uint32_t leader = (lane == 0) ? 1u : 0u;
-        const CUtensorMap *kvmap = a.maps + (size_t)Lyr * 7 + 1;
-#pragma unroll 1
-        for (int p = 0; p < nphase; p++) {
-            const int l = p / 5, k = p - 5 * l;
-            if (l == Lyr) {
-                produce_gemv(a.op[OPI_LMHEAD], a.maps + (size_t)Lyr * 7, a.lm_meta, sm, rs, cta, ncta, leader, policy);
-            } else if (k == 1) {
-                produce_attn(a, a.layers[l], kvmap, sm, rs, cta, ncta, pos, leader, policy);
-            } else {
-                const int oi = (k == 0) ? OPI_QKV : (k - 1);       // k = 2,3,4 -> OPI_O, OPI_GATEUP, OPI_DOWN
-                const int mi = (k == 0) ? 0 : (k == 2 ? 3 : (k == 3 ? 4 : 6));  // first tensor map of the op within the layer's seven
-                produce_gemv(a.op[oi], a.maps + (size_t)l * 7 + mi, a.layers[l].meta[oi], sm, rs, cta, ncta, leader, policy);
-            }
+    // register budget: 20 warps x 96 registers at launch; warpgroup 0 (producer, epilogue, two spare warps) gives most of its share back
+    // and the 16 consumer warps grow to 112 (per scheduler: 32 + 4 x 112 <= 5 x 96 registers per lane)
+    if (warp < kAuxWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+        if (warp == 3) return;
+        if (warp == 0) {
+            // ================= loader: every byte this CTA needs from HBM, in consumption order =================
+            producer_walk<false>(a, sm, cta, ncta, pos, lane);
+            return;
         }
-        return;
-    }
+        if (warp == 2) {
+            // ================= L2 prefetcher: the same walk, kPrefetchAhead stages ahead =================
+            if (a.l2_prefetch) producer_walk<true>(a, sm, cta, ncta, pos, lane);
+            return;
+        }
     if (warp == 1) {
         // ================= epilogue warp =================
         Red es;
@@ -797,12 +1025,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
         if (lane == 0) red_release_gpu(a.done);
         return;
     }
+        return;  // (not reached: every warp of warpgroup 0 has returned above)
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
 
     // ================= consumers =================
-    const int ctid = tid - 64;
-    const int cw = warp - 2;
+    const int ctid = tid - 32 * kAuxWarps;
+    const int cw = warp - kAuxWarps;
     Ring rs;
     Red cs;
+    if (ctid < 256) sm.rope[ctid] = (ctid < 128) ? a.cos[(size_t)pos * 128 + ctid] : a.sin[(size_t)pos * 128 + ctid - 128];  // visible after the first phase's barrier
 #pragma unroll 1
     for (int p = 0; p < nphase; p++) {
         const int l = p / 5, k = p - 5 * l;
@@ -810,7 +1042,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
         if (ctid == 0) stamp(a, cta, nphase, p, 0);
         if (l < Lyr && k == 1) {
             // ---- RoPE + KV append + attention ----
-            attention_phase(a, a.layers[l], sm, rs, tag_in, tag_base + 2u * (uint32_t)p + 1u, tag_base + 2u * (uint32_t)p, cta, ncta, pos, ctid, cw, lane);
+            attention_phase(a, a.layers[l], sm, rs, tag_in, tag_base + 2u * (uint32_t)p + 1u, tag_base + 2u * (uint32_t)p, cta, ncta, pos, ctid, cw, lane, p, nphase);
             if (ctid == 0) stamp(a, cta, nphase, p, 2);
             named_bar_sync(1, kConsumerThreads);  // the scratch aliases the activation planes of the next phase
             continue;
@@ -832,7 +1064,12 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             inv = stage_rms(a, op, sm, delta, tag_in, gamma, token, p == 0, work, cta, ctid, cw, lane);
         }
         if (ctid == 0) stamp(a, cta, nphase, p, 1);
-        if (work) consume_gemv(op, sm, rs, cs, inv, cta, ncta, cw, lane);
+        if (work) {
+            if (op.plan[0].bw[0] == 16 && (op.NG & 15) == 0)
+                consume_gemv_dense(op, sm, rs, cs, inv, cta, ncta, cw, lane);
+            else
+                consume_gemv(op, sm, rs, cs, inv, cta, ncta, cw, lane);
+        }
         if (ctid == 0) stamp(a, cta, nphase, p, 2);
         named_bar_sync(1, kConsumerThreads);  // every warp is done with the planes before the next phase overwrites them
     }
@@ -866,7 +1103,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
 
 // ------------------------------------------------------------------------------------------------------------ repack kernel
 // scales half[rows][sf_w] + zeros u32[rows][zeros_w] (QM_CUDA, llm/tools/quantize_methods.py:370-442) -> one 1280-byte record per
-// (16-row tile, 32-group stage): scales half[32 groups][16 rows], zeros u64[32 groups] (nibble r = zero point of row r).
+// (16-row tile, 32-group stage): scales half[32 groups][8][2] (rows g and g + 8 adjacent), then zero points u8[32 groups][8][2] in the same order.
 __global__ void repack_meta_kernel(W4Seg s0, W4Seg s1, W4Seg s2, int nseg, int pair, int NG, int zeros_w, int sf_w, int S, int num_tiles, uint8_t *out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tile, s, gi)
     if (idx >= num_tiles * S * kStageGroups) return;
@@ -874,8 +1111,8 @@ __global__ void repack_meta_kernel(W4Seg s0, W4Seg s1, W4Seg s2, int nseg, int p
     const int tile = su / S, s = su - tile * S;
     const int G = kStageGroups * s + gi;
     uint8_t *rec = out + (size_t)su * kMetaBytes;
-    __half *so = reinterpret_cast<__half *>(rec) + gi * 16;
-    unsigned long long z = 0ull;
+    __half *so = reinterpret_cast<__half *>(rec) + gi * 16;  // [g][2]: rows g and g + 8 adjacent
+    uint8_t *zo = rec + 1024 + gi * 16;                        // zero points, same order, one byte each
     for (int r = 0; r < 16; r++) {
         const W4Seg *seg = &s0;
         int row;
@@ -893,17 +1130,64 @@ __global__ void repack_meta_kernel(W4Seg s0, W4Seg s1, W4Seg s2, int nseg, int p
                 }
             }
         }
+        const int slot = (r & 7) * 2 + (r >> 3);
         if (G < NG) {
-            so[r] = seg->scales[(size_t)row * sf_w + G];
-            z |= (unsigned long long)((seg->zeros[(size_t)row * zeros_w + (G >> 3)] >> ((G & 7) * 4)) & 0xFu) << (4 * r);
+            so[slot] = seg->scales[(size_t)row * sf_w + G];
+            zo[slot] = (uint8_t)((seg->zeros[(size_t)row * zeros_w + (G >> 3)] >> ((G & 7) * 4)) & 0xFu);
         } else {
-            so[r] = __float2half(0.f);
+            so[slot] = __float2half(0.f);
+            zo[slot] = 0;
         }
     }
-    reinterpret_cast<unsigned long long *>(rec + 1024)[gi] = z;
 }
 
 }  // namespace
+
+BoxPlan make_box_plan(int n, int *widths, int *nwidths) {
+    BoxPlan pl{};
+    int w[kMaxBoxes], nb = 0;
+    // Dense boxes of up to 16 groups.  (Odd widths -- 9+9+7+7 -- make the weight LDS.128 conflict free, but rows of 576 / 448 bytes are
+    // not multiples of the 128-byte L2 line: measured 25 % SLOWER end to end, profiles/README.md; kept selectable for the record.)
+    const bool odd = getenv("TCE_PK_ODD_BOXES") != nullptr;
+    if (!odd) {
+        w[nb++] = n < 16 ? n : 16;
+        if (n > 16) w[nb++] = n - 16;
+    } else if (n <= 15 && (n & 1)) {
+        w[nb++] = n;
+    } else if (n <= 30) {
+        const int a = ((n / 2) & 1) ? n / 2 : n / 2 + 1;  // two odd parts
+        w[nb++] = a;
+        w[nb++] = n - a;
+    } else if (n == 31) {
+        w[nb++] = 15;
+        w[nb++] = 15;
+        w[nb++] = 1;
+    } else {  // 32
+        w[nb++] = 9;
+        w[nb++] = 9;
+        w[nb++] = 7;
+        w[nb++] = 7;
+    }
+    int g0 = 0, off = 0;
+    for (int i = 0; i < nb; i++) {
+        pl.b0[i] = g0;
+        pl.bw[i] = w[i];
+        pl.off[i] = off;
+        int m = -1;
+        for (int k = 0; k < *nwidths; k++)
+            if (widths[k] == w[i]) m = k;
+        if (m < 0 && *nwidths < kMapsPerMat) {
+            m = (*nwidths)++;
+            widths[m] = w[i];
+        }
+        pl.map[i] = m;  // -1: more distinct widths than maps (caller rejects)
+        g0 += w[i];
+        off += 16 * w[i] * 64;
+        pl.bytes += 16 * w[i] * 64;
+    }
+    pl.nbox = nb;
+    return pl;
+}
 
 int attn_scratch_bytes(int nrep) { return 8 * 136 * 2 + kCW * nrep * 128 * 4 + kCW * nrep * 2 * 4; }
 
@@ -915,7 +1199,7 @@ int attn_nsplit_max(int ncta, int KVH, int max_ctx) {
 }
 
 static size_t fixed_bytes(int xs_bytes, int max_ng, int E) {
-    return (size_t)xs_bytes + (size_t)E * 4 + (size_t)max_ng * 12 + (size_t)kRedBufs * kCW * 16 * 4 + 32 * 4 + (size_t)(2 * kMaxStages + 2 * kRedBufs) * 8 + 16 + 1024;
+    return (size_t)xs_bytes + (size_t)E * 4 + (size_t)max_ng * 12 + (size_t)kRedBufs * kCW * 16 * 4 + 32 * 4 + 256 * 4 + (size_t)(2 * kMaxStages + 2 * kRedBufs) * 8 + 16 + 1024;
 }
 int pick_stages(int smem_optin, int xs_bytes, int max_ng, int E) {
     const long long avail = (long long)smem_optin - (long long)fixed_bytes(xs_bytes, max_ng, E);

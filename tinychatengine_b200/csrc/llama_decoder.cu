@@ -425,7 +425,6 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         pk::GemvOp o{};
         o.IC = IC;
         o.NG = IC / kW4Group;
-        o.sg = o.NG < 16 ? o.NG : 16;
         o.S = (o.NG + pk::kStageGroups - 1) / pk::kStageGroups;
         o.num_tiles = rows / 16;
         o.nseg = nseg;
@@ -434,9 +433,10 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         o.rows1 = rows1;
         o.x_mode = x_mode;
         o.epi = epi;
-        o.box_bytes = 16 * o.sg * 64;
         return o;
     };
+    // TMA box plans (odd box widths, see persistent.h) and the distinct widths each op needs a tensor map for
+    int widths[pk::OPI_COUNT][pk::kMapsPerMat] = {}, nwidths[pk::OPI_COUNT] = {};
     const bool tp = tp_ > 1;
     a.op[pk::OPI_QKV] = mk(E, (H + 2 * KVH) * hd, 3, 0, H * hd, KVH * hd, pk::PX_RMS_F32, pk::PE_HALF_LL);
     a.op[pk::OPI_O] = mk(H * hd, E, 1, 0, E, 0, pk::PX_HALF, pk::PE_DELTA_LL);
@@ -445,6 +445,11 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     a.op[pk::OPI_LMHEAD] = mk(E, V, 1, 0, V, 0, pk::PX_RMS_F32, pk::PE_LOGITS);
     int max_ic = 0, max_ng = 0;
     for (int i = 0; i < pk::OPI_COUNT; i++) {
+        const int NG = a.op[i].NG, full = NG < pk::kStageGroups ? NG : pk::kStageGroups, rem = NG % pk::kStageGroups;
+        a.op[i].plan[0] = pk::make_box_plan(full, widths[i], &nwidths[i]);
+        a.op[i].plan[1] = (NG > pk::kStageGroups && rem) ? pk::make_box_plan(rem, widths[i], &nwidths[i]) : a.op[i].plan[0];
+        for (int k = 0; k < pk::kMaxBoxes; k++)
+            if ((k < a.op[i].plan[0].nbox && a.op[i].plan[0].map[k] < 0) || (k < a.op[i].plan[1].nbox && a.op[i].plan[1].map[k] < 0)) return no("too many box widths");
         if (a.op[i].IC > max_ic) max_ic = a.op[i].IC;
         if (a.op[i].NG > max_ng) max_ng = a.op[i].NG;
         if (a.op[i].IC % kW4Group || a.op[i].num_tiles < 1) return no("bad GEMV shape");
@@ -462,6 +467,7 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         if (want >= 2 && want < a.nst) a.nst = want;
     }
     if (a.nst < 2) return no("shared memory too small for the persistent kernel");
+    a.l2_prefetch = getenv("TCE_PK_L2_PREFETCH") ? atoi(getenv("TCE_PK_L2_PREFETCH")) : 0;
 
     auto dalloc = [&](size_t bytes) -> void * {
         void *p = nullptr;
@@ -471,7 +477,8 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     };
     cudaStream_t s = ctx_->stream;
     // ---- tensor maps: [Lyr][7] + lm_head + KV cache ----
-    std::vector<CUtensorMap> maps((size_t)Lyr * 7 + 2);
+    std::vector<CUtensorMap> maps(((size_t)Lyr * 7 + 1) * pk::kMapsPerMat + 1);
+    memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
     std::vector<pk::LayerDesc> descs(Lyr);
     const size_t per_kv = (size_t)KVH * cfg_.max_ctx;  // rows per (layer, K|V) slab
     for (int l = 0; l < Lyr; l++) {
@@ -480,7 +487,8 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         const int opi[7] = {pk::OPI_QKV, pk::OPI_QKV, pk::OPI_QKV, pk::OPI_O, pk::OPI_GATEUP, pk::OPI_GATEUP, pk::OPI_DOWN};
         for (int i = 0; i < 7; i++) {
             const pk::GemvOp &o = a.op[opi[i]];
-            DCK(encode_w4_tmap(&maps[(size_t)l * 7 + i], t7[i]->w, t7[i]->oc, t7[i]->ic, o.sg, o.pair ? 8 : 16));
+            for (int k = 0; k < nwidths[opi[i]]; k++)
+                DCK(encode_w4_tmap(&maps[((size_t)l * 7 + i) * pk::kMapsPerMat + k], t7[i]->w, t7[i]->oc, t7[i]->ic, widths[opi[i]][k], o.pair ? 8 : 16));
         }
         pk::LayerDesc &D = descs[l];
         memset(&D, 0, sizeof(D));
@@ -504,13 +512,14 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     }
     {
         const pk::GemvOp &o = a.op[pk::OPI_LMHEAD];
-        DCK(encode_w4_tmap(&maps[(size_t)Lyr * 7], w_.lm_head.w, w_.lm_head.oc, w_.lm_head.ic, o.sg, 16));
+        for (int k = 0; k < nwidths[pk::OPI_LMHEAD]; k++)
+            DCK(encode_w4_tmap(&maps[(size_t)Lyr * 7 * pk::kMapsPerMat + k], w_.lm_head.w, w_.lm_head.oc, w_.lm_head.ic, widths[pk::OPI_LMHEAD][k], 16));
         uint8_t *m = (uint8_t *)dalloc((size_t)o.num_tiles * o.S * pk::kMetaBytes);
         if (!m) return cudaErrorMemoryAllocation;
         const W4Seg lm[1] = {seg_of(w_.lm_head)};
         DCK(pk::repack_meta(ctx_, lm, 1, 0, o.IC, m, s));
         a.lm_meta = m;
-        DCK(pk::encode_kv_tmap(&maps[(size_t)Lyr * 7 + 1], d_kv_, (long long)Lyr * 2 * per_kv));
+        DCK(pk::encode_kv_tmap(&maps[((size_t)Lyr * 7 + 1) * pk::kMapsPerMat], d_kv_, (long long)Lyr * 2 * per_kv));
     }
     CUtensorMap *dmaps = (CUtensorMap *)dalloc(maps.size() * sizeof(CUtensorMap));
     pk::LayerDesc *ddesc = (pk::LayerDesc *)dalloc(descs.size() * sizeof(pk::LayerDesc));
@@ -572,7 +581,7 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         a.delta_ll[1] = a.delta_ll[0] + E;
     }
     if (getenv("TCE_PK_DEBUG") && atoi(getenv("TCE_PK_DEBUG"))) {
-        const size_t n = (size_t)ncta * ((size_t)5 * Lyr + 1) * 4 * sizeof(unsigned long long);
+        const size_t n = (size_t)ncta * ((size_t)5 * Lyr + 1) * 8 * sizeof(unsigned long long);
         a.dbg = (unsigned long long *)dalloc(n);
         if (!a.dbg) return cudaErrorMemoryAllocation;
         DCK(cudaMemset(a.dbg, 0, n));

@@ -11,7 +11,7 @@
 //    weight box into a ring of KArgs::nst stages (8 by default) guarded by full/empty mbarriers, L2 evict-first; the tile's
 //    scales/zeros slabs (1-D bulk copies, UBLKCP) ride on the first stage's barrier.  Producers depend on nothing but the weights,
 //    so they run ahead of everything else (in particular of the consumers' activation staging).
-//  * consumers (CW warps): 128-bit LDS of the packed nibbles; activations held as four int8 planes (29-bit block fixed point per
+//  * consumers (CW warps): 128-bit LDS of the packed nibbles; activations held as four int8 planes (32-bit block fixed point per
 //    128-group, exact integer accumulation); mma.sync.m16n8k32 u8 x s8 -> s32; per-group epilogue
 //    tot += (s * step) * (acc - z * sum_X).  One activation row (decode, consume1): the four planes ride in MMA columns 0..3 and
 //    nibbles become bytes with one mask each (even slots w & 0x0f0f0f0f, odd slots w & 0xf0f0f0f0 = 16 x nibble, shifted back
@@ -33,7 +33,7 @@ constexpr int kStageBytes = 16 * kStageGroups * 64;  // 16 KiB: dense [16 rows][
 constexpr int kStages = 4;         // default ring depth (persistent kernel); the per-op kernel picks the deepest ring that fits (KArgs::nst)
 constexpr int kMaxStages = 12;
 constexpr int kRedBufs = 3;
-constexpr float kActQ = 266338304.f;  // 127 * 2^21: activation fixed-point full scale (four int8 planes)
+constexpr float kActQ = 2130706432.f;  // 127 * 2^24: activation fixed-point full scale (four balanced base-256 digits = int8 planes)
 constexpr int kProducerWarps = 1;        // a stage is one UTMALDG (two in gate/up pair mode): a single elected lane keeps up
 // per-tile scales/zeros slabs in flight: ring depth + 1 (a tile spans >= 1 stage)
 
@@ -116,7 +116,7 @@ template <int NCOLS, int CW>
 struct Layout {
     static constexpr int kXPad = (NCOLS > 1) ? 64 : 0;  // column pitch = 64 (mod 128) B for the per-column B loads
     static constexpr int kVals = 16 * NCOLS;
-    // four int8 planes per activation (29-bit block fixed point): planes (p3, p2) interleaved in region A (2 B per element),
+    // four int8 planes per activation (32-bit block fixed point): planes (p3, p2) interleaved in region A (2 B per element),
     // planes (p1, p0) in region B that follows region A of the same column
     static __host__ __device__ int x_pitch(int IC) { return IC * 4 + kXPad; }
     // one meta slot = scales half[16][zeros_w*8] followed by zeros uint32[16][zeros_w] = 320 * zeros_w bytes
@@ -124,7 +124,7 @@ struct Layout {
     static __host__ __device__ size_t off_meta(int nst) { return (size_t)nst * kStageBytes; }
     static __host__ __device__ size_t off_xs(int IC, int nst) { return off_meta(nst) + (size_t)(nst + 1) * meta_slot_bytes(IC); }
     static __host__ __device__ size_t off_gx(int IC, int nst) { return off_xs(IC, nst) + (size_t)NCOLS * x_pitch(IC); }
-    // gx: float step[NCOLS][NG] followed by int gsum[NCOLS][NG][2] = {128 * sum(p3) + sum(p2), 128 * sum(p1) + sum(p0)}
+    // gx: float step[NCOLS][NG] followed by int gsum[NCOLS][NG][2] = {256 * sum(p3) + sum(p2), 256 * sum(p1) + sum(p0)}
     static __host__ __device__ size_t off_red(int IC, int nst) { return off_gx(IC, nst) + (size_t)3 * NCOLS * (IC / 128) * sizeof(float); }
     static __host__ __device__ size_t off_rms(int IC, int nst) { return off_red(IC, nst) + (size_t)kRedBufs * CW * kVals * sizeof(float); }
     static __host__ __device__ size_t off_bar(int IC, int nst) { return (off_rms(IC, nst) + (size_t)NCOLS * CW * sizeof(float) + 15) & ~(size_t)15; }
@@ -431,42 +431,43 @@ TCE_DEVINL void epilogue(const KArgs &a, const Smem &sm, RedState &es, int cta, 
 // step and integer sums.  Must be called by all 32 lanes of a warp (half-warp shuffles); `valid` masks the stores.
 template <int NCOLS>
 TCE_DEVINL void emit_unit(uint8_t *xcol, int IC, float *gx, int *gsum, int ui, bool valid, const float (&v)[8], int lane) {
-    // Activations enter the integer tensor path as 29-bit block fixed point: per 128-group,
-    // X = rint(x * Q / max|x|), Q = 127 * 2^21, X = 2^21*p3 + 2^14*p2 + 2^7*p1 + p0  (four int8 planes: p3 in [-127,127], the others in
-    // [-64,64]).  |x - step*X| <= max(|x| * 2^-24, max|x_group| * 2^-29): every fp16 activation whose magnitude is within 2^17 of the
-    // largest of its group keeps all of its 11 significand bits, i.e. the planes carry what the reference's exact fp16 -> fp32
-    // conversion carries (gemv_cuda.cu:181-184) unless a group spans more than 5 decades.  The integer dot products that follow are
+    // Activations enter the integer tensor path as 32-bit block fixed point: per 128-group,
+    // X = rint(x * Q / max|x|), Q = 127 * 2^24, X = 2^24*p3 + 2^16*p2 + 2^8*p1 + p0  (four int8 planes = the balanced base-256 digits of
+    // X, p3 in [-127,127], the others in [-128,127]).  |x - step*X| <= max(|x| * 2^-24, max|x_group| * 2^-32): every fp16 activation whose
+    // magnitude is within 2^20 of the largest of its group keeps all of its 11 significand bits, i.e. the planes carry what the reference's
+    // exact fp16 -> fp32 conversion carries (gemv_cuda.cu:181-184) unless a group spans more than 6 decades.  The integer dot products that follow are
     // exact.  The extra planes cost no MMA: the four planes ride in MMA columns 0..3 of the same instruction.
     float amax = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    // group maximum over the 16 lanes that hold the group: non-negative floats order like their bit patterns
+    const unsigned half_mask = 0xFFFFu << (lane & 16);
+    amax = __uint_as_float(__reduce_max_sync(half_mask, __float_as_uint(amax)));
     const float qinv = (amax > 0.f) ? (kActQ / amax) : 0.f;
-    int p3[8], p2[8], p1[8], p0[8], sxh = 0, sxl = 0;
+    // balanced base-256 digits of X in one go: (X + 0x80808080) ^ 0x80808080 holds p3..p0 as signed bytes (the carries between the
+    // digits are the carries of the addition)
+    uint32_t Z[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int X = __float2int_rn(v[i] * qinv);
-        p3[i] = (X + (1 << 20)) >> 21;
-        const int r = X - (p3[i] << 21);
-        p2[i] = (r + (1 << 13)) >> 14;
-        const int r2 = r - (p2[i] << 14);
-        p1[i] = (r2 + 64) >> 7;
-        p0[i] = r2 - (p1[i] << 7);
-        sxh += (p3[i] << 7) + p2[i];
-        sxl += (p1[i] << 7) + p0[i];
-    }
+    for (int i = 0; i < 8; i++) Z[i] = ((uint32_t)__float2int_rn(v[i] * qinv) + 0x80808080u) ^ 0x80808080u;
     // B-fragment order of mma.m16n8k32: k-slots 4t..4t+3 <- elements (0,2,4,6) of the word (the bytes of
-    // w & 0x0f0f0f0f), k-slots 16+4t.. <- elements (1,3,5,7) (the bytes of (w>>4) & 0x0f0f0f0f).
-    auto pack4 = [](int b0, int b1, int b2, int b3) {
-        return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
-    };
-    const uint32_t o3e = pack4(p3[0], p3[2], p3[4], p3[6]), o3o = pack4(p3[1], p3[3], p3[5], p3[7]);
-    const uint32_t o2e = pack4(p2[0], p2[2], p2[4], p2[6]), o2o = pack4(p2[1], p2[3], p2[5], p2[7]);
-    const uint32_t o1e = pack4(p1[0], p1[2], p1[4], p1[6]), o1o = pack4(p1[1], p1[3], p1[5], p1[7]);
-    const uint32_t o0e = pack4(p0[0], p0[2], p0[4], p0[6]), o0o = pack4(p0[1], p0[3], p0[5], p0[7]);
+    // w & 0x0f0f0f0f), k-slots 16+4t.. <- elements (1,3,5,7) (the bytes of (w>>4) & 0x0f0f0f0f).  4x4 byte transposes:
+    uint32_t o3e, o2e, o1e, o0e, o3o, o2o, o1o, o0o;
+    {
+        const uint32_t t0 = __byte_perm(Z[0], Z[2], 0x6240), t1 = __byte_perm(Z[0], Z[2], 0x7351);  // (p0a p0b p2a p2b), (p1a p1b p3a p3b)
+        const uint32_t u0 = __byte_perm(Z[4], Z[6], 0x6240), u1 = __byte_perm(Z[4], Z[6], 0x7351);
+        o0e = __byte_perm(t0, u0, 0x5410); o2e = __byte_perm(t0, u0, 0x7632);
+        o1e = __byte_perm(t1, u1, 0x5410); o3e = __byte_perm(t1, u1, 0x7632);
+    }
+    {
+        const uint32_t t0 = __byte_perm(Z[1], Z[3], 0x6240), t1 = __byte_perm(Z[1], Z[3], 0x7351);
+        const uint32_t u0 = __byte_perm(Z[5], Z[7], 0x6240), u1 = __byte_perm(Z[5], Z[7], 0x7351);
+        o0o = __byte_perm(t0, u0, 0x5410); o2o = __byte_perm(t0, u0, 0x7632);
+        o1o = __byte_perm(t1, u1, 0x5410); o3o = __byte_perm(t1, u1, 0x7632);
+    }
+    // digit sums of the unit (signed byte dot products with 1)
+    const int s3 = __dp4a((int)o3e, 0x01010101, __dp4a((int)o3o, 0x01010101, 0)), s2 = __dp4a((int)o2e, 0x01010101, __dp4a((int)o2o, 0x01010101, 0));
+    const int s1 = __dp4a((int)o1e, 0x01010101, __dp4a((int)o1o, 0x01010101, 0)), s0 = __dp4a((int)o0e, 0x01010101, __dp4a((int)o0o, 0x01010101, 0));
+    int sxh = s3 * 256 + s2, sxl = s1 * 256 + s0;
     const int G = ui >> 4, tj = ui & 15;  // ui = G*16 + 4*t + j
     if (NCOLS == 1) {
         // single-column layout (consume1).  Region A (planes p3 | p2) and region B (at byte IC*2, planes p1 | p0), each per group
@@ -492,15 +493,12 @@ TCE_DEVINL void emit_unit(uint8_t *xcol, int IC, float *gx, int *gsum, int ui, b
             *reinterpret_cast<uint4 *>(xcol + (size_t)IC * 2 + (size_t)pos * 16) = make_uint4(o1e, o1o, o0e, o0o);
         }
     }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        sxh += __shfl_xor_sync(0xffffffffu, sxh, o);
-        sxl += __shfl_xor_sync(0xffffffffu, sxl, o);
-    }
+    sxh = __reduce_add_sync(half_mask, sxh);
+    sxl = __reduce_add_sync(half_mask, sxl);
     if (valid && (lane & 15) == 0) {
         gx[G] = (amax > 0.f) ? (amax / kActQ) : 0.f;  // step of the group
-        gsum[G * 2] = sxh;                            // 128 * sum(p3) + sum(p2) over the group
-        gsum[G * 2 + 1] = sxl;                        // 128 * sum(p1) + sum(p0)
+        gsum[G * 2] = sxh;                            // 256 * sum(p3) + sum(p2) over the group
+        gsum[G * 2 + 1] = sxl;                        // 256 * sum(p1) + sum(p0)
     }
 }
 
@@ -639,13 +637,13 @@ TCE_DEVINL void stage_activations(const KArgs &a, const Smem &sm, int x_pitch, i
 // Two MMAs per parity take words (0,1) and (2,3) of the lane's 16-byte weight load as their two k halves.
 struct Lane1 {  // lane-constant operands of the single-column consumer
     const uint8_t *xlane;  // this lane's activation chunk of group 0 (256 B per group)
-    float lscale;          // t = 0: 2^14 (columns 0,1 = planes p3,p2), t = 1: 1 (columns 2,3 = planes p1,p0), else 0 (don't-care columns)
+    float lscale;          // t = 0: 2^16 (columns 0,1 = planes p3,p2), t = 1: 1 (columns 2,3 = planes p1,p0), else 0 (don't-care columns)
     int gsel;              // which of the two group sums this lane subtracts (t & 1)
 };
 TCE_DEVINL Lane1 make_lane1(const uint8_t *xs, int IC, int g, int t) {
     Lane1 L;
     L.xlane = xs + (size_t)((g >> 1) & 1) * IC * 2 + (size_t)(t * 2 + (g & 1)) * 16;  // column g & 3 supplies plane 3 - (g & 3)
-    L.lscale = (t == 0) ? 16384.f : (t == 1 ? 1.f : 0.f);
+    L.lscale = (t == 0) ? 65536.f : (t == 1 ? 1.f : 0.f);
     L.gsel = t & 1;
     return L;
 }
@@ -660,12 +658,12 @@ TCE_DEVINL void unit1(const Lane1 &L, const uint4 wa, const uint4 wb, int G, flo
     mma_m16n8k32_u8s8_z(accH, wa.x & MH, wb.x & MH, wa.y & MH, wb.y & MH, xo.x, xo.y);
     mma_m16n8k32_u8s8(accL, wa.z & ML, wb.z & ML, wa.w & ML, wb.w & ML, xe.z, xe.w);
     mma_m16n8k32_u8s8(accH, wa.z & MH, wb.z & MH, wa.w & MH, wb.w & MH, xo.z, xo.w);
-    // X = 2^21*p3 + 2^14*p2 + 2^7*p1 + p0; odd slots carry 16 x nibble: exact integer group result sum_k q*X - z*sum_k X, held as a
-    // (p3,p2) part on t = 0 (in units of 2^14) and a (p1,p0) part on t = 1
+    // X = 2^24*p3 + 2^16*p2 + 2^8*p1 + p0; odd slots carry 16 x nibble: exact integer group result sum_k q*X - z*sum_k X, held as a
+    // (p3,p2) part on t = 0 (in units of 2^16) and a (p1,p0) part on t = 1
     const int sxv = gsum[2 * G + L.gsel];
     const float st = gx[G] * L.lscale;
-    const int vA = ((accL[0] + (accH[0] >> 4)) << 7) + (accL[1] + (accH[1] >> 4)) - zAq * sxv;
-    const int vB = ((accL[2] + (accH[2] >> 4)) << 7) + (accL[3] + (accH[3] >> 4)) - zBq * sxv;
+    const int vA = ((accL[0] + (accH[0] >> 4)) << 8) + (accL[1] + (accH[1] >> 4)) - zAq * sxv;
+    const int vB = ((accL[2] + (accH[2] >> 4)) << 8) + (accL[3] + (accH[3] >> 4)) - zBq * sxv;
     totA += (sAq * st) * (float)vA;
     totB += (sBq * st) * (float)vB;
 }
@@ -804,13 +802,13 @@ TCE_DEVINL void consume(const KArgs &a, const Smem &sm, RingState &rs, RedState 
                         mma_m16n8k32_u8s8(c1, a0, a1, a2, a3, xw.x, xw.y);
                         mma_m16n8k32_u8s8(c0, a0, a1, a2, a3, xw.z, xw.w);
                     }
-                    // exact integer group result: sum_k q*X - z*sum_k X, X = 2^21*p3 + 2^14*p2 + 2^7*p1 + p0, kept as a (p3,p2) part in
-                    // units of 2^14 and a (p1,p0) part (the full integer does not fit 32 bits)
+                    // exact integer group result: sum_k q*X - z*sum_k X, X = 2^24*p3 + 2^16*p2 + 2^8*p1 + p0, kept as a (p3,p2) part in
+                    // units of 2^16 and a (p1,p0) part (the full integer does not fit 32 bits)
                     {
                         const int *gs0 = sm.gsum + ((2 * t) * a.NG + G) * 2, *gs1 = sm.gsum + ((2 * t + 1) * a.NG + G) * 2;
                         const float st0 = sm.gx[(2 * t) * a.NG + G], st1 = sm.gx[(2 * t + 1) * a.NG + G];
                         auto comb = [](int h3, int h2, int l1, int l0, int z, const int *gs) {
-                            return 16384.f * (float)((h3 << 7) + h2 - z * gs[0]) + (float)((l1 << 7) + l0 - z * gs[1]);
+                            return 65536.f * (float)((h3 << 8) + h2 - z * gs[0]) + (float)((l1 << 8) + l0 - z * gs[1]);
                         };
                         tot[0] += (sAq * st0) * comb(c3[0], c2[0], c1[0], c0[0], zAq, gs0);
                         tot[1] += (sAq * st1) * comb(c3[1], c2[1], c1[1], c0[1], zAq, gs1);

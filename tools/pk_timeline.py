@@ -40,7 +40,9 @@ def main():
     torch.cuda.synchronize()
     ptr = ctx.L.tce_llama_debug_buffer(model.h, 4)
     assert ptr, "no debug buffer: TCE_PK_DEBUG=1 must be set before the model is created"
-    raw = _tensor_from_ptr(ptr, (ncta * nphase * 4 * 2,), torch.int32, 0).cpu().numpy().view(np.uint64).reshape(ncta, nphase, 4).astype(np.float64)
+    raw = _tensor_from_ptr(ptr, (ncta * nphase * 8 * 2,), torch.int32, 0).cpu().numpy().view(np.uint64).reshape(ncta, nphase, 8).astype(np.float64)
+    if args.out:
+        np.save(args.out.replace(".json", "") + "_raw.npy", raw)
     t0 = raw[:, 0, 0].min()
     T = (raw - t0) / 1e3  # us
     T[raw == 0] = np.nan
@@ -51,6 +53,16 @@ def main():
     names = {0: "qkv", 1: "attn", 2: "o_proj", 3: "gate_up", 4: "down"}
     total = np.nanmax(T[:, -1, 3]) if not np.all(np.isnan(T[:, -1, 3])) else np.nanmax(T)
     print(f"kernel span (first barrier-pass stamp -> last arrival): {total:.1f} us over {nphase} phases, ctx {args.ctx}")
+    # attention sub-steps (medians over the CTAs that own chunks and over layers): time since the CTA entered the phase
+    att = {4: [], 5: [], 6: [], 2: []}
+    for p in range(1, nphase - 1):
+        if p % 5 == 1:
+            for k in att:
+                d = T[:, p, k] - T[:, p, 0]
+                if not np.all(np.isnan(d)):
+                    att[k].append(np.nanmedian(d))
+    print("attention, since phase entry (median): q roped+bar %.2f  chunks done %.2f  partial written %.2f  phase left %.2f us" %
+          tuple(float(np.median(att[k])) if att[k] else float("nan") for k in (4, 5, 6, 2)))
     acc = {}
     for p in range(1, nphase - 1):
         k = p % 5
@@ -61,7 +73,8 @@ def main():
         arrived = T[:, p, 3]
         d = {"barrier_us": np.nanmedian(opened) - prev_done, "stage_us": np.nanmedian(staged - opened) if k != 1 else 0.0,
              "consume_us": np.nanmedian(consumed - (staged if k != 1 else opened)), "tail_us": np.nanmax(arrived) - np.nanmedian(consumed),
-             "phase_us": np.nanmax(arrived) - prev_done, "skew_us": np.nanmax(consumed) - np.nanmin(consumed)}
+             "phase_us": np.nanmax(arrived) - prev_done, "skew_us": np.nanmax(consumed) - np.nanmin(consumed),
+             "hop_us": (np.nanmedian(staged) if k != 1 else np.nanmedian(T[:, p, 4])) - prev_done, "etail_us": np.nanmedian(arrived - consumed)}
         acc.setdefault(k, []).append(d)
     summ = {}
     for k, lst in sorted(acc.items()):
@@ -70,7 +83,7 @@ def main():
         m["hbm_floor_us"] = bytes_of[k] / 6.5696e6
         summ[names[k]] = m
         print(f"{names[k]:8s} phase {m['phase_us']:6.2f} us (HBM floor {m['hbm_floor_us']:5.2f})  barrier {m['barrier_us']:5.2f}  stage {m['stage_us']:5.2f}  "
-              f"consume {m['consume_us']:6.2f}  tail {m['tail_us']:5.2f}  skew {m['skew_us']:5.2f}  -> {m['GBps']:7.0f} GB/s")
+              f"consume {m['consume_us']:6.2f}  tail {m['tail_us']:5.2f}  skew {m['skew_us']:5.2f}  hop {m['hop_us']:5.2f}  etail {m['etail_us']:5.2f}  -> {m['GBps']:7.0f} GB/s")
     lm = nphase - 1
     prev_done = np.nanmax(T[:, lm - 1, 3])
     print(f"lm_head  phase {np.nanmax(T[:, lm, 3]) - prev_done:6.2f} us")
