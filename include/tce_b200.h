@@ -160,6 +160,17 @@ typedef struct tce_llama tce_llama;
 
 TCE_API int tce_llama_create(tce_ctx *ctx, const tce_llama_config *cfg, const tce_llama_weights *w, tce_llama **out);
 TCE_API int tce_llama_destroy(tce_llama *m);
+/* ---- loading the reference's model zoo format --------------------------------------------------------------------
+ * Build the model from a parameter tree on disk, as the reference's constructors do (Int4LlamaForCausalLM(param_path, config),
+ * llm/src/nn_modules/cuda/Int4llamaForCausalLM.cu:7-15 and below): <dir>/decoder/{embed_tokens,norm,layer<i>/...}, <dir>/lm_head, INT4 ops
+ * in the QM_CUDA flavour (weight_int4.bin / scaling_factor_int4.bin / zero_point_int4.bin, llm/tools/model_quantizer.py:35-66), q|k|v either
+ * merged (self_attn/qkv_proj, llm/tools/llama_qkv_merger.py) or separate.  cfg gives the geometry (the reference's model_config); file
+ * sizes are checked against it.  The model owns its device copies.  Single GPU.                                                    */
+TCE_API int tce_llama_load_dir(tce_ctx *ctx, const char *dir, const tce_llama_config *cfg, tce_llama **out);
+/* QM_x86 op (llm/tools/quantize_methods.py:188-243: uint8 [oc][ic/2] with byte e of each 64-weight run = w[e] | w[32+e] << 4, fp32 scales
+ * [oc][ic/32], zero point 8) -> QM_CUDA op arrays (w uint32 [oc][ic/8], scales fp16 [oc][zeros_w*8], zeros uint32 [oc][zeros_w]) on the HOST:
+ * exact dequantisation followed by the QM_CUDA quantisation rule (group 128).  Lossy by construction (32- vs 128-channel scales).  */
+TCE_API int tce_w4_import_x86(const void *qs_u8, const float *scales_f32, int oc, int ic, void *w_out, void *scales_f16_out, void *zeros_out);
 /* inputs resident: tokpos = device int[2] {token id, position}; logits stay on the device */
 TCE_API int tce_llama_decode(tce_llama *m, const int *tokpos_dev);
 /* end to end: token/pos from the host, fp32 logits[vocab] copied back to `logits_host` (may be NULL) and the
@@ -170,6 +181,29 @@ TCE_API int tce_llama_decode_host(tce_llama *m, int token, int pos, float *logit
  * sampler reads, LLaMAGenerate.cu:160-166) copied to logits_host (may be NULL), greedy token to next_token (may be NULL).
  * Linears run as tcgen05 GEMMs, attention as a causal flash kernel.  Synchronous.  Single GPU (tp_size == 1).                */
 TCE_API int tce_llama_prefill(tce_llama *m, const int *tokens_host, int n, int pos0, float *logits_host, int *next_token);
+/* ---- sampling + generate loop on the device -------------------------------------------------------------
+ * The reference copies n_vocab logits to the host every token and samples there (llm/src/nn_modules/cuda/LLaMAGenerate.cu:112-166 with
+ * llm/src/Generate.cc:14-136,304-327: repetition / frequency / presence penalties over the last `repeat_last_n` tokens, then greedy when
+ * temp <= 0, else top-k -> top-p -> temperature -> softmax -> one draw).  Same chain, same order, one kernel next to the logits.
+ * Fields as in the reference's opt_params (llm/include/Generate.h:48-72); tail-free / typical / mirostat are not offered (identity at
+ * the reference's defaults).  temp > 0 needs 1 <= top_k <= 1024 (TCE_ERR_UNSUPPORTED otherwise).  The draw is an inverse-CDF lookup with
+ * a counter-based uniform of (seed, draw index).                                                                                  */
+typedef struct tce_sampling {
+    int top_k;
+    float top_p, temp, repeat_penalty, frequency_penalty, presence_penalty;
+    int repeat_last_n; /* < 0: the whole window */
+    unsigned long long seed;
+} tce_sampling;
+/* one sampling step: logits_dev float[n_vocab] (penalised IN PLACE), window_host = the recent tokens, oldest first (may be NULL/0).
+ * Returns the token in *token_host and, when the three cand_* pointers are given, the surviving candidates (logit-descending) with their
+ * final probabilities (cand_* arrays must hold max(1, top_k) entries).  Synchronous.                                            */
+TCE_API int tce_sample(tce_ctx *ctx, float *logits_dev, int n_vocab, const int *window_host, int n_window, const tce_sampling *cfg,
+                       unsigned long long draw_index, int *token_host, int *cand_ids_host, float *cand_probs_host, int *cand_count_host);
+/* generate loop: decode `first_token` at position pos0, sample, feed the sample back, ... for at most n_predict tokens or until eos_id
+ * is drawn or the context is full.  history_host (n_history recent tokens, oldest first) seeds the penalty window.  Only the generated
+ * ids (4 bytes each) cross PCIe.  Single GPU (tp_size == 1).                                                                       */
+TCE_API int tce_llama_generate(tce_llama *m, int first_token, int pos0, int n_predict, const tce_sampling *cfg, const int *history_host,
+                               int n_history, int eos_id, int *out_tokens_host, int *n_out);
 TCE_API const float *tce_llama_logits(tce_llama *m);          /* device float[vocab] */
 TCE_API void *tce_llama_kv_cache(tce_llama *m, int layer, int which); /* which: 0 K, 1 V; half[KVH][max_ctx][hd] */
 TCE_API int tce_llama_kernels_per_step(tce_llama *m);

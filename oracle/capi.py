@@ -237,6 +237,32 @@ def ref_cuda():
     return _REF_CUDA
 
 
+_REF_GEN = None
+
+
+def ref_sample_candidates(logits, window=(), top_k=40, top_p=0.95, temp=0.8, repeat_penalty=1.1, frequency_penalty=0.0, presence_penalty=0.0):
+    """The reference's own sampling chain (llm/src/Generate.cc compiled in place, oracle/_ref/libtce_ref_generate.so) in the order of
+    LLaMAGenerate.cu:112-166, without the final draw: -> (ids, probs) of the surviving candidates."""
+    global _REF_GEN
+    if _REF_GEN is None:
+        import os
+
+        so = REF_DIR / "libtce_ref_generate.so"
+        if not so.exists():
+            raise FileNotFoundError(f"{so} not built (needs /root/reference; run `make -C oracle ref`)")
+        L = C.CDLL(str(so), mode=os.RTLD_LAZY)  # Generate.h drags in model classes the sampling functions never call
+        L.ref_sample_candidates.restype = C.c_int
+        L.ref_sample_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_void_p, C.c_void_p]
+        _REF_GEN = L
+    lg = np.ascontiguousarray(logits, dtype=np.float32)
+    win = np.ascontiguousarray(np.asarray(list(window), dtype=np.int32))
+    ids = np.zeros(lg.size, dtype=np.int32)
+    probs = np.zeros(lg.size, dtype=np.float32)
+    n = _REF_GEN.ref_sample_candidates(lg.ctypes.data, lg.size, win.ctypes.data if win.size else None, int(win.size), int(top_k), float(top_p), float(temp),
+                                       float(repeat_penalty), float(frequency_penalty), float(presence_penalty), ids.ctypes.data, probs.ctypes.data)
+    return ids[:n].copy(), probs[:n].copy()
+
+
 def ref_naive_mat_mul_int4(A, B, scales, zero_point=8.0, block_size=128, kind="generic"):
     A = np.ascontiguousarray(A, np.float32)
     M, IC = A.shape

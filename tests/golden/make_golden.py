@@ -158,6 +158,23 @@ def main():
         out, fk, fv = capi.ref_int4_llama_attention(d, hidden, E, H, KVH, prefill, steps, max_sq)
     np.savez_compressed(OUT / "llama_attention_module.npz", hidden=hidden, sel_q=sel["q"], sel_k=sel["k"], sel_v=sel["v"], sel_o=sel["o"], out=out,
                         final_k=fk, final_v=fv, H=H, KVH=KVH, prefill=prefill, steps=steps, max_sq=max_sq, alpha=alpha, theta=np.float32(10000.0))
+    # the reference's sampling chain (llm/src/Generate.cc via oracle/_ref/libtce_ref_generate.so): candidate sets + probabilities for a few
+    # configurations over one logits vector with distinct values (the order among equal logits is unspecified in the reference)
+    V = 4096
+    logits = (rng.standard_normal(V) * 3.0).astype(np.float32)
+    window = rng.integers(0, V, 64).astype(np.int32)
+    window[5] = window[9] = int(np.argmax(logits))  # the favourite is penalised, twice in the window
+    cases = [dict(top_k=40, top_p=0.95, temp=0.8, repeat_penalty=1.1, frequency_penalty=0.0, presence_penalty=0.0),
+             dict(top_k=40, top_p=0.5, temp=1.3, repeat_penalty=1.3, frequency_penalty=0.2, presence_penalty=0.1),
+             dict(top_k=200, top_p=1.0, temp=0.7, repeat_penalty=1.0, frequency_penalty=0.0, presence_penalty=0.0),
+             dict(top_k=1, top_p=0.95, temp=0.8, repeat_penalty=1.1, frequency_penalty=0.0, presence_penalty=0.0),
+             dict(top_k=40, top_p=0.95, temp=0.0, repeat_penalty=1.5, frequency_penalty=0.0, presence_penalty=0.0)]
+    samp = {"logits": logits, "window": window, "n_cases": len(cases)}
+    for i, c in enumerate(cases):
+        ids, probs = capi.ref_sample_candidates(logits, window, **c)
+        samp[f"ids{i}"], samp[f"probs{i}"] = ids, probs
+        samp[f"cfg{i}"] = np.array([c["top_k"], c["top_p"], c["temp"], c["repeat_penalty"], c["frequency_penalty"], c["presence_penalty"]], dtype=np.float64)
+    np.savez_compressed(OUT / "sampling.npz", **samp)
     print("golden fixtures written to", OUT)
 
 

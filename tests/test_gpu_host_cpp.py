@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 
 
 def test_reference_style_op_tests_through_cpp_surface():
-    exe = ROOT / "tinychatengine_b200" / "lib" / "test_host"
+    exe = ROOT / "tests" / "cpp" / "test_host"
     if not exe.exists():
-        subprocess.run(["make", "-s", "-C", str(ROOT / "tinychatengine_b200" / "host")], check=True)
+        subprocess.run(["make", "-s", "-C", str(ROOT / "tinychatengine_b200" / "host"), "test_host"], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr

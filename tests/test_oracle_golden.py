@@ -232,3 +232,47 @@ def test_norms_match_the_compiled_reference_ops():
         got8 = np.zeros((rows, dim), np.int8)
         capi.lib().orc_layernorm_q(x8, w, b, got8, rows, dim)
         assert np.array_equal(got8, want8)
+
+
+# ---- token sampling: oracle/sampling.py against the reference's Generate.cc -------------------------------------
+def _sampling_cases(golden_dir):
+    g = np.load(golden_dir / "sampling.npz")
+    for i in range(int(g["n_cases"])):
+        c = g[f"cfg{i}"]
+        cfg = dict(top_k=int(c[0]), top_p=float(c[1]), temp=float(c[2]), repeat_penalty=float(c[3]), frequency_penalty=float(c[4]), presence_penalty=float(c[5]))
+        yield g["logits"], g["window"], cfg, g[f"ids{i}"], g[f"probs{i}"]
+
+
+def test_sampling_oracle_matches_reference_fixture(golden_dir):
+    """tests/golden/sampling.npz was produced by the reference's own sample_* functions (make_golden.py)."""
+    from oracle import sampling
+
+    for logits, window, cfg, ids, probs in _sampling_cases(golden_dir):
+        oi, op = sampling.candidates(logits, window, **cfg)
+        assert np.array_equal(oi, ids), cfg
+        np.testing.assert_allclose(op, probs, rtol=0, atol=1e-6)
+
+
+def test_sampling_oracle_matches_reference_live(golden_dir):
+    """Same, against the compiled reference on fresh inputs (only where /root/reference was available to build oracle/_ref)."""
+    from oracle import capi, sampling
+
+    try:
+        capi.ref_sample_candidates(np.zeros(4, np.float32), (), top_k=2)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libtce_ref_generate.so not built")
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        V = int(rng.integers(50, 3000))
+        logits = (rng.standard_normal(V) * rng.uniform(0.5, 6)).astype(np.float32)
+        window = rng.integers(0, V, int(rng.integers(0, 100))).astype(np.int32)
+        cfg = dict(top_k=int(rng.integers(1, 80)), top_p=float(rng.uniform(0.3, 1.0)), temp=float(rng.uniform(0.2, 1.5)),
+                   repeat_penalty=float(rng.uniform(1.0, 1.5)), frequency_penalty=float(rng.uniform(0, 0.3)), presence_penalty=float(rng.uniform(0, 0.3)))
+        ri, rp = capi.ref_sample_candidates(logits, window, **cfg)
+        oi, op = sampling.candidates(logits, window, **cfg)
+        assert np.array_equal(oi, ri), (trial, cfg)
+        np.testing.assert_allclose(op, rp, rtol=0, atol=1e-6)
+    # the draw: inverse CDF over the candidate probabilities
+    ids, probs = sampling.candidates(logits, window, **cfg)
+    assert sampling.draw(ids, probs, 0.0) == int(ids[0]) and sampling.draw(ids, probs, 0.999999) == int(ids[-1])
+    assert 0.0 <= sampling.uniform01(1234, 5) < 1.0

@@ -31,6 +31,13 @@ class LlamaWeights(C.Structure):
                 ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p)]
 
 
+class Sampling(C.Structure):
+    """tce_sampling (include/tce_b200.h): the sampling fields of the reference's opt_params (llm/include/Generate.h:48-72)."""
+    _fields_ = [("top_k", C.c_int), ("top_p", C.c_float), ("temp", C.c_float), ("repeat_penalty", C.c_float), ("frequency_penalty", C.c_float),
+                ("presence_penalty", C.c_float), ("repeat_last_n", C.c_int), ("seed", C.c_ulonglong)]
+
+
+
 # every symbol include/tce_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this table)
 SIGNATURES = {
     "tce_version": (C.c_int, []),
@@ -58,9 +65,14 @@ SIGNATURES = {
     "tce_add_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong]),
     "tce_llama_create": (C.c_int, [C.c_void_p, C.POINTER(LlamaConfig), C.POINTER(LlamaWeights), C.POINTER(C.c_void_p)]),
     "tce_llama_destroy": (C.c_int, [C.c_void_p]),
+    "tce_llama_load_dir": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(LlamaConfig), C.POINTER(C.c_void_p)]),
+    "tce_w4_import_x86": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p] * 3),
     "tce_llama_decode": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tce_llama_decode_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "tce_llama_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "tce_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(Sampling), C.c_ulonglong, C.POINTER(C.c_int), C.c_void_p, C.c_void_p,
+                             C.POINTER(C.c_int)]),
+    "tce_llama_generate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Sampling), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "tce_llama_logits": (C.c_void_p, [C.c_void_p]),
     "tce_llama_kv_cache": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "tce_llama_kernels_per_step": (C.c_int, [C.c_void_p]),

@@ -397,6 +397,22 @@ int tce_llama_create(tce_ctx *ctx, const tce_llama_config *cfg, const tce_llama_
     *out = reinterpret_cast<tce_llama *>(d);
     return TCE_OK;
 }
+int tce_llama_load_dir(tce_ctx *ctx, const char *dir, const tce_llama_config *cfg, tce_llama **out) {
+    if (!ctx || !dir || !cfg || !out) return fail(TCE_ERR_INVALID, "tce_llama_load_dir: null argument");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    std::string err;
+    LlamaDecoder *d = load_llama_dir(&ctx->c, ctx->attn_chunk, dir, *cfg, &err);
+    if (!d) return fail(TCE_ERR_INVALID, "tce_llama_load_dir: %s", err.c_str());
+    *out = reinterpret_cast<tce_llama *>(d);
+    return TCE_OK;
+}
+int tce_w4_import_x86(const void *qs_u8, const float *scales_f32, int oc, int ic, void *w_out, void *scales_f16_out, void *zeros_out) {
+    if (!qs_u8 || !scales_f32 || !w_out || !scales_f16_out || !zeros_out) return fail(TCE_ERR_INVALID, "tce_w4_import_x86: null argument");
+    if (import_x86(static_cast<const uint8_t *>(qs_u8), scales_f32, oc, ic, static_cast<uint32_t *>(w_out), static_cast<__half *>(scales_f16_out),
+                   static_cast<uint32_t *>(zeros_out)))
+        return fail(TCE_ERR_INVALID, "tce_w4_import_x86: ic must be a multiple of 128");
+    return TCE_OK;
+}
 int tce_llama_destroy(tce_llama *m) {
     delete reinterpret_cast<LlamaDecoder *>(m);
     return TCE_OK;
@@ -422,6 +438,73 @@ int tce_llama_prefill(tce_llama *m, const int *tokens_host, int n, int pos0, flo
     if (e == cudaErrorNotSupported) return fail(TCE_ERR_UNSUPPORTED, "tce_llama_prefill: %s", err.c_str());
     if (e == cudaErrorInvalidValue) return fail(TCE_ERR_INVALID, "tce_llama_prefill: bad tokens / n=%d pos0=%d", n, pos0);
     if (e != cudaSuccess) return fail(TCE_ERR_CUDA, "tce_llama_prefill: %s (%s)", cudaGetErrorString(e), err.c_str());
+    return TCE_OK;
+}
+int tce_llama_generate(tce_llama *m, int first_token, int pos0, int n_predict, const tce_sampling *cfg, const int *history_host, int n_history, int eos_id,
+                       int *out_tokens_host, int *n_out) {
+    if (!m || !cfg || !n_out) return fail(TCE_ERR_INVALID, "tce_llama_generate: null argument");
+    std::string err;
+    cudaError_t e = reinterpret_cast<LlamaDecoder *>(m)->generate(first_token, pos0, n_predict, *cfg, history_host, n_history, eos_id, out_tokens_host, n_out, &err);
+    if (e == cudaErrorNotSupported) return fail(TCE_ERR_UNSUPPORTED, "tce_llama_generate: %s", err.c_str());
+    if (e == cudaErrorInvalidValue) return fail(TCE_ERR_INVALID, "tce_llama_generate: bad token / position / count");
+    if (e != cudaSuccess) return fail(TCE_ERR_CUDA, "tce_llama_generate: %s (%s)", cudaGetErrorString(e), err.c_str());
+    return TCE_OK;
+}
+int tce_sample(tce_ctx *ctx, float *logits_dev, int n_vocab, const int *window_host, int n_window, const tce_sampling *cfg, unsigned long long draw_index,
+               int *token_host, int *cand_ids_host, float *cand_probs_host, int *cand_count_host) {
+    if (!ctx || !logits_dev || !cfg || !token_host || n_vocab < 1 || n_window < 0 || (n_window > 0 && !window_host))
+        return fail(TCE_ERR_INVALID, "tce_sample: bad argument");
+    CK(cudaSetDevice(ctx->c.device), "cudaSetDevice");
+    const bool want_cand = cand_ids_host && cand_probs_host && cand_count_host;
+    const int kcap = 1024;
+    int *scratch = nullptr;  // [0] token, [1] head, [2] cand count, [4..] window, then cand ids, cand probs
+    const size_t words = 4 + (size_t)(n_window > 0 ? n_window : 1) + 2 * (size_t)kcap;
+    CK(cudaMalloc((void **)&scratch, words * sizeof(int)), "tce_sample: scratch");
+    cudaStream_t s = ctx->c.stream;
+    int *win = scratch + 4, *cids = win + (n_window > 0 ? n_window : 1);
+    float *cprob = reinterpret_cast<float *>(cids + kcap);
+    const int ctl[4] = {0, n_window, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(scratch, ctl, sizeof(ctl), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && n_window > 0) e = cudaMemcpyAsync(win, window_host, (size_t)n_window * sizeof(int), cudaMemcpyHostToDevice, s);
+    SampleArgs a{};
+    a.logits = logits_dev;
+    a.n_vocab = n_vocab;
+    a.top_k = cfg->top_k;
+    a.top_p = cfg->top_p;
+    a.temp = cfg->temp;
+    a.repeat_penalty = cfg->repeat_penalty;
+    a.frequency_penalty = cfg->frequency_penalty;
+    a.presence_penalty = cfg->presence_penalty;
+    a.repeat_last_n = cfg->repeat_last_n;
+    a.seed = cfg->seed;
+    a.draw_index = draw_index;
+    if (n_window > 0) {
+        a.hist = win;
+        a.hist_cap = n_window;
+    }
+    a.out_token = scratch;
+    if (want_cand) {
+        a.dbg_ids = cids;
+        a.dbg_probs = cprob;
+        a.dbg_size = scratch + 2;
+    }
+    // a fixed window: the ring is exactly full (head == capacity), and the draw index is not advanced by the head
+    int *head = scratch + 1;
+    a.hist_head = n_window > 0 ? head : nullptr;
+    if (n_window > 0) a.draw_index = draw_index - (unsigned long long)n_window;
+    if (e == cudaSuccess) e = launch_sample(&ctx->c, a, s);
+    int out[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, scratch, sizeof(out), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && want_cand && out[2] > 0) {
+        e = cudaMemcpy(cand_ids_host, cids, (size_t)out[2] * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(cand_probs_host, cprob, (size_t)out[2] * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(scratch);
+    if (e == cudaErrorNotSupported) return fail(TCE_ERR_UNSUPPORTED, "tce_sample: temp > 0 needs 1 <= top_k <= 1024");
+    if (e != cudaSuccess) return fail(TCE_ERR_CUDA, "tce_sample: %s", cudaGetErrorString(e));
+    *token_host = out[0];
+    if (want_cand) *cand_count_host = out[2];
     return TCE_OK;
 }
 const float *tce_llama_logits(tce_llama *m) { return m ? reinterpret_cast<LlamaDecoder *>(m)->logits() : nullptr; }

@@ -65,6 +65,9 @@ TCE_DEVINL uint2 ld_ll1(const uint2 *p, bool sys) {
         asm volatile("ld.relaxed.gpu.global.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
     return r;
 }
+// A failed poll waits this long before it asks L2 again: thousands of threads spinning without a pause fill the L2 request queues and
+// stretch every round trip (their own and the producers' stores) to ~0.5 us (profiles/README.md, run 11).
+constexpr unsigned kPollBackoffNs = 100;
 constexpr long long kSpinLimit = 20000000000LL;  // ~10 s: a peer rank may legitimately start its kernel later
 // spin until both words of the pair carry `tag`
 TCE_DEVINL uint4 wait_ll2(const uint2 *p, uint32_t tag, bool sys) {
@@ -72,6 +75,7 @@ TCE_DEVINL uint4 wait_ll2(const uint2 *p, uint32_t tag, bool sys) {
     if (r.y == tag && r.w == tag) return r;
     const long long t0 = clock64();
     while (true) {
+        __nanosleep(kPollBackoffNs);
         r = ld_ll2(p, sys);
         if (r.y == tag && r.w == tag) return r;
         if (clock64() - t0 > kSpinLimit) __trap();
@@ -82,6 +86,7 @@ TCE_DEVINL uint32_t wait_ll1(const uint2 *p, uint32_t tag, bool sys) {
     if (r.y == tag) return r.x;
     const long long t0 = clock64();
     while (true) {
+        __nanosleep(kPollBackoffNs);
         r = ld_ll1(p, sys);
         if (r.y == tag) return r.x;
         if (clock64() - t0 > kSpinLimit) __trap();
@@ -100,6 +105,7 @@ TCE_DEVINL void wait_ll2xN(const uint2 *p, uint32_t tag, bool sys, uint4 (&r)[N]
         if (ok) return;
         if (t0 == 0) t0 = clock64();
         if (clock64() - t0 > kSpinLimit) __trap();
+        __nanosleep(kPollBackoffNs);
     }
 }
 
@@ -423,31 +429,62 @@ TCE_DEVINL int rot_unit(int u, int units, int cta) {
 }
 
 // fp16 input vector (attention output / SiLU*mul activations) published as {half2, tag} words -> activation planes
-TCE_DEVINL void stage_half(const GemvOp &op, const PSmem &sm, const uint2 *src, uint32_t tag, int cta, int ctid, int lane) {
+TCE_DEVINL void stage_half(const Args &a, const GemvOp &op, const PSmem &sm, const uint2 *src, uint32_t tag, int cta, int ctid, int lane, int p, int nphase) {
     const int units = op.IC / 8;  // 8 halfs = 4 words = 32 B per unit
-    for (int ui0 = 0; ui0 < units; ui0 += kConsumerThreads) {  // warp-uniform trip count
-        const int u = ui0 + ctid;
-        const bool valid = u < units;
-        const int ui = valid ? rot_unit(u, units, cta) : 0;
-        float v[8];
+    constexpr int PRE = 4;        // iterations whose words are requested together: one L2 round trip for up to 4 * 512 units
+    for (int ub = 0; ub < units; ub += PRE * kConsumerThreads) {
+        uint4 w[PRE][2];
+        int ui[PRE];
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = 0.f;
-        if (valid) {
-            uint4 w[2];
-            wait_ll2xN<2>(src + (size_t)ui * 4, tag, false, w);
-            const float2 f0 = h2_to_f2(w[0].x), f1 = h2_to_f2(w[0].z), f2 = h2_to_f2(w[1].x), f3 = h2_to_f2(w[1].z);
+        for (int k = 0; k < PRE; k++) {
+            const int u = ub + k * kConsumerThreads + ctid;
+            ui[k] = (u < units) ? rot_unit(u, units, cta) : -1;
+            w[k][0] = w[k][1] = make_uint4(0u, tag, 0u, tag);
+            if (ui[k] >= 0) {
+                w[k][0] = ld_ll2(src + (size_t)ui[k] * 4, false);
+                w[k][1] = ld_ll2(src + (size_t)ui[k] * 4 + 2, false);
+            }
+        }
+        {
+            long long t0 = 0;
+            while (true) {  // every word of the block that is not there yet is asked for again in the same round
+                bool ok = true;
+#pragma unroll
+                for (int k = 0; k < PRE; k++) ok = ok && w[k][0].y == tag && w[k][0].w == tag && w[k][1].y == tag && w[k][1].w == tag;
+                if (ok) break;
+                if (t0 == 0) t0 = clock64();
+                if (clock64() - t0 > kSpinLimit) __trap();
+                __nanosleep(kPollBackoffNs);
+#pragma unroll
+                for (int k = 0; k < PRE; k++) {
+                    if (ui[k] >= 0 && !(w[k][0].y == tag && w[k][0].w == tag && w[k][1].y == tag && w[k][1].w == tag)) {
+                        w[k][0] = ld_ll2(src + (size_t)ui[k] * 4, false);
+                        w[k][1] = ld_ll2(src + (size_t)ui[k] * 4 + 2, false);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (ub == 0 && ctid == 0) stamp(a, cta, nphase, p, 4);
+#pragma unroll
+        for (int k = 0; k < PRE; k++) {
+            if (ub + k * kConsumerThreads >= units) break;  // warp-uniform
+            const bool valid = ui[k] >= 0;
+            float v[8];
+            const float2 f0 = h2_to_f2(w[k][0].x), f1 = h2_to_f2(w[k][0].z), f2 = h2_to_f2(w[k][1].x), f3 = h2_to_f2(w[k][1].z);
             v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
             v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+            gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, valid ? ui[k] : 0, valid, v, lane);
         }
-        gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, ui, valid, v, lane);
     }
+    if (ctid == 0) stamp(a, cta, nphase, p, 5);
     named_bar_sync(1, kConsumerThreads);
 }
 
 // fp32 residual stream with fused RMSNorm.  Every CTA holds the stream in shared memory; `delta` (o_proj or down_proj outputs of all
 // tensor-parallel ranks, {float, tag} words) is added to it here by every CTA in the same (rank) order.  Returns 1/rms: y = inv * W (x . gamma).
 TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, const uint2 *delta, uint32_t tag, const float *gamma, int token, bool first,
-                           bool emit, int cta, int ctid, int cw, int lane) {
+                           bool emit, int cta, int ctid, int cw, int lane, int p, int nphase) {
     const int units = op.IC / 8;
     const bool sys = a.tp_size > 1;
     float ss = 0.f;
@@ -483,6 +520,7 @@ TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, con
                     x[0] += __uint_as_float(w[0].x); x[1] += __uint_as_float(w[0].z); x[2] += __uint_as_float(w[1].x); x[3] += __uint_as_float(w[1].z);
                     x[4] += __uint_as_float(w[2].x); x[5] += __uint_as_float(w[2].z); x[6] += __uint_as_float(w[3].x); x[7] += __uint_as_float(w[3].z);
                 }
+                if (ui0 == 0 && ctid == 0) stamp(a, cta, nphase, p, 4);
             }
             *reinterpret_cast<float4 *>(sm.resid + (size_t)ui * 8) = make_float4(x[0], x[1], x[2], x[3]);
             *reinterpret_cast<float4 *>(sm.resid + (size_t)ui * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
@@ -498,6 +536,7 @@ TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, con
     if (!emit) return 1.f;
     ss = warp_sum(ss);
     if (lane == 0) sm.rms[cw] = ss;
+    if (ctid == 0) stamp(a, cta, nphase, p, 5);
     named_bar_sync(1, kConsumerThreads);
     float tot = 0.f;
 #pragma unroll
@@ -795,6 +834,7 @@ TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &
             const bool mine = (((c - sp.ch0) & 3) == (cw >> 2)) && (kbase <= pos);
             const bool has_new = mine && pos < kbase + 16;
             mbar_wait_u32(sm.full_u32 + (uint32_t)rs.stage * 8u, rs.phase);
+            if (c == sp.ch0 && ctid == 0) stamp(a, cta, nphase, p, 7);
             if (mine) {
                 uint8_t *kst = sm.ring + (size_t)rs.stage * kStageBytes, *vst = kst + kHalfBytes;
                 if (has_new) {
@@ -925,26 +965,45 @@ TCE_DEVINL void attention_phase(const Args &a, const LayerDesc &L, const PSmem &
     for (int task = cta + cw * ncta; task < ntask; task += ncta * kCW) {
         const int head = task >> 2, d = ((task & 3) << 5) + lane;
         const uint2 *base = a.part_ll + (size_t)head * a.nsplit_max * 130;
-        // lane s < nsplit fetches (m, l) of split s; the maximum and the weights are formed with shuffles
-        float ms = -INFINITY, ls = 0.f;
-        if (lane < sp.nsplit) {
-            ms = __uint_as_float(wait_ll1(base + (size_t)lane * 130 + 128, tag_part, false));
-            ls = __uint_as_float(wait_ll1(base + (size_t)lane * 130 + 129, tag_part, false));
+        // lane s < nsplit fetches (m, l) of split s; the maximum and the weights are formed with shuffles.  All requests of a round
+        // (the statistics and up to kRound partial outputs) are in flight together: one L2 round trip when the partials are there.
+        constexpr int kRound = 20;
+        uint2 wm = make_uint2(0u, tag_part), wl = wm;
+        uint2 ow[kRound];
+#pragma unroll
+        for (int i = 0; i < kRound; i++) ow[i] = make_uint2(0u, tag_part);
+        {
+            const bool stat = lane < sp.nsplit;
+            if (stat) wm.y = wl.y = tag_part + 1u;  // "not here yet"
+#pragma unroll
+            for (int i = 0; i < kRound; i++)
+                if (i < sp.nsplit) ow[i].y = tag_part + 1u;
+            long long t0 = 0;
+            while (true) {
+                if (wm.y != tag_part) wm = ld_ll1(base + (size_t)lane * 130 + 128, false);
+                if (wl.y != tag_part) wl = ld_ll1(base + (size_t)lane * 130 + 129, false);
+#pragma unroll
+                for (int i = 0; i < kRound; i++)
+                    if (ow[i].y != tag_part) ow[i] = ld_ll1(base + (size_t)i * 130 + d, false);
+                bool ok = wm.y == tag_part && wl.y == tag_part;
+#pragma unroll
+                for (int i = 0; i < kRound; i++) ok = ok && ow[i].y == tag_part;
+                if (ok) break;
+                if (t0 == 0) t0 = clock64();
+                if (clock64() - t0 > kSpinLimit) __trap();
+                __nanosleep(kPollBackoffNs);
+            }
+            __syncwarp();
         }
+        const float ms = (lane < sp.nsplit) ? __uint_as_float(wm.x) : -INFINITY, ls = (lane < sp.nsplit) ? __uint_as_float(wl.x) : 0.f;
         const float M = warp_max(ms);
         const float wgt = (lane < sp.nsplit) ? __expf(ms - M) : 0.f;
         const float Lt = warp_sum(wgt * ls);
         float acc = 0.f;
-        for (int s0 = 0; s0 < sp.nsplit; s0 += 8) {
-            uint2 ow[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) ow[i] = (s0 + i < sp.nsplit) ? ld_ll1(base + (size_t)(s0 + i) * 130 + d, false) : make_uint2(0u, tag_part);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (ow[i].y != tag_part) ow[i].x = wait_ll1(base + (size_t)(s0 + i) * 130 + d, tag_part, false);
-                acc += __shfl_sync(0xffffffffu, wgt, (s0 + i) & 31) * __uint_as_float(ow[i].x);
-            }
-        }
+        for (int i = 0; i < kRound; i++) acc += __shfl_sync(0xffffffffu, wgt, i) * __uint_as_float(ow[i].x);
+        for (int s0 = kRound; s0 < sp.nsplit; s0++)
+            acc += __shfl_sync(0xffffffffu, wgt, s0) * __uint_as_float(wait_ll1(base + (size_t)s0 * 130 + d, tag_part, false));
         const float y = acc / Lt;
         const float yhi = __shfl_down_sync(0xffffffffu, y, 1);
         if (!(lane & 1)) st_ll(a.attn_ll + (size_t)head * 64 + (d >> 1), pack_half2(y, yhi), tag_out, false);
@@ -1054,14 +1113,14 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
         const bool work = t1 > t0;
         float inv = 1.f;
         if (oi == OPI_O) {
-            if (work) stage_half(op, sm, a.attn_ll, tag_in, cta, ctid, lane);
+            if (work) stage_half(a, op, sm, a.attn_ll, tag_in, cta, ctid, lane, p, nphase);
         } else if (oi == OPI_DOWN) {
-            if (work) stage_half(op, sm, a.act_ll, tag_in, cta, ctid, lane);
+            if (work) stage_half(a, op, sm, a.act_ll, tag_in, cta, ctid, lane, p, nphase);
         } else {
             // the residual copy of this CTA must see every o_proj / down_proj output, whether or not the CTA owns tiles of this phase
             const float *gamma = (oi == OPI_LMHEAD) ? a.final_norm : (oi == OPI_QKV ? a.layers[l].input_norm : a.layers[l].post_norm);
             const uint2 *delta = (oi == OPI_GATEUP) ? a.delta_ll[0] : a.delta_ll[1];
-            inv = stage_rms(a, op, sm, delta, tag_in, gamma, token, p == 0, work, cta, ctid, cw, lane);
+            inv = stage_rms(a, op, sm, delta, tag_in, gamma, token, p == 0, work, cta, ctid, cw, lane, p, nphase);
         }
         if (ctid == 0) stamp(a, cta, nphase, p, 1);
         if (work) {

@@ -145,6 +145,7 @@ LlamaDecoder::~LlamaDecoder() {
     cudaFree(d_act_);
     cudaFree(d_logits_);
     cudaFree(d_tokpos_);
+    cudaFree(d_gen_);
     cudaFree(d_next_);
     cudaFree(pf_x_);
     cudaFree(pf_xn_);
@@ -696,6 +697,75 @@ cudaError_t LlamaDecoder::decode_host(int token, int pos, float *logits_host, in
     DCK(cudaStreamSynchronize(s));
     if (logits_host) memcpy(logits_host, h_logits_, (size_t)cfg_.vocab_size * sizeof(float));
     if (next_token) *next_token = *h_next_;
+    return cudaSuccess;
+}
+
+// Generate loop (LLaMAGenerate.cu:67-252 without the tokenizer / console parts): every token is one decode step plus one sampler launch, both
+// enqueued back to back; the sampler writes the next step's {token, position} on the device.  The host only looks at the stop flag every
+// few tokens, and copies the generated ids out at the end.
+cudaError_t LlamaDecoder::generate(int first_token, int pos0, int n_predict, const tce_sampling &sc, const int *history_host, int n_history, int eos_id,
+                                   int *out_tokens_host, int *n_out, std::string *err) {
+    if (cfg_.tp_size > 1) {
+        if (err) *err = "generate: single GPU only (the vocabulary is sharded under tensor parallelism)";
+        return cudaErrorNotSupported;
+    }
+    const int cap = cfg_.max_ctx;
+    if (first_token < 0 || first_token >= cfg_.vocab_size || pos0 < 0 || pos0 >= cap || n_predict < 0 || n_history < 0 || n_history > cap || !n_out ||
+        (n_predict > 0 && !out_tokens_host))
+        return cudaErrorInvalidValue;
+    if (sc.temp > 0.f && (sc.top_k <= 0 || sc.top_k > 1024) && cfg_.vocab_size > 1024) {
+        if (err) *err = "generate: temp > 0 needs 1 <= top_k <= 1024";
+        return cudaErrorNotSupported;
+    }
+    if (n_predict > cap - pos0) n_predict = cap - pos0;
+    cudaStream_t s = ctx_->stream;
+    if (!d_gen_) DCK(cudaMalloc((void **)&d_gen_, (size_t)(4 + 2 * cap) * sizeof(int)));
+    int *hist = d_gen_ + 4, *out_list = d_gen_ + 4 + cap;
+    DCK(cudaMemsetAsync(d_gen_, 0, (size_t)(4 + 2 * cap) * sizeof(int), s));
+    if (n_history > 0) DCK(cudaMemcpyAsync(hist, history_host, (size_t)n_history * sizeof(int), cudaMemcpyHostToDevice, s));
+    const int ctl0[4] = {n_history, 0, 0, 0};
+    DCK(cudaMemcpyAsync(d_gen_, ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, s));
+    h_tokpos_[0] = first_token;
+    h_tokpos_[1] = pos0;
+    h_tokpos_[2] = 0;
+    DCK(cudaMemcpyAsync(d_tokpos_, h_tokpos_, 3 * sizeof(int), cudaMemcpyHostToDevice, s));
+    SampleArgs a{};
+    a.logits = d_logits_;
+    a.n_vocab = cfg_.vocab_size;
+    a.top_k = sc.top_k;
+    a.top_p = sc.top_p;
+    a.temp = sc.temp;
+    a.repeat_penalty = sc.repeat_penalty;
+    a.frequency_penalty = sc.frequency_penalty;
+    a.presence_penalty = sc.presence_penalty;
+    a.repeat_last_n = sc.repeat_last_n;
+    a.seed = sc.seed;
+    a.draw_index = 0;
+    a.hist = hist;
+    a.hist_head = d_gen_;
+    a.hist_cap = cap;
+    a.eos_id = eos_id;
+    a.tokpos = d_tokpos_;
+    a.out_list = out_list;
+    a.out_count = d_gen_ + 1;
+    a.out_cap = cap;
+    a.stop = d_gen_ + 2;
+    int ctl[4] = {0, 0, 0, 0};
+    constexpr int kCheckEvery = 16;
+    for (int i = 0; i < n_predict; i++) {
+        DCK(enqueue_step(d_tokpos_, s, ctx_->use_pdl));
+        DCK(launch_sample(ctx_, a, s));
+        if ((i + 1) % kCheckEvery == 0 && i + 1 < n_predict) {
+            DCK(cudaMemcpyAsync(ctl, d_gen_, sizeof(ctl), cudaMemcpyDeviceToHost, s));
+            DCK(cudaStreamSynchronize(s));
+            if (ctl[2]) break;
+        }
+    }
+    DCK(cudaMemcpyAsync(ctl, d_gen_, sizeof(ctl), cudaMemcpyDeviceToHost, s));
+    DCK(cudaStreamSynchronize(s));
+    const int n = ctl[1] < cap ? ctl[1] : cap;
+    if (n > 0) DCK(cudaMemcpy(out_tokens_host, out_list, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = n;
     return cudaSuccess;
 }
 

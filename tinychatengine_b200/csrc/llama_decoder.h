@@ -17,6 +17,8 @@ class LlamaDecoder {
     ~LlamaDecoder();
     cudaError_t decode_device(const int *tokpos_dev, std::string *err);
     cudaError_t decode_host(int token, int pos, float *logits_host, int *next_token, std::string *err);
+    cudaError_t generate(int first_token, int pos0, int n_predict, const tce_sampling &sc, const int *history_host, int n_history, int eos_id,
+                         int *out_tokens_host, int *n_out, std::string *err);
     // prompt processing: n tokens at positions pos0..pos0+n-1 in one pass (tensor-core GEMMs + causal flash attention)
     cudaError_t prefill(const int *tokens_host, int n, int pos0, float *logits_host, int *next_token, std::string *err);
     const float *logits() const { return d_logits_; }
@@ -35,6 +37,7 @@ class LlamaDecoder {
     cudaError_t enqueue_gemvs(int *count);
     cudaError_t tp_handle(void *out64);
     cudaError_t tp_connect(const void *handles);
+    void adopt(void *device_allocation) { pk_allocs_.push_back(device_allocation); }  // freed with the model (loader.cu)
 
    private:
     LlamaDecoder() = default;
@@ -81,6 +84,7 @@ class LlamaDecoder {
     float *d_logits_ = nullptr;     // [V]
     int *d_tokpos_ = nullptr;       // {token, pos} staged for the host entry point
     int *d_next_ = nullptr;         // greedy arg-max
+    int *d_gen_ = nullptr;          // generate loop: [0] history head, [1] output count, [2] stop flag, then history ring [max_ctx], output list [max_ctx]
     float *d_cos_ = nullptr, *d_sin_ = nullptr;
     bool own_rope_ = false;
     // prompt-processing activations, [pf_cap_] rows each (allocated on first use)
@@ -106,5 +110,9 @@ class LlamaDecoder {
     bool atomic_residual_ = true;  // o_proj/down_proj partial tiles use RED.ADD (TCE_DETERMINISTIC=1 turns it off)
     int kernels_per_step_ = 0;
 };
+
+// loader.cu: the reference's on-disk INT4 tree -> a model that owns its device copies
+LlamaDecoder *load_llama_dir(Ctx *ctx, int attn_chunk, const char *dir, tce_llama_config cfg, std::string *err);
+int import_x86(const uint8_t *qs, const float *scales_f32, int oc, int ic, uint32_t *w_out, __half *scales_out, uint32_t *zeros_out);
 
 }  // namespace tce

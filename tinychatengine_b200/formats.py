@@ -86,3 +86,27 @@ def save_qm_cuda_dir(path: str | Path, w: np.ndarray, zeros: np.ndarray, scales:
     np.ascontiguousarray(w, np.uint32).tofile(path / "weight_int4.bin")
     np.ascontiguousarray(scales, np.float16).tofile(path / "scaling_factor_int4.bin")
     np.ascontiguousarray(zeros, np.uint32).tofile(path / "zero_point_int4.bin")
+
+
+# ---- QM_x86 (CPU build) flavour: llm/tools/quantize_methods.py:188-243 (quantize_row_q4_3), group 32 ---------------------------------
+def quantize_qm_x86(weight: np.ndarray):
+    """fp32 [OC, IC] -> (qs uint8 [OC, IC/2], scales fp32 [OC, IC/32]): d = (element of largest magnitude) / -8 per 32-group,
+    q = trunc(clip(x/d + 8.5, 0, 15)); byte e of every 64-weight run = q[e] | q[32 + e] << 4; zero point 8."""
+    oc, ic = weight.shape
+    x = np.ascontiguousarray(weight, np.float32).reshape(-1, 32)
+    idx = np.argmax(np.abs(x), axis=1)
+    d = (x[np.arange(x.shape[0]), idx] / np.float32(-8)).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        inv = np.where(d != 0, np.float32(1.0) / d, np.float32(0)).astype(np.float32)
+    q = ((x * inv[:, None]) + np.float32(8.5)).clip(0, 15).astype(np.uint8).reshape(-1, 64)
+    qs = (q[:, :32] | (q[:, 32:] << 4)).astype(np.uint8)
+    return qs.reshape(oc, ic // 2), d.reshape(oc, ic // 32)
+
+
+def dequantize_qm_x86(qs: np.ndarray, scales: np.ndarray) -> np.ndarray:
+    oc = qs.shape[0]
+    b = qs.reshape(-1, 32)
+    q = np.concatenate([(b & 0xF), (b >> 4)], axis=1).astype(np.float32) - np.float32(8)  # [runs, 64]
+    d = scales.reshape(-1, 2)
+    w = np.concatenate([q[:, :32] * d[:, :1], q[:, 32:] * d[:, 1:]], axis=1)
+    return w.reshape(oc, -1).astype(np.float32)

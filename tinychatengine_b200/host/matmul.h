@@ -5,13 +5,17 @@
 // with the reference's kernels/matmul.h:52-100, so objects filled by the reference's llm/ call sites (Linear_half_int4::forward
 // llm/src/ops/cuda/linear.cu:5-40, W8A8B8O8Linear::forward llm/src/ops/W8A8B8O8Linear.cc:38-78, the BMM_S8T_* wrappers, ...) can be
 // handed to this library unchanged; tests/test_host_header_abi.py compiles an offsetof/sizeof probe against both headers.
-// Only the methods the reference's kernels/cuda/ directory defines are declared (and defined in matmul_operator.cu), plus the
-// gemm_forward_cuda* slot it declares without defining.  Backend-independent methods (naive_mat_mul_int4*, naive_mat_mul_int8,
-// mat_mul_transposed, CHECK_MATRICES*) keep coming from the reference's own kernels/*.cc and header, see INTEGRATION.md.
+// The class declares every method of the reference's matmul::MatmulOperator (kernels/matmul.h:110-166), so a call site written against
+// the reference header also compiles against this one.  matmul_operator.cu DEFINES the ones the reference's kernels/cuda/ directory
+// defines (TCE_MATMUL_OPS) plus the gemm_forward_cuda* slot it declares without defining; the rest (TCE_MATMUL_OPS_ELSEWHERE) are the
+// backend-independent or other-backend methods: no CUDA call site of the reference reaches them, and a full build keeps taking them
+// from the reference's own kernels/*.cc.  tests/test_gpu_callsites.py goes one step further and compiles the
+// reference's call sites against the reference's OWN header (-DTCE_REFERENCE_MATMUL_H=...) and this library.
 #ifndef TCE_HOST_MATMUL_H
 #define TCE_HOST_MATMUL_H
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <sys/time.h>
 
 // host-side fp16 type of the reference (half_float::half) when its header is reachable, a storage-only stand-in otherwise
 #if defined(__has_include)
@@ -65,16 +69,37 @@ namespace matmul {
     X(mat_mul_accelerator_int8_fast_2x2_32unroll_nobias_ofp32) X(mat_mul_accelerator_int8_fast_2x2_32unroll_nobias_ofp32_batch)      \
     X(mat_mul_accelerator_int8_fast_2x2_32unroll_bfp32_ofp32) X(mat_mul_accelerator_int8_fast_2x2_32unroll_bfp32_ofp32_over_column)
 
+// declared for source compatibility, defined outside this library (X: const params, Y: mutable params -- as in the reference)
+#define TCE_MATMUL_OPS_ELSEWHERE(X, Y)                                                                                               \
+    X(mat_mul_transposed) X(mat_mul_accelerator_transposed_fastover_column_bias) X(mat_mul_accelerator_untransposed_fastover_column) \
+    X(naive_mat_mul_int8) X(naive_mat_mul_int4) X(naive_mat_mul_int4_with_offset) X(mat_mul_cuda)                                    \
+    Y(mat_mul_accelerator_int8_int4_fast_no_offset) Y(gemv_accelerator_int8_int4_fast_no_offset)                                     \
+    Y(gemm_accelerator_int8_int4_fast_no_offset) Y(gemm_accelerator_int8_int4_fast_no_offset_v2) Y(cblas_gemm_accelerator_no_offset)
+
+struct thread_args {  // kernels/matmul.h:94-101 (CPU worker-thread argument block; unused by the CUDA backend)
+    const struct matrix *A, *B, *C;
+    const struct matmul_params *params;
+    int start_i, end_i, blk_size;
+};
+
 class MatmulOperator {  // stateless, constructed per call by the reference's wrappers
    public:
 #define TCE_DECLARE_OP(name) void name(const struct matmul_params *params);
+#define TCE_DECLARE_OP_MUT(name) void name(struct matmul_params *params);
     TCE_MATMUL_OPS(TCE_DECLARE_OP)
+    TCE_MATMUL_OPS_ELSEWHERE(TCE_DECLARE_OP, TCE_DECLARE_OP_MUT)
 #undef TCE_DECLARE_OP
+#undef TCE_DECLARE_OP_MUT
     // the prefill GEMM slot (kernels/matmul.h:142-145: declared, never defined by the reference): tcgen05 GEMM for M >= 16
     void gemm_forward_cuda(const struct matmul_params *params, int split_k_iters);
     void gemm_forward_cuda_8splits(const struct matmul_params *params, float16_t *split_8_buffer);
     void gemm_forward_cuda_half(const struct matmul_params *params, int split_k_iters);
     void gemm_forward_cuda_half_test(const struct matmul_params *params, int split_k_iters);
+
+   private:  // kernels/matmul.h:149-153
+    float interval_to_us(struct timeval *start, struct timeval *end);
+    void CHECK_MATRICES(const struct matrix *A, const struct matrix *B, const struct matrix *C);
+    void CHECK_MATRICES_int4weight(const struct matrix *A, const struct matrix *B, const struct matrix *C);
 };
 
 }  // namespace matmul

@@ -183,6 +183,55 @@ class LlamaModel:
         self.kernels_per_step = ctx.L.tce_llama_kernels_per_step(h)
         torch.cuda.synchronize(dev)
 
+    @classmethod
+    def load_dir(cls, ctx: Context, path, geom: LlamaGeometry, max_ctx: int = 4096):
+        """Model built by the C++ loader from a parameter tree in the reference's on-disk layout (tce_llama_load_dir); the library owns the
+        device copies.  `geom` plays the role of the reference's model_config."""
+        self = cls.__new__(cls)
+        self.ctx, self.geom, self.max_ctx = ctx, geom, max_ctx
+        self.tp_rank, self.tp_size = 0, 1
+        self.W, self.tensors = None, []
+        g = geom
+        self.cfg = _lib.LlamaConfig(g.num_layers, g.num_heads, g.num_kv_heads, g.head_dim, g.embed_dim, g.hidden_dim, g.vocab_size, max_ctx,
+                                    g.rms_eps, g.rope_theta, 0.0, 0, 1)
+        h = C.c_void_p()
+        _lib.check(ctx.L.tce_llama_load_dir(ctx.h, str(path).encode(), C.byref(self.cfg), C.byref(h)), "tce_llama_load_dir")
+        self.h = h
+        self.kernels_per_step = ctx.L.tce_llama_kernels_per_step(h)
+        return self
+
+    def save_dir(self, path):
+        """Write this model's (synthetic) weights as a parameter tree in the reference's QM_CUDA on-disk layout (tests, examples):
+        the inverse of load_dir.  q|k|v are written merged under self_attn/qkv_proj, as llm/tools/llama_qkv_merger.py leaves them."""
+        from pathlib import Path
+
+        import numpy as np
+
+        from . import formats
+
+        root = Path(path)
+        W = self.W
+
+        def f32(t, p):
+            p.parent.mkdir(parents=True, exist_ok=True)
+            t.detach().float().cpu().numpy().astype(np.float32).tofile(p)
+
+        def w4(t, p):
+            formats.save_qm_cuda_dir(p, t[0].cpu().numpy().view(np.uint32), t[1].cpu().numpy().view(np.uint32), t[2].cpu().numpy())
+
+        f32(W["embed"], root / "decoder" / "embed_tokens" / "weight.bin")
+        f32(W["final_norm"], root / "decoder" / "norm" / "weight.bin")
+        for l, T in enumerate(W["layers"]):
+            lp = root / "decoder" / f"layer{l}"
+            f32(T["input_norm"], lp / "input_layernorm" / "weight.bin")
+            f32(T["post_norm"], lp / "post_attention_layernorm" / "weight.bin")
+            merged = tuple(torch.cat([T[n][i] for n in ("q", "k", "v")], dim=0) for i in range(3))
+            w4(merged, lp / "self_attn" / "qkv_proj")
+            w4(T["o"], lp / "self_attn" / "o_proj")
+            for n in ("gate", "up", "down"):
+                w4(T[n], lp / f"{n}_proj")
+        w4(W["lm_head"], root / "lm_head")
+
     def tp_connect(self, group=None):
         """Exchange the IPC handles of the peer-visible buffers over torch.distributed and map the peers."""
         import torch.distributed as dist
@@ -198,6 +247,7 @@ class LlamaModel:
         blob = b"".join(bytes(o.cpu().tolist()) for o in out)
         buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         _lib.check(self.ctx.L.tce_llama_tp_connect(self.h, C.cast(buf, C.c_void_p)), "tce_llama_tp_connect")
+        self.kernels_per_step = self.ctx.L.tce_llama_kernels_per_step(self.h)  # the step's form is only known once the peers are mapped
         dist.barrier(group=group)
 
     def layer_tensors(self, l: int):
@@ -215,6 +265,21 @@ class LlamaModel:
         p = None if logits_host is None else C.c_void_p(logits_host.data_ptr())
         _lib.check(self.ctx.L.tce_llama_decode_host(self.h, int(token), int(pos), p, C.byref(nxt)), "tce_llama_decode_host")
         return nxt.value
+
+    def generate(self, first_token: int, pos0: int, n_predict: int, *, history=(), eos_id: int = -1, top_k=40, top_p=0.95, temp=0.8, repeat_penalty=1.1,
+                 frequency_penalty=0.0, presence_penalty=0.0, repeat_last_n=64, seed=0):
+        """Device generate loop (decode + sample per token, only the ids come back); defaults are the reference's opt_params."""
+        import numpy as np
+
+        cfg = _lib.Sampling(int(top_k), float(top_p), float(temp), float(repeat_penalty), float(frequency_penalty), float(presence_penalty),
+                            int(repeat_last_n), int(seed))
+        hist = np.ascontiguousarray(np.asarray(list(history), dtype=np.int32))
+        out = np.zeros(max(1, n_predict), dtype=np.int32)
+        n = C.c_int(0)
+        _lib.check(self.ctx.L.tce_llama_generate(self.h, int(first_token), int(pos0), int(n_predict), C.byref(cfg),
+                                                 hist.ctypes.data_as(C.c_void_p) if hist.size else None, int(hist.size), int(eos_id),
+                                                 out.ctypes.data_as(C.c_void_p), C.byref(n)), "tce_llama_generate")
+        return out[:n.value].tolist()
 
     def prefill(self, tokens, pos0: int = 0, logits_host=None) -> int:
         """Prompt processing: all `tokens` (host ints) at positions pos0.. in one pass; returns the greedy next token."""

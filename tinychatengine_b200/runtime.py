@@ -130,6 +130,28 @@ class Context:
         _lib.check(self.L.tce_add_f32(self.h, _ptr(a), _ptr(b), _ptr(out), a.numel()), "tce_add_f32")
         return out
 
+    def sample(self, logits, window=(), *, top_k=40, top_p=0.95, temp=0.8, repeat_penalty=1.1, frequency_penalty=0.0, presence_penalty=0.0,
+               repeat_last_n=64, seed=0, draw_index=0, candidates=False):
+        """One device sampling step on `logits` (float32 CUDA tensor, penalised in place); defaults are the reference's opt_params.
+        Returns the token, or (token, ids, probs) with candidates=True."""
+        import ctypes as C
+
+        import numpy as np
+
+        cfg = _lib.Sampling(int(top_k), float(top_p), float(temp), float(repeat_penalty), float(frequency_penalty), float(presence_penalty),
+                            int(repeat_last_n), int(seed))
+        win = np.ascontiguousarray(np.asarray(list(window), dtype=np.int32))
+        tok, cnt = C.c_int(-1), C.c_int(0)
+        kcap = max(1, min(1024, int(top_k) if top_k > 0 else logits.numel()))
+        ids = np.zeros(kcap, dtype=np.int32)
+        probs = np.zeros(kcap, dtype=np.float32)
+        _lib.check(self.L.tce_sample(self.h, _ptr(logits), logits.numel(), win.ctypes.data_as(C.c_void_p) if win.size else None, int(win.size), C.byref(cfg),
+                                     int(draw_index), C.byref(tok), ids.ctypes.data_as(C.c_void_p) if candidates else None,
+                                     probs.ctypes.data_as(C.c_void_p) if candidates else None, C.byref(cnt) if candidates else None), "tce_sample")
+        if candidates:
+            return tok.value, ids[:cnt.value].copy(), probs[:cnt.value].copy()
+        return tok.value
+
     def argmax_f32(self, x, out=None):
         if out is None:
             out = torch.empty((1,), dtype=torch.int32, device=x.device)

@@ -54,15 +54,15 @@ def main():
     total = np.nanmax(T[:, -1, 3]) if not np.all(np.isnan(T[:, -1, 3])) else np.nanmax(T)
     print(f"kernel span (first barrier-pass stamp -> last arrival): {total:.1f} us over {nphase} phases, ctx {args.ctx}")
     # attention sub-steps (medians over the CTAs that own chunks and over layers): time since the CTA entered the phase
-    att = {4: [], 5: [], 6: [], 2: []}
+    att = {4: [], 7: [], 5: [], 6: [], 2: []}
     for p in range(1, nphase - 1):
         if p % 5 == 1:
             for k in att:
                 d = T[:, p, k] - T[:, p, 0]
                 if not np.all(np.isnan(d)):
                     att[k].append(np.nanmedian(d))
-    print("attention, since phase entry (median): q roped+bar %.2f  chunks done %.2f  partial written %.2f  phase left %.2f us" %
-          tuple(float(np.median(att[k])) if att[k] else float("nan") for k in (4, 5, 6, 2)))
+    print("attention, since phase entry (median): q roped+bar %.2f  first stage landed %.2f  chunks done %.2f  partial written %.2f  phase left %.2f us" %
+          tuple(float(np.median(att[k])) if att[k] else float("nan") for k in (4, 7, 5, 6, 2)))
     acc = {}
     for p in range(1, nphase - 1):
         k = p % 5

@@ -22,6 +22,10 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     name = sys.argv[1] if len(sys.argv) > 1 else "tiny-gqa"
     g = GEOMETRIES[name]
+    if len(sys.argv) > 2:  # optional: keep only the first N layers (full-width geometry, short model)
+        from tinychatengine_b200.llama import LlamaGeometry
+
+        g = LlamaGeometry(g.name, int(sys.argv[2]), g.num_heads, g.num_kv_heads, g.embed_dim, g.hidden_dim, g.vocab_size, g.rms_eps, g.rope_theta)
     if g.num_kv_heads % world or (g.hidden_dim // world) % 128:
         raise SystemExit(f"{name}: does not split over {world} ranks on 128-channel group boundaries")
     ctx = Context(local)
@@ -29,6 +33,8 @@ def main():
     Wl, gl = shard_weights(W, g, rank, world)
     model = LlamaModel(ctx, gl, max_ctx=256, weights=Wl, tp_rank=rank, tp_size=world)
     model.tp_connect()
+    if rank == 0:
+        print(f"TP_CHECK kernels per step: {model.kernels_per_step} (1 = persistent kernel with NVLink peer stores)", flush=True)
     ref = None
     if rank == 0:
         os.environ["TCE_PERSISTENT"] = "0"  # the single-GPU reference runs one kernel per op
