@@ -16,6 +16,10 @@ single-GPU run of the same weights before timing.  One JSON line on stdout (rank
 from __future__ import annotations
 
 import argparse
+import os as _os
+
+_os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not land on stdout next to the JSON line
+
 import json
 import os
 import sys

@@ -17,3 +17,36 @@ def test_reference_style_op_tests_through_cpp_surface():
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("Passed!") >= 10 and "Fail!" not in r.stdout
+
+
+def test_int4llama_for_causal_lm_module_shell(tmp_path):
+    """The reference's top-level module API (Int4LlamaForCausalLM(param_path, config).forward(...), llm/include/nn_modules/Int4llamaForCausalLM.h)
+    on this library: a C++ driver in the style of the reference's tests/cuda/test_Int4llamaForCausalLM.cu loads a parameter tree from disk, runs a
+    prompt pass and then decodes through past_keys / past_values; its greedy ids equal the Python-driven decode of the same weights."""
+    import torch
+
+    from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
+    from tinychatengine_b200.runtime import Context
+
+    exe = ROOT / "tests" / "cpp" / "test_int4llama"
+    if not exe.exists():
+        subprocess.run(["make", "-s", "-C", str(ROOT / "tinychatengine_b200" / "host"), "test_host"], check=True)
+    ctx = Context(0)
+    g = GEOMETRIES["tiny-gqa"]
+    m = LlamaModel(ctx, g, max_ctx=64, seed=9, random_zeros=True)
+    m.save_dir(tmp_path / "tree")
+    m.close()
+    m = LlamaModel.load_dir(ctx, tmp_path / "tree", g, max_ctx=64)  # the same tree (fp16 rotary tables included) through the Python binding
+    prompt, n_decode = [3, 17, 400, 5, 77], 6
+    nxt = m.prefill(prompt, 0)
+    want = [nxt]
+    for i in range(1, n_decode):
+        nxt = m.decode_host(nxt, len(prompt) + i - 1)
+        want.append(nxt)
+    m.close()
+    ctx.close()
+    args = [str(exe), str(tmp_path / "tree"), g.num_layers, g.num_heads, g.num_kv_heads, g.embed_dim, g.hidden_dim, g.vocab_size, 64, g.rms_eps, n_decode] + prompt
+    r = subprocess.run([str(a) for a in args], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Passed!" in r.stdout, r.stdout + r.stderr
+    got = [int(t) for t in r.stdout.split("ids", 1)[1].split("\n")[0].split()]
+    assert got == want, (got, want)

@@ -840,6 +840,21 @@ cudaError_t LlamaDecoder::prefill_reserve(int n) {
 // expanded into consecutive row ranges of the fp16 scratch and multiplied by ONE GEMM (q|k|v and gate|up share their input)
 cudaError_t LlamaDecoder::prefill_linear(const tce_w4_tensor *const *ts, int count, const __half *x, void *C, long long ldc, int n, bool add_f32) {
     const int ic = ts[0]->ic;
+    const int mode = w4_gemm_mode();
+    if (mode == W4G_FUSED || mode == W4G_PAIR_FUSED) {
+        // one launch per tensor, each writing its column range of C: the packed weights are unpacked inside the GEMM's tile pipeline
+        size_t c0 = 0;
+        for (int i = 0; i < count; i++) {
+            const tce_w4_tensor &t = *ts[i];
+            void *Ci = add_f32 ? static_cast<void *>(static_cast<float *>(C) + c0) : static_cast<void *>(static_cast<__half *>(C) + c0);
+            if (mode == W4G_PAIR_FUSED)
+                DCK(launch_gemm_w4_pair(ctx_, x, ic, (const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, Ci, ldc, n, t.oc, ic, add_f32 ? 1 : 0));
+            else
+                DCK(launch_gemm_w4_tc(ctx_, x, ic, (const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, Ci, ldc, n, t.oc, ic, add_f32 ? 1 : 0));
+            c0 += (size_t)t.oc;
+        }
+        return cudaSuccess;
+    }
     size_t rows = 0;
     for (int i = 0; i < count; i++) rows += (size_t)ts[i]->oc;
     DCK(w4_scratch_reserve(ctx_, rows * ic));
@@ -849,6 +864,7 @@ cudaError_t LlamaDecoder::prefill_linear(const tce_w4_tensor *const *ts, int cou
         DCK(launch_w4_expand(ctx_, (const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, ctx_->w16_scratch + r0 * ic, t.oc, ic));
         r0 += (size_t)t.oc;
     }
+    if (mode == W4G_PAIR) return launch_gemm_f16_pair(ctx_, x, ic, ctx_->w16_scratch, ic, C, ldc, n, (int)rows, ic, add_f32 ? 1 : 0);
     return launch_gemm_f16_tc(ctx_, x, ic, ctx_->w16_scratch, ic, C, ldc, n, (int)rows, ic, add_f32 ? 1 : 0);
 }
 

@@ -200,7 +200,7 @@ class LlamaModel:
         self.kernels_per_step = ctx.L.tce_llama_kernels_per_step(h)
         return self
 
-    def save_dir(self, path):
+    def save_dir(self, path, rotary: bool = True):
         """Write this model's (synthetic) weights as a parameter tree in the reference's QM_CUDA on-disk layout (tests, examples):
         the inverse of load_dir.  q|k|v are written merged under self_attn/qkv_proj, as llm/tools/llama_qkv_merger.py leaves them."""
         from pathlib import Path
@@ -231,6 +231,21 @@ class LlamaModel:
             for n in ("gate", "up", "down"):
                 w4(T[n], lp / f"{n}_proj")
         w4(W["lm_head"], root / "lm_head")
+        if rotary:
+            # rotary_emb tables and the qk scale as the reference trees carry them (fp16; llm/tools/rotary_emb_exporter.py, read by
+            # RotaryPosEmb_cuda's constructor and Int4llamaAttention.cu:82): a tree with tables overrides rope_theta on load
+            g = self.geom
+            hd = g.head_dim
+            inv = 1.0 / (g.rope_theta ** (np.arange(0, hd, 2, dtype=np.float64) / hd))
+            ang = np.arange(self.max_ctx)[:, None] * inv[None, :]
+            emb = np.concatenate([ang, ang], axis=1)
+            for l in range(g.num_layers):
+                sa = root / "decoder" / f"layer{l}" / "self_attn"
+                (sa / "rotary_emb").mkdir(parents=True, exist_ok=True)
+                (sa / "qk_bmm").mkdir(parents=True, exist_ok=True)
+                np.cos(emb).astype(np.float16).tofile(sa / "rotary_emb" / "cos_cached_half.bin")
+                np.sin(emb).astype(np.float16).tofile(sa / "rotary_emb" / "sin_cached_half.bin")
+                np.array([1.0 / np.sqrt(hd)], dtype=np.float16).tofile(sa / "qk_bmm" / "alpha_half.bin")
 
     def tp_connect(self, group=None):
         """Exchange the IPC handles of the peer-visible buffers over torch.distributed and map the peers."""

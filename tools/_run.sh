@@ -1,2 +1,2 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_sampling.py -q --timeout 600 > gpurun_out/r02_t_sampling.log 2>&1; tail -40 gpurun_out/r02_t_sampling.log
+TCE_W4_GEMM=pair_fused timeout 120 python tools/gemm_pair_check.py > gpurun_out/r02_gemm_pair_fused.jsonl 2>&1; tail -12 gpurun_out/r02_gemm_pair_fused.jsonl
