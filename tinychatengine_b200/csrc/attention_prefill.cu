@@ -17,26 +17,30 @@ constexpr int kQB = 64;        // query rows per CTA (16 per warp)
 constexpr int kKT = 64;        // cached rows per tile
 constexpr int kPitch = HD + 8; // halves; 272-byte rows: conflict-free fragment loads and 16-byte aligned ldmatrix rows
 
-__global__ void __launch_bounds__(64) rope_kv_append_kernel(const AttnPrefillArgs a) {
-    const int i = blockIdx.x, hh = blockIdx.y, j = threadIdx.x;  // token, head slot (q heads then kv heads), dim pair (j, j + 64)
+// one 256-thread block per token; a warp per head slot (q heads, then kv heads), a lane per pair of adjacent dims and their rotate-half
+// partners: 4-byte loads / stores, the position's cos / sin rows read as float2
+__global__ void __launch_bounds__(256) rope_kv_append_kernel(const AttnPrefillArgs a) {
+    const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int QKV = (a.num_heads + 2 * a.num_kv_heads) * HD;
     const int pos = a.pos0 + i;
-    const float *cosr = a.cos + (size_t)pos * HD, *sinr = a.sin + (size_t)pos * HD;
-    __half *row = a.qkv + (size_t)i * QKV + (size_t)hh * HD;  // q head hh, or k head hh - H (k follows q in the fused projection)
-    const float x0 = __half2float(row[j]), x1 = __half2float(row[j + HD / 2]);
-    const float r0 = x0 * cosr[j] + (-x1) * sinr[j];
-    const float r1 = x1 * cosr[j + HD / 2] + x0 * sinr[j + HD / 2];
-    if (hh < a.num_heads) {
-        row[j] = __float2half(r0);
-        row[j + HD / 2] = __float2half(r1);
-    } else {
-        const int kvh = hh - a.num_heads;
-        __half *kc = a.k_cache + ((size_t)kvh * a.max_ctx + pos) * HD, *vc = a.v_cache + ((size_t)kvh * a.max_ctx + pos) * HD;
-        const __half *v = a.qkv + (size_t)i * QKV + (size_t)(a.num_heads + a.num_kv_heads + kvh) * HD;
-        kc[j] = __float2half(r0);
-        kc[j + HD / 2] = __float2half(r1);
-        vc[j] = v[j];
-        vc[j + HD / 2] = v[j + HD / 2];
+    const float2 c0 = *reinterpret_cast<const float2 *>(a.cos + (size_t)pos * HD + 2 * lane), c1 = *reinterpret_cast<const float2 *>(a.cos + (size_t)pos * HD + HD / 2 + 2 * lane);
+    const float2 s0 = *reinterpret_cast<const float2 *>(a.sin + (size_t)pos * HD + 2 * lane), s1 = *reinterpret_cast<const float2 *>(a.sin + (size_t)pos * HD + HD / 2 + 2 * lane);
+    for (int hh = warp; hh < a.num_heads + a.num_kv_heads; hh += 8) {
+        __half *row = a.qkv + (size_t)i * QKV + (size_t)hh * HD;  // q head hh, or k head hh - H (k follows q in the fused projection)
+        const float2 x0 = __half22float2(*reinterpret_cast<const __half2 *>(row + 2 * lane)), x1 = __half22float2(*reinterpret_cast<const __half2 *>(row + HD / 2 + 2 * lane));
+        const __half2 r0 = __floats2half2_rn(x0.x * c0.x + (-x1.x) * s0.x, x0.y * c0.y + (-x1.y) * s0.y);
+        const __half2 r1 = __floats2half2_rn(x1.x * c1.x + x0.x * s1.x, x1.y * c1.y + x0.y * s1.y);
+        if (hh < a.num_heads) {
+            *reinterpret_cast<__half2 *>(row + 2 * lane) = r0;
+            *reinterpret_cast<__half2 *>(row + HD / 2 + 2 * lane) = r1;
+        } else {
+            const int kvh = hh - a.num_heads;
+            __half *kc = a.k_cache + ((size_t)kvh * a.max_ctx + pos) * HD, *vc = a.v_cache + ((size_t)kvh * a.max_ctx + pos) * HD;
+            const __half *v = a.qkv + (size_t)i * QKV + (size_t)(a.num_heads + a.num_kv_heads + kvh) * HD;
+            *reinterpret_cast<__half2 *>(kc + 2 * lane) = r0;
+            *reinterpret_cast<__half2 *>(kc + HD / 2 + 2 * lane) = r1;
+            *reinterpret_cast<uint2 *>(vc + 4 * lane) = *reinterpret_cast<const uint2 *>(v + 4 * lane);  // 32 lanes x 4 halfs = the 128-dim row
+        }
     }
 }
 
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPrefillArgs
 
 cudaError_t launch_attn_prefill(Ctx *ctx, const AttnPrefillArgs &a) {
     if (a.head_dim != HD || a.n < 1 || a.pos0 < 0 || a.pos0 + a.n > a.max_ctx || a.num_heads % a.num_kv_heads) return cudaErrorInvalidValue;
-    rope_kv_append_kernel<<<dim3(a.n, a.num_heads + a.num_kv_heads), 64, 0, ctx->stream>>>(a);
+    rope_kv_append_kernel<<<a.n, 256, 0, ctx->stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     attn_prefill_kernel<<<dim3((a.n + kQB - 1) / kQB, a.num_heads), 128, 0, ctx->stream>>>(a);

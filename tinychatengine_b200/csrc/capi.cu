@@ -234,7 +234,7 @@ int tce_w4a16_gemm(tce_ctx *ctx, const void *x, const void *w, const void *zeros
     }
     CK(w4_scratch_reserve(&ctx->c, (size_t)OC * IC), "w16 scratch");
     CK(launch_w4_expand(&ctx->c, (const uint32_t *)w, (const uint32_t *)zeros, (const __half *)scales, ctx->c.w16_scratch, OC, IC), "w4_expand");
-    if (mode == W4G_PAIR)
+    if (mode == W4G_PAIR || mode == W4G_PAIR_OVERLAP)  // a single call has no next linear to overlap with
         CK(launch_gemm_f16_pair(&ctx->c, (const __half *)x, IC, ctx->c.w16_scratch, IC, (__half *)y, OC, M, OC, IC, 0), "tce_w4a16_gemm");
     else
         CK(launch_gemm_f16_tc(&ctx->c, (const __half *)x, IC, ctx->c.w16_scratch, IC, (__half *)y, OC, M, OC, IC), "tce_w4a16_gemm");

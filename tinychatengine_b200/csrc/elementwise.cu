@@ -152,7 +152,40 @@ __global__ void embedding_rows_kernel(const __half *__restrict__ table, const in
     for (int i = threadIdx.x; i < E / 2; i += blockDim.x) dst[i] = __half22float2(row[i]);
 }
 
-__global__ void rmsnorm_rows_f32_kernel(const float *__restrict__ x, const float *__restrict__ gamma, __half *__restrict__ y, int dim, float eps) {
+// one 256-thread block per row; the row stays in registers between the two passes (dim <= 256 * 4 * kRmsVec), 16-byte loads, 8-byte stores
+constexpr int kRmsVec = 8;  // float4 per thread: rows up to 8192 channels
+__global__ void __launch_bounds__(256) rmsnorm_rows_f32_kernel(const float *__restrict__ x, const float *__restrict__ gamma, __half *__restrict__ y, int dim, float eps) {
+    __shared__ float sred[8];
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)blockIdx.x * dim);
+    const float4 *gr = reinterpret_cast<const float4 *>(gamma);
+    uint2 *yr = reinterpret_cast<uint2 *>(y + (size_t)blockIdx.x * dim);
+    const int nv = dim >> 2;
+    float4 v[kRmsVec];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRmsVec; k++) {
+        const int i = threadIdx.x + k * 256;
+        v[k] = i < nv ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) tot += sred[w];
+    const float inv = rsqrtf(tot / (float)dim + eps);
+#pragma unroll
+    for (int k = 0; k < kRmsVec; k++) {
+        const int i = threadIdx.x + k * 256;
+        if (i < nv) {
+            const float4 g = gr[i];
+            yr[i] = make_uint2(pack_half2((v[k].x * inv) * g.x, (v[k].y * inv) * g.y), pack_half2((v[k].z * inv) * g.z, (v[k].w * inv) * g.w));
+        }
+    }
+}
+// general shapes (dim not a multiple of 4, or longer than the register tile)
+__global__ void rmsnorm_rows_f32_generic_kernel(const float *__restrict__ x, const float *__restrict__ gamma, __half *__restrict__ y, int dim, float eps) {
     __shared__ float sred[32];
     const float *xr = x + (size_t)blockIdx.x * dim;
     __half *yr = y + (size_t)blockIdx.x * dim;
@@ -167,8 +200,24 @@ __global__ void rmsnorm_rows_f32_kernel(const float *__restrict__ x, const float
     for (int i = threadIdx.x; i < dim; i += blockDim.x) yr[i] = __float2half((xr[i] * inv) * gamma[i]);
 }
 
-// act[r][c] = SiLU(gu[r][c]) * gu[r][F + c]   (SiLuMul_half, cuda/Int4llamaDecoderLayer.cu:12-30; fp32 math)
-__global__ void silu_mul_rows_kernel(const __half *__restrict__ gu, __half *__restrict__ act, int F, long long total) {
+// act[r][c] = SiLU(gu[r][c]) * gu[r][F + c]   (SiLuMul_half, cuda/Int4llamaDecoderLayer.cu:12-30; fp32 math); 8 channels per thread
+__global__ void silu_mul_rows_kernel(const __half *__restrict__ gu, __half *__restrict__ act, int F, long long total8) {
+    const int F8 = F >> 3;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total8; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / F8;
+        const int c8 = (int)(e - r * F8);
+        const uint4 g4 = *reinterpret_cast<const uint4 *>(gu + r * 2 * F + (size_t)c8 * 8), u4 = *reinterpret_cast<const uint4 *>(gu + r * 2 * F + F + (size_t)c8 * 8);
+        const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 g = __half22float2(*reinterpret_cast<const __half2 *>(&gw[i])), u = __half22float2(*reinterpret_cast<const __half2 *>(&uw[i]));
+            o[i] = pack_half2((g.x / (1.f + __expf(-g.x))) * u.x, (g.y / (1.f + __expf(-g.y))) * u.y);
+        }
+        *reinterpret_cast<uint4 *>(act + e * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+__global__ void silu_mul_rows_generic_kernel(const __half *__restrict__ gu, __half *__restrict__ act, int F, long long total) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long r = e / F;
         const int c = (int)(e % F);
@@ -214,13 +263,21 @@ cudaError_t launch_embedding_rows(Ctx *ctx, const __half *table, const int *toke
     return cudaGetLastError();
 }
 cudaError_t launch_rmsnorm_rows_f32(Ctx *ctx, const float *x, const float *gamma, __half *y, int rows, int dim, float eps) {
-    rmsnorm_rows_f32_kernel<<<rows, 256, 0, ctx->stream>>>(x, gamma, y, dim, eps);
+    if ((dim & 3) == 0 && dim <= 256 * 4 * kRmsVec && !(((uintptr_t)x | (uintptr_t)gamma) & 15) && !((uintptr_t)y & 7))
+        rmsnorm_rows_f32_kernel<<<rows, 256, 0, ctx->stream>>>(x, gamma, y, dim, eps);
+    else
+        rmsnorm_rows_f32_generic_kernel<<<rows, 256, 0, ctx->stream>>>(x, gamma, y, dim, eps);
     return cudaGetLastError();
 }
 cudaError_t launch_silu_mul_rows(Ctx *ctx, const __half *gu, __half *act, int rows, int F) {
     const long long total = (long long)rows * F;
-    const long long nb = (total + 255) / 256;
-    silu_mul_rows_kernel<<<(unsigned)(nb < 4096 ? nb : 4096), 256, 0, ctx->stream>>>(gu, act, F, total);
+    if ((F & 7) == 0 && !(((uintptr_t)gu | (uintptr_t)act) & 15)) {
+        const long long total8 = total >> 3, nb = (total8 + 255) / 256;
+        silu_mul_rows_kernel<<<(unsigned)(nb < 8192 ? nb : 8192), 256, 0, ctx->stream>>>(gu, act, F, total8);
+    } else {
+        const long long nb = (total + 255) / 256;
+        silu_mul_rows_generic_kernel<<<(unsigned)(nb < 4096 ? nb : 4096), 256, 0, ctx->stream>>>(gu, act, F, total);
+    }
     return cudaGetLastError();
 }
 

@@ -34,11 +34,14 @@ constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 
 template <bool FUSED>
 struct Cfg {
-    static constexpr int kAStages = FUSED ? 5 : 6;   // ring of activation tiles (FUSED: + packed weight tiles in the same slots)
+    static constexpr int kAStages = 6;               // ring of activation tiles (not FUSED: + this CTA's fp16 weight tile in the same slot)
     static constexpr int kOpStages = FUSED ? 4 : 0;  // ring of dequantised operand tiles
-    static constexpr int kSlotBytes = kABytes + (FUSED ? kRawHalf : kBHalfBytes);
-    static constexpr int kThreads = 32 * (6 + (FUSED ? kDq * kDqGroups : 0));
-    static constexpr size_t kSmem = 1024 + (size_t)kAStages * kSlotBytes + (size_t)kOpStages * kBHalfBytes;
+    static constexpr int kRawStages = FUSED ? 12 : 0;  // ring of packed weight tiles: its own, deeper ring -- 4 KiB per k-block buys the look-ahead
+                                                       // that hides the load latency in front of the dequant warps (a shared 5-slot ring left the
+                                                       // tensor pipe at 42 %: a slot was only re-requested after its MMA had retired)
+    static constexpr int kSlotBytes = kABytes + (FUSED ? 0 : kBHalfBytes);
+    static constexpr int kThreads = 32 * (6 + (FUSED ? kDq * kDqGroups + 1 : 0));  // FUSED: + one warp that loads the packed tiles
+    static constexpr size_t kSmem = 1024 + (size_t)kAStages * kSlotBytes + (size_t)kOpStages * kBHalfBytes + (size_t)kRawStages * kRawHalf;
 };
 
 struct PairArgs {
@@ -51,6 +54,8 @@ struct PairArgs {
     void *C;
     long long ldc;
     int add_f32;
+    int silu_F;  // > 0: W = [gate (F rows); up (F rows)], the pair's two halves are the SAME 128 channels of gate (CTA 0) and up (CTA 1), and the
+                 // epilogue writes act[M][F] = SiLU(gate) * up (SiLuMul_half, llm/src/nn_modules/cuda/Int4llamaDecoderLayer.cu:12-30; fp32 math)
 };
 
 TCE_DEVINL uint32_t cluster_rank() {
@@ -139,15 +144,16 @@ TCE_DEVINL uint4 dequant_word2(uint32_t w, uint32_t zmagic, __half2 s2) {  // 8 
 template <bool FUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads, 1) gemm_pair_kernel(const __grid_constant__ PairArgs a) {
     using C = Cfg<FUSED>;
-    constexpr int AS = C::kAStages, OS = FUSED ? C::kOpStages : 1;
+    constexpr int AS = C::kAStages, OS = FUSED ? C::kOpStages : 1, RS = FUSED ? C::kRawStages : 1;
     extern __shared__ uint8_t smem_raw[];
     // barriers live at identical offsets in both CTAs (multicast commits and remote arrives address "the same barrier in the other CTA")
-    __shared__ __align__(8) uint64_t a_full[AS], a_empty[AS], raw_full[AS], op_full[OS], op_empty[OS], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t a_full[AS], a_empty[AS], raw_full[RS], raw_empty[RS], op_full[OS], op_empty[OS], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t *base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    uint8_t *sSlot = base;                                    // [AS][A 16 KiB | B half (fp16 16 KiB, or packed 4 KiB)]
-    uint8_t *sOp = base + (size_t)AS * C::kSlotBytes;         // FUSED: [OS][16 KiB]
+    uint8_t *sSlot = base;                                    // [AS][A 16 KiB (| B half fp16 16 KiB when not FUSED)]
+    uint8_t *sOp = base + (size_t)AS * C::kSlotBytes;         // FUSED: [OS][16 KiB] dequantised operand tiles
+    uint8_t *sRaw = sOp + (size_t)(FUSED ? OS : 0) * kBHalfBytes;  // FUSED: [RS][4 KiB] packed tiles
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const bool leader = rank == 0;
@@ -157,8 +163,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads
     if (threadIdx.x == 0) {
         for (int s = 0; s < AS; s++) {
             mbar_init(&a_full[s], 1);                          // leader: its own expect_tx arrival; bytes from both CTAs
-            mbar_init(&a_empty[s], FUSED ? 1 + kDq : 1);       // multicast MMA commit (+ this CTA's dequant warps, which read the packed tile)
+            mbar_init(&a_empty[s], 1);                         // multicast MMA commit
+        }
+        for (int s = 0; s < RS; s++) {
             mbar_init(&raw_full[s], 1);                        // FUSED: this CTA's packed tile (local TMA)
+            mbar_init(&raw_empty[s], kDq);                     // the dequant warps of the group that owns the k-block
         }
         for (int s = 0; s < OS; s++) {
             mbar_init(&op_full[s], 2 * kDq);                   // leader: dequant warps of both CTAs
@@ -186,15 +195,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads
             uint32_t ph = 0;
             for (int t = cl; t < tiles_total; t += ncl) {
                 const int mb = t % a.m_blocks, nb = t / a.m_blocks;
-                const int row0 = mb * 256 + (int)rank * kBlockM, wrow0 = nb * kPairN + (int)rank * kHalfN;
+                const int row0 = mb * 256 + (int)rank * kBlockM;
+                const int wrow0 = a.silu_F > 0 ? nb * kHalfN + (int)rank * a.silu_F : nb * kPairN + (int)rank * kHalfN;
                 for (int kb = 0; kb < a.k_blocks; kb++) {
                     mbar_wait(&a_empty[s], ph ^ 1u);
                     uint8_t *dst = sSlot + (size_t)s * C::kSlotBytes;
                     if (FUSED) {
                         if (leader) mbar_arrive_expect_tx(&a_full[s], 2 * kABytes);
                         tma_load_2d_pair(dst, &a.tmA, kb * 64, row0, &a_full[s]);
-                        mbar_arrive_expect_tx(&raw_full[s], kRawHalf);
-                        tma_load_2d(dst + kABytes, &a.tmB, kb * 8, wrow0, &raw_full[s]);
                     } else {
                         if (leader) mbar_arrive_expect_tx(&a_full[s], 2 * (kABytes + kBHalfBytes));
                         tma_load_2d_pair(dst, &a.tmA, kb * 64, row0, &a_full[s]);
@@ -255,6 +263,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads
             tc_fence_after();
             const int row = mb * 256 + (int)rank * kBlockM + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kPairN);
+            if (a.silu_F > 0) {
+                // accumulator columns 0..127 = gate, 128..255 = up of output channels nb * 128 ..: act = SiLU(gate) * up
+#pragma unroll 1
+                for (int c = 0; c < kHalfN / 32; c++) {
+                    uint32_t g[32], u[32];
+                    tmem_ld32(taddr + (uint32_t)(c * 32), g);
+                    tmem_ld32(taddr + (uint32_t)(kHalfN + c * 32), u);
+                    tmem_ld_wait();
+                    const int col0 = nb * kHalfN + c * 32;
+                    if (row < a.M && col0 < a.silu_F) {
+                        __half *dst = reinterpret_cast<__half *>(a.C) + (size_t)row * a.ldc + col0;
+                        uint32_t o[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float g0 = __uint_as_float(g[2 * i]), g1 = __uint_as_float(g[2 * i + 1]);
+                            o[i] = pack_half2((g0 / (1.f + __expf(-g0))) * __uint_as_float(u[2 * i]), (g1 / (1.f + __expf(-g1))) * __uint_as_float(u[2 * i + 1]));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; i++) reinterpret_cast<uint4 *>(dst)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_cluster(&tempty_bar[acc], 0);
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < kPairN / 32; c++) {
                 uint32_t v[32];
@@ -303,6 +336,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads
             tc_fence_before();
             mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA thread may overwrite this accumulator (in both CTAs)
         }
+    } else if (FUSED && warp == 6 + kDq * kDqGroups) {
+        // ------------------------------------------------------------------------------- packed-weight producer (both CTAs, local barriers)
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = cl; t < tiles_total; t += ncl) {
+                const int nb = t / a.m_blocks;
+                const int wrow0 = nb * kPairN + (int)rank * kHalfN;
+                for (int kb = 0; kb < a.k_blocks; kb++) {
+                    mbar_wait(&raw_empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&raw_full[s], kRawHalf);
+                    tma_load_2d(sRaw + (size_t)s * kRawHalf, &a.tmB, kb * 8, wrow0, &raw_full[s]);
+                    if (++s == RS) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
     } else if (FUSED) {
         // ------------------------------------------------------------------------------- dequant warps: thread r owns weight row r of this CTA's half;
         // group `grp` takes the k-blocks kb = grp (mod kDqGroups).  K % 128 == 0 makes k_blocks even, so a group sees the same half of every
@@ -333,13 +386,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads
                 const __half2 s2 = __half2half2(s_nxt);
                 if (live && g + 1 < ngroups) s_nxt = srow[g + 1];
                 const long long kk = kbase + kb;
-                const int s = (int)(kk % AS), os = (int)(kk % OS);
-                const uint32_t ph = (uint32_t)((kk / AS) & 1), oph = (uint32_t)((kk / OS) & 1);
+                const int s = (int)(kk % RS), os = (int)(kk % OS);
+                const uint32_t ph = (uint32_t)((kk / RS) & 1), oph = (uint32_t)((kk / OS) & 1);
                 mbar_wait(&raw_full[s], ph);
-                const uint8_t *src = sSlot + (size_t)s * C::kSlotBytes + kABytes + (size_t)r * 32;
+                const uint8_t *src = sRaw + (size_t)s * kRawHalf + (size_t)r * 32;
                 const uint4 w0 = *reinterpret_cast<const uint4 *>(src), w1 = *reinterpret_cast<const uint4 *>(src + 16);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_empty[s]);  // the packed tile is in registers (the slot still waits for the MMA commit)
+                if (lane == 0) mbar_arrive(&raw_empty[s]);  // the packed tile is in registers
                 const uint32_t ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
                 uint4 o[8];
 #pragma unroll
@@ -406,12 +459,14 @@ cudaError_t launch_pair(Ctx *ctx, PairArgs &a) {
 int w4_gemm_mode() {
     static const int mode = [] {
         const char *e = getenv("TCE_W4_GEMM");
-        if (!e) return (int)W4G_EXPAND;
+        if (!e) return (int)W4G_PAIR_OVERLAP;  // measured best on B200 (profiles/README.md): CTA-pair GEMM, expansion of the next linear overlapped
         const std::string v(e);
         if (v == "fused") return (int)W4G_FUSED;
         if (v == "pair") return (int)W4G_PAIR;
         if (v == "pair_fused") return (int)W4G_PAIR_FUSED;
-        return (int)W4G_EXPAND;
+        if (v == "pair_overlap") return (int)W4G_PAIR_OVERLAP;
+        if (v == "expand") return (int)W4G_EXPAND;
+        return (int)W4G_PAIR_OVERLAP;
     }();
     return mode;
 }
@@ -429,6 +484,22 @@ cudaError_t launch_gemm_f16_pair(Ctx *ctx, const __half *X, long long ldx, const
     a.C = C;
     a.ldc = ldc;
     a.add_f32 = add_f32;
+    return launch_pair<false>(ctx, a);
+}
+
+// act[M][F] = SiLU(X Wg^T) * (X Wu^T), W = fp16 [2F][K] with the gate rows first; F % 128 == 0, ldc % 8 == 0
+cudaError_t launch_gemm_f16_pair_silu(Ctx *ctx, const __half *X, long long ldx, const __half *W, long long ldw, __half *act, long long ldc, int M, int F, int K) {
+    if (M < 1 || F < 128 || (F % kHalfN) || K < 64 || (K % 64) || (ldx % 8) || (ldw % 8) || (ldc % 8) || !encoder2()) return cudaErrorInvalidValue;
+    PairArgs a = {};
+    if (!encode_f16(&a.tmA, X, M, K, ldx) || !encode_f16(&a.tmB, W, 2LL * F, K, ldw)) return cudaErrorInvalidValue;
+    a.M = M;
+    a.N = F;
+    a.k_blocks = K / 64;
+    a.m_blocks = (M + 255) / 256;
+    a.n_blocks = F / kHalfN;
+    a.C = act;
+    a.ldc = ldc;
+    a.silu_F = F;
     return launch_pair<false>(ctx, a);
 }
 

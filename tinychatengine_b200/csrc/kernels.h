@@ -108,10 +108,11 @@ cudaError_t launch_gemm_f16_tc(Ctx *ctx, const __half *A, long long lda, const _
 cudaError_t launch_gemm_w4_tc(Ctx *ctx, const __half *X, long long ldx, const uint32_t *w, const uint32_t *zeros, const __half *scales, void *C, long long ldc,
                               int M, int N, int K, int add_f32);
 // which W4A16 large-M GEMM runs (TCE_W4_GEMM=expand|fused|pair|pair_fused; the default is the measured best, profiles/README.md)
-enum W4GemmMode : int { W4G_EXPAND = 0, W4G_FUSED = 1, W4G_PAIR = 2, W4G_PAIR_FUSED = 3 };
+enum W4GemmMode : int { W4G_EXPAND = 0, W4G_FUSED = 1, W4G_PAIR = 2, W4G_PAIR_FUSED = 3, W4G_PAIR_OVERLAP = 4 };
 int w4_gemm_mode();
 // CTA-pair variants (gemm_tc2.cu): tcgen05.mma.cta_group::2 on 256 x 256 tiles, W as fp16 or as packed int4 (unpack fused)
 cudaError_t launch_gemm_f16_pair(Ctx *ctx, const __half *X, long long ldx, const __half *W, long long ldw, void *C, long long ldc, int M, int N, int K, int add_f32);
+cudaError_t launch_gemm_f16_pair_silu(Ctx *ctx, const __half *X, long long ldx, const __half *W, long long ldw, __half *act, long long ldc, int M, int F, int K);
 cudaError_t launch_gemm_w4_pair(Ctx *ctx, const __half *X, long long ldx, const uint32_t *w, const uint32_t *zeros, const __half *scales, void *C, long long ldc,
                                 int M, int N, int K, int add_f32);
 cudaError_t w4_scratch_reserve(Ctx *ctx, size_t elems);  // grows ctx->w16_scratch (may synchronise the device)

@@ -146,6 +146,12 @@ LlamaDecoder::~LlamaDecoder() {
     cudaFree(d_logits_);
     cudaFree(d_tokpos_);
     cudaFree(d_gen_);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(pf_w16_[b]);
+        if (pf_expanded_[b]) cudaEventDestroy(pf_expanded_[b]);
+        if (pf_consumed_[b]) cudaEventDestroy(pf_consumed_[b]);
+    }
+    if (pf_side_) cudaStreamDestroy(pf_side_);
     cudaFree(d_next_);
     cudaFree(pf_x_);
     cudaFree(pf_xn_);
@@ -838,7 +844,7 @@ cudaError_t LlamaDecoder::prefill_reserve(int n) {
 
 // C[n][sum oc] (row-major, leading dimension ldc) = X[n][ic] * [deq(t0); deq(t1); ...]^T : the `count` weight matrices (same ic) are
 // expanded into consecutive row ranges of the fp16 scratch and multiplied by ONE GEMM (q|k|v and gate|up share their input)
-cudaError_t LlamaDecoder::prefill_linear(const tce_w4_tensor *const *ts, int count, const __half *x, void *C, long long ldc, int n, bool add_f32) {
+cudaError_t LlamaDecoder::prefill_linear(const tce_w4_tensor *const *ts, int count, const __half *x, void *C, long long ldc, int n, bool add_f32, bool silu) {
     const int ic = ts[0]->ic;
     const int mode = w4_gemm_mode();
     if (mode == W4G_FUSED || mode == W4G_PAIR_FUSED) {
@@ -857,6 +863,18 @@ cudaError_t LlamaDecoder::prefill_linear(const tce_w4_tensor *const *ts, int cou
     }
     size_t rows = 0;
     for (int i = 0; i < count; i++) rows += (size_t)ts[i]->oc;
+    if (mode == W4G_PAIR_OVERLAP && !pf_jobs_.empty()) {
+        // this job's weights were expanded on the side stream while the previous GEMM ran; queue the next job's expansion, then run
+        const int j = pf_next_job_++;
+        const int b = j & 1;
+        if (j + 1 < (int)pf_jobs_.size()) DCK(pf_expand_job(j + 1));
+        DCK(cudaStreamWaitEvent(ctx_->stream, pf_expanded_[b], 0));
+        if (silu)
+            DCK(launch_gemm_f16_pair_silu(ctx_, x, ic, pf_w16_[b], ic, (__half *)C, ldc, n, (int)(rows / 2), ic));
+        else
+            DCK(launch_gemm_f16_pair(ctx_, x, ic, pf_w16_[b], ic, C, ldc, n, (int)rows, ic, add_f32 ? 1 : 0));
+        return cudaEventRecord(pf_consumed_[b], ctx_->stream);
+    }
     DCK(w4_scratch_reserve(ctx_, rows * ic));
     size_t r0 = 0;
     for (int i = 0; i < count; i++) {
@@ -864,8 +882,26 @@ cudaError_t LlamaDecoder::prefill_linear(const tce_w4_tensor *const *ts, int cou
         DCK(launch_w4_expand(ctx_, (const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, ctx_->w16_scratch + r0 * ic, t.oc, ic));
         r0 += (size_t)t.oc;
     }
-    if (mode == W4G_PAIR) return launch_gemm_f16_pair(ctx_, x, ic, ctx_->w16_scratch, ic, C, ldc, n, (int)rows, ic, add_f32 ? 1 : 0);
+    if (silu) return launch_gemm_f16_pair_silu(ctx_, x, ic, ctx_->w16_scratch, ic, (__half *)C, ldc, n, (int)(rows / 2), ic);
+    if (mode == W4G_PAIR || mode == W4G_PAIR_OVERLAP) return launch_gemm_f16_pair(ctx_, x, ic, ctx_->w16_scratch, ic, C, ldc, n, (int)rows, ic, add_f32 ? 1 : 0);
     return launch_gemm_f16_tc(ctx_, x, ic, ctx_->w16_scratch, ic, C, ldc, n, (int)rows, ic, add_f32 ? 1 : 0);
+}
+
+// expansion of job j into scratch half (j & 1) on the side stream, after the GEMM that last read that half
+cudaError_t LlamaDecoder::pf_expand_job(int j) {
+    const PfJob &job = pf_jobs_[j];
+    const int b = j & 1;
+    Ctx side = *ctx_;
+    side.stream = pf_side_;
+    if (j >= 2) DCK(cudaStreamWaitEvent(pf_side_, pf_consumed_[b], 0));
+    size_t r0 = 0;
+    const int ic = job.ts[0]->ic;
+    for (int i = 0; i < job.count; i++) {
+        const tce_w4_tensor &t = *job.ts[i];
+        DCK(launch_w4_expand(&side, (const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, pf_w16_[b] + r0 * ic, t.oc, ic));
+        r0 += (size_t)t.oc;
+    }
+    return cudaEventRecord(pf_expanded_[b], pf_side_);
 }
 
 cudaError_t LlamaDecoder::prefill(const int *tokens_host, int n, int pos0, float *logits_host, int *next_token, std::string *err) {
@@ -877,6 +913,35 @@ cudaError_t LlamaDecoder::prefill(const int *tokens_host, int n, int pos0, float
     for (int i = 0; i < n; i++)
         if (tokens_host[i] < 0 || tokens_host[i] >= cfg_.vocab_size) return cudaErrorInvalidValue;
     DCK(prefill_reserve(n));
+    if (w4_gemm_mode() == W4G_PAIR_OVERLAP) {
+        if (pf_jobs_.empty()) {
+            size_t need = 0;
+            for (int l = 0; l < cfg_.num_layers; l++) {
+                const tce_llama_layer &L = layers_[l];
+                pf_jobs_.push_back(PfJob{{&L.q, &L.k, &L.v}, 3});
+                pf_jobs_.push_back(PfJob{{&L.o, nullptr, nullptr}, 1});
+                pf_jobs_.push_back(PfJob{{&L.gate, &L.up, nullptr}, 2});
+                pf_jobs_.push_back(PfJob{{&L.down, nullptr, nullptr}, 1});
+            }
+            for (const PfJob &jb : pf_jobs_) {
+                size_t e = 0;
+                for (int i = 0; i < jb.count; i++) e += (size_t)jb.ts[i]->oc * jb.ts[i]->ic;
+                need = e > need ? e : need;
+            }
+            for (int b = 0; b < 2; b++) {
+                DCK(cudaMalloc((void **)&pf_w16_[b], need * sizeof(__half)));
+                DCK(cudaEventCreateWithFlags(&pf_expanded_[b], cudaEventDisableTiming));
+                DCK(cudaEventCreateWithFlags(&pf_consumed_[b], cudaEventDisableTiming));
+            }
+            pf_w16_elems_ = need;
+            DCK(cudaStreamCreateWithFlags(&pf_side_, cudaStreamNonBlocking));
+        }
+        pf_next_job_ = 0;
+        // the side stream starts after everything already queued on the main stream (a previous prompt's GEMMs read the scratch)
+        DCK(cudaEventRecord(pf_consumed_[0], ctx_->stream));
+        DCK(cudaStreamWaitEvent(pf_side_, pf_consumed_[0], 0));
+        DCK(pf_expand_job(0));
+    }
     cudaStream_t s = ctx_->stream;
     const int E = cfg_.embed_dim, F = cfg_.hidden_dim, H = cfg_.num_heads, KVH = cfg_.num_kv_heads, hd = cfg_.head_dim;
     const long long Q = (long long)(H + 2 * KVH) * hd;
@@ -904,8 +969,13 @@ cudaError_t LlamaDecoder::prefill(const int *tokens_host, int n, int pos0, float
         DCK(launch_attn_prefill(ctx_, a));
         DCK(prefill_linear(o1, 1, pf_att_, pf_x_, E, n, true));  // residual add in the GEMM epilogue
         DCK(launch_rmsnorm_rows_f32(ctx_, pf_x_, L.post_norm, pf_xn_, n, E, cfg_.rms_eps));
-        DCK(prefill_linear(gu, 2, pf_xn_, pf_gu_, 2LL * F, n, false));
-        DCK(launch_silu_mul_rows(ctx_, pf_gu_, pf_act_, n, F));
+        const int gm = w4_gemm_mode();
+        if ((gm == W4G_PAIR || gm == W4G_PAIR_OVERLAP) && (F % 128) == 0) {
+            DCK(prefill_linear(gu, 2, pf_xn_, pf_act_, F, n, false, true));  // SiLU(gate) * up in the GEMM epilogue: gate|up never reach HBM
+        } else {
+            DCK(prefill_linear(gu, 2, pf_xn_, pf_gu_, 2LL * F, n, false));
+            DCK(launch_silu_mul_rows(ctx_, pf_gu_, pf_act_, n, F));
+        }
         DCK(prefill_linear(d1, 1, pf_act_, pf_x_, E, n, true));
     }
     // only the last position feeds the sampler: final RMSNorm + lm_head as the decode step's last GEMV, then arg-max
