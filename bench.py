@@ -18,6 +18,7 @@ from __future__ import annotations
 import argparse
 import os as _os
 
+_os.environ["NCCL_DEBUG"] = _os.environ.get("TCE_NCCL_DEBUG", "WARN")  # a pod-wide NCCL_DEBUG=VERSION prints to stdout
 _os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not land on stdout next to the JSON line
 
 import json

@@ -188,6 +188,8 @@ struct PSmem {
     float *rope;        // cos[128] | sin[128] of the token position
     uint64_t *full, *empty, *red_full, *red_empty;
     int *issued;        // stages the loader has issued so far (read by the L2 prefetch warp)
+    uint64_t *rx;       // pair staging: counts the bytes the partner has mirrored into this CTA for the current staging
+    int *free_gen;      // pair staging: written by the partner: the number of phases it has finished (its buffers may be overwritten)
     uint32_t ring_u32, xs_u32, gx_u32, gsum_u32, full_u32, empty_u32, redfull_u32, redempty_u32;
     int nst;
 };
@@ -216,7 +218,9 @@ TCE_DEVINL PSmem carve(uint8_t *raw, const Args &a) {
     s.empty = s.full + a.nst;
     s.red_full = s.empty + a.nst;
     s.red_empty = s.red_full + kRedBufs;
-    s.issued = reinterpret_cast<int *>(s.red_empty + kRedBufs);
+    s.rx = s.red_empty + kRedBufs;
+    s.issued = reinterpret_cast<int *>(s.rx + 1);
+    s.free_gen = s.issued + 1;
     s.ring_u32 = smem_u32(s.ring);
     s.xs_u32 = smem_u32(s.xs);
     s.gx_u32 = smem_u32(s.gx);
@@ -418,6 +422,44 @@ TCE_DEVINL void producer_walk(const Args &a, const PSmem &sm, int cta, int ncta,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------ pair staging (clusters of two CTAs)
+// Every CTA needs the whole quantised input vector of a GEMV phase.  In pair mode the two CTAs of a cluster split that work: CTA `rank` polls and
+// quantises the 128-groups g = rank (mod 2) and mirrors planes / steps / sums into its partner with st.async (remote shared-memory stores that
+// complete transaction bytes on the partner's `rx` mbarrier: no fence, no flag).  A CTA tells its partner when its buffers may be overwritten
+// (`free_gen` = phases finished, a relaxed remote store: it only orders the partner's writes after this CTA's reads).
+struct PairCtx {
+    bool on = false;
+    uint32_t rank = 0;
+    gemv::PairDst dst = {0u, 0u, 0u, 0u};
+    uint32_t r_rms = 0, r_free = 0;  // partner's rms[16..31] and free_gen
+    uint32_t nstage = 0;             // stagings done so far (parity of the rx barrier)
+};
+TCE_DEVINL uint32_t map_to_cta(uint32_t local_u32, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_u32), "r"(rank));
+    return r;
+}
+TCE_DEVINL void st_cluster_u32(uint32_t raddr, uint32_t v) { asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(v) : "memory"); }
+// groups a CTA stages itself / expects from its partner
+TCE_DEVINL int own_groups(const PairCtx &pc, int NG) { return pc.on ? (NG + 1 - (int)pc.rank) / 2 : NG; }
+TCE_DEVINL int peer_groups(const PairCtx &pc, int NG) { return pc.on ? (NG + (int)pc.rank) / 2 : 0; }
+// before the first mirrored store of phase p: the partner has finished phase p - 1 (it no longer reads the buffers this CTA writes into)
+TCE_DEVINL void wait_partner_free(const PSmem &sm, const PairCtx &pc, int p) {
+    if (!pc.on || p == 0) return;
+    const long long t0 = clock64();
+    while (lds_volatile_i32(sm.free_gen) < p) {
+        if (clock64() - t0 > kSpinLimit) __trap();
+    }
+}
+// arm the rx barrier for this staging (one thread) / wait for the partner's bytes (every consumer thread)
+TCE_DEVINL void rx_expect(const PSmem &sm, const PairCtx &pc, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(sm.rx)), "r"(bytes) : "memory");
+}
+TCE_DEVINL void rx_wait(const PSmem &sm, PairCtx &pc) {
+    mbar_wait_u32(smem_u32(sm.rx), pc.nstage & 1u);
+    pc.nstage++;
+}
+
 // ------------------------------------------------------------------------------------------------------------ consumers: staging
 // unit rotation: CTA c starts its walk over the input vector `rot` groups further on, so that the 148 CTAs do not all pull the same
 // L2 lines at the same moment.  Whole groups (16 units) keep the half-warp amax shuffles of emit_unit intact.
@@ -429,8 +471,14 @@ TCE_DEVINL int rot_unit(int u, int units, int cta) {
 }
 
 // fp16 input vector (attention output / SiLU*mul activations) published as {half2, tag} words -> activation planes
-TCE_DEVINL void stage_half(const Args &a, const GemvOp &op, const PSmem &sm, const uint2 *src, uint32_t tag, int cta, int ctid, int lane, int p, int nphase) {
-    const int units = op.IC / 8;  // 8 halfs = 4 words = 32 B per unit
+TCE_DEVINL void stage_half(const Args &a, const GemvOp &op, const PSmem &sm, PairCtx &pc, const uint2 *src, uint32_t tag, int cta, int ctid, int lane, int p,
+                           int nphase) {
+    const int ng_own = own_groups(pc, op.NG);
+    const int units = ng_own * 16;  // 8 halfs = 4 words = 32 B per unit; this CTA's groups only (pair mode: every other group)
+    if (pc.on) {
+        if (ctid == 0) rx_expect(sm, pc, (uint32_t)peer_groups(pc, op.NG) * 524u);  // 16 units x 32 B of planes + step + two sums per group
+        wait_partner_free(sm, pc, p);
+    }
     constexpr int PRE = 4;        // iterations whose words are requested together: one L2 round trip for up to 4 * 512 units
     for (int ub = 0; ub < units; ub += PRE * kConsumerThreads) {
         uint4 w[PRE][2];
@@ -438,7 +486,11 @@ TCE_DEVINL void stage_half(const Args &a, const GemvOp &op, const PSmem &sm, con
 #pragma unroll
         for (int k = 0; k < PRE; k++) {
             const int u = ub + k * kConsumerThreads + ctid;
-            ui[k] = (u < units) ? rot_unit(u, units, cta) : -1;
+            ui[k] = -1;
+            if (u < units) {
+                const int ru = rot_unit(u, units, cta);  // index among this CTA's groups
+                ui[k] = pc.on ? (((ru >> 4) * 2 + (int)pc.rank) << 4) | (ru & 15) : ru;
+            }
             w[k][0] = w[k][1] = make_uint4(0u, tag, 0u, tag);
             if (ui[k] >= 0) {
                 w[k][0] = ld_ll2(src + (size_t)ui[k] * 4, false);
@@ -474,24 +526,71 @@ TCE_DEVINL void stage_half(const Args &a, const GemvOp &op, const PSmem &sm, con
             const float2 f0 = h2_to_f2(w[k][0].x), f1 = h2_to_f2(w[k][0].z), f2 = h2_to_f2(w[k][1].x), f3 = h2_to_f2(w[k][1].z);
             v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
             v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
-            gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, valid ? ui[k] : 0, valid, v, lane);
+            if (pc.on)
+                gemv::emit_unit<1, true>(sm.xs, op.IC, sm.gx, sm.gsum, valid ? ui[k] : 0, valid, v, lane, &pc.dst);
+            else
+                gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, valid ? ui[k] : 0, valid, v, lane);
         }
     }
     if (ctid == 0) stamp(a, cta, nphase, p, 5);
     named_bar_sync(1, kConsumerThreads);
+    if (pc.on) rx_wait(sm, pc);
+}
+
+// Tensor parallel: x[0..7] += the eight output words of every rank's slot, in rank order (bit-identical on all ranks).  The slots of two ranks
+// are requested together: one L2 round trip per pair of ranks instead of one per rank (measured at P = 8: the per-rank round trips made 8 GPUs
+// slower than 4; a batch of four needs 64 payload registers and pushed the whole kernel into spills).
+TCE_DEVINL void tp_accumulate(float (&x)[8], const uint2 *slot0, int tp_size, int E, uint32_t tag) {
+    int pr = 0;
+    for (; pr + 2 <= tp_size; pr += 2) {
+        const uint2 *pa = slot0 + (size_t)pr * E, *pb = pa + E;
+        uint4 wa[4], wb[4];
+        long long t0 = 0;
+        while (true) {  // both slots are (re)requested in every round: one round trip when the words are there
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < 4; i++) wa[i] = ld_ll2(pa + 2 * i, true);
+#pragma unroll
+            for (int i = 0; i < 4; i++) wb[i] = ld_ll2(pb + 2 * i, true);
+#pragma unroll
+            for (int i = 0; i < 4; i++) ok = ok && wa[i].y == tag && wa[i].w == tag && wb[i].y == tag && wb[i].w == tag;
+            if (ok) break;
+            if (t0 == 0) t0 = clock64();
+            if (clock64() - t0 > kSpinLimit) __trap();
+            __nanosleep(kPollBackoffNs);
+        }
+        x[0] += __uint_as_float(wa[0].x); x[1] += __uint_as_float(wa[0].z); x[2] += __uint_as_float(wa[1].x); x[3] += __uint_as_float(wa[1].z);
+        x[4] += __uint_as_float(wa[2].x); x[5] += __uint_as_float(wa[2].z); x[6] += __uint_as_float(wa[3].x); x[7] += __uint_as_float(wa[3].z);
+        x[0] += __uint_as_float(wb[0].x); x[1] += __uint_as_float(wb[0].z); x[2] += __uint_as_float(wb[1].x); x[3] += __uint_as_float(wb[1].z);
+        x[4] += __uint_as_float(wb[2].x); x[5] += __uint_as_float(wb[2].z); x[6] += __uint_as_float(wb[3].x); x[7] += __uint_as_float(wb[3].z);
+    }
+    if (pr < tp_size) {
+        uint4 w[4];
+        wait_ll2xN<4>(slot0 + (size_t)pr * E, tag, true, w);
+        x[0] += __uint_as_float(w[0].x); x[1] += __uint_as_float(w[0].z); x[2] += __uint_as_float(w[1].x); x[3] += __uint_as_float(w[1].z);
+        x[4] += __uint_as_float(w[2].x); x[5] += __uint_as_float(w[2].z); x[6] += __uint_as_float(w[3].x); x[7] += __uint_as_float(w[3].z);
+    }
 }
 
 // fp32 residual stream with fused RMSNorm.  Every CTA holds the stream in shared memory; `delta` (o_proj or down_proj outputs of all
 // tensor-parallel ranks, {float, tag} words) is added to it here by every CTA in the same (rank) order.  Returns 1/rms: y = inv * W (x . gamma).
-TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, const uint2 *delta, uint32_t tag, const float *gamma, int token, bool first,
-                           bool emit, int cta, int ctid, int cw, int lane, int p, int nphase) {
-    const int units = op.IC / 8;
+TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, PairCtx &pc, const uint2 *delta, uint32_t tag, const float *gamma, int token,
+                           bool first, bool emit, int cta, int ctid, int cw, int lane, int p, int nphase) {
+    const int units = own_groups(pc, op.NG) * 16;  // pair mode: this CTA keeps (and normalises) every other 128-group of the residual stream
     const bool sys = a.tp_size > 1;
+    if (pc.on && emit) {
+        if (ctid == 0) rx_expect(sm, pc, (uint32_t)peer_groups(pc, op.NG) * 524u + (uint32_t)kCW * 4u);  // + the partner's 16 partial sums of squares
+        wait_partner_free(sm, pc, p);
+    }
     float ss = 0.f;
     for (int ui0 = 0; ui0 < units; ui0 += kConsumerThreads) {  // warp-uniform trip count
         const int u = ui0 + ctid;
         const bool valid = u < units;
-        const int ui = valid ? rot_unit(u, units, cta) : 0;
+        int ui = 0;
+        if (valid) {
+            const int ru = rot_unit(u, units, cta);
+            ui = pc.on ? (((ru >> 4) * 2 + (int)pc.rank) << 4) | (ru & 15) : ru;
+        }
         float x[8], v[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) x[i] = 0.f;
@@ -514,11 +613,15 @@ TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, con
                 const float4 r1 = *reinterpret_cast<const float4 *>(sm.resid + (size_t)ui * 8 + 4);
                 x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; x[3] = r0.w;
                 x[4] = r1.x; x[5] = r1.y; x[6] = r1.z; x[7] = r1.w;
-                for (int pr = 0; pr < a.tp_size; pr++) {  // residual += sum over ranks, in rank order (bit-identical everywhere)
+                // residual += sum over ranks, in rank order (bit-identical everywhere).  The slots of up to four ranks are requested together:
+                // one L2 round trip per batch instead of one per rank (measured at P = 8: the per-rank round trips made 8 GPUs slower than 4)
+                if (a.tp_size == 1) {
                     uint4 w[4];
-                    wait_ll2xN<4>(delta + (size_t)pr * a.E + (size_t)ui * 8, tag, sys, w);
+                    wait_ll2xN<4>(delta + (size_t)ui * 8, tag, false, w);
                     x[0] += __uint_as_float(w[0].x); x[1] += __uint_as_float(w[0].z); x[2] += __uint_as_float(w[1].x); x[3] += __uint_as_float(w[1].z);
                     x[4] += __uint_as_float(w[2].x); x[5] += __uint_as_float(w[2].z); x[6] += __uint_as_float(w[3].x); x[7] += __uint_as_float(w[3].z);
+                } else {
+                    tp_accumulate(x, delta + (size_t)ui * 8, a.tp_size, a.E, tag);
                 }
                 if (ui0 == 0 && ctid == 0) stamp(a, cta, nphase, p, 4);
             }
@@ -530,17 +633,25 @@ TCE_DEVINL float stage_rms(const Args &a, const GemvOp &op, const PSmem &sm, con
             for (int i = 0; i < 8; i++) ss += x[i] * x[i];
             v[0] = x[0] * g0.x; v[1] = x[1] * g0.y; v[2] = x[2] * g0.z; v[3] = x[3] * g0.w;
             v[4] = x[4] * g1.x; v[5] = x[5] * g1.y; v[6] = x[6] * g1.z; v[7] = x[7] * g1.w;
-            gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, ui, valid, v, lane);
+            if (pc.on)
+                gemv::emit_unit<1, true>(sm.xs, op.IC, sm.gx, sm.gsum, ui, valid, v, lane, &pc.dst);
+            else
+                gemv::emit_unit<1>(sm.xs, op.IC, sm.gx, sm.gsum, ui, valid, v, lane);
         }
     }
     if (!emit) return 1.f;
     ss = warp_sum(ss);
-    if (lane == 0) sm.rms[cw] = ss;
+    // partial sums of squares: slot (staging rank, warp) on both CTAs of a pair, so that both add them in the same order
+    if (lane == 0) {
+        sm.rms[pc.rank * kCW + cw] = ss;
+        if (pc.on) gemv::st_async_b32(pc.r_rms + (uint32_t)(pc.rank * kCW + cw) * 4u, __float_as_uint(ss), pc.dst.bar);
+    }
     if (ctid == 0) stamp(a, cta, nphase, p, 5);
     named_bar_sync(1, kConsumerThreads);
+    if (pc.on) rx_wait(sm, pc);
     float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < kCW; w++) tot += sm.rms[w];
+    const int nparts = pc.on ? 2 * kCW : kCW;
+    for (int w = 0; w < nparts; w++) tot += sm.rms[w];
     return rsqrtf(tot / (float)op.IC + a.eps);  // LlamaRMSNorm (llm/src/ops/LlamaRMSNorm.cc): x / sqrt(mean(x^2) + eps) * weight
 }
 
@@ -1034,9 +1145,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             mbar_init(&sm.red_empty[lane - 16], 1);
         }
         if (lane == 31) *sm.issued = 0;
+        if (lane == 30) {
+            mbar_init(sm.rx, 1);
+            *sm.free_gen = 0;
+        }
         mbar_fence_init();
     }
     __syncthreads();
+    PairCtx pc;
+    if (a.pair) {
+        // both CTAs of the cluster have initialised their barriers before either sends
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        pc.on = true;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(pc.rank));
+        const uint32_t peer = pc.rank ^ 1u;
+        pc.dst.xs = map_to_cta(sm.xs_u32, peer);
+        pc.dst.gx = map_to_cta(sm.gx_u32, peer);
+        pc.dst.gsum = map_to_cta(sm.gsum_u32, peer);
+        pc.dst.bar = map_to_cta(smem_u32(sm.rx), peer);
+        pc.r_rms = map_to_cta(smem_u32(sm.rms), peer);
+        pc.r_free = map_to_cta(smem_u32(sm.free_gen), peer);
+    }
     // phase p = 5 * layer + k, k: 0 RMSNorm + q|k|v, 1 attention, 2 o_proj, 3 RMSNorm + gate|up, 4 down_proj; p = 5 * Lyr: lm_head
     const int nphase = 5 * Lyr + 1;
     const unsigned epoch = *a.epoch;
@@ -1104,6 +1234,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
             attention_phase(a, a.layers[l], sm, rs, tag_in, tag_base + 2u * (uint32_t)p + 1u, tag_base + 2u * (uint32_t)p, cta, ncta, pos, ctid, cw, lane, p, nphase);
             if (ctid == 0) stamp(a, cta, nphase, p, 2);
             named_bar_sync(1, kConsumerThreads);  // the scratch aliases the activation planes of the next phase
+            if (pc.on && ctid == 0) st_cluster_u32(pc.r_free, (uint32_t)(p + 1));  // the partner may mirror the next phase's planes into this CTA
             continue;
         }
         const int oi = (l == Lyr) ? OPI_LMHEAD : ((k == 0) ? OPI_QKV : (k - 1));
@@ -1111,16 +1242,22 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
         int t0, t1;
         partition(op, cta, ncta, t0, t1);
         const bool work = t1 > t0;
+        bool stage = work;  // pair mode: a CTA stages its half whenever either CTA of the pair has tiles in this phase
+        if (pc.on) {
+            int u0, u1;
+            partition(op, cta ^ 1, ncta, u0, u1);
+            stage = work || u1 > u0;
+        }
         float inv = 1.f;
         if (oi == OPI_O) {
-            if (work) stage_half(a, op, sm, a.attn_ll, tag_in, cta, ctid, lane, p, nphase);
+            if (stage) stage_half(a, op, sm, pc, a.attn_ll, tag_in, cta, ctid, lane, p, nphase);
         } else if (oi == OPI_DOWN) {
-            if (work) stage_half(a, op, sm, a.act_ll, tag_in, cta, ctid, lane, p, nphase);
+            if (stage) stage_half(a, op, sm, pc, a.act_ll, tag_in, cta, ctid, lane, p, nphase);
         } else {
             // the residual copy of this CTA must see every o_proj / down_proj output, whether or not the CTA owns tiles of this phase
             const float *gamma = (oi == OPI_LMHEAD) ? a.final_norm : (oi == OPI_QKV ? a.layers[l].input_norm : a.layers[l].post_norm);
             const uint2 *delta = (oi == OPI_GATEUP) ? a.delta_ll[0] : a.delta_ll[1];
-            inv = stage_rms(a, op, sm, delta, tag_in, gamma, token, p == 0, work, cta, ctid, cw, lane, p, nphase);
+            inv = stage_rms(a, op, sm, pc, delta, tag_in, gamma, token, p == 0, stage, cta, ctid, cw, lane, p, nphase);
         }
         if (ctid == 0) stamp(a, cta, nphase, p, 1);
         if (work) {
@@ -1131,6 +1268,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_persistent_kernel(const __
         }
         if (ctid == 0) stamp(a, cta, nphase, p, 2);
         named_bar_sync(1, kConsumerThreads);  // every warp is done with the planes before the next phase overwrites them
+        if (pc.on && ctid == 0 && p + 1 < nphase) st_cluster_u32(pc.r_free, (uint32_t)(p + 1));  // (not after the last phase: the partner may be gone)
     }
     // ---- greedy token: decoded once every CTA's epilogue has contributed its maximum ----
     if (cta == 0 && ctid == 0) {
@@ -1298,6 +1436,30 @@ cudaError_t encode_kv_tmap(CUtensorMap *out, const void *kv, long long rows) {
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// can the grid run as co-resident clusters of two CTAs (one per TPC)?
+bool pair_supported(Ctx *ctx, const Args &a) {
+    if (ctx->num_sms % 2) return false;
+    const size_t smem = smem_bytes(a);
+    if (cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin) != cudaSuccess) return false;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctx->num_sms);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, decode_persistent_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return nclusters * 2 >= ctx->num_sms;
+}
+
 cudaError_t launch(Ctx *ctx, const Args &a, cudaStream_t stream) {
     const size_t smem = smem_bytes(a);
     if ((int)smem > ctx->smem_optin) return cudaErrorInvalidConfiguration;
@@ -1308,11 +1470,18 @@ cudaError_t launch(Ctx *ctx, const Args &a, cudaStream_t stream) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident: they wait for each other's results
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (a.pair) {  // clusters of two CTAs (one TPC) share the activation staging over distributed shared memory
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     return cudaLaunchKernelEx(&cfg, decode_persistent_kernel, a);
 }
 

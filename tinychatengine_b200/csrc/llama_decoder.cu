@@ -475,6 +475,7 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     }
     if (a.nst < 2) return no("shared memory too small for the persistent kernel");
     a.l2_prefetch = getenv("TCE_PK_L2_PREFETCH") ? atoi(getenv("TCE_PK_L2_PREFETCH")) : 0;
+    a.pair = 0;  // decided below, once the shared-memory footprint is known
 
     auto dalloc = [&](size_t bytes) -> void * {
         void *p = nullptr;
@@ -594,6 +595,9 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         DCK(cudaMemset(a.dbg, 0, n));
     }
     if ((int)pk::smem_bytes(a) > ctx_->smem_optin) return no("shared memory");
+    // pair staging (clusters of two CTAs share the activation staging over DSMEM): on unless switched off or the device cannot co-schedule
+    // num_sms / 2 such clusters (+3 % on one B200, profiles/README.md)
+    a.pair = (!getenv("TCE_PK_PAIR") || atoi(getenv("TCE_PK_PAIR")) != 0) && pk::pair_supported(ctx_, a) ? 1 : 0;
     pargs_ = a;
     return cudaSuccess;
 }

@@ -88,6 +88,8 @@ struct Args {
     int nsplit_max;
     int nst;                     // ring depth
     int l2_prefetch;             // 1: a second producer warp prefetches the stages into L2 ahead of the loader
+    int pair;                    // 1: launched as clusters of two CTAs that share the activation staging: each polls and quantises every other
+                                 // 128-group and mirrors the result into its partner's shared memory (st.async over DSMEM)
     int xs_bytes;                // activation-plane buffer (also the attention scratch)
     int max_ng;
     // tensor parallel (tp_size > 1): every rank writes its o_proj / down_proj outputs into slot `tp_rank` of every rank's delta buffers
@@ -104,6 +106,7 @@ int pick_stages(int smem_optin, int xs_bytes, int max_ng, int E);
 int attn_scratch_bytes(int nrep);
 int attn_nsplit_max(int ncta, int KVH, int max_ctx);
 cudaError_t launch(Ctx *ctx, const Args &a, cudaStream_t stream);
+bool pair_supported(Ctx *ctx, const Args &a);  // the grid fits as co-resident clusters of two CTAs
 // one-off repack of a (possibly multi-segment / gate-up paired) matrix's scales and zeros into per-stage records
 cudaError_t repack_meta(Ctx *ctx, const W4Seg *segs, int nseg, int pair, int IC, uint8_t *out, cudaStream_t stream);
 cudaError_t encode_kv_tmap(CUtensorMap *out, const void *kv, long long rows);
