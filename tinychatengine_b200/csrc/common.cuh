@@ -91,6 +91,15 @@ TCE_DEVINL void tma_load_2d_pred(void *dst_smem, const void *tmap, int x, int y,
         : "memory");
 }
 
+TCE_DEVINL void tma_load_3d_pred(void *dst_smem, const void *tmap, int x, int y, int z, uint64_t *bar, uint64_t policy, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %7, 0;\n\t"
+        "@p cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;\n\t}" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(policy), "r"(pred)
+        : "memory");
+}
+
 TCE_DEVINL void bulk_g2s_nohint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))

@@ -153,6 +153,11 @@ TCE_DEVINL void tma_prefetch_2d_pred(const void *tmap, int x, int y, uint32_t pr
                  "r"(pred)
                  : "memory");
 }
+TCE_DEVINL void tma_prefetch_3d_pred(const void *tmap, int x, int y, int z, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t@p cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n\t}" ::"l"(tmap), "r"(x),
+                 "r"(y), "r"(z), "r"(pred)
+                 : "memory");
+}
 TCE_DEVINL void bulk_prefetch_pred(const void *src, uint32_t bytes, uint32_t pred) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}" ::"l"(src), "r"(bytes), "r"(pred) : "memory");
 }
@@ -340,9 +345,15 @@ TCE_DEVINL void produce_gemv(const GemvOp &op, const CUtensorMap *m0, const uint
                 const int xw = (kStageGroups * s + pl.b0[b]) * 16;  // first 32-bit word of the box within the row
                 uint8_t *d = dst + pl.off[b];
                 if (op.pair) {  // matrices of an op are kMapsPerMat maps apart
-                    if (PF) {
+                    if (PF && op.unit) {
+                        tma_prefetch_3d_pred(m0 + pl.map[b], 0, tile * 8, xw >> 4, leader);
+                        tma_prefetch_3d_pred(m0 + kMapsPerMat + pl.map[b], 0, tile * 8, xw >> 4, leader);
+                    } else if (PF) {
                         tma_prefetch_2d_pred(m0 + pl.map[b], xw, tile * 8, leader);
                         tma_prefetch_2d_pred(m0 + kMapsPerMat + pl.map[b], xw, tile * 8, leader);
+                    } else if (op.unit) {
+                        tma_load_3d_pred(d, m0 + pl.map[b], 0, tile * 8, xw >> 4, bar, policy, leader);
+                        tma_load_3d_pred(d + 8 * pl.bw[b] * 64, m0 + kMapsPerMat + pl.map[b], 0, tile * 8, xw >> 4, bar, policy, leader);
                     } else {
                         tma_load_2d_pred(d, m0 + pl.map[b], xw, tile * 8, bar, policy, leader);
                         tma_load_2d_pred(d + 8 * pl.bw[b] * 64, m0 + kMapsPerMat + pl.map[b], xw, tile * 8, bar, policy, leader);
@@ -358,8 +369,12 @@ TCE_DEVINL void produce_gemv(const GemvOp &op, const CUtensorMap *m0, const uint
                             m = m0 + 2 * kMapsPerMat;
                         }
                     }
-                    if (PF)
+                    if (PF && op.unit)
+                        tma_prefetch_3d_pred(m + pl.map[b], 0, row, xw >> 4, leader);
+                    else if (PF)
                         tma_prefetch_2d_pred(m + pl.map[b], xw, row, leader);
+                    else if (op.unit)
+                        tma_load_3d_pred(d, m + pl.map[b], 0, row, xw >> 4, bar, policy, leader);
                     else
                         tma_load_2d_pred(d, m + pl.map[b], xw, row, bar, policy, leader);
                 }
@@ -715,7 +730,10 @@ TCE_DEVINL void consume_gemv_dense(const GemvOp &op, const PSmem &sm, Ring &rs, 
     int t0, t1;
     partition(op, cta, ncta, t0, t1);
     const int NG = op.NG, S = op.S;
-    const uint32_t w_lane = (uint32_t)g * 1024u + (uint32_t)t * 16u + (uint32_t)cw * 64u;               // row g of group cw, this lane's 16-byte chunk
+    // row g of group cw, this lane's 16-byte chunk.  Row-major boxes: rows 1 KiB apart (2-way bank conflict between rows g, g + 1 of a quarter-warp);
+    // unit boxes: the 16 rows of a group 64 B apart (conflict free), gate | up pairs as two 8-row regions
+    const uint32_t w_lane = op.unit ? (uint32_t)cw * (op.pair ? 512u : 1024u) + (uint32_t)g * 64u + (uint32_t)t * 16u : (uint32_t)g * 1024u + (uint32_t)t * 16u + (uint32_t)cw * 64u;
+    const uint32_t wb_off = op.unit ? (op.pair ? 8192u : 512u) : 8192u;  // row g + 8
     const uint32_t m_lane = (uint32_t)kMetaOff + (uint32_t)(cw * 8 + g) * 4u;                            // scales of rows g, g + 8 of group cw
     const uint32_t z_lane = (uint32_t)kMetaOff + 1024u + (uint32_t)(cw * 8 + g) * 2u;
     const uint32_t x_lane = sm.xs_u32 + (uint32_t)((g >> 1) & 1) * (uint32_t)op.IC * 2u + (uint32_t)(t * 2 + (g & 1)) * 16u + (uint32_t)cw * 256u;
@@ -733,7 +751,7 @@ TCE_DEVINL void consume_gemv_dense(const GemvOp &op, const PSmem &sm, Ring &rs, 
             const uint32_t xb_ = x_lane + (uint32_t)s * (kStageGroups * 256u), sb_ = s_lane + (uint32_t)s * (kStageGroups * 8u), qb_ = q_lane + (uint32_t)s * (kStageGroups * 4u);
             UnitRegs u0, u1;
             u0.wa = lds_u4(wb_);
-            u0.wb = lds_u4(wb_ + 8192u);
+            u0.wb = lds_u4(wb_ + wb_off);
             u0.xe = u0.xo = u1.xe = u1.xo = make_uint4(0u, 0u, 0u, 0u);
             if (xl) {
                 u0.xe = lds_u4(xb_);
@@ -745,7 +763,7 @@ TCE_DEVINL void consume_gemv_dense(const GemvOp &op, const PSmem &sm, Ring &rs, 
             u0.st = lds_f32(qb_);
             if (two) {
                 u1.wa = lds_u4(wb_ + 16384u);
-                u1.wb = lds_u4(wb_ + 16384u + 8192u);
+                u1.wb = lds_u4(wb_ + 16384u + wb_off);
                 if (xl) {
                     u1.xe = lds_u4(xb_ + 4096u);
                     u1.xo = lds_u4(xb_ + 4096u + 128u);

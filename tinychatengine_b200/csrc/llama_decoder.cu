@@ -457,6 +457,9 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         a.op[i].plan[1] = (NG > pk::kStageGroups && rem) ? pk::make_box_plan(rem, widths[i], &nwidths[i]) : a.op[i].plan[0];
         for (int k = 0; k < pk::kMaxBoxes; k++)
             if ((k < a.op[i].plan[0].nbox && a.op[i].plan[0].map[k] < 0) || (k < a.op[i].plan[1].nbox && a.op[i].plan[1].map[k] < 0)) return no("too many box widths");
+        // unit boxes ([group][row][64 B], conflict-free LDS.128) where the dense consumer applies (every stage made of 16-group boxes)
+        static const bool want_units = !getenv("TCE_PK_UNIT_BOXES") || atoi(getenv("TCE_PK_UNIT_BOXES")) != 0;  // default on: +1.3 % (profiles/README.md)
+        a.op[i].unit = (want_units && a.op[i].plan[0].bw[0] == 16 && (NG & 15) == 0) ? 1 : 0;
         if (a.op[i].IC > max_ic) max_ic = a.op[i].IC;
         if (a.op[i].NG > max_ng) max_ng = a.op[i].NG;
         if (a.op[i].IC % kW4Group || a.op[i].num_tiles < 1) return no("bad GEMV shape");
@@ -496,7 +499,8 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
         for (int i = 0; i < 7; i++) {
             const pk::GemvOp &o = a.op[opi[i]];
             for (int k = 0; k < nwidths[opi[i]]; k++)
-                DCK(encode_w4_tmap(&maps[((size_t)l * 7 + i) * pk::kMapsPerMat + k], t7[i]->w, t7[i]->oc, t7[i]->ic, widths[opi[i]][k], o.pair ? 8 : 16));
+                DCK((o.unit ? encode_w4_tmap_units : encode_w4_tmap)(&maps[((size_t)l * 7 + i) * pk::kMapsPerMat + k], t7[i]->w, t7[i]->oc, t7[i]->ic, widths[opi[i]][k],
+                                                                   o.pair ? 8 : 16));
         }
         pk::LayerDesc &D = descs[l];
         memset(&D, 0, sizeof(D));
@@ -521,7 +525,8 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     {
         const pk::GemvOp &o = a.op[pk::OPI_LMHEAD];
         for (int k = 0; k < nwidths[pk::OPI_LMHEAD]; k++)
-            DCK(encode_w4_tmap(&maps[(size_t)Lyr * 7 * pk::kMapsPerMat + k], w_.lm_head.w, w_.lm_head.oc, w_.lm_head.ic, widths[pk::OPI_LMHEAD][k], 16));
+            DCK((o.unit ? encode_w4_tmap_units : encode_w4_tmap)(&maps[(size_t)Lyr * 7 * pk::kMapsPerMat + k], w_.lm_head.w, w_.lm_head.oc, w_.lm_head.ic,
+                                                               widths[pk::OPI_LMHEAD][k], 16));
         uint8_t *m = (uint8_t *)dalloc((size_t)o.num_tiles * o.S * pk::kMetaBytes);
         if (!m) return cudaErrorMemoryAllocation;
         const W4Seg lm[1] = {seg_of(w_.lm_head)};

@@ -50,6 +50,7 @@ struct GemvOp {
     int nseg, pair;      // row segments (q|k|v = 3); pair = gate/up interleave
     int rows0, rows1;    // rows of segments 0 and 1 (tile -> segment)
     int x_mode, epi;
+    int unit;            // 1: the op's tensor maps are the 3-D [group][row][64 B] views: a (tile, group) unit is 1 KiB contiguous in the stage
 };
 
 struct LayerDesc {       // per layer, global memory
