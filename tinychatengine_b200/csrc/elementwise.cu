@@ -112,18 +112,33 @@ __global__ void rmsnorm_f16_kernel(const __half *__restrict__ x, const float *__
 // row is spread over the block, with the reference's operation order and no FMA contraction.  One block per row.
 __global__ void layernorm_q_kernel(const float *__restrict__ x, const float *__restrict__ weight, const float *__restrict__ bias, int8_t *__restrict__ out,
                                    int dim) {
-    extern __shared__ float srow[];  // [dim] + 2
+    extern __shared__ __align__(16) float srow[];  // [dim] + 2
     const float *xr = x + (size_t)blockIdx.x * dim;
     for (int i = threadIdx.x; i < dim; i += blockDim.x) srow[i] = xr[i];
     __syncthreads();
     if (threadIdx.x == 0) {
+        // 16-byte loads in front of the dependent add chains: the chain (4 cycles per element) is what remains
         float mean = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < dim; k++) mean = __fadd_rn(mean, srow[k]);
+        int k = 0;
+        for (; k + 4 <= dim; k += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(srow + k);
+            mean = __fadd_rn(mean, v.x);
+            mean = __fadd_rn(mean, v.y);
+            mean = __fadd_rn(mean, v.z);
+            mean = __fadd_rn(mean, v.w);
+        }
+        for (; k < dim; k++) mean = __fadd_rn(mean, srow[k]);
         mean = __fdiv_rn(mean, (float)dim);
         float sq = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < dim; k++) {
+        for (k = 0; k + 4 <= dim; k += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(srow + k);
+            const float d0 = __fsub_rn(v.x, mean), d1 = __fsub_rn(v.y, mean), d2 = __fsub_rn(v.z, mean), d3 = __fsub_rn(v.w, mean);
+            sq = __fadd_rn(sq, __fmul_rn(d0, d0));
+            sq = __fadd_rn(sq, __fmul_rn(d1, d1));
+            sq = __fadd_rn(sq, __fmul_rn(d2, d2));
+            sq = __fadd_rn(sq, __fmul_rn(d3, d3));
+        }
+        for (; k < dim; k++) {
             const float d = __fsub_rn(srow[k], mean);
             sq = __fadd_rn(sq, __fmul_rn(d, d));
         }

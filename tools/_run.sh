@@ -1,3 +1,3 @@
 set -x
-TCE_PK_PAIR=0 timeout 600 ncu --set full --import-source on --clock-control none -k regex:decode_persistent -s 3 -c 1 -f -o gpurun_out/r02_pk_final python bench.py --steps 1 --warmup 3 --ctx 2048 --no-cpu-baseline --no-extras > gpurun_out/r02_ncu_final.log 2>&1; tail -3 gpurun_out/r02_ncu_final.log | cut -c1-200
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"w8a8|gemm_tc|opt_int8|layernorm|add_f32|attn" -c 400 --csv --log-file gpurun_out/r02_w8a8_launches.csv python tools/w8a8_layer_bench.py > gpurun_out/r02_w8a8_ncu.log 2>&1; tail -2 gpurun_out/r02_w8a8_ncu.log | cut -c1-300; wc -l gpurun_out/r02_w8a8_launches.csv
+timeout 900 python -m pytest tests/test_gpu_opt_attention.py tests/test_gpu_callsites.py tests/test_gpu_misc.py tests/test_gpu_host_cpp.py -q --timeout 600 > gpurun_out/r02_t_opt.log 2>&1; tail -5 gpurun_out/r02_t_opt.log
+timeout 300 python tools/w8a8_layer_bench.py > gpurun_out/r02_w8a8_layer.json 2>&1; tail -1 gpurun_out/r02_w8a8_layer.json | cut -c1-700
