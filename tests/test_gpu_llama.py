@@ -201,3 +201,38 @@ def test_load_dir_reference_tree(tmp_path):
     for m in (a, b, c):
         m.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("mega", ["1", "0"])
+def test_device_resident_token_and_position_are_range_checked(mega, monkeypatch):
+    """tce_llama_decode takes {token, position} from device memory, so the host cannot validate them: the kernels must.  A position beyond the
+    cache / a token beyond the table neither crashes nor writes outside the KV slab (the next valid step still matches a fresh model), on the
+    persistent kernel and on the kernel-per-op path."""
+    monkeypatch.setenv("TCE_PERSISTENT", mega)
+    from tinychatengine_b200.llama import GEOMETRIES, LlamaModel
+    from tinychatengine_b200.runtime import Context
+
+    ctx = Context(0)
+    g = GEOMETRIES["tiny-gqa"]
+    a = LlamaModel(ctx, g, max_ctx=32, seed=4)
+    b = LlamaModel(ctx, g, max_ctx=32, seed=4)
+    la, lb = torch.empty(g.vocab_size), torch.empty(g.vocab_size)
+    assert a.decode_host(5, 0, la) == b.decode_host(5, 0, lb)
+    kv_before = [a.kv_cache(l, w).clone() for l in range(g.num_layers) for w in (0, 1)]
+    for bad in ([5, 32], [5, 10**6], [5, -1], [g.vocab_size, 31], [-3, 31]):
+        a.decode(torch.tensor(bad, dtype=torch.int32, device="cuda"))
+    torch.cuda.synchronize()
+    kv_after = [a.kv_cache(l, w) for l in range(g.num_layers) for w in (0, 1)]
+    # rows 1..30 were never legitimately written: still zero on the persistent kernel (it refuses the step); the per-op path clamps the position into
+    # the slab, which may touch the last row but nothing outside the tensor
+    for x, y in zip(kv_before, kv_after):
+        assert torch.equal(x[:, 1:31], y[:, 1:31])
+    na, nb = a.decode_host(7, 1, la), b.decode_host(7, 1, lb)
+    assert na == nb
+    if mega == "1":
+        assert torch.equal(la, lb)
+    else:  # the kernel-per-op path finishes split tiles with fp32 atomics: equal up to summation order
+        assert float((la - lb).abs().max() / lb.abs().max()) < 1e-5
+    a.close()
+    b.close()
+    ctx.close()

@@ -114,6 +114,7 @@ int tce_ctx_destroy(tce_ctx *ctx) {
 int tce_ctx_set_stream(tce_ctx *ctx, void *s) {
     if (!ctx) return fail(TCE_ERR_INVALID, "null ctx");
     ctx->c.stream = (cudaStream_t)s;
+    ctx->c.option_gen++;
     return TCE_OK;
 }
 
@@ -164,6 +165,7 @@ int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
         ctx->attn_chunk = value;
     else
         return fail(TCE_ERR_INVALID, "unknown option %s", name);
+    ctx->c.option_gen++;  // graphs captured under the old settings are stale
     return TCE_OK;
 }
 

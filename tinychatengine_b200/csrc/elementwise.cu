@@ -7,10 +7,23 @@
 namespace tce {
 namespace {
 
-__global__ void embedding_kernel(const __half *__restrict__ table, const int *__restrict__ token, float *__restrict__ resid, int E) {
+// `guard` (optional): {rows of the table, max_ctx} bound the device-resident {token, position}; out-of-range values are clamped before any kernel of the
+// step uses them (the attention kernel reads the position from safe[1]) and flagged in safe[2], so a bad id can never index past the table / KV slab
+__global__ void embedding_kernel(const __half *__restrict__ table, const int *__restrict__ token, float *__restrict__ resid, int E, int rows, int max_ctx,
+                                 int *__restrict__ safe) {
     pdl_launch_dependents();
     pdl_wait();
-    const int tok = *token;
+    int tok = *token;
+    if (safe) {
+        const int pos = token[1];
+        const bool bad = tok < 0 || tok >= rows || pos < 0 || pos >= max_ctx;
+        tok = tok < 0 ? 0 : (tok >= rows ? rows - 1 : tok);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            safe[0] = tok;
+            safe[1] = pos < 0 ? 0 : (pos >= max_ctx ? max_ctx - 1 : pos);
+            safe[2] = bad ? 1 : 0;
+        }
+    }
     const __half2 *row = reinterpret_cast<const __half2 *>(table + (size_t)tok * E);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E / 2; i += gridDim.x * blockDim.x) {
         const float2 f = __half22float2(row[i]);
@@ -256,11 +269,11 @@ cudaError_t launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, dim3 
 
 }  // namespace
 
-cudaError_t launch_embedding(Ctx *ctx, const __half *table, const int *token, float *resid, int E, bool pdl) {
+cudaError_t launch_embedding(Ctx *ctx, const __half *table, const int *token, float *resid, int E, bool pdl, int rows, int max_ctx, int *safe) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     launch_cfg(cfg, attr, dim3(4), dim3(256), ctx->stream, pdl);
-    return cudaLaunchKernelEx(&cfg, embedding_kernel, table, token, resid, E);
+    return cudaLaunchKernelEx(&cfg, embedding_kernel, table, token, resid, E, rows, max_ctx, safe);
 }
 
 cudaError_t launch_argmax(Ctx *ctx, const float *logits, int n, int *out, bool pdl) {

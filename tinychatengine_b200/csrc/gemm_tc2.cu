@@ -54,6 +54,8 @@ struct PairArgs {
     void *C;
     long long ldc;
     int add_f32;
+    int pn;      // output columns per tile of the fp16-weight kernel: 256, or 128 where 256-wide tiles quantise badly onto the 74 clusters (N = 5120:
+                 // 160 tiles = 2.16 waves); each CTA stages pn / 2 weight rows.  The fused and SiLU variants use 256.
     int silu_F;  // > 0: W = [gate (F rows); up (F rows)], the pair's two halves are the SAME 128 channels of gate (CTA 0) and up (CTA 1), and the
                  // epilogue writes act[M][F] = SiLU(gate) * up (SiLuMul_half, llm/src/nn_modules/cuda/Int4llamaDecoderLayer.cu:12-30; fp32 math)
 };
@@ -196,7 +198,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads
             for (int t = cl; t < tiles_total; t += ncl) {
                 const int mb = t % a.m_blocks, nb = t / a.m_blocks;
                 const int row0 = mb * 256 + (int)rank * kBlockM;
-                const int wrow0 = a.silu_F > 0 ? nb * kHalfN + (int)rank * a.silu_F : nb * kPairN + (int)rank * kHalfN;
+                const int pn = FUSED ? kPairN : a.pn, hn = pn >> 1;
+                const int wrow0 = a.silu_F > 0 ? nb * kHalfN + (int)rank * a.silu_F : nb * pn + (int)rank * hn;
                 for (int kb = 0; kb < a.k_blocks; kb++) {
                     mbar_wait(&a_empty[s], ph ^ 1u);
                     uint8_t *dst = sSlot + (size_t)s * C::kSlotBytes;
@@ -204,7 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads
                         if (leader) mbar_arrive_expect_tx(&a_full[s], 2 * kABytes);
                         tma_load_2d_pair(dst, &a.tmA, kb * 64, row0, &a_full[s]);
                     } else {
-                        if (leader) mbar_arrive_expect_tx(&a_full[s], 2 * (kABytes + kBHalfBytes));
+                        if (leader) mbar_arrive_expect_tx(&a_full[s], 2 * (kABytes + hn * 128));
                         tma_load_2d_pair(dst, &a.tmA, kb * 64, row0, &a_full[s]);
                         tma_load_2d_pair(dst + kABytes, &a.tmB, kb * 64, wrow0, &a_full[s]);
                     }
@@ -219,7 +222,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------- MMA issuer (leader CTA only)
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(kPairN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // F32 acc, f16 x f16, K-major, N 256, M 256
+            const uint32_t idesc = (1u << 4) | ((uint32_t)((FUSED ? kPairN : a.pn) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // F32 acc, f16 x f16, K-major, N, M 256
             int s = 0, os = 0, it = 0;
             uint32_t ph = 0, oph = 0;
             for (int t = cl; t < tiles_total; t += ncl, it++) {
@@ -288,12 +291,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<FUSED>::kThreads
                 mbar_arrive_cluster(&tempty_bar[acc], 0);
                 continue;
             }
+            const int pn = FUSED ? kPairN : a.pn;
 #pragma unroll 1
-            for (int c = 0; c < kPairN / 32; c++) {
+            for (int c = 0; c < pn / 32; c++) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
                 tmem_ld_wait();
-                const int col0 = nb * kPairN + c * 32;
+                const int col0 = nb * pn + c * 32;
                 if (row < a.M && col0 < a.N) {
                     const int n = min(32, a.N - col0);
                     if (a.add_f32) {
@@ -428,10 +432,10 @@ EncodeFn2 encoder2() {
     return fn;
 }
 
-bool encode_f16(CUtensorMap *out, const void *base, long long rows, long long K, long long ld) {
+bool encode_f16(CUtensorMap *out, const void *base, long long rows, long long K, long long ld, int box_rows = 128) {
     const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)(ld * 2)};
-    const cuuint32_t box[2] = {64u, 128u};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return encoder2()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -475,12 +479,21 @@ int w4_gemm_mode() {
 cudaError_t launch_gemm_f16_pair(Ctx *ctx, const __half *X, long long ldx, const __half *W, long long ldw, void *C, long long ldc, int M, int N, int K, int add_f32) {
     if (M < 1 || N < 1 || K < 64 || (K % 64) || (ldx % 8) || (ldw % 8) || !encoder2()) return cudaErrorInvalidValue;
     PairArgs a = {};
-    if (!encode_f16(&a.tmA, X, M, K, ldx) || !encode_f16(&a.tmB, W, N, K, ldw)) return cudaErrorInvalidValue;
     a.M = M;
     a.N = N;
     a.k_blocks = K / 64;
     a.m_blocks = (M + 255) / 256;
-    a.n_blocks = (N + kPairN - 1) / kPairN;
+    // tile width by wave quantisation over the clusters: rounds x width (x a small penalty for the narrower tile: the activation tile is re-read per N block)
+    const int clusters = ctx->num_sms / 2;
+    auto cost = [&](int pn, double pen) {
+        const long long tiles = (long long)a.m_blocks * ((N + pn - 1) / pn);
+        return (double)((tiles + clusters - 1) / clusters) * pn * pen;
+    };
+    // measured: 128-wide tiles run at 0.70 of the 256-wide rate per FLOP (the activation tile is read twice as often from shared memory), which
+    // costs more than the wave quantisation it removes (13B o / down: 919 / 973 -> 640 / 673 TFLOP/s): a penalty of 1.45 keeps them for tiny N only
+    a.pn = cost(128, 1.45) < cost(256, 1.0) ? 128 : 256;
+    if (!encode_f16(&a.tmA, X, M, K, ldx) || !encode_f16(&a.tmB, W, N, K, ldw, a.pn / 2)) return cudaErrorInvalidValue;
+    a.n_blocks = (N + a.pn - 1) / a.pn;
     a.C = C;
     a.ldc = ldc;
     a.add_f32 = add_f32;
@@ -499,6 +512,7 @@ cudaError_t launch_gemm_f16_pair_silu(Ctx *ctx, const __half *X, long long ldx, 
     a.n_blocks = F / kHalfN;
     a.C = act;
     a.ldc = ldc;
+    a.pn = kPairN;
     a.silu_F = F;
     return launch_pair<false>(ctx, a);
 }
@@ -527,6 +541,7 @@ cudaError_t launch_gemm_w4_pair(Ctx *ctx, const __half *X, long long ldx, const 
     a.k_blocks = K / 64;
     a.m_blocks = (M + 255) / 256;
     a.n_blocks = (N + kPairN - 1) / kPairN;
+    a.pn = kPairN;
     a.C = C;
     a.ldc = ldc;
     a.add_f32 = add_f32;

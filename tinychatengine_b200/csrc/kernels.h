@@ -24,6 +24,7 @@ struct Ctx {
     float *attn_ws = nullptr;
     size_t attn_ws_bytes = 0;
     unsigned *attn_counters = nullptr;
+    unsigned option_gen = 0;       // bumped by every tce_ctx_set_option / set_stream: captured CUDA graphs hold the context by value and are rebuilt
     unsigned attn_seed_epoch = 0;  // calls of the int8 OPT attention so far (tags the in-kernel seed hand-off)
     // decode attention: CTAs per thread-block cluster (one cluster per KV head, DSMEM merge); 0 = independent splits + global merge.
     // Measured on B200: the cluster flavour is 2.2 us per layer SLOWER (cluster co-scheduling + two cluster barriers), so it is off.

@@ -37,7 +37,7 @@ cudaError_t launch_rmsnorm_rows_f32(Ctx *ctx, const float *x, const float *gamma
 cudaError_t launch_silu_mul_rows(Ctx *ctx, const __half *gu, __half *act, int rows, int F);
 
 // resid_f32[E] = (float) table[token][:]   (reference: CPU Embedding + float2half, cuda/Int4llamaDecoder.cu:62-69)
-cudaError_t launch_embedding(Ctx *ctx, const __half *table, const int *token, float *resid, int E, bool pdl);
+cudaError_t launch_embedding(Ctx *ctx, const __half *table, const int *token, float *resid, int E, bool pdl, int rows = 0, int max_ctx = 0, int *safe = nullptr);
 // argmax over fp32 logits -> int (first index of the maximum, like arg_max.cc)
 cudaError_t launch_argmax(Ctx *ctx, const float *logits, int n, int *out, bool pdl);
 

@@ -69,6 +69,8 @@ LlamaDecoder *LlamaDecoder::create(Ctx *ctx, int attn_chunk, const tce_llama_con
     A((void **)&d->d_next_, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(d->d_kv_, 0, kv_elems * sizeof(__half));
     if (e == cudaSuccess) e = cudaMemset(d->d_tokpos_, 0, 4 * sizeof(int));  // [3] = tensor-parallel step counter, advanced on the device
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d->d_tokpos_safe_, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(d->d_tokpos_safe_, 0, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_tokpos_, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_logits_, (size_t)V * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_next_, sizeof(int));
@@ -146,6 +148,7 @@ LlamaDecoder::~LlamaDecoder() {
     cudaFree(d_logits_);
     cudaFree(d_tokpos_);
     cudaFree(d_gen_);
+    cudaFree(d_tokpos_safe_);
     for (int b = 0; b < 2; b++) {
         cudaFree(pf_w16_[b]);
         if (pf_expanded_[b]) cudaEventDestroy(pf_expanded_[b]);
@@ -182,6 +185,7 @@ void *LlamaDecoder::kv_cache(int layer, int which) const {
 static W4Seg seg_of(const tce_w4_tensor &t) { return W4Seg{(const uint32_t *)t.w, (const uint32_t *)t.zeros, (const __half *)t.scales, t.oc}; }
 
 cudaError_t LlamaDecoder::enqueue_gemvs(int *count) {
+    if (tp_ > 1) return cudaErrorNotSupported;  // the GEMVs of a tensor-parallel step poll their peers: without the rest of the step they would spin
     *count = 4 * cfg_.num_layers + 1;
     return enqueue_step(d_tokpos_, ctx_->stream, false, true);
 }
@@ -621,7 +625,9 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
         const bool use_pdl = pdl && !first && tp_ == 1;  // TP steps keep plain edges around the peer-flag kernels
         switch (op.type) {
             case OP_EMBED:
-                if (!gemv_only) DCK(launch_embedding(c, (const __half *)w_.embed_f16, tokpos, d_resid_, cfg_.embed_dim, false));  // residual buffer 0
+                // also range-checks the device-resident {token, position} and publishes the clamped pair for the attention launches of this step
+                if (!gemv_only)
+                    DCK(launch_embedding(c, (const __half *)w_.embed_f16, tokpos, d_resid_, cfg_.embed_dim, false, cfg_.vocab_size * tp_, cfg_.max_ctx, d_tokpos_safe_));
                 break;
             case OP_GEMV: {
                 W4GemvParams p = op.g;
@@ -632,7 +638,7 @@ cudaError_t LlamaDecoder::enqueue_step(const int *tokpos, cudaStream_t s, bool p
             case OP_ATTN:
                 if (!gemv_only) {
                     AttnDecodeArgs a = op.at;
-                    a.pos = tokpos + 1;
+                    a.pos = d_tokpos_safe_ + 1;  // the position after the embedding kernel's range check
                     DCK(launch_attn_decode(c, a, use_pdl));
                 }
                 break;
@@ -678,6 +684,7 @@ cudaError_t LlamaDecoder::build_graphs(std::string *err) {
         if (g) cudaGraphDestroy(g);
         if (e == cudaSuccess) {
             graphs_ok_ = true;
+            graphs_gen_ = ctx_->option_gen;
             if (!pdl) ctx_->use_pdl = false;
             return cudaSuccess;
         }
@@ -697,6 +704,11 @@ cudaError_t LlamaDecoder::decode_host(int token, int pos, float *logits_host, in
     h_tokpos_[1] = pos;
     h_tokpos_[2] = 0;
     cudaStream_t s = ctx_->stream;
+    if (graphs_ok_ && graphs_gen_ != ctx_->option_gen) {  // an option or the stream changed since capture: the graph holds the old context by value
+        cudaGraphExecDestroy(g_host_);
+        g_host_ = nullptr;
+        graphs_ok_ = false;
+    }
     if (use_graphs_ && !graphs_ok_) {
         cudaError_t e = build_graphs(err);
         if (e != cudaSuccess) use_graphs_ = false;
@@ -787,7 +799,7 @@ cudaError_t LlamaDecoder::generate(int first_token, int pos0, int n_predict, con
 cudaError_t LlamaDecoder::decode_device(const int *tokpos_dev, std::string *err) {
     cudaStream_t s = ctx_->stream;
     if (tp_ > 1 && !tp_connected_) return cudaErrorNotReady;
-    if (use_graphs_ && (g_dev_ == nullptr || g_dev_src_ != tokpos_dev)) {
+    if (use_graphs_ && (g_dev_ == nullptr || g_dev_src_ != tokpos_dev || g_dev_gen_ != ctx_->option_gen)) {
         if (g_dev_) {
             cudaGraphExecDestroy(g_dev_);
             g_dev_ = nullptr;
@@ -814,6 +826,7 @@ cudaError_t LlamaDecoder::decode_device(const int *tokpos_dev, std::string *err)
             }
         }
         g_dev_src_ = tokpos_dev;
+        g_dev_gen_ = ctx_->option_gen;
     }
     if (use_graphs_ && g_dev_) return cudaGraphLaunch(g_dev_, s);
     return enqueue_step(tokpos_dev, s, ctx_->use_pdl);

@@ -116,6 +116,8 @@ class LlamaDecoder {
     cudaGraphExec_t g_dev_ = nullptr;     // copy tokpos (D2D) + step
     const int *g_dev_src_ = nullptr;
     bool graphs_ok_ = false;
+    unsigned graphs_gen_ = 0, g_dev_gen_ = 0;       // ctx_->option_gen at capture time
+    int *d_tokpos_safe_ = nullptr;  // kernel-per-op path: {token, position} after the device-side range check (+ [2] unused, [3] TP step counter alias)
     bool use_graphs_ = true;
     bool atomic_residual_ = true;  // o_proj/down_proj partial tiles use RED.ADD (TCE_DETERMINISTIC=1 turns it off)
     int kernels_per_step_ = 0;

@@ -1,10 +1,12 @@
-// tp.cu -- the small kernels of tensor-parallel decode over NVLink peer memory (no NCCL on the data path).
+// tp.cu -- the small kernels of the KERNEL-PER-OP tensor-parallel decode path (the fallback for shapes outside the persistent kernel's
+// envelope; Llama-3-8B and the other benchmarked geometries run the persistent kernel, where the all-reduce is peer stores of tagged words
+// inside decode_persistent.cu and none of these kernels is launched).  No NCCL on the data path.
 //
 // Collective = all-reduce of the row-parallel GEMV outputs (o_proj, down_proj), realised as
 //   (1) the GEMV epilogue storing its finished fp32 outputs into slot `rank` of EVERY rank's gather buffer
 //       (EPI_TP_SCATTER_F32, w4a16_gemv_impl.cuh: peer stores, tile by tile while the GEMV is still running),
-//   (2) tp_signal_kernel: one release-store of a sequence number into every peer's flag word once the GEMV kernel
-//       has completed (stream order), and
+//   (2) one release-store of a sequence number into every peer's flag word once the GEMV has finished: by the last CTA of the GEMV itself
+//       (fused signal, w4a16_gemv_impl.cuh) -- tp_signal_kernel below is the stand-alone form kept for the arg-max exchange -- and
 //   (3) the next GEMV's prologue: acquire-poll the P local flags, then residual += sum over ranks in rank order
 //       (X_RMSNORM_F32 + tp_in).
 // The greedy token needs one more exchange: every rank scatters the arg-max key of its vocabulary shard.
