@@ -130,13 +130,15 @@ class CpuReferenceDecode:
     down) + lm_head -- cycling over `distinct` separately allocated layers so that the weights do not stay cache resident; attention
     and norms are not included (they are < 1 % of the reference's CPU time at batch 1)."""
 
-    def __init__(self, geom, distinct: int = 4):
+    def __init__(self, geom, distinct: int = 4, threads: int = 0, with_lm_head: bool = True):
         import numpy as np
 
         from oracle import capi
 
         self.np, self.capi, self.geom = np, capi, geom
-        self.cores = os.cpu_count() or 1
+        # the reference's worker pool is a function-local static sized by the FIRST call of the process (kernels/avx/matmul_avx_int8_int4.cc:340), so
+        # the thread count is fixed here, before any call; `threads` = 0: every host thread
+        self.cores = threads if threads > 0 else (os.cpu_count() or 1)
         if capi.ref_available("avx"):
             self.kind, self.X = "reference", capi.ref("avx")
         else:
@@ -146,8 +148,9 @@ class CpuReferenceDecode:
         rng = np.random.default_rng(0)
         self.distinct = max(1, min(distinct, geom.num_layers))
         self.layers = [[(self._make(oc, ic, rng), oc, ic) for oc, ic in shapes] for _ in range(self.distinct)]
-        self.lm = (self._make(geom.vocab_size, E, rng), geom.vocab_size, E)
-        self.token()  # warm-up (also creates the reference's static thread pool with `cores` threads)
+        self.lm = (self._make(geom.vocab_size if with_lm_head else 128, E, rng), geom.vocab_size if with_lm_head else 128, E)
+        if with_lm_head:
+            self.token()  # warm-up (also creates the reference's static thread pool with `cores` threads)
 
     def _make(self, oc, ic, rng):
         np, capi = self.np, self.capi
@@ -177,14 +180,76 @@ class CpuReferenceDecode:
         self._run(*self.lm)
         return time.perf_counter() - t0
 
+    def ops(self):
+        """the linears of one token in execution order: (tensors, oc, ic, weight bytes)"""
+        seq = []
+        for l in range(self.geom.num_layers):
+            for t, oc, ic in self.layers[l % self.distinct]:
+                seq.append((t, oc, ic, oc * ic // 2))
+        seq.append((*self.lm, self.lm[1] * self.lm[2] // 2))
+        return seq
+
+    def slice_runner(self, slices: int):
+        """Bounded samples: a step = the next 1/`slices` of a token's linears (by weight bytes, in execution order, continuing where the previous
+        step stopped), so that `slices` consecutive steps are exactly one full token.  Returns step() -> (seconds, fraction of a token done)."""
+        seq = self.ops()
+        total = float(sum(o[3] for o in seq))
+        state = {"i": 0}
+
+        def step():
+            done, t0 = 0.0, time.perf_counter()
+            while True:
+                t, oc, ic, nbytes = seq[state["i"] % len(seq)]
+                self._run(t, oc, ic)
+                state["i"] += 1
+                done += nbytes
+                if done >= total / slices - 1e-9:
+                    break
+            return time.perf_counter() - t0, done / total
+
+        return step
+
     def describe(self, n):
         g = self.geom
         return (f"{n} full tokens: every linear of a {g.name} decode step ({g.num_layers} layers x 7 + lm_head) through the reference's W4A8 AVX kernel "
                 f"(g32 CPU format), {self.distinct} distinct layers' weights cycled; attention/norms not included")
 
 
+def pick_reference_threads(model: str) -> int:
+    """NUM_THREAD is the reference user's choice (llm/application/chat.cc:123,156).  Its static pthread pool does not scale to every thread of a
+    128-thread host (measured: 128 threads are ~8x slower than 8 on the linears of a token), so the arm uses the best of a few counts, each probed
+    in its own process (the pool size is fixed by a process's first call) on one layer's seven linears."""
+    import subprocess
+
+    cores = os.cpu_count() or 1
+    best, best_t = cores, float("inf")
+    for c in sorted({x for x in (4, 8, 16, 32, 64, cores) if x <= cores}):
+        try:
+            r = subprocess.run([sys.executable, str(Path(__file__).resolve()), "--probe-threads", str(c), "--model", model], capture_output=True, text=True,
+                               timeout=180)
+            t = float(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            continue
+        if t < best_t:
+            best, best_t = c, t
+    return best
+
+
+def probe_threads(args):
+    from tinychatengine_b200.llama import GEOMETRIES
+
+    ref = CpuReferenceDecode(GEOMETRIES[args.model], distinct=1, threads=args.probe_threads, with_lm_head=False)
+    ts = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        for t, oc, ic in ref.layers[0]:
+            ref._run(t, oc, ic)
+        ts.append(time.perf_counter() - t0)
+    print(sorted(ts)[1])
+
+
 def cpu_baseline(geom, budget_s: float):
-    ref = CpuReferenceDecode(geom)
+    ref = CpuReferenceDecode(geom, threads=pick_reference_threads(geom.name))
     times = []
     t0 = time.perf_counter()
     while not times or (time.perf_counter() - t0 < budget_s and len(times) < 16):
@@ -200,20 +265,30 @@ def run_reference(args):
     from tinychatengine_b200.llama import GEOMETRIES
 
     geom = GEOMETRIES[args.model]
-    ref = CpuReferenceDecode(geom)
+    ref = CpuReferenceDecode(geom, threads=pick_reference_threads(geom.name))
+    # a step is a bounded sample of the token: K steps + W warm-up steps must end within a few minutes whatever K is.  One full token costs t_tok on
+    # this host (measured by the constructor's warm-up token and one more here); a step covers 1/slices of a token's linears, continuing in execution
+    # order, so every linear is timed in proportion and `slices` steps are exactly one token.
+    t_tok = ref.token()
+    budget_s = 150.0
+    slices = max(1, int(-(-(args.steps + args.warmup) * t_tok // budget_s)))
+    step = ref.slice_runner(slices)
     for _ in range(args.warmup):
-        ref.token()
+        step()
     t0 = time.perf_counter()
-    times = [ref.token() for _ in range(args.steps)]
+    samples = [step() for _ in range(args.steps)]
     wall = time.perf_counter() - t0
-    tok_s = args.steps / sum(times)
+    times = [t for t, _ in samples]
+    tok_s = sum(f for _, f in samples) / sum(times)
     tp = args.gpus > 1 and args.parallel == "tp"
     line = {"impl": "reference", "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * sum(times) / args.steps, "ms_per_token": 1e3 / tok_s, "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
             "dtype": "w4a8 (int8 act x int4 weight, fp32 acc)", "data": "synthetic",
             "config": workload_config(geom, args, args.gpus, tp),  # the same workload as our arm; the reference has no GPU path here: rank 0's host cores
-            "reference_path": "the reference's AVX W4A8 kernels (oracle/_ref, compiled in place) on all host threads; each step = one full token's linears",
-            "cpu_baseline": {"value": tok_s, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.describe(args.steps)},
+            "reference_path": f"the reference's AVX W4A8 kernels (oracle/_ref, compiled in place) with NUM_THREAD = {ref.cores} (the fastest of 4..{os.cpu_count()} probed on this host); "
+                              f"each step = 1/{slices} of a token's linears in execution order ({slices} steps = one full token)",
+            "cpu_baseline": {"value": tok_s, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                             "sample": f"{args.steps} steps of 1/{slices} token each = {sum(f for _, f in samples):.2f} tokens; " + ref.describe(0).split(": ", 1)[1]},
             "e2e": {"value": tok_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, "wall_s": wall}
     print(json.dumps(line), flush=True)
 
@@ -478,6 +553,7 @@ def main():
     ap.add_argument("--ctx", type=int, default=-1, help="fixed context length for every step (default: sweep 1 -> max_ctx)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--probe-threads", type=int, default=0, help=argparse.SUPPRESS)  # internal: time one layer's linears on the reference with N threads
     ap.add_argument("--no-extras", action="store_true", help="skip gpu_reference / prefill_13b_2048 / w8a8_7b (N = 1 only)")
     # N > 1 default = tensor-parallel decode of ONE sequence (BASELINE config 5, strong scaling); "replicas" = one independent batch-1
     # sequence per GPU (no data-path collective, weak scaling), also reported as `replicas_tok_s` beside the tensor-parallel value
@@ -486,6 +562,9 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.probe_threads:
+        probe_threads(args)
+        return
     if args.impl == "reference":
         if args.steps == 128:
             args.steps = 8  # a full token costs seconds on the host: keep the default invocation within minutes

@@ -40,28 +40,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(const __gr
     attn_item<NREP>(a, smem, bar, flag, parity, blockIdx.x, blockIdx.y, tid, *a.pos, [] { __syncthreads(); });
 }
 
-// Cluster flavour: grid = (CL, KVH), one cluster of CL CTAs per KV head; the context is divided evenly over the CTAs at run time
-// (a.chunk is the shared-memory row capacity = ceil(max_ctx / CL)) and the partial results are merged over distributed shared memory.
-template <int NREP, int CL>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_cluster_kernel(const __grid_constant__ AttnDecodeArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + smem_bytes(NREP, a.chunk));
-    int *flag = reinterpret_cast<int *>(bar + 2);
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    pdl_launch_dependents();
-    pdl_wait();
-    uint32_t rank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    uint32_t parity = 0;
-    attn_item<NREP, CL>(a, smem, bar, flag, parity, blockIdx.y, (int)rank, tid, *a.pos, [] { __syncthreads(); });
-}
-
 size_t attn_smem_bytes(int nrep, int chunk) { return smem_bytes(nrep, chunk) + 2 * sizeof(uint64_t) + 16; }
 
 template <int NREP>
@@ -87,68 +65,12 @@ cudaError_t launch(Ctx *ctx, const AttnDecodeArgs &a, bool pdl) {
     return cudaLaunchKernelEx(&cfg, attn_decode_kernel<NREP>, a);
 }
 
-// returns cudaErrorNotSupported when this cluster size cannot be used (shared memory, or the device cannot co-schedule the cluster)
-template <int NREP, int CL>
-cudaError_t launch_cluster(Ctx *ctx, AttnDecodeArgs a, bool pdl) {
-    a.chunk = (((a.max_ctx + CL - 1) / CL) + 7) & ~7;
-    const size_t smem = attn_smem_bytes(NREP, a.chunk);
-    if ((int)smem > ctx->smem_optin) return cudaErrorNotSupported;
-    auto kern = attn_decode_cluster_kernel<NREP, CL>;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CL, a.num_kv_heads);
-    cfg.blockDim = dim3(kAttnThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    static int usable = -1;  // per instantiation: probed once
-    if (usable < 0) {
-        usable = 0;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
-        if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        int nclusters = 0;
-        cfg.numAttrs = 1;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
-        if (e == cudaSuccess && nclusters >= 1) usable = 1;
-        cudaGetLastError();  // a failed probe must not poison later launches
-    }
-    if (!usable) return cudaErrorNotSupported;
-    cfg.numAttrs = pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, kern, a);
-}
-
-template <int CL>
-cudaError_t launch_cluster_nrep(Ctx *ctx, const AttnDecodeArgs &a, int nrep, bool pdl) {
-    switch (nrep) {
-        case 1: return launch_cluster<1, CL>(ctx, a, pdl);
-        case 2: return launch_cluster<2, CL>(ctx, a, pdl);
-        case 4: return launch_cluster<4, CL>(ctx, a, pdl);
-        case 8: return launch_cluster<8, CL>(ctx, a, pdl);
-        default: return cudaErrorNotSupported;
-    }
-}
-
 }  // namespace
 
 cudaError_t launch_attn_decode(Ctx *ctx, AttnDecodeArgs a, bool pdl) {
     if (a.head_dim != HD) return cudaErrorNotSupported;
     if (a.num_heads % a.num_kv_heads) return cudaErrorInvalidValue;
     const int nrep = a.num_heads / a.num_kv_heads;
-    // preferred: one thread-block cluster per KV head, merge over distributed shared memory (ctx->attn_cluster = 16, 8 or 0 = off)
-    if (ctx->attn_cluster >= 16) {
-        const cudaError_t e = launch_cluster_nrep<16>(ctx, a, nrep, pdl);
-        if (e != cudaErrorNotSupported) return e;
-    }
-    if (ctx->attn_cluster >= 8) {
-        const cudaError_t e = launch_cluster_nrep<8>(ctx, a, nrep, pdl);
-        if (e != cudaErrorNotSupported) return e;
-    }
     if (a.chunk <= 0) a.chunk = 128;
     a.nsplit_max = (a.max_ctx + a.chunk - 1) / a.chunk;
     const size_t need = (size_t)a.num_heads * a.nsplit_max * (HD + 2) * sizeof(float);

@@ -40,23 +40,10 @@ TCE_DEVINL void ldmatrix_x4_t(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t
 // exactly those threads (__syncthreads in the stand-alone kernel, a named barrier inside the persistent kernel).
 // The H/KVH query heads of the KV head are the (up to 8) columns of one MMA tile: scores and P.V run on mma.sync m16n8k16 with
 // fp16 operands (q * alpha, K, P, V) and fp32 accumulation; a scalar version of the two products cost ~6 of the kernel's ~18 us.
-// ---- thread-block-cluster helpers (CL > 0: the splits of one KV head are the CTAs of one cluster) ----
-TCE_DEVINL void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-TCE_DEVINL float ld_dsmem_f32(const float *local_ptr, uint32_t cta_rank) {  // the same shared-memory location in CTA `cta_rank` of the cluster
-    uint32_t raddr;
-    float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_ptr)), "r"(cta_rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
-    return v;
-}
-
-// CL == 0: splits are independent CTAs, merged through global partial records by the last CTA of the KV head to arrive.
-// CL  > 0: `split` is the CTA's rank in a cluster of CL CTAs that covers the whole context of the KV head (rows are divided evenly
-//          at run time); partial results stay in shared memory and are merged over distributed shared memory -- no global round trip,
-//          no fence, no atomic, no serial last-CTA tail.
-template <int NREP, int CL = 0, typename SyncFn>
+// Splits are independent CTAs, merged through global partial records by the last CTA of the KV head to arrive.  (A thread-block-cluster flavour --
+// one cluster of 8 / 16 CTAs per KV head, partials merged over distributed shared memory -- was implemented and measured in round 1: 2.2 us per
+// layer SLOWER (cluster co-scheduling + two cluster barriers); removed in round 2, where the decode step's attention lives in the persistent kernel.)
+template <int NREP, typename SyncFn>
 TCE_DEVINL void attn_item(const AttnDecodeArgs &a, uint8_t *smem, uint64_t *bar, int *flag, uint32_t &bar_parity, int kvh, int split, int tid, int pos,
                           SyncFn sync) {
     static_assert(NREP <= 8, "the query heads of one KV head ride in the 8 MMA columns");
@@ -75,9 +62,9 @@ TCE_DEVINL void attn_item(const AttnDecodeArgs &a, uint8_t *smem, uint64_t *bar,
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, qd = lane & 3;
     sync();  // the previous item of this CTA (persistent kernel) may still be reading the shared buffers
     const int T = pos + 1;        // visible positions
-    const int rows_per = (CL > 0) ? (T + CL - 1) / CL : chunk;
+    const int rows_per = chunk;
     const int t0 = min(T, split * rows_per);
-    if (CL == 0 && t0 >= T) return;  // empty split
+    if (t0 >= T) return;  // empty split
     const int t1 = min(T, t0 + rows_per);
     const int nrows = t1 - t0;       // cluster mode: may be 0 (the CTA then contributes m = -inf, l = 0, o = 0)
     const bool owns_new = (pos >= t0 && pos < t1);
@@ -219,59 +206,6 @@ TCE_DEVINL void attn_item(const AttnDecodeArgs &a, uint8_t *smem, uint64_t *bar,
         }
     }
     sync();
-
-    if constexpr (CL > 0) {
-        // ---- cluster merge over distributed shared memory ----
-        // own partial -> sPart[NREP][HD + 2] (the probability buffer is free now): unnormalised o, then m, l
-        float *sPart = sP;
-        constexpr int PS = HD + 2;
-        for (int i = tid; i < NREP * HD; i += kAttnThreads) {
-            const int r = i / HD, d = i % HD;
-            sPart[r * PS + d] = sO[i];
-            if (d == 0) {
-                sPart[r * PS + HD] = m_loc[r];
-                sPart[r * PS + HD + 1] = l_loc[r];
-            }
-        }
-        cluster_sync_all();  // every CTA's partial is visible cluster-wide
-        // gather the CL x NREP (m, l) pairs, derive per-head weights w[r][s] = exp(m_s - M_r) / L_r
-        float *sW = sRed;  // [NREP][CL] weights
-        float *sML = sRed + NREP * CL;  // [NREP][CL][2]
-        for (int i = tid; i < NREP * CL * 2; i += kAttnThreads) {
-            const int r = i / (CL * 2), s = (i / 2) % CL, which = i & 1;
-            sML[i] = ld_dsmem_f32(&sPart[r * PS + HD + which], (uint32_t)s);
-        }
-        sync();
-        for (int i = tid; i < NREP * CL; i += kAttnThreads) {
-            const int r = i / CL, s = i % CL;
-            float M = -INFINITY;
-#pragma unroll
-            for (int q = 0; q < CL; q++) M = fmaxf(M, sML[(r * CL + q) * 2]);
-            float L = 0.f;
-#pragma unroll
-            for (int q = 0; q < CL; q++) {
-                const float mq = sML[(r * CL + q) * 2];
-                L += (mq == -INFINITY ? 0.f : __expf(mq - M)) * sML[(r * CL + q) * 2 + 1];
-            }
-            const float ms = sML[(r * CL + s) * 2];
-            sW[i] = (ms == -INFINITY ? 0.f : __expf(ms - M)) / L;
-        }
-        sync();
-        // this CTA finishes outputs [split * NO/CL, (split+1) * NO/CL): LPO lanes per output walk the CL partials
-        constexpr int NO = NREP * HD, SL = NO / CL, LPO = kAttnThreads / SL;
-        static_assert(NO % CL == 0 && kAttnThreads % SL == 0 && LPO <= 32 && (LPO & (LPO - 1)) == 0, "cluster merge mapping");
-        {
-            const int oi = split * SL + tid / LPO, j = tid % LPO;
-            const int r = oi / HD, d = oi % HD;
-            float acc = 0.f;
-            for (int s = j; s < CL; s += LPO) acc += sW[r * CL + s] * ld_dsmem_f32(&sPart[r * PS + d], (uint32_t)s);
-#pragma unroll
-            for (int o = LPO / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (j == 0) a.out[(size_t)(kvh * NREP + r) * HD + d] = __float2half(acc);
-        }
-        cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
-        return;
-    }
 
     // ---- per-split result (unnormalised o, m, l) ----
     const int nsplit_active = (T + chunk - 1) / chunk;

@@ -83,7 +83,6 @@ int tce_ctx_create(int device, tce_ctx **out) {
     c.pdl_early = env_int("TCE_PDL_EARLY", 1);
     c.use_pdl = env_int("TCE_USE_PDL", 1) != 0;  // programmatic dependent launch, dependents resident from kernel entry: +3 % (profiles/r01_pdl_matrix.txt)
     ctx->attn_chunk = env_int("TCE_ATTN_CHUNK", 256);  // cached rows per CTA: 256 measured best (64: -8 %, 128: -2 %; profiles/README.md)
-    c.attn_cluster = env_int("TCE_ATTN_CLUSTER", 0);
     c.gemv_max_ctas = c.num_sms * 4;
     c.gemv_max_tiles = 32768;
     CK(cudaMalloc(&c.gemv_partials, (size_t)c.gemv_max_ctas * 2 * 16 * 8 * sizeof(float)), "cudaMalloc gemv partials");
@@ -160,7 +159,7 @@ int tce_ctx_set_option(tce_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "gemm_min_m"))  // smallest M served by the tcgen05 GEMMs (W4A16 prefill slot, W8A8); below it the weight-streaming kernels run
         ctx->c.gemm_min_m = value < 1 ? 1 : value;
     else if (!strcmp(name, "attn_cluster"))
-        ctx->c.attn_cluster = value;
+        (void)value;  // accepted and ignored: the cluster flavour of the stand-alone decode attention was removed (measured slower)
     else if (!strcmp(name, "attn_chunk"))
         ctx->attn_chunk = value;
     else

@@ -26,9 +26,6 @@ struct Ctx {
     unsigned *attn_counters = nullptr;
     unsigned option_gen = 0;       // bumped by every tce_ctx_set_option / set_stream: captured CUDA graphs hold the context by value and are rebuilt
     unsigned attn_seed_epoch = 0;  // calls of the int8 OPT attention so far (tags the in-kernel seed hand-off)
-    // decode attention: CTAs per thread-block cluster (one cluster per KV head, DSMEM merge); 0 = independent splits + global merge.
-    // Measured on B200: the cluster flavour is 2.2 us per layer SLOWER (cluster co-scheduling + two cluster barriers), so it is off.
-    int attn_cluster = 0;
     // tunables (env overridable, see ctx.cu)
     int gemv_impl = 1;      // 0 = simple warp-per-row, 1 = TMA + mma.sync stream-K
     int gemv_ctas_per_sm = 1;
