@@ -67,7 +67,8 @@ TCE_DEVINL uint2 ld_ll1(const uint2 *p, bool sys) {
 }
 // A failed poll waits this long before it asks L2 again: thousands of threads spinning without a pause fill the L2 request queues and
 // stretch every round trip (their own and the producers' stores) to ~0.5 us (profiles/README.md, run 11).
-constexpr unsigned kPollBackoffNs = 100;
+__constant__ unsigned g_poll_ns = 100;  // TCE_PK_POLL_NS (set_poll_backoff)
+#define kPollBackoffNs g_poll_ns
 constexpr long long kSpinLimit = 20000000000LL;  // ~10 s: a peer rank may legitimately start its kernel later
 // spin until both words of the pair carry `tag`
 TCE_DEVINL uint4 wait_ll2(const uint2 *p, uint32_t tag, bool sys) {
@@ -1477,6 +1478,8 @@ bool pair_supported(Ctx *ctx, const Args &a) {
     }
     return nclusters * 2 >= ctx->num_sms;
 }
+
+cudaError_t set_poll_backoff(unsigned ns) { return cudaMemcpyToSymbol(g_poll_ns, &ns, sizeof(ns)); }
 
 cudaError_t launch(Ctx *ctx, const Args &a, cudaStream_t stream) {
     const size_t smem = smem_bytes(a);

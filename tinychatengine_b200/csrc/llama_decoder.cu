@@ -483,6 +483,7 @@ cudaError_t LlamaDecoder::build_persistent(std::string *err) {
     if (a.nst < 2) return no("shared memory too small for the persistent kernel");
     a.l2_prefetch = getenv("TCE_PK_L2_PREFETCH") ? atoi(getenv("TCE_PK_L2_PREFETCH")) : 0;
     a.pair = 0;  // decided below, once the shared-memory footprint is known
+    if (getenv("TCE_PK_POLL_NS")) DCK(pk::set_poll_backoff((unsigned)atoi(getenv("TCE_PK_POLL_NS"))));
 
     auto dalloc = [&](size_t bytes) -> void * {
         void *p = nullptr;

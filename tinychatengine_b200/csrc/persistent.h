@@ -107,7 +107,8 @@ int pick_stages(int smem_optin, int xs_bytes, int max_ng, int E);
 int attn_scratch_bytes(int nrep);
 int attn_nsplit_max(int ncta, int KVH, int max_ctx);
 cudaError_t launch(Ctx *ctx, const Args &a, cudaStream_t stream);
-bool pair_supported(Ctx *ctx, const Args &a);  // the grid fits as co-resident clusters of two CTAs
+bool pair_supported(Ctx *ctx, const Args &a);
+cudaError_t set_poll_backoff(unsigned ns);  // pause of a failed hand-off poll before it asks L2 again (default 100 ns)  // the grid fits as co-resident clusters of two CTAs
 // one-off repack of a (possibly multi-segment / gate-up paired) matrix's scales and zeros into per-stage records
 cudaError_t repack_meta(Ctx *ctx, const W4Seg *segs, int nseg, int pair, int IC, uint8_t *out, cudaStream_t stream);
 cudaError_t encode_kv_tmap(CUtensorMap *out, const void *kv, long long rows);
