@@ -1496,14 +1496,29 @@ cudaError_t launch(Ctx *ctx, const Args &a, cudaStream_t stream) {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (a.pair) {  // clusters of two CTAs (one TPC) share the activation staging over distributed shared memory
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = 2;
-        attr[1].val.clusterDim.y = 1;
-        attr[1].val.clusterDim.z = 1;
-        cfg.numAttrs = 2;
+    static bool pair_refused = false;  // a cluster launch was refused once in this process
+    if (a.pair && !pair_refused) {
+        // Clusters of two CTAs (one TPC) share the activation staging over distributed shared memory.  Launched with the cluster attribute ALONE:
+        // profilers (ncu) cannot intercept a launch that is both cooperative and clustered (LaunchFailed), and co-residency -- what the cooperative
+        // attribute would assert -- is established instead by pair_supported(): one CTA per SM fits for all num_sms / 2 clusters, and the step is the only
+        // work on its stream.  A CTA that were not resident would surface through the bounded spins (__trap after ~10 s), not as a silent hang.
+        cudaLaunchAttribute cattr[1];
+        cattr[0].id = cudaLaunchAttributeClusterDimension;
+        cattr[0].val.clusterDim.x = 2;
+        cattr[0].val.clusterDim.y = 1;
+        cattr[0].val.clusterDim.z = 1;
+        cfg.attrs = cattr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, decode_persistent_kernel, a);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();  // a launch-configuration error is not sticky: run without clusters (every CTA stages the whole vector itself)
+        pair_refused = true;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
     }
-    return cudaLaunchKernelEx(&cfg, decode_persistent_kernel, a);
+    Args single = a;
+    single.pair = 0;
+    return cudaLaunchKernelEx(&cfg, decode_persistent_kernel, single);
 }
 
 }  // namespace pk
