@@ -232,7 +232,7 @@ def test_device_resident_token_and_position_are_range_checked(mega, monkeypatch)
     if mega == "1":
         assert torch.equal(la, lb)
     else:  # the kernel-per-op path finishes split tiles with fp32 atomics: equal up to summation order
-        assert float((la - lb).abs().max() / lb.abs().max()) < 1e-5
+        assert float((la - lb).abs().max() / lb.abs().max()) < 1e-4
     a.close()
     b.close()
     ctx.close()

@@ -1,2 +1,2 @@
 set -x
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"decode_persistent|sample_kernel|attn_prefill" -c 6 --csv --log-file gpurun_out/r02_smoke_launches.csv python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke_ncu.log 2>&1; tail -4 gpurun_out/r02_smoke_ncu.log; grep -c decode_persistent gpurun_out/r02_smoke_launches.csv; tail -5 gpurun_out/r02_smoke_launches.csv | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_llama.py tests/test_gpu_attention.py -q --timeout 600 > gpurun_out/r02_t_llama.log 2>&1; tail -4 gpurun_out/r02_t_llama.log
