@@ -175,7 +175,31 @@ def main():
         samp[f"ids{i}"], samp[f"probs{i}"] = ids, probs
         samp[f"cfg{i}"] = np.array([c["top_k"], c["top_p"], c["temp"], c["repeat_penalty"], c["frequency_penalty"], c["presence_penalty"]], dtype=np.float64)
     np.savez_compressed(OUT / "sampling.npz", **samp)
+    make_llama_model()
     print("golden fixtures written to", OUT)
+
+
+def make_llama_model():
+    """The reference's WHOLE CPU model -- Int4LlamaForCausalLM -> Int4llamaDecoder -> Int4llamaDecoderLayer -> Int4llamaAttention, compiled in place
+    (oracle/_ref/libtce_ref_llama_model.so) -- on a synthetic two-layer GQA model: logits of a 6-token prompt pass and 3 decode steps.  Only the
+    seed travels (the weights are regenerated from it; `weights_crc` guards the generator), so the fixture stays a few KB.  Pins the composition
+    oracle/llama_ref.py::llama_forward, which tests/helpers.py::oracle_decode_step runs for the GPU parity tests."""
+    import zlib
+
+    from oracle import capi, llama_ref
+
+    E, H, KVH, L, F, V, prefill, steps, max_sq, seed, theta, eps = 256, 4, 2, 2, 512, 320, 6, 3, 640, 20260926, 500000.0, 1e-5
+    rng = np.random.default_rng(seed)
+    model = llama_ref.random_model(rng, E, H, KVH, L, F, V)
+    tokens = rng.integers(0, V, prefill + steps).astype(np.int32)
+    hd = E // H
+    cosb, sinb = capi.rope_tables(max_sq, hd, theta)
+    with tempfile.TemporaryDirectory() as d:
+        handles = llama_ref.write_llama_model_params(d, model, cosb, sinb, np.float32(1.0 / np.sqrt(hd)))
+        logits = llama_ref.ref_int4_llama_causal_lm(d, tokens, E, H, KVH, L, F, V, prefill, steps, max_sq, eps)
+    crc = zlib.crc32(handles["lm_head"][0].tobytes()) ^ zlib.crc32(handles["layers"][0]["down"][0].tobytes())
+    np.savez_compressed(OUT / "llama_model.npz", dims=np.array([E, H, KVH, L, F, V, prefill, steps, max_sq, seed], np.int64), theta=np.float64(theta),
+                        eps=np.float64(eps), tokens=tokens, logits=logits, weights_crc=np.uint32(crc))
 
 
 if __name__ == "__main__":

@@ -29,40 +29,26 @@ def np_w4(t):
 
 
 def oracle_decode_step(model, token, pos, past_k, past_v):
-    """One decode step of the synthetic Llama composed from oracle pieces (tce_oracle.c), mirroring the fused
-    GPU path's rounding points: fp32 residual, RMSNorm output -> fp16, projections -> fp16, attention out -> fp16,
-    SiLU*mul -> fp16, logits fp32.  past_k/past_v: per-layer lists of [KVH, pos, hd] fp32 arrays (or None)."""
+    """One decode step of the synthetic Llama composed from oracle pieces (tce_oracle.c) by oracle/llama_ref.py::llama_forward -- the composition that
+    is pinned against the reference's own Int4LlamaForCausalLM (tests/test_oracle_golden.py::test_llama_model_*) -- with the fused GPU path's
+    arithmetic plugged in: W4A16 GEMV oracle for the projections and fp16 at the GPU path's rounding points (RMSNorm output, projections, attention
+    out, SiLU*mul, the appended key row); fp32 residual and logits.  past_k/past_v: per-layer lists of [KVH, pos, hd] fp32 arrays (or None)."""
+    from oracle import llama_ref
+
     g = model.geom
-    hd, H, KVH = g.head_dim, g.num_heads, g.num_kv_heads
-    cosb, sinb = capi.rope_tables(model.max_ctx, hd, g.rope_theta)
-    x = model.embed[token].float().cpu().numpy()[None, :].astype(np.float32)  # resid fp32 [1,E]
-    new_k, new_v = [], []
-    alpha = 1.0 / np.sqrt(hd)
+    cosb, sinb = capi.rope_tables(model.max_ctx, g.head_dim, g.rope_theta)
+    assert pos == (0 if past_k[0] is None else past_k[0].shape[1])
 
-    def gemv(xh, name, l=None):
-        t = model.layer_tensors(l)[name] if l is not None else model.tensors[-1]
+    def linear(xh, t):
         w, z, s = np_w4(t)
-        return capi.w4a16_gemv(xh.astype(np.float16), w, z, s)
+        return capi.w4a16_gemv(np.asarray(xh).astype(np.float16), w, z, s)
 
+    layers = []
     for l in range(g.num_layers):
         lt = model.layer_tensors(l)
-        xn = capi.rmsnorm(x, lt["input_norm"].cpu().numpy(), g.rms_eps).astype(np.float16)
-        q = gemv(xn, "q", l).astype(np.float16).astype(np.float32)
-        k = gemv(xn, "k", l).astype(np.float16).astype(np.float32)
-        v = gemv(xn, "v", l).astype(np.float16).astype(np.float32)
-        mask = capi.causal_mask(1, pos)
-        out, fk, fv = capi.llama_attention_core(q, k, v, past_k[l], past_v[l], mask, cosb, sinb, alpha, H, KVH, hd)
-        # the cache holds fp16: round the appended row the way the kernel stores it
-        fk[:, -1, :] = fk[:, -1, :].astype(np.float16).astype(np.float32)
-        new_k.append(fk)
-        new_v.append(fv)
-        o = gemv(out.astype(np.float16), "o", l)
-        x = x + o
-        xn = capi.rmsnorm(x, lt["post_norm"].cpu().numpy(), g.rms_eps).astype(np.float16)
-        gate = gemv(xn, "gate", l)
-        up = gemv(xn, "up", l)
-        act = (gate / (1.0 + np.exp(-gate)) * up).astype(np.float16)
-        x = x + gemv(act, "down", l)
-    xn = capi.rmsnorm(x, model.final_norm.cpu().numpy(), g.rms_eps).astype(np.float16)
-    logits = gemv(xn, None, None)
+        layers.append({**{n: lt[n] for n in llama_ref.LINEARS}, "input_norm": lt["input_norm"].cpu().numpy(), "post_norm": lt["post_norm"].cpu().numpy()})
+    logits, new_k, new_v = llama_ref.llama_forward(
+        [token], past_k, past_v, embed_row=lambda t: model.embed[t].float().cpu().numpy(), layers=layers, final_norm=model.final_norm.cpu().numpy(),
+        lm_head=model.tensors[-1], linear=linear, cosb=cosb, sinb=sinb, H=g.num_heads, KVH=g.num_kv_heads, hd=g.head_dim, eps=g.rms_eps,
+        rnd=lambda a: np.asarray(a).astype(np.float16), round_new_k=lambda a: a.astype(np.float16).astype(np.float32))
     return logits[0], new_k, new_v

@@ -210,6 +210,69 @@ def test_llama_attention_module_live(E, H, KVH, prefill, steps, seed, tmp_path):
     assert diff.max() <= np.abs(want).max() / 100
 
 
+def test_llama_model_composition_golden(golden_dir):
+    """oracle/llama_ref.py::llama_forward -- the composition of a Llama step that tests/helpers.py::oracle_decode_step runs for the GPU parity tests
+    -- fed with the reference CPU build's arithmetic (fp32, W4A8 projections) reproduces the logits of the reference's WHOLE model
+    (Int4LlamaForCausalLM::forward compiled in place: prompt pass of 6 tokens + 3 decode steps, 2 layers, GQA 4:2) to fp32 round-off."""
+    import zlib
+
+    from oracle import llama_ref
+
+    g = np.load(golden_dir / "llama_model.npz")
+    E, H, KVH, L, F, V, prefill, steps, max_sq, seed = (int(v) for v in g["dims"])
+    rng = np.random.default_rng(seed)
+    model = llama_ref.random_model(rng, E, H, KVH, L, F, V)
+    tokens = rng.integers(0, V, prefill + steps).astype(np.int32)
+    assert np.array_equal(tokens, g["tokens"]), "numpy's generator stream changed: regenerate tests/golden/llama_model.npz"
+    handles = llama_ref.quantized_handles(model)
+    crc = zlib.crc32(handles["lm_head"][0].tobytes()) ^ zlib.crc32(handles["layers"][0]["down"][0].tobytes())
+    assert crc == int(g["weights_crc"]), "synthetic weights differ from the fixture's: regenerate tests/golden/llama_model.npz"
+    cosb, sinb = capi.rope_tables(max_sq, E // H, float(g["theta"]))
+    got = llama_ref.oracle_int4_llama_causal_lm(model, handles, tokens, cosb, sinb, H, KVH, prefill, steps, float(g["eps"]))
+    want = g["logits"]
+    assert got.shape == want.shape == (prefill + steps, V)
+    _check_model_logits(got, want)
+
+
+def _check_model_logits(got, want):
+    """fp32 round-off (measured 2-6e-7 of the maximum) -- unless an activation that sits within round-off of an int8 rounding boundary of the W4A8
+    activation quantiser (kernels/avx/matmul_avx_int8_int4.cc:259-316, the one discontinuity of the CPU path) rounds the other way on this host:
+    seen on 5 of 40 seeds, echo <= 8e-3 of the maximum.  A wrong composition (order of norm / residual / activation) is an O(1) error."""
+    import warnings
+
+    rel = float(np.abs(got - want).max() / np.abs(want).max())
+    assert rel <= 3e-2, rel
+    if rel > 5e-6:
+        warnings.warn(f"int8 activation-rounding flip against the reference build: logits differ by {rel:.1e} of the maximum instead of ~3e-7")
+
+
+@pytest.mark.skipif(not (capi.REF_DIR / "libtce_ref_llama_model.so").exists(), reason="reference model build (oracle/_ref) not present")
+@pytest.mark.parametrize("E,H,KVH,L,F,V,prefill,steps,seed", [(256, 2, 2, 1, 256, 128, 1, 4, 2), (512, 4, 1, 2, 1024, 256, 9, 2, 3), (256, 4, 4, 3, 512, 192, 4, 1, 4)])
+def test_llama_model_composition_live(E, H, KVH, L, F, V, prefill, steps, seed, tmp_path):
+    """Same pin against the live reference build: MHA, GQA and MQA, one to three layers, prompt-only / decode-only heavy call patterns."""
+    from oracle import llama_ref
+
+    rng = np.random.default_rng(seed)
+    model = llama_ref.random_model(rng, E, H, KVH, L, F, V)
+    tokens = rng.integers(0, V, prefill + steps).astype(np.int32)
+    cosb, sinb = capi.rope_tables(640, E // H, 10000.0)
+    handles = llama_ref.write_llama_model_params(tmp_path, model, cosb, sinb, np.float32(1.0 / np.sqrt(E // H)))
+    want = llama_ref.ref_int4_llama_causal_lm(tmp_path, tokens, E, H, KVH, L, F, V, prefill, steps, 640, 1e-6)
+    got = llama_ref.oracle_int4_llama_causal_lm(model, handles, tokens, cosb, sinb, H, KVH, prefill, steps, 1e-6)
+    _check_model_logits(got, want)
+
+
+def test_oracle_decode_step_is_the_pinned_composition():
+    """tests/helpers.py::oracle_decode_step (the checker of the GPU decode step) goes through llama_forward -- no second statement of the layer
+    order exists in the test tree."""
+    import inspect
+
+    import helpers
+
+    src = inspect.getsource(helpers.oracle_decode_step)
+    assert "llama_ref.llama_forward(" in src and "rmsnorm" not in src and "llama_attention_core" not in src
+
+
 @pytest.mark.skipif(not (capi.REF_DIR / "libtce_ref_modules.so").exists(), reason="reference module build (oracle/_ref) not present")
 def test_norms_match_the_compiled_reference_ops():
     """orc_rmsnorm / orc_layernorm_q vs the reference's LlamaRMSNorm::forward / LayerNormQ::forward (compiled in place, strict IEEE

@@ -45,11 +45,11 @@ size_t attn_smem_bytes(int nrep, int chunk) { return smem_bytes(nrep, chunk) + 2
 template <int NREP>
 cudaError_t launch(Ctx *ctx, const AttnDecodeArgs &a, bool pdl) {
     const size_t smem = attn_smem_bytes(NREP, a.chunk);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.pending(ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<NREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_once.done(ctx->device);
     }
     if ((int)smem > ctx->smem_optin) return cudaErrorInvalidConfiguration;
     cudaLaunchConfig_t cfg = {};

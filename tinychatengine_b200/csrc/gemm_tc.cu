@@ -154,11 +154,11 @@ cudaError_t launch(Ctx *ctx, GemmArgs &a, const void *A, long long lda, const vo
     a.n_blocks = (a.N + BLOCK_N - 1) / BLOCK_N;
     auto kern = tc::gemm_tc_kernel<BLOCK_N, STAGES, I8, Epi>;
     constexpr size_t smem = tc::smem_bytes<BLOCK_N, STAGES>();
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
+    static DeviceOnce attr_once;  // per instantiation
+    if (attr_once.pending(ctx->device)) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_once.done(ctx->device);
     }
     const int tiles = a.m_blocks * a.n_blocks;
     const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;

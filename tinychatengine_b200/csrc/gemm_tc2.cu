@@ -445,11 +445,11 @@ template <bool FUSED>
 cudaError_t launch_pair(Ctx *ctx, PairArgs &a) {
     using C = Cfg<FUSED>;
     auto kern = gemm_pair_kernel<FUSED>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.pending(ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_once.done(ctx->device);
     }
     const int tiles = a.m_blocks * a.n_blocks;
     int clusters = ctx->num_sms / 2;

@@ -341,11 +341,11 @@ cudaError_t launch_gemm_w4_tc(Ctx *ctx, const __half *X, long long ldx, const ui
     a.C = C;
     a.ldc = ldc;
     a.add_f32 = add_f32;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.pending(ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_w4_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kW4Smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_once.done(ctx->device);
     }
     const int tiles = a.m_blocks * a.n_blocks;
     const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;

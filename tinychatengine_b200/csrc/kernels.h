@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace tce {
 
 // One context per (device, stream).  Owns the small workspaces the kernels need; never owns caller data.
@@ -37,6 +39,14 @@ struct Ctx {
     __half *w16_scratch = nullptr;
     size_t w16_scratch_elems = 0;
     int gemm_min_m = 16;
+};
+
+// One-time kernel attribute setup (cudaFuncSetAttribute) is per (kernel, DEVICE): a process may hold contexts on several devices, so each launch site
+// keeps one bit per device instead of one flag per process.  Setting the attribute twice from two racing threads is harmless.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool pending(int device) const { return !((mask.load(std::memory_order_acquire) >> (device & 63)) & 1ull); }
+    void done(int device) { mask.fetch_or(1ull << (device & 63), std::memory_order_release); }
 };
 
 constexpr int kW4Group = 128;  // QK for QM_CUDA (llm/include/common.h:17-21)

@@ -260,11 +260,11 @@ template <int NCOLS, int CW>
 cudaError_t launch_mma(Ctx *ctx, const KArgs &a_in, bool pdl) {
     KArgs a = a_in;
     if ((int)Layout<NCOLS, CW>::bytes(a.IC, kStages) > ctx->smem_optin) return cudaErrorInvalidConfiguration;
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
+    static DeviceOnce attr_once;  // per template instantiation
+    if (attr_once.pending(ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(w4a16_gemv_kernel<NCOLS, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_once.done(ctx->device);
     }
     const long long U = (long long)a.num_tiles * a.NG;
     // Two co-resident CTAs per SM (two independent TMA rings, 16 consumer warps) stream ~25 % faster than one on large
