@@ -5,7 +5,11 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
+#include <string>
 #include <vector>
 
 #include "Int8OPTAttention.h"
@@ -219,6 +223,107 @@ static void test_Int8OPTAttention(int E, int H, int prefill) {
     report(name, ok);
 }
 
+// The reference's constructor form: Int8OPTAttention(param_path, config, ops...) fills the six operators from a parameter tree on disk
+// (llm/src/nn_modules/Int8OPTAttention.cc:60-81; file names of llm/src/ops/W8A8*.cc / BMM_S8T_*.cc).  A module loaded that way must be
+// bit-identical to one built from operators that were handed the same bytes directly.
+static void write_file(const std::string &path, const void *data, size_t bytes) {
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f || fwrite(data, 1, bytes, f) != bytes) {
+        fprintf(stderr, "cannot write %s\n", path.c_str());
+        exit(2);
+    }
+    fclose(f);
+}
+static void test_Int8OPTAttention_param_path(int E, int H, int sqlen) {
+    struct model_config cfg;
+    cfg.num_heads = H; cfg.embed_dim = E; cfg.num_layers = 1; cfg.max_sqlen = 256;
+    Int8OPTAttention::initialized_memory(cfg);
+    const float a_qkv = 0.0009f, b_qkv = 0.9f, qk_alpha = 0.0007f, pv_alpha = 0.011f, a_out = 0.0008f;
+    char tmpl[] = "/tmp/tce_opt_attn_XXXXXX";
+    const char *root_c = mkdtemp(tmpl);
+    if (!root_c) { report("Int8OPTAttention(param_path, ...): mkdtemp", false); return; }
+    const std::string root(root_c);
+    // direct operators (weights in managed memory) and a second, zero-filled set that the constructor must fill from the files
+    int8_t *w[4], *w2[4], *b8[3], *b82[3];
+    const char *names[4] = {"q_proj", "k_proj", "v_proj", "out_proj"};
+    float *bo = managed<float>(E), *bo2 = managed<float>(E);
+    for (int i = 0; i < E; i++) { bo[i] = rndn(); bo2[i] = 0.f; }
+    for (int i = 0; i < 4; i++) {
+        w[i] = rand_s8((size_t)E * E);
+        w2[i] = managed<int8_t>((size_t)E * E);
+        memset(w2[i], 0, (size_t)E * E);
+        if (i < 3) { b8[i] = rand_s8(E); b82[i] = managed<int8_t>(E); memset(b82[i], 0, E); }
+        const std::string d = root + "/" + names[i];
+        mkdir(d.c_str(), 0700);
+        write_file(d + "/weight.bin", w[i], (size_t)E * E);
+        if (i < 3) {
+            write_file(d + "/bias_int8.bin", b8[i], E);
+            write_file(d + "/alpha.bin", &a_qkv, 4);
+            write_file(d + "/beta.bin", &b_qkv, 4);
+        } else {
+            write_file(d + "/bias.bin", bo, (size_t)E * 4);
+            write_file(d + "/alpha.bin", &a_out, 4);
+        }
+    }
+    mkdir((root + "/qk_bmm").c_str(), 0700);
+    mkdir((root + "/pv_bmm").c_str(), 0700);
+    write_file(root + "/qk_bmm/alpha.bin", &qk_alpha, 4);
+    write_file(root + "/pv_bmm/alpha.bin", &pv_alpha, 4);
+    auto lin = [&](int8_t *wp, int8_t *bp, float a, float b) {
+        W8A8B8O8Linear_params p = {Matrix3D<int8_t>(wp, 1, E, E), Matrix3D<int8_t>(bp, 1, 1, E), a, b};
+        return W8A8B8O8Linear(p);
+    };
+    W8A8B8O8Linear q1 = lin(w[0], b8[0], a_qkv, b_qkv), k1 = lin(w[1], b8[1], a_qkv, b_qkv), v1 = lin(w[2], b8[2], a_qkv, b_qkv);
+    W8A8B8O8Linear q2 = lin(w2[0], b82[0], 0.f, 0.f), k2 = lin(w2[1], b82[1], 0.f, 0.f), v2 = lin(w2[2], b82[2], 0.f, 0.f);
+    W8A8BFP32OFP32Linear_params po1 = {Matrix3D<int8_t>(w[3], 1, E, E), Matrix3D<float>(bo, 1, 1, E), a_out};
+    W8A8BFP32OFP32Linear_params po2 = {Matrix3D<int8_t>(w2[3], 1, E, E), Matrix3D<float>(bo2, 1, 1, E), 0.f};
+    W8A8BFP32OFP32Linear o1(po1), o2(po2);
+    BMM_S8T_S8N_F32T qk1(qk_alpha), qk2;
+    BMM_S8T_S8N_S8T pv1(pv_alpha), pv2;
+    Int8OPTAttention direct(cfg, qk1, pv1, k1, v1, q1, o1);
+    bool ok = true;
+    try {
+        Int8OPTAttention loaded(root, cfg, qk2, pv2, k2, v2, q2, o2);
+        cudaDeviceSynchronize();
+        // the caller's operators were filled in place, as in the reference
+        ok &= qk2.alpha == qk_alpha && pv2.alpha == pv_alpha && q2.alpha == a_qkv && k2.beta == b_qkv && o2.alpha == a_out;
+        for (int i = 0; i < 4; i++) ok &= memcmp(w[i], w2[i], (size_t)E * E) == 0;
+        for (int i = 0; i < 3; i++) ok &= memcmp(b8[i], b82[i], E) == 0;
+        ok &= memcmp(bo, bo2, (size_t)E * 4) == 0;
+        int8_t *x = rand_s8((size_t)sqlen * E);
+        float *mask = managed<float>((size_t)sqlen * sqlen);
+        for (int i = 0; i < sqlen; i++)
+            for (int j = 0; j < sqlen; j++) mask[(size_t)i * sqlen + j] = j > i ? -3.402823466e38f : 0.f;
+        Matrix3D<int8_t> X(x, 1, sqlen, E);
+        Matrix3D<float> M(mask, 1, sqlen, sqlen);
+        std::vector<float> a((size_t)sqlen * E), b(a.size());
+        Int8OPTAttention_output o = direct.forward(Int8OPTAttention_input(X, M, 0));
+        cudaMemcpy(a.data(), o.attn_output.m_data, a.size() * 4, cudaMemcpyDeviceToHost);
+        o = loaded.forward(Int8OPTAttention_input(X, M, 0));
+        cudaMemcpy(b.data(), o.attn_output.m_data, b.size() * 4, cudaMemcpyDeviceToHost);
+        ok &= memcmp(a.data(), b.data(), a.size() * 4) == 0;
+        bool nonzero = false;
+        for (float f : a) nonzero |= f != 0.f;
+        ok &= nonzero;
+        cudaFree(x); cudaFree(mask);
+    } catch (const char *msg) {
+        fprintf(stderr, "unexpected throw: %s\n", msg);
+        ok = false;
+    }
+    // a missing file throws a C string, like read_to_array (llm/src/utils.cc:16-25)
+    bool threw = false;
+    remove((root + "/pv_bmm/alpha.bin").c_str());
+    try {
+        Int8OPTAttention broken(root, cfg, qk2, pv2, k2, v2, q2, o2);
+    } catch (const char *) {
+        threw = true;
+    }
+    ok &= threw;
+    char name[112];
+    snprintf(name, sizeof(name), "Int8OPTAttention(param_path, ...) E=%d H=%d: loaded == direct (bit exact), missing file throws", E, H);
+    report(name, ok);
+}
+
 int main() {
     // shapes of the reference's op tests (llm/tests/cuda/test_ops.cu:671-724, non_cuda/test_ops.cc:177-478)
     test_Linear_half_int4(1, 11008, 4096);
@@ -231,6 +336,7 @@ int main() {
     test_BMMs(12, 64, 64, 64, 0.0021f);
     test_BMMs(12, 1, 300, 64, 0.0021f);
     test_Int8OPTAttention(768, 12, 9);
+    test_Int8OPTAttention_param_path(256, 4, 5);
     printf("%d failure(s)\n", failures);
     return failures ? 1 : 0;
 }

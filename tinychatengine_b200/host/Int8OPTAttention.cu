@@ -51,6 +51,25 @@ Int8OPTAttention::Int8OPTAttention(const struct model_config config, BMM_S8T_S8N
     assert(config.embed_dim % config.num_heads == 0);
 }
 
+Int8OPTAttention::Int8OPTAttention(std::string param_path, const struct model_config config, BMM_S8T_S8N_F32T &qk_bmm_, BMM_S8T_S8N_S8T &pv_bmm_,
+                                   W8A8B8O8Linear &k_proj_, W8A8B8O8Linear &v_proj_, W8A8B8O8Linear &q_proj_, W8A8BFP32OFP32Linear &out_proj_)
+    : embed_dim(config.embed_dim), num_heads(config.num_heads), head_dim(config.embed_dim / config.num_heads) {
+    assert(config.embed_dim % config.num_heads == 0);
+    // load order and directory names of llm/src/nn_modules/Int8OPTAttention.cc:63-68; the caller's operators are filled in place, as there
+    load_BMM_S8T_S8N_F32T(qk_bmm_, param_path + "/qk_bmm");
+    load_BMM_S8T_S8N_S8T(pv_bmm_, param_path + "/pv_bmm");
+    load_W8A8B8O8Linear_params(k_proj_, param_path + "/k_proj");
+    load_W8A8B8O8Linear_params(v_proj_, param_path + "/v_proj");
+    load_W8A8B8O8Linear_params(q_proj_, param_path + "/q_proj");
+    load_W8A8BFP32OFP32Linear_params(out_proj_, param_path + "/out_proj");
+    qk_bmm = qk_bmm_;
+    pv_bmm = pv_bmm_;
+    k_proj = k_proj_;
+    v_proj = v_proj_;
+    q_proj = q_proj_;
+    out_proj = out_proj_;
+}
+
 struct Int8OPTAttention_output Int8OPTAttention::forward(const struct Int8OPTAttention_input &input) {
     struct Int8OPTAttention_output output;
     const int sqlen = input.hidden_states.m_dim_y, b = input.hidden_states.m_dim_x;

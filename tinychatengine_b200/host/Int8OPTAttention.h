@@ -3,8 +3,9 @@
 //
 // Contract kept for the reference's callers (Int8OPTDecoderLayer): the same type names, the same fields in the input / output
 // structs, forward() returning fp32 attn_output [1][sqlen][E] and the concatenated int8 K / V [H][tgz][hd] as past_key_value out of
-// two alternating per-layer buffers.  Differences: every buffer lives in device memory, and the module is constructed from operators
-// that already hold their weights (reading `param_path` is outside the hot path).
+// two alternating per-layer buffers.  Differences: every buffer lives in device memory.  Both constructors exist: the reference's
+// (param_path first: loads the six operators from `<param_path>/{qk_bmm,pv_bmm,k_proj,v_proj,q_proj,out_proj}` like
+// llm/src/nn_modules/Int8OPTAttention.cc:60-81) and one taking operators that already hold their weights.
 #ifndef TCE_HOST_INT8OPTATTENTION_H
 #define TCE_HOST_INT8OPTATTENTION_H
 #include <utility>
@@ -43,7 +44,10 @@ struct Int8OPTAttention_input {
 class Int8OPTAttention {
    public:
     Int8OPTAttention() {}
-    // operator argument order as in the reference constructor (…, qk_bmm, pv_bmm, k_proj, v_proj, q_proj, out_proj)
+    // the reference's constructor (llm/include/nn_modules/Int8OPTAttention.h:33-35): fills the operators from the parameter tree, then keeps copies
+    Int8OPTAttention(std::string param_path, const struct model_config config, BMM_S8T_S8N_F32T &qk_bmm, BMM_S8T_S8N_S8T &pv_bmm, W8A8B8O8Linear &k_proj,
+                     W8A8B8O8Linear &v_proj, W8A8B8O8Linear &q_proj, W8A8BFP32OFP32Linear &out_proj);
+    // same operator order, operators already loaded
     Int8OPTAttention(const struct model_config config, BMM_S8T_S8N_F32T &qk_bmm, BMM_S8T_S8N_S8T &pv_bmm, W8A8B8O8Linear &k_proj, W8A8B8O8Linear &v_proj,
                      W8A8B8O8Linear &q_proj, W8A8BFP32OFP32Linear &out_proj);
     // device scratch + the two alternating KV buffers per layer (llm/src/nn_modules/Int8OPTAttention.cc:27-58)

@@ -1,7 +1,57 @@
 // ops.cu -- forward() bodies of the L2 op classes: parameter blocks filled as the reference wrappers fill them.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "ops.h"
+
+// read `bytes` of a parameter file into `dst` (host, managed or device memory).  Failure behaviour of the reference's read_to_array
+// (llm/src/utils.cc:16-25): print the reason and throw a C string.
+static void read_param_file(const std::string &path, void *dst, size_t bytes, bool host_scalar = false) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) {
+        printf("%s: %s\n", strerror(errno), path.c_str());
+        throw("Expected error...");
+    }
+    std::vector<char> host(bytes);
+    const size_t got = fread(host.data(), 1, bytes, f);
+    fclose(f);
+    if (got != bytes) {
+        printf("short read (%zu of %zu bytes): %s\n", got, bytes, path.c_str());
+        throw("Expected error...");
+    }
+    if (host_scalar) {  // alpha / beta: members of the op object
+        memcpy(dst, host.data(), bytes);
+        return;
+    }
+    if (cudaMemcpy(dst, host.data(), bytes, cudaMemcpyDefault) != cudaSuccess) {
+        printf("cudaMemcpy of %zu bytes failed: %s\n", bytes, path.c_str());
+        throw("Expected error...");
+    }
+}
+
+void load_W8A8B8O8Linear_params(W8A8B8O8Linear &op, std::string prefix) {
+    read_param_file(prefix + "/weight.bin", op.params.B.int8_data_ptr, (size_t)op.params.B.length());
+    read_param_file(prefix + "/bias_int8.bin", op.params.bias.int8_data_ptr, (size_t)op.params.bias.length());
+    read_param_file(prefix + "/alpha.bin", &op.alpha, sizeof(float), true);
+    read_param_file(prefix + "/beta.bin", &op.beta, sizeof(float), true);
+    op.params.alpha = op.alpha;
+    op.params.beta = op.beta;
+    op.params.A.qparams.scale = op.alpha;
+}
+
+void load_W8A8BFP32OFP32Linear_params(W8A8BFP32OFP32Linear &op, std::string prefix) {
+    read_param_file(prefix + "/weight.bin", op.params.B.int8_data_ptr, (size_t)op.params.B.length());
+    read_param_file(prefix + "/bias.bin", op.params.bias.data_ptr, (size_t)op.params.bias.length() * sizeof(float));
+    read_param_file(prefix + "/alpha.bin", &op.alpha, sizeof(float), true);
+}
+
+void load_BMM_S8T_S8N_F32T(BMM_S8T_S8N_F32T &op, std::string prefix) { read_param_file(prefix + "/alpha.bin", &op.alpha, sizeof(float), true); }
+
+void load_BMM_S8T_S8N_S8T(BMM_S8T_S8N_S8T &op, std::string prefix) { read_param_file(prefix + "/alpha.bin", &op.alpha, sizeof(float), true); }
 
 void Linear_half_int4::forward(const Matrix3D<float16_t> &x, Matrix3D<float16_t> &output) {
     assert(output.m_dim_x == 1);

@@ -5,6 +5,8 @@
 #define TCE_HOST_OPS_H
 #include <assert.h>
 
+#include <string>
+
 #include "matmul.h"
 
 #define QK 128  // llm/include/common.h:17-21 under QM_CUDA
@@ -69,5 +71,13 @@ class BMM_S8T_S8N_S8T {  // llm/src/ops/BMM_S8T_S8N_S8T.cc:12-64
     void forward(const Matrix3D<int8_t> &x, const Matrix3D<int8_t> &weight, Matrix3D<int8_t> &output);
     float alpha;
 };
+
+// Parameter loading with the reference's names, file names and error behaviour (`throw const char *` on I/O failure, llm/src/utils.cc:16-25):
+// llm/src/ops/W8A8B8O8Linear.cc:6-13, W8A8BFP32OFP32Linear.cc:6-10, BMM_S8T_S8N_F32T.cc:6-8, BMM_S8T_S8N_S8T.cc:6-8.  The op's buffers may be host,
+// managed or device memory (the bytes travel with cudaMemcpyDefault).
+void load_W8A8B8O8Linear_params(W8A8B8O8Linear &op, std::string prefix);        // weight.bin, bias_int8.bin, alpha.bin, beta.bin
+void load_W8A8BFP32OFP32Linear_params(W8A8BFP32OFP32Linear &op, std::string prefix);  // weight.bin, bias.bin, alpha.bin
+void load_BMM_S8T_S8N_F32T(BMM_S8T_S8N_F32T &op, std::string prefix);           // alpha.bin
+void load_BMM_S8T_S8N_S8T(BMM_S8T_S8N_S8T &op, std::string prefix);             // alpha.bin
 
 #endif
