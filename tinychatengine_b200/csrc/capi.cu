@@ -85,14 +85,18 @@ int tce_ctx_create(int device, tce_ctx **out) {
     ctx->attn_chunk = env_int("TCE_ATTN_CHUNK", 256);  // cached rows per CTA: 256 measured best (64: -8 %, 128: -2 %; profiles/README.md)
     c.gemv_max_ctas = c.num_sms * 4;
     c.gemv_max_tiles = 32768;
-    CK(cudaMalloc(&c.gemv_partials, (size_t)c.gemv_max_ctas * 2 * 16 * 8 * sizeof(float)), "cudaMalloc gemv partials");
-    CK(cudaMalloc(&c.gemv_counters, (size_t)c.gemv_max_tiles * sizeof(unsigned)), "cudaMalloc gemv counters");
-    CK(cudaMemset(c.gemv_counters, 0, (size_t)c.gemv_max_tiles * sizeof(unsigned)), "cudaMemset");
     c.attn_ws_bytes = (size_t)128 * 1024 * 130 * sizeof(float);  // heads * splits * (128 + 2): 128 heads x 1024 splits
-    CK(cudaMalloc(&c.attn_ws, c.attn_ws_bytes), "cudaMalloc attn ws");
-    CK(cudaMalloc(&c.attn_counters, 1024 * sizeof(unsigned)), "cudaMalloc attn counters");
-    CK(cudaMemset(c.attn_counters, 0, 1024 * sizeof(unsigned)), "cudaMemset");
-    CK(cudaDeviceSynchronize(), "ctx init");
+    cudaError_t ie = cudaMalloc(&c.gemv_partials, (size_t)c.gemv_max_ctas * 2 * 16 * 8 * sizeof(float));
+    if (ie == cudaSuccess) ie = cudaMalloc(&c.gemv_counters, (size_t)c.gemv_max_tiles * sizeof(unsigned));
+    if (ie == cudaSuccess) ie = cudaMemset(c.gemv_counters, 0, (size_t)c.gemv_max_tiles * sizeof(unsigned));
+    if (ie == cudaSuccess) ie = cudaMalloc(&c.attn_ws, c.attn_ws_bytes);
+    if (ie == cudaSuccess) ie = cudaMalloc(&c.attn_counters, 1024 * sizeof(unsigned));
+    if (ie == cudaSuccess) ie = cudaMemset(c.attn_counters, 0, 1024 * sizeof(unsigned));
+    if (ie == cudaSuccess) ie = cudaDeviceSynchronize();
+    if (ie != cudaSuccess) {  // a half-built context is released, not leaked (cudaFree(nullptr) is a no-op)
+        tce_ctx_destroy(ctx);
+        return tce_fail_cuda(ie, "tce_ctx_create: workspace allocation");
+    }
     *out = ctx;
     return TCE_OK;
 }
