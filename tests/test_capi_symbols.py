@@ -122,3 +122,39 @@ def test_zeros_width_matches_reference_rule(built_lib):
     for ic in (128, 1024, 1152, 4096, 5120, 11008, 13824, 14336):
         assert L.tce_zeros_width(ic, 128) == quant.calculate_zeros_width(ic, 128) == formats.zeros_width(ic, 128)
     assert L.tce_zeros_width(11008, 128) == 11 and L.tce_zeros_width(4096, 64) == 8
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/tce_b200.h is the FFI contract: it must compile as C99 on its own (no C++ / CUDA / torch types in any signature)."""
+    import subprocess
+
+    src = tmp_path / "h.c"
+    src.write_text('#include "tce_b200.h"\nint main(void) { return tce_version() < 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", f"-I{ROOT / 'include'}", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_product_never_touches_the_oracle(built_lib):
+    """oracle/ is the checker: nothing under tinychatengine_b200/ may import, link or open it (the product path must fail without the CUDA
+    library, not fall back to the CPU restatement), and bench.py may execute it only in the cpu_baseline / --impl reference legs."""
+    import subprocess
+
+    pkg = ROOT / "tinychatengine_b200"
+    offenders = []
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")) + list(pkg.rglob("Makefile")):
+        if "build" in p.relative_to(pkg).parts[:1]:
+            continue
+        for n, line in enumerate(p.read_text(errors="replace").splitlines(), 1):
+            code = line.split("//")[0].split("#")[0] if p.suffix != ".py" else line.split("#")[0]
+            if re.search(r"\boracle\b|libtce_oracle|tce_oracle|orc_[a-z]", code) and "tests/cpp" not in line:
+                offenders.append(f"{p.relative_to(ROOT)}:{n}: {line.strip()}")
+    assert not offenders, "\n".join(offenders)
+    # the shipped libraries do not link the oracle or any reference build
+    for so in (pkg / "lib").glob("*.so"):
+        needed = subprocess.run(["readelf", "-d", str(so)], capture_output=True, text=True).stdout
+        assert "tce_oracle" not in needed and "tce_ref" not in needed, so
+    # bench.py: every use of oracle/ sits inside the CPU-baseline class or the reference arm
+    text = (ROOT / "bench.py").read_text()
+    gpu_arm = text[text.index("def run_ours"):text.index("def main")]
+    body = re.sub(r"cpu_baseline\([^\n]*", "", gpu_arm)
+    assert "oracle" not in body and "capi" not in body

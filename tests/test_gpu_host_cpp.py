@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 def test_reference_style_op_tests_through_cpp_surface():
     exe = ROOT / "tests" / "cpp" / "test_host"
     if not exe.exists():
-        subprocess.run(["make", "-s", "-C", str(ROOT / "tinychatengine_b200" / "host"), "test_host"], check=True)
+        subprocess.run(["make", "-s", "-C", str(ROOT / "tests" / "cpp")], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
@@ -30,7 +30,7 @@ def test_int4llama_for_causal_lm_module_shell(tmp_path):
 
     exe = ROOT / "tests" / "cpp" / "test_int4llama"
     if not exe.exists():
-        subprocess.run(["make", "-s", "-C", str(ROOT / "tinychatengine_b200" / "host"), "test_host"], check=True)
+        subprocess.run(["make", "-s", "-C", str(ROOT / "tests" / "cpp")], check=True)
     ctx = Context(0)
     g = GEOMETRIES["tiny-gqa"]
     m = LlamaModel(ctx, g, max_ctx=64, seed=9, random_zeros=True)

@@ -10,3 +10,4 @@ for v in pair pair_fused; do
   head -12 gpurun_out/r02_ncu_gemm_$v.txt
 done
 ls -la gpurun_out
+timeout 200 python -m pytest tests/test_gpu_llama.py -x -q --timeout 180 > gpurun_out/r02_t_llama_final.log 2>&1; echo "pytest llama rc=$?"; tail -3 gpurun_out/r02_t_llama_final.log
