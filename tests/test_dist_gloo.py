@@ -23,6 +23,13 @@ def test_tensor_parallel_exchanges_world2_gloo():
     assert r.returncode == 0 and "GLOO_TP_OK 2" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
 
 
+def test_tensor_parallel_decode_steps_world2_gloo():
+    """Whole decode steps, tensor parallel over 2 ranks on the host (shard_weights + the pinned llama_forward composition + gloo collectives),
+    equal the single-rank steps of the same weights: the host-side contract of BASELINE config 5."""
+    r = torchrun(2, 29623, str(ROOT / "tests" / "dist_step_worker.py"))
+    assert r.returncode == 0 and "GLOO_TP_STEP_OK 2" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
 @pytest.mark.skipif(not capi.ref_available("avx"), reason="reference AVX build (oracle/_ref) not present")
 def test_bench_reference_arm_under_torchrun_prints_one_line():
     r = torchrun(2, 29622, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--model", "tiny-gqa")
