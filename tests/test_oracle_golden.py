@@ -210,6 +210,39 @@ def test_llama_attention_module_live(E, H, KVH, prefill, steps, seed, tmp_path):
     assert diff.max() <= np.abs(want).max() / 100
 
 
+def test_w4a8_linear_restatement_matches_avx_fixture(golden_dir):
+    """oracle/llama_ref.py::w4a8_linear (the projection arithmetic of the reference's CPU build: int8 activations per 32-block x int4 weights,
+    kernels/avx/matmul_avx_int8_int4.cc) against the output of the compiled AVX kernel stored in kernels_avx.npz."""
+    from oracle import llama_ref
+
+    g = np.load(golden_dir / "kernels_avx.npz")
+    got = llama_ref.w4a8_linear(g["A"], (llama_ref.unpack_q4_3(g["qs"]), g["d"].astype(np.float32)))
+    assert got.shape == g["C"].shape
+    assert np.abs(got - g["C"]).max() <= 2e-6 * np.abs(g["C"]).max()
+
+
+@pytest.mark.skipif(not capi.ref_available("avx"), reason="reference AVX build (oracle/_ref) not present")
+@pytest.mark.parametrize("M,IC,OC,seed", [(1, 4096, 256, 1), (3, 1024, 64, 2), (8, 512, 128, 3)])
+def test_w4a8_linear_restatement_matches_avx_live(M, IC, OC, seed):
+    from oracle import llama_ref, quant
+
+    rng = np.random.default_rng(seed)
+    w = (rng.standard_normal((OC, IC)) * 0.02).astype(np.float32)
+    qs, d = quant.quantize_q4_3(w)
+    A = capi.aligned_empty((M, IC), np.float32)
+    A[:] = rng.standard_normal((M, IC)).astype(np.float32)
+    Bq = capi.aligned_empty(qs.shape, np.uint8)
+    Bq[:] = qs
+    S = capi.aligned_empty(d.shape, np.float32)
+    S[:] = d
+    Cx = capi.aligned_empty((M, OC), np.float32)
+    xi8 = capi.aligned_empty((M * IC,), np.int8)
+    xs = capi.aligned_empty((M * IC // 32,), np.float32)
+    capi.ref("avx").ref_w4a8_avx(A.ctypes.data, Bq.ctypes.data, S.ctypes.data, Cx.ctypes.data, xi8.ctypes.data, xs.ctypes.data, M, IC, OC, 2)
+    got = llama_ref.w4a8_linear(np.array(A), (llama_ref.unpack_q4_3(qs), d.astype(np.float32)))
+    assert np.abs(got - Cx).max() <= 2e-6 * np.abs(Cx).max()
+
+
 def test_llama_model_composition_golden(golden_dir):
     """oracle/llama_ref.py::llama_forward -- the composition of a Llama step that tests/helpers.py::oracle_decode_step runs for the GPU parity tests
     -- fed with the reference CPU build's arithmetic (fp32, W4A8 projections) reproduces the logits of the reference's WHOLE model
