@@ -1,5 +1,5 @@
 // attention_impl.cuh -- device-side body of the per-token KV-cache attention (one (kv head, split) work item),
-// shared by the stand-alone kernel (attention.cu) and the persistent decode kernel (decode_megakernel.cu).
+// shared by the stand-alone kernel (attention.cu) and the persistent decode kernel (decode_persistent.cu).
 // See attention.cu for the design notes and reference citations.
 #pragma once
 #include "common.cuh"

@@ -1,5 +1,5 @@
 // w4a16_gemv_impl.cuh -- device-side roles of the W4A16 group-128 GEMV (producer / consumer / epilogue), shared by
-// the stand-alone kernel (w4a16_gemv.cu) and the persistent decode kernel (decode_megakernel.cu).
+// the stand-alone kernel (w4a16_gemv.cu) and the persistent decode kernel (decode_persistent.cu).
 //
 // Data contract = the reference's QM_CUDA layout (kernels/cuda/gemv_cuda.cu:140-260, quantize_methods.py:370-442):
 //     w uint32[OC][IC/8] sequential nibbles, zeros uint32[OC][zeros_w] (nibble g = zero of group g),
