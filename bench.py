@@ -258,6 +258,98 @@ def cpu_baseline(geom, budget_s: float):
     return {"value": 1.0 / med, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.describe(len(times))}
 
 
+def cpu_baseline_w8a8(budget_s: float = 6.0):
+    """configs[2] beside the GPU number: the six linears of one Int8OPTDecoderLayer-shaped layer at the Llama-2-7B widths, M = 1, through the
+    reference's own AVX int8 kernels (oracle/_ref/libtce_ref_avx.so: mat_mul_accelerator_int8_fast_32unroll_over_column for q/k/v/fc1,
+    ..._bfp32_ofp32_over_column for out_proj/fc2 -- the methods W8A8B8O8Linear / W8A8BFP32OFP32Linear call at m == 1, kernels/avx/matmul_avx_int8.cc),
+    NUM_THREAD = the fastest of a few (these kernels create their threads per call); the BMMs / softmax / LayerNormQ of the layer are not included."""
+    import numpy as np
+
+    from oracle import capi
+
+    if not capi.ref_available("avx"):
+        return {"unavailable": "oracle/_ref/libtce_ref_avx.so not built"}
+    E, F = 4096, 11008
+    rng = np.random.default_rng(1)
+    mats = []  # (variant, A, B, bias8, biasf, q_min): weights of 3 distinct layers are cycled so that they do not stay cache resident
+    for _ in range(3):
+        layer = []
+        for variant, n, k, q_min in ((1, E, E, -128), (1, E, E, -128), (1, E, E, -128), (5, E, E, -128), (1, F, E, 0), (5, E, F, -128)):
+            B = capi.aligned_empty((n, k), np.int8)
+            B[:] = rng.integers(-127, 128, (n, k), dtype=np.int8)
+            A = capi.aligned_empty((1, k), np.int8)
+            A[:] = rng.integers(-127, 128, (1, k), dtype=np.int8)
+            b8 = rng.integers(-127, 128, (n,), dtype=np.int8) if variant == 1 else None
+            bf = rng.standard_normal(n).astype(np.float32) if variant == 5 else None
+            layer.append((variant, A, B, b8, bf, q_min))
+        mats.append(layer)
+    wbytes = 4 * E * E + 2 * E * F
+
+    def one_layer(layer, threads):
+        t0 = time.perf_counter()
+        for variant, A, B, b8, bf, q_min in layer:
+            capi.ref_int8_matmul(variant, A, B, b8, bf, 0.00050354, 0.0213013, q_min, 127, kind="avx", num_thread=threads)
+        return time.perf_counter() - t0
+
+    cores = os.cpu_count() or 1
+    cands = [c for c in (4, 8, 16, 32) if c <= cores] or [1]  # the over_column kernels need N % (8 * threads) == 0: 4096 and 11008 allow up to 32
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        one_layer(mats[0], c)
+        t = min(one_layer(mats[i % 3], c) for i in range(1, 4))
+        if t < best_t:
+            best, best_t = c, t
+    times, t0, i = [], time.perf_counter(), 0
+    while not times or (time.perf_counter() - t0 < budget_s and len(times) < 64):
+        times.append(one_layer(mats[i % 3], best))
+        i += 1
+    med = sorted(times)[len(times) // 2]
+    return {"ms_per_layer_linears": med * 1e3, "weight_GB_per_s": wbytes / med / 1e9, "tok_s_at_32_layers": 1.0 / (32 * med), "cores": best, "kind": "reference",
+            "sample": f"{len(times)} passes over the six linears of one layer (M = 1; q/k/v/o 4096x4096, fc1 11008x4096 ReLU, fc2 4096x11008), 3 layers' weights cycled; "
+                      "the reference's AVX int8 kernels; attention BMMs / softmax / LayerNormQ not included"}
+
+
+def cpu_baseline_prefill(cores: int, model: str = "llama2-13b", m: int = 128):
+    """configs[3] beside the GPU number, as SURVEY.md 8(d) asks: the reference's AVX W4A8 path on a REDUCED prompt -- the seven linears of one layer of the
+    13B model at M = 128 rows (2048 rows of all 40 layers would take minutes) -- timed once after a warm-up and scaled to tokens/s of the full model
+    (x num_layers; attention / norms / lm_head not included), labelled as such.  `cores`: the pool size this process already fixed (see CpuReferenceDecode)."""
+    import numpy as np
+
+    from oracle import capi
+    from tinychatengine_b200.llama import GEOMETRIES
+
+    if not capi.ref_available("avx"):
+        return {"unavailable": "oracle/_ref/libtce_ref_avx.so not built"}
+    g = GEOMETRIES[model]
+    hd, E, F = g.head_dim, g.embed_dim, g.hidden_dim
+    shapes = [(g.num_heads * hd, E), (g.num_kv_heads * hd, E), (g.num_kv_heads * hd, E), (E, g.num_heads * hd), (F, E), (F, E), (E, F)]
+    rng = np.random.default_rng(2)
+    X = capi.ref("avx")
+    ops = []
+    for oc, ic in shapes:
+        B = capi.aligned_empty((oc, ic // 2), np.uint8)
+        B[:] = rng.integers(0, 256, (oc, ic // 2), dtype=np.uint8)
+        S = capi.aligned_empty((oc, ic // 32), np.float32)
+        S[:] = (rng.random((oc, ic // 32), dtype=np.float32) + 0.5) * 0.004
+        A = capi.aligned_empty((m, ic), np.float32)
+        A[:] = rng.standard_normal((m, ic), dtype=np.float32)
+        ops.append((A, B, S, capi.aligned_empty((m, oc), np.float32), capi.aligned_empty((m * ic,), np.int8), capi.aligned_empty((m * ic // 32,), np.float32), oc, ic))
+
+    def layer():
+        t0 = time.perf_counter()
+        for A, B, S, Cc, xi8, xs, oc, ic in ops:
+            X.ref_w4a8_avx(A.ctypes.data, B.ctypes.data, S.ctypes.data, Cc.ctypes.data, xi8.ctypes.data, xs.ctypes.data, m, ic, oc, cores)
+        return time.perf_counter() - t0
+
+    layer()
+    t = min(layer(), layer())
+    flops = 2.0 * m * sum(oc * ic for *_, oc, ic in ops)
+    return {"model": model, "rows": m, "s_per_layer_linears": t, "linear_tflops": flops / t / 1e12, "tok_per_s_scaled": m / (t * g.num_layers), "cores": cores,
+            "kind": "reference",
+            "sample": f"one layer's seven linears at M = {m} through the reference's W4A8 AVX kernel (g32 CPU format), best of 2 after a warm-up; "
+                      f"tok/s scaled by {g.num_layers} layers (attention, norms, lm_head not included): an estimate, not a measurement of a {2048}-token prompt"}
+
+
 def run_reference(args):
     rank, _, world = env_rank()
     if rank != 0:
@@ -558,6 +650,15 @@ def run_ours(args):
                 line["cpu_baseline"] = cpu_baseline(geom, args.cpu_budget)
             except Exception as ex:  # the baseline must never hide the GPU number
                 line["cpu_baseline"] = {"error": repr(ex)}
+            # the reference's CPU path timed beside the two secondary configs as well (bounded samples)
+            if "extra" in line:
+                for key, fn in (("w8a8_7b", lambda: cpu_baseline_w8a8(min(6.0, args.cpu_budget))),
+                                ("prefill_13b_2048", lambda: cpu_baseline_prefill(int(line["cpu_baseline"].get("cores", 8))))):
+                    if isinstance(line["extra"].get(key), dict):
+                        try:
+                            line["extra"][key]["cpu_baseline"] = fn()
+                        except Exception as ex:
+                            line["extra"][key]["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
