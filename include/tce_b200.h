@@ -51,7 +51,8 @@ TCE_API int tce_ctx_read_gemv_timing(tce_ctx *ctx, unsigned long long *host_out,
  * Replaces MatmulOperator::gemv_forward_cuda (kernels/cuda/gemv_cuda.cu:213-260), called by
  * Linear_half_int4::forward (llm/src/ops/cuda/linear.cu:5-40).
  *   x half[M][IC], w uint32[OC][IC/8], zeros uint32[OC][zeros_w], scales half[OC][zeros_w*8], y half[M][OC]
- *   zeros_w = tce_zeros_width(IC, group); group must be 128 (QK under QM_CUDA, llm/include/common.h:17-21).
+ *   zeros_w = tce_zeros_width(IC, group); group 128 (QK under QM_CUDA, llm/include/common.h:17-21) or 64 (gemv_kernel_g64,
+ *   kernels/cuda/gemv_cuda.cu:68-123: GEMV only; the GEMM entry point takes 128).
  * Any M: M <= 8 is one pass over the weights, larger M loops in blocks of 8 rows.                        */
 TCE_API int tce_zeros_width(int in_features, int group_size);
 TCE_API int tce_w4a16_gemv(tce_ctx *ctx, const void *x, const void *w, const void *zeros, const void *scales, void *y,
