@@ -127,8 +127,9 @@ class CpuReferenceDecode:
     """The linears of one decode token driven through the reference's own CPU kernel (Linear_FP_int4::forward's
     mat_mul_accelerator_int8_int4_fast_no_offset, QM_x86 g32 format, oracle/ref_shim.cc fills matmul_params like
     llm/src/ops/linear.cc:171-236) with all host threads.  `token()` runs EVERY linear of a token once -- num_layers x (q k v o gate up
-    down) + lm_head -- cycling over `distinct` separately allocated layers so that the weights do not stay cache resident; attention
-    and norms are not included (they are < 1 % of the reference's CPU time at batch 1)."""
+    down) + lm_head -- cycling over `distinct` separately allocated layers so that the weights do not stay cache resident.  Attention
+    and norms are NOT part of the timed value, which therefore flatters the reference: reference_attention_cost() below measures what its
+    attention module adds per token on the same host and the lines report it next to the value."""
 
     def __init__(self, geom, distinct: int = 4, threads: int = 0, with_lm_head: bool = True):
         import numpy as np
@@ -212,7 +213,44 @@ class CpuReferenceDecode:
     def describe(self, n):
         g = self.geom
         return (f"{n} full tokens: every linear of a {g.name} decode step ({g.num_layers} layers x 7 + lm_head) through the reference's W4A8 AVX kernel "
-                f"(g32 CPU format), {self.distinct} distinct layers' weights cycled; attention/norms not included")
+                f"(g32 CPU format), {self.distinct} distinct layers' weights cycled; attention/norms not included (see excluded_attention)")
+
+
+def reference_attention_cost(geom, cores: int, ctx: int = 512, steps: int = 8):
+    """What the linears-only CPU number leaves out, measured instead of assumed: one layer of the reference's OWN Int4llamaAttention module (CPU build
+    compiled in place, oracle/_ref/libtce_ref_llama.so: q/k/v/o linears, RoPE, KV concat, the GQA `repeat` copies, BMM_F32T, softmax --
+    llm/src/nn_modules/non_cuda/Int4llamaAttention.cc:288-442) at this model's widths, timed per single-token call after a prompt of 1 and of `ctx`
+    tokens with NUM_THREAD = `cores`.  The difference is the attention core at that context; x num_layers = its cost per token.  Bounded: a few seconds."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+
+    from oracle import capi
+
+    if not (capi.REF_DIR / "libtce_ref_llama.so").exists():
+        return {"unavailable": "oracle/_ref/libtce_ref_llama.so not built"}
+    hd, E, H, KVH = geom.head_dim, geom.embed_dim, geom.num_heads, geom.num_kv_heads
+    rng = np.random.default_rng(3)
+    W = {name: (rng.standard_normal((rows, E)) * 0.02).astype(np.float32) for name, rows in (("q_proj", H * hd), ("k_proj", KVH * hd), ("v_proj", KVH * hd), ("o_proj", E))}
+    max_sq = ctx + steps + 8
+    cosb, sinb = capi.rope_tables(max_sq, hd, geom.rope_theta)
+    root = tempfile.mkdtemp(prefix="tce_ref_attn_")
+    try:
+        capi.write_llama_attention_params(root, W, cosb, sinb, np.float32(1.0 / np.sqrt(hd)))
+        per_step = {}
+        for past in (1, ctx):
+            hidden = rng.standard_normal((past + steps, E)).astype(np.float32)
+            *_, secs = capi.ref_int4_llama_attention(root, hidden, E, H, KVH, past, steps, max_sq, num_thread=cores, timing=True)
+            per_step[past] = secs / steps
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    core = max(0.0, per_step[ctx] - per_step[1])
+    return {"module": "Int4llamaAttention::forward (reference CPU build), one layer, single-token calls", "cores": cores, "ctx": ctx,
+            "ms_per_layer_at_ctx_1": per_step[1] * 1e3, f"ms_per_layer_at_ctx_{ctx}": per_step[ctx] * 1e3,
+            "attention_core_ms_per_token": core * 1e3 * geom.num_layers,
+            "note": f"the timed value covers the linears only; at ctx {ctx} the reference's attention core (everything in the module besides its four linears) adds this "
+                    f"many ms per token ({geom.num_layers} layers), growing about linearly with the context"}
 
 
 def pick_reference_threads(model: str) -> int:
@@ -255,7 +293,12 @@ def cpu_baseline(geom, budget_s: float):
     while not times or (time.perf_counter() - t0 < budget_s and len(times) < 16):
         times.append(ref.token())
     med = sorted(times)[len(times) // 2]
-    return {"value": 1.0 / med, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.describe(len(times))}
+    out = {"value": 1.0 / med, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.describe(len(times))}
+    try:
+        out["excluded_attention"] = reference_attention_cost(geom, ref.cores)
+    except Exception as ex:
+        out["excluded_attention"] = {"error": repr(ex)}
+    return out
 
 
 def cpu_baseline_w8a8(budget_s: float = 6.0):
@@ -382,6 +425,13 @@ def run_reference(args):
             "cpu_baseline": {"value": tok_s, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
                              "sample": f"{args.steps} steps of 1/{slices} token each = {sum(f for _, f in samples):.2f} tokens; " + ref.describe(0).split(": ", 1)[1]},
             "e2e": {"value": tok_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, "wall_s": wall}
+    try:  # what the value leaves out, measured on this host (never allowed to hide the line)
+        line["excluded_attention"] = reference_attention_cost(geom, ref.cores)
+        core_ms = line["excluded_attention"].get("attention_core_ms_per_token")
+        if core_ms is not None:
+            line["excluded_attention"]["tok_s_with_attention_at_that_ctx"] = 1e3 / (1e3 / tok_s + core_ms)
+    except Exception as ex:
+        line["excluded_attention"] = {"error": repr(ex)}
     print(json.dumps(line), flush=True)
 
 

@@ -487,22 +487,26 @@ def write_llama_attention_params(root, W, cosb, sinb, alpha):
     np.array([alpha], np.float32).tofile(os.path.join(d, "alpha.bin"))
 
 
-def ref_int4_llama_attention(param_root, hidden, E, H, KVH, prefill, decode_steps, max_sqlen):
-    """Runs the REFERENCE Int4llamaAttention::forward (CPU).  Returns (out fp32 [T][E], K, V fp32 [KVH][T][hd])."""
+def ref_int4_llama_attention(param_root, hidden, E, H, KVH, prefill, decode_steps, max_sqlen, num_thread=None, timing=False):
+    """Runs the REFERENCE Int4llamaAttention::forward (CPU).  Returns (out fp32 [T][E], K, V fp32 [KVH][T][hd]); with timing=True also the wall
+    seconds of the decode steps alone.  num_thread: the reference's NUM_THREAD global (its worker pool is sized by the first call of the process)."""
     so = REF_DIR / "libtce_ref_llama.so"
     if not so.exists():
         raise FileNotFoundError(f"{so} not built (needs /root/reference; run `make -C oracle ref`)")
     L = C.CDLL(str(so))
-    L.ref_int4_llama_attention.argtypes = [C.c_char_p] + [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    if num_thread is not None:
+        C.c_int.in_dll(L, "NUM_THREAD").value = int(num_thread)
+    L.ref_int4_llama_attention_timed.argtypes = [C.c_char_p] + [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     hidden = np.ascontiguousarray(hidden, np.float32)
     T, hd = prefill + decode_steps, E // H
     out = np.zeros((T, E), np.float32)
     fk = np.zeros((KVH, T, hd), np.float32)
     fv = np.zeros((KVH, T, hd), np.float32)
-    n = L.ref_int4_llama_attention(str(param_root).encode(), E, H, KVH, max_sqlen, hidden.ctypes.data, prefill, decode_steps, out.ctypes.data,
-                                   fk.ctypes.data, fv.ctypes.data)
+    secs = C.c_double(0.0)
+    n = L.ref_int4_llama_attention_timed(str(param_root).encode(), E, H, KVH, max_sqlen, hidden.ctypes.data, prefill, decode_steps, out.ctypes.data,
+                                         fk.ctypes.data, fv.ctypes.data, C.addressof(secs))
     assert n == T
-    return out, fk, fv
+    return (out, fk, fv, secs.value) if timing else (out, fk, fv)
 
 
 def oracle_llama_attention_module(hidden, sel, cosb, sinb, alpha, H, KVH, prefill, decode_steps):

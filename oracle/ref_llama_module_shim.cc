@@ -5,6 +5,7 @@
 // rotary_emb/{cos,sin}_cached.bin, qk_bmm/alpha.bin, written by oracle/capi.py), and Int4llamaAttention::forward runs a prefill
 // followed by single-token steps fed with the returned past_key_value, exactly like Int4llamaDecoderLayer does
 // (llm/src/nn_modules/non_cuda/Int4llamaDecoderLayer.cc).  It pins oracle/tce_oracle.c's orc_llama_attention_core.
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -21,15 +22,19 @@ extern "C" {
 
 // hidden: fp32 [T][E] (prefill rows, then one row per decode step).  out: fp32 [T][E] in call order.
 // final_k / final_v: fp32 [KVH][T][hd] (post-RoPE keys) after the last call.
-int ref_int4_llama_attention(const char *param_path, int E, int H, int KVH, int max_sqlen, const float *hidden, int prefill, int decode_steps, float *out,
-                             float *final_k, float *final_v) {
+// decode_seconds (may be NULL): wall time of the single-token calls alone (the constructor and the prompt pass are outside it) -- bench.py uses it to
+// state what the reference's attention module costs per token on the host next to the linears-only CPU baseline.
+int ref_int4_llama_attention_timed(const char *param_path, int E, int H, int KVH, int max_sqlen, const float *hidden, int prefill, int decode_steps, float *out,
+                                   float *final_k, float *final_v, double *decode_seconds) {
     struct model_config cfg(1, H, KVH, 1, max_sqlen, E, 4 * E, 32000, 1, 1e-5f);
     Int4llamaAttention::initialized_memory(cfg);
     Int4llamaAttention attn(std::string(param_path), cfg, 0);
     const int hd = E / H;
     Matrix3D<float> past_k, past_v;
     int past = 0, row = 0;
+    std::chrono::steady_clock::time_point t_decode;
     for (int call = 0; call < 1 + decode_steps; call++) {
+        if (call == 1) t_decode = std::chrono::steady_clock::now();
         const int sqlen = call == 0 ? prefill : 1, tgz = past + sqlen;
         // Int4llamaDecoder::prepare_decoder_attention_mask (non_cuda/Int4llamaDecoder.cc): 0 on/below the diagonal, lowest float above
         std::vector<float> mask((size_t)sqlen * tgz, 0.f);
@@ -46,8 +51,14 @@ int ref_int4_llama_attention(const char *param_path, int E, int H, int KVH, int 
         past = tgz;
         row += sqlen;
     }
+    if (decode_seconds) *decode_seconds = decode_steps > 0 ? std::chrono::duration<double>(std::chrono::steady_clock::now() - t_decode).count() : 0.0;
     memcpy(final_k, past_k.m_data, (size_t)KVH * past * hd * sizeof(float));
     memcpy(final_v, past_v.m_data, (size_t)KVH * past * hd * sizeof(float));
     return past;
+}
+
+int ref_int4_llama_attention(const char *param_path, int E, int H, int KVH, int max_sqlen, const float *hidden, int prefill, int decode_steps, float *out,
+                             float *final_k, float *final_v) {
+    return ref_int4_llama_attention_timed(param_path, E, H, KVH, max_sqlen, hidden, prefill, decode_steps, out, final_k, final_v, nullptr);
 }
 }

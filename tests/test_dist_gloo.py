@@ -38,3 +38,6 @@ def test_bench_reference_arm_under_torchrun_prints_one_line():
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0
+    # what the linears-only value leaves out is measured on the host, not assumed
+    ex = d["excluded_attention"]
+    assert "error" not in ex and ex["attention_core_ms_per_token"] >= 0 and ex["tok_s_with_attention_at_that_ctx"] <= d["value"]
