@@ -10,7 +10,7 @@
  *
  * Parity pinning: the reference ships no golden vectors for this path (llm/assets is a download), so the
  * oracle is pinned against the reference's own sources compiled in place (oracle/_ref, see
- * oracle/ref_shim.cc + tests/test_oracle_vs_ref.py) and against fixtures generated from that build
+ * oracle/ref_*shim.cc + tests/test_oracle_golden.py) and against fixtures generated from that build
  * (tests/golden/, generator tests/golden/make_golden.py).
  */
 #include <math.h>
