@@ -9,6 +9,6 @@ TEST INFRASTRUCTURE ONLY: importable from tests/, ``__graft_entry__.smoke()`` an
   (llm/tools/quantize_methods.py) used to make byte-identical packed inputs.
 
 Parity pinning status: the reference's golden tensors (llm/assets, a download) are absent, so the oracle is
-pinned against the reference sources compiled here (tests/test_oracle_vs_ref.py, runs whenever oracle/_ref
+pinned against the reference sources compiled here (tests/test_oracle_golden.py, runs whenever oracle/_ref
 exists) and against committed fixtures generated from that build (tests/golden/).
 """
